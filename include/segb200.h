@@ -1,0 +1,210 @@
+/* segb200.h — C ABI of the B200-native segmentation hot path.
+ *
+ * The reference (nathanin/segmentation) has no FFI of its own: its hot path is
+ * the set of TensorFlow-1.x ops that `sess.run(self.train_op_list)`
+ * (/root/reference/models/basemodel.py:484) and `sess.run(self.inference_ops)`
+ * (/root/reference/models/basemodel.py:529) execute for the graphs built by
+ * models/unet.py:109-175, models/fcn.py:93-220, models/deconvolution.py:101-178.
+ * Each entry point below replaces one of those TF ops (cited per function) with a
+ * hand-written sm_100a kernel.  See INTEGRATION.md for the binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions; every call returns int32 status
+ *     (0 = ok, <0 = seg_status); seg_last_error_string() is thread-local.
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns all
+ *     buffers; the library allocates nothing on the hot path.
+ *   - every entry takes `stream` (a cudaStream_t passed as void*), enqueues and
+ *     returns: stream-ordered, no hidden synchronisation, CUDA-graph capturable.
+ *   - activations are NHWC bf16 described by seg_view (channel stride 1),
+ *     logits / loss / gradients of parameters are fp32, weights are fp32 masters
+ *     in TF layouts (HWIO conv, HWOI transposed conv) plus bf16 shadows in the
+ *     same layout with channels padded (see seg_adam_multi).
+ */
+#ifndef SEGB200_H_
+#define SEGB200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SEG_API __attribute__((visibility("default")))
+#else
+#define SEG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum seg_status {
+  SEG_OK = 0,
+  SEG_E_BAD_SHAPE = -1,
+  SEG_E_ALIGN = -2,
+  SEG_E_WORKSPACE = -3,
+  SEG_E_ARCH = -4,
+  SEG_E_CUDA = -5,
+  SEG_E_UNSUPPORTED = -6
+} seg_status;
+
+/* NHWC view: element (n,y,x,c) lives at ptr[n*sn + y*sh + x*sw + c].  Crops and
+ * channel slices of a larger tensor are expressed by ptr offset + strides, which
+ * is how tf.image.resize_image_with_crop_or_pad (models/unet.py:140) and
+ * tf.concat (models/unet.py:141) cost no kernel here. */
+typedef struct seg_view {
+  void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+} seg_view;
+
+enum { SEG_IMPL_UMMA = 0, SEG_IMPL_SIMT = 1 };
+
+enum {
+  SEG_EPI_BIAS = 1,       /* + bias[co]                                  */
+  SEG_EPI_RELU = 2,       /* max(.,0)  (slim default activation_fn)      */
+  SEG_EPI_OUT_F32 = 4,    /* y is fp32 (logits) instead of bf16          */
+  SEG_EPI_RELU_MASK = 8   /* dgrad only: zero where mask_src <= 0        */
+};
+
+/* Convolution geometry shared by fwd / dgrad / wgrad.  x may be the virtual
+ * concatenation [x | x2] along channels (x2 nullable): Cin = x.c + x2.c. */
+typedef struct seg_conv_desc {
+  int32_t kh, kw, stride;
+  int32_t pad_t, pad_l, pad_b, pad_r; /* explicit TF-SAME / VALID padding */
+  int32_t cin, cout;                  /* logical (unpadded) channel counts */
+  int32_t cin_pad, cout_pad;          /* channel counts of the bf16 shadow */
+  int32_t flags;                      /* SEG_EPI_*                         */
+  int32_t impl;                       /* SEG_IMPL_*                        */
+} seg_conv_desc;
+
+/* ---- library / device -------------------------------------------------- */
+SEG_API int32_t seg_version(void);
+/* 0 iff the current device is compute capability 10.0 (sm_100a kernels). */
+SEG_API int32_t seg_device_check(void);
+SEG_API const char* seg_last_error_string(void);
+
+/* ---- convolution: replaces Conv2D(+BiasAdd+Relu), Conv2DBackpropInput,
+ * Conv2DBackpropFilter emitted for slim.convolution2d
+ * (models/unet.py:111-167, models/fcn.py:110-128, models/deconvolution.py:109-174) */
+SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
+                       const void* w_bf16, const float* bias, const seg_view* y, void* stream);
+/* dx (and dx2 for a virtual concat) = conv_input_grad(dz).  mask_src/mask_src2
+ * (nullable, same geometry as dx/dx2) apply the ReluGrad of the layer that
+ * produced x.  dz is the gradient w.r.t. this conv's PRE-activation output. */
+SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
+                         const seg_view* dx, const seg_view* dx2, const seg_view* mask_src,
+                         const seg_view* mask_src2, void* stream);
+/* dw (fp32, master layout [kh][kw][cin][cout]) += x^T * dz;  caller zeroes dw. */
+SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
+                         const seg_view* dz, float* dw, void* stream);
+
+/* ---- transposed convolution: replaces Conv2DBackpropInput (+BiasAdd+Relu) and
+ * its gradients for slim.convolution2d_transpose (models/unet.py:138,145,152,159;
+ * models/deconvolution.py:150,156,159,166).  Weights HWOI [kh][kw][cout][cin].
+ * Output geometry comes from y: VALID => y.h = x.h*s + max(k-s,0). */
+SEG_API int32_t seg_deconv2d_fwd(const seg_conv_desc* d, const seg_view* x, const void* w_bf16,
+                         const float* bias, const seg_view* y, void* stream);
+SEG_API int32_t seg_deconv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
+                           const seg_view* dx, const seg_view* mask_src, void* stream);
+SEG_API int32_t seg_deconv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* dz,
+                           float* dw, void* stream);
+
+/* db[c] += sum over pixels of dz[...,c]  (BiasAddGrad).  Caller zeroes db. */
+SEG_API int32_t seg_bias_grad(const seg_view* dz, float* db, void* stream);
+
+/* ---- max-pool with argmax: replaces MaxPool / MaxPoolGrad of slim.max_pool2d
+ * (models/unet.py:120,124,128,132; models/fcn.py:117-125;
+ * models/deconvolution.py:118,130,138).  VALID, k in {2,3}, stride s.
+ * argmax: uint8 window slot dy*k+dx of the FIRST max in row-major window order
+ * (dense [n][ho][wo][c]).  Backward is a gather:
+ *   dx = relu_mask(pool_grad(dy) + add), add (nullable) = gradient arriving from
+ * a second consumer of x, given as a view positioned at (add_y0, add_x0) in x
+ * (zero outside) — covers the U-Net skip crop (models/unet.py:140-141). */
+SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const seg_view* y,
+                        uint8_t* argmax, void* stream);
+SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                        const seg_view* add, int32_t add_y0, int32_t add_x0,
+                        const seg_view* mask_src, const seg_view* dx, void* stream);
+
+/* ---- depthwise bilinear x f upsample: replaces tf.nn.conv2d_transpose with the
+ * constant diagonal filter bank of utils/upsampling.py:27-46 (models/fcn.py:142,
+ * 163,171,199,207,215), SAME, k = 2f - f%2, fused with the skip add
+ * (models/fcn.py:204,212).  out = up(x) + add (add nullable).  fp32 or bf16 out. */
+SEG_API int32_t seg_bilinear_upsample_fwd(const seg_view* x, int32_t factor, const seg_view* add,
+                                  const seg_view* y, int32_t y_is_f32, void* stream);
+SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32, int32_t factor,
+                                  const seg_view* dx, void* stream);
+
+/* ---- tf.image.resize_bilinear legacy (models/deconvolution.py:163) */
+SEG_API int32_t seg_resize_bilinear_fwd(const seg_view* x, const seg_view* y, void* stream);
+SEG_API int32_t seg_resize_bilinear_bwd(const seg_view* dy, const seg_view* dx, void* stream);
+
+/* ---- slim.batch_norm (center only, after ReLU; models/deconvolution.py:116...)
+ * stats: sum[c], sumsq[c] (fp32, caller zeroes).  apply: y=(x-mean)*rstd+beta.
+ * finalize turns sums into mean / rstd and updates the moving statistics. */
+SEG_API int32_t seg_batchnorm_stats(const seg_view* x, float* sum, float* sumsq, void* stream);
+SEG_API int32_t seg_batchnorm_finalize(const float* sum, const float* sumsq, int64_t count, int32_t c,
+                               float eps, float decay, float* mean, float* rstd,
+                               float* moving_mean, float* moving_var, void* stream);
+SEG_API int32_t seg_batchnorm_apply(const seg_view* x, const float* mean, const float* rstd,
+                            const float* beta, const seg_view* y, void* stream);
+/* inference form: mean / var are the moving statistics */
+SEG_API int32_t seg_batchnorm_infer(const seg_view* x, const float* moving_mean,
+                            const float* moving_var, float eps, const float* beta,
+                            const seg_view* y, void* stream);
+/* bwd pass 1: dbeta[c] += sum dy, dxhat[c] += sum dy*xhat;  pass 2 writes dx and
+ * applies the ReluGrad of the producing conv (x itself is the mask source). */
+SEG_API int32_t seg_batchnorm_bwd_reduce(const seg_view* dy, const seg_view* x, const float* mean,
+                                 const float* rstd, float* dbeta, float* dxhat, void* stream);
+SEG_API int32_t seg_batchnorm_bwd_apply(const seg_view* dy, const seg_view* x, const float* mean,
+                                const float* rstd, const float* dbeta, const float* dxhat,
+                                int64_t count, int32_t relu_mask, const seg_view* dx,
+                                void* stream);
+
+/* ---- slim.dropout keep 0.5 (models/deconvolution.py:129,144,154): Philox-4x32-10
+ * keyed by (seed, stream_id), element e -> counter e/4, word e%4; the same call
+ * applied to a gradient is the backward.  y = x * keep / keep_prob. */
+SEG_API int32_t seg_dropout(const seg_view* x, uint64_t seed, uint32_t stream_id, float keep_prob,
+                    const seg_view* y, void* stream);
+
+/* ---- loss: one_hot + softmax_cross_entropy_with_logits + reduce_mean and its
+ * gradient (models/basemodel.py:59-70,194,360).  logits fp32 [n,h,w,c]; labels
+ * uint8 view (c == 1; may be a centre crop of the full mask, models/unet.py:71-72).
+ * loss_sum += sum_pixels xent (caller zeroes; mean = loss_sum / pixels);
+ * dlogits (nullable) = (softmax - onehot) / pixels, bf16 with channels padded to
+ * dlogits.c (zero filled). */
+SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view* labels,
+                                 float* loss_sum, const seg_view* dlogits, void* stream);
+
+/* ---- inference head (models/unet.py:76-79): probs = sigmoid(logits) (fp32),
+ * labelmap = float32(argmax(sigmoid(logits), 3)), first index on ties. */
+SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* labelmap,
+                           void* stream);
+
+/* ---- MC-dropout statistics: probs [t][count] -> mean[count], var[count]
+ * (population variance over the t passes, Welford). */
+SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, float* mean, float* var,
+                        void* stream);
+
+/* ---- optimizer: tf.train.AdamOptimizer (models/basemodel.py:321,366), epsilon
+ * outside the bias correction.  One launch over a flat fp32 parameter buffer.
+ * `segments` (device, int32[6*nseg]) maps master elements to the padded bf16
+ * shadow: {master_off, numel, inner(=last dim), inner_pad, mid(=dim -2), mid_pad}.
+ * grad is scaled by grad_scale (1/world_size for data-parallel) and zeroed. */
+SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, void* shadow_bf16,
+                       const int32_t* segments, const int64_t* shadow_offsets, int32_t nseg,
+                       int64_t numel, float lr_t, float beta1, float beta2, float eps,
+                       float grad_scale, void* stream);
+
+/* ---- layout helpers */
+/* fp32 NHWC [n,h,w,c] -> bf16 NHWC with channels zero-padded to y.c */
+SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, void* stream);
+SEG_API int32_t seg_fill_zero(void* ptr, int64_t bytes, void* stream);
+
+/* ---- self-test hooks used by tests/ (tcgen05 descriptor probes) */
+SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, const void* a,
+                       const void* b, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGB200_H_ */

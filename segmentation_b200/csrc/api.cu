@@ -1,0 +1,191 @@
+// C ABI: library/device entry points and the convolution family (dispatch between
+// the tcgen05 implicit-GEMM path and the CUDA-core path selected by desc->impl).
+#include <stdarg.h>
+#include <string.h>
+
+#include "simt_conv.cuh"
+
+namespace segb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// umma_conv.cu
+int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
+                  const float* bias, const seg_view& y, cudaStream_t st);
+int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, const seg_view& dx,
+                    const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
+                    cudaStream_t st);
+int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
+                    const seg_view& dz, float* dw, cudaStream_t st);
+int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
+                    const seg_view& y, cudaStream_t st);
+int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
+                      const seg_view& dx, const seg_view* mask, cudaStream_t st);
+int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
+                      cudaStream_t st);
+int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, float* d,
+               cudaStream_t st);
+
+static bool desc_ok(const seg_conv_desc* d) {
+  return d && d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->cin >= 1 && d->cout >= 1 &&
+         d->cin_pad >= d->cin && d->cout_pad >= d->cout && d->cin_pad % 8 == 0 &&
+         d->cout_pad % 8 == 0;
+}
+
+}  // namespace segb
+
+using namespace segb;
+
+extern "C" {
+
+SEG_API int32_t seg_version(void) { return 100; }
+
+SEG_API const char* seg_last_error_string(void) { return g_err; }
+
+SEG_API int32_t seg_device_check(void) {
+  int dev = 0;
+  SEG_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SEG_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  SEG_REQUIRE(prop.major == 10 && prop.minor == 0, SEG_E_ARCH,
+              "segb200 needs compute capability 10.0 (sm_100a); device %d is %d.%d (%s)", dev,
+              prop.major, prop.minor, prop.name);
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
+                       const void* w_bf16, const float* bias, const seg_view* y, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && w_bf16 && y, SEG_E_BAD_SHAPE, "conv2d_fwd: bad argument");
+  SEG_REQUIRE(y->h == (x->h + d->pad_t + d->pad_b - d->kh) / d->stride + 1 &&
+                  y->w == (x->w + d->pad_l + d->pad_r - d->kw) / d->stride + 1 && y->n == x->n,
+              SEG_E_BAD_SHAPE, "conv2d_fwd: output geometry mismatch (%dx%d)", y->h, y->w);
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "conv2d_fwd: bias missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->impl == SEG_IMPL_UMMA) return umma_conv_fwd(*d, *x, x2, w_bf16, bias, *y, st);
+  DirectParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = *x;
+  P.x2 = x2 ? *x2 : null_view();
+  P.w = reinterpret_cast<const bf16*>(w_bf16);
+  P.bias = bias;
+  P.y = *y;
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.in_pad = d->cin_pad; P.out_pad = d->cout_pad;
+  P.flags = d->flags & (SEG_EPI_BIAS | SEG_EPI_RELU | SEG_EPI_OUT_F32);
+  return simt_direct(P, st);
+}
+
+SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
+                         const seg_view* dx, const seg_view* dx2, const seg_view* mask_src,
+                         const seg_view* mask_src2, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && dz && w_bf16 && dx, SEG_E_BAD_SHAPE, "conv2d_dgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  seg_conv_desc dd = *d;
+  dd.flags = (mask_src || mask_src2) ? SEG_EPI_RELU_MASK : 0;
+  if (d->impl == SEG_IMPL_UMMA)
+    return umma_conv_dgrad(dd, *dz, w_bf16, *dx, dx2, mask_src, mask_src2, st);
+  TransParams P;
+  memset(&P, 0, sizeof(P));
+  P.src = *dz;
+  P.src.c = d->cout;          // padded dz channels hold zeros; skip them
+  P.w = reinterpret_cast<const bf16*>(w_bf16);
+  P.out = *dx;
+  P.out2 = dx2 ? *dx2 : null_view();
+  P.mask = mask_src ? *mask_src : null_view();
+  P.mask2 = mask_src2 ? *mask_src2 : null_view();
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.oc_pad = d->cin_pad; P.ic_pad = d->cout_pad;
+  P.flags = dd.flags;
+  return simt_transposed(P, st);
+}
+
+SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
+                         const seg_view* dz, float* dw, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && dz && dw, SEG_E_BAD_SHAPE, "conv2d_wgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->impl == SEG_IMPL_UMMA) return umma_conv_wgrad(*d, *x, x2, *dz, dw, st);
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.big = *x;
+  P.big2 = x2 ? *x2 : null_view();
+  P.small_ = *dz;
+  P.dw = dw;
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.BC = d->cin; P.SC = d->cout;
+  return simt_wgrad(P, st);
+}
+
+SEG_API int32_t seg_deconv2d_fwd(const seg_conv_desc* d, const seg_view* x, const void* w_bf16,
+                         const float* bias, const seg_view* y, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && w_bf16 && y, SEG_E_BAD_SHAPE, "deconv2d_fwd: bad argument");
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "deconv2d_fwd: bias missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->impl == SEG_IMPL_UMMA) return umma_deconv_fwd(*d, *x, w_bf16, bias, *y, st);
+  TransParams P;
+  memset(&P, 0, sizeof(P));
+  P.src = *x;
+  P.src.c = d->cin;
+  P.w = reinterpret_cast<const bf16*>(w_bf16);
+  P.bias = bias;
+  P.out = *y;
+  P.out2 = null_view();
+  P.mask = null_view();
+  P.mask2 = null_view();
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.oc_pad = d->cout_pad; P.ic_pad = d->cin_pad;
+  P.flags = d->flags & (SEG_EPI_BIAS | SEG_EPI_RELU | SEG_EPI_OUT_F32);
+  return simt_transposed(P, st);
+}
+
+SEG_API int32_t seg_deconv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
+                           const seg_view* dx, const seg_view* mask_src, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && dz && w_bf16 && dx, SEG_E_BAD_SHAPE, "deconv2d_dgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  seg_conv_desc dd = *d;
+  dd.flags = mask_src ? SEG_EPI_RELU_MASK : 0;
+  if (d->impl == SEG_IMPL_UMMA) return umma_deconv_dgrad(dd, *dz, w_bf16, *dx, mask_src, st);
+  DirectParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = *dz;
+  P.x.c = d->cout;
+  P.x2 = null_view();
+  P.w = reinterpret_cast<const bf16*>(w_bf16);
+  P.y = *dx;
+  P.mask = mask_src ? *mask_src : null_view();
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.in_pad = d->cout_pad; P.out_pad = d->cin_pad;
+  P.flags = dd.flags;
+  return simt_direct(P, st);
+}
+
+SEG_API int32_t seg_deconv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* dz,
+                           float* dw, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && dz && dw, SEG_E_BAD_SHAPE, "deconv2d_wgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->impl == SEG_IMPL_UMMA) return umma_deconv_wgrad(*d, *x, *dz, dw, st);
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.big = *dz;
+  P.big2 = null_view();
+  P.small_ = *x;
+  P.dw = dw;
+  P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
+  P.BC = d->cout; P.SC = d->cin;
+  return simt_wgrad(P, st);
+}
+
+SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, const void* a,
+                       const void* b, float* d, void* stream) {
+  SEG_REQUIRE(a && b && d && m > 0 && n % 16 == 0 && k % 16 == 0, SEG_E_BAD_SHAPE,
+              "probe_umma: bad argument");
+  return umma_probe(mode, m, n, k, a, b, d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

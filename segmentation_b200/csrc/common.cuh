@@ -1,0 +1,68 @@
+// Shared host/device helpers for the segb200 library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/segb200.h"
+
+namespace segb {
+
+typedef __nv_bfloat16 bf16;
+
+// thread-local last error text (seg_last_error_string)
+void set_error(const char* fmt, ...);
+
+#define SEG_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      segb::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                      cudaGetErrorString(_e));                                            \
+      return SEG_E_CUDA;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+#define SEG_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      segb::set_error(__VA_ARGS__);    \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+#define SEG_LAUNCH_CHECK() SEG_CHECK_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ const bf16* view_at(const seg_view& v, int n, int y, int x) {
+  return reinterpret_cast<const bf16*>(v.ptr) + n * v.sn + y * v.sh + x * v.sw;
+}
+__device__ __forceinline__ bf16* view_at_mut(const seg_view& v, int n, int y, int x) {
+  return reinterpret_cast<bf16*>(v.ptr) + n * v.sn + y * v.sh + x * v.sw;
+}
+
+static inline bool view_dense(const seg_view& v) {
+  return v.sw == v.c && v.sh == (int64_t)v.w * v.c && v.sn == (int64_t)v.h * v.w * v.c;
+}
+
+static inline seg_view null_view() {
+  seg_view v;
+  v.ptr = nullptr;
+  v.n = v.h = v.w = v.c = 0;
+  v.sn = v.sh = v.sw = 0;
+  return v;
+}
+
+}  // namespace segb

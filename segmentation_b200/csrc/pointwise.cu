@@ -1,0 +1,775 @@
+// Memory-bound kernels of the segmentation hot path: max-pool with argmax,
+// bilinear upsampling / resize, batch-norm, dropout, softmax cross-entropy,
+// inference head, MC statistics, Adam, layout helpers.  All are HBM-bound:
+// 16-byte vector accesses on the channel axis where the channel count allows,
+// grid-stride loops sized from the SM count, warp-shuffle reductions.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace segb {
+
+static int grid_for(int64_t total, int block) {
+  int64_t g = ceil_div64(total, block);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+#define GRID_STRIDE(i, total)                                                   \
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total); \
+       i += (int64_t)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------- max-pool
+template <int VEC>
+__global__ void maxpool_fwd_kernel(seg_view x, int k, int s, seg_view y, uint8_t* argmax) {
+  const int cv = y.c / VEC;
+  const int64_t total = (int64_t)y.n * y.h * y.w * cv;
+  GRID_STRIDE(idx, total) {
+    const int c0 = (idx % cv) * VEC;
+    int64_t m = idx / cv;
+    const int q = m % y.w;
+    m /= y.w;
+    const int p = m % y.h;
+    const int n = m / y.h;
+    float best[VEC];
+    uint8_t slot[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; slot[j] = 0; }
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        const bf16* xp = view_at(x, n, p * s + dy, q * s + dx) + c0;
+        float v[VEC];
+        if (VEC == 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(xp);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[2 * j] = bf16_lo(w[j]); v[2 * j + 1] = bf16_hi(w[j]); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) v[j] = __bfloat162float(xp[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (v[j] > best[j] || (dy == 0 && dx == 0)) {   // strict >: first max wins
+            best[j] = v[j];
+            slot[j] = (uint8_t)(dy * k + dx);
+          }
+      }
+    bf16* yp = view_at_mut(y, n, p, q) + c0;
+    uint8_t* ap = argmax + (((int64_t)n * y.h + p) * y.w + q) * y.c + c0;
+    if (VEC == 8) {
+      uint4 o;
+      o.x = pack_bf16x2(best[0], best[1]);
+      o.y = pack_bf16x2(best[2], best[3]);
+      o.z = pack_bf16x2(best[4], best[5]);
+      o.w = pack_bf16x2(best[6], best[7]);
+      *reinterpret_cast<uint4*>(yp) = o;
+      uint2 a;
+      a.x = slot[0] | (slot[1] << 8) | (slot[2] << 16) | ((uint32_t)slot[3] << 24);
+      a.y = slot[4] | (slot[5] << 8) | (slot[6] << 16) | ((uint32_t)slot[7] << 24);
+      *reinterpret_cast<uint2*>(ap) = a;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { yp[j] = __float2bfloat16(best[j]); ap[j] = slot[j]; }
+    }
+  }
+}
+
+// dx = relu_mask(route(dy, argmax) + add).  Non-overlapping windows (k == s).
+template <int VEC>
+__global__ void maxpool_bwd_kernel(seg_view dy, const uint8_t* argmax, int k, int s, seg_view add,
+                                   int add_y0, int add_x0, seg_view mask, seg_view dx) {
+  const int cv = dx.c / VEC;
+  const int64_t total = (int64_t)dx.n * dx.h * dx.w * cv;
+  GRID_STRIDE(idx, total) {
+    const int c0 = (idx % cv) * VEC;
+    int64_t m = idx / cv;
+    const int xx = m % dx.w;
+    m /= dx.w;
+    const int yy = m % dx.h;
+    const int n = m / dx.h;
+    float g[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g[j] = 0.f;
+    const int p = yy / s, q = xx / s;
+    if (p < dy.h && q < dy.w) {
+      const uint8_t me = (uint8_t)((yy - p * s) * k + (xx - q * s));
+      const bf16* gp = view_at(dy, n, p, q) + c0;
+      const uint8_t* ap = argmax + (((int64_t)n * dy.h + p) * dy.w + q) * dy.c + c0;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (ap[j] == me) g[j] = __bfloat162float(gp[j]);
+    }
+    if (add.ptr) {
+      const int ay = yy - add_y0, ax = xx - add_x0;
+      if (ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
+        const bf16* p2 = view_at(add, n, ay, ax) + c0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) g[j] += __bfloat162float(p2[j]);
+      }
+    }
+    if (mask.ptr) {
+      const bf16* mp = view_at(mask, n, yy, xx) + c0;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (!(__bfloat162float(mp[j]) > 0.f)) g[j] = 0.f;
+    }
+    bf16* op = view_at_mut(dx, n, yy, xx) + c0;
+    if (VEC == 8) {
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]);
+      o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]);
+      o.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(op) = o;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) op[j] = __float2bfloat16(g[j]);
+    }
+  }
+}
+
+static bool vec8_ok(const seg_view& v) {
+  return v.c % 8 == 0 && v.sw % 8 == 0 && v.sh % 8 == 0 && v.sn % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0;
+}
+
+// ------------------------------------------------- FCN depthwise bilinear
+// weight of tap a (0..k-1) of upsample_filt(k): 1 - |a - center| / F   (double)
+__device__ __forceinline__ double bil_w(int a, int k) {
+  const int F = (k + 1) / 2;
+  const double center = (k & 1) ? (double)(F - 1) : (double)F - 0.5;
+  return 1.0 - fabs((double)a - center) / (double)F;
+}
+
+__global__ void bilinear_up_fwd_kernel(seg_view x, int f, seg_view add, seg_view y, int y_f32) {
+  const int k = 2 * f - (f & 1);
+  const int before = (k - f) / 2;
+  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % y.c;
+    int64_t m = idx / y.c;
+    const int ox = m % y.w;
+    m /= y.w;
+    const int oy = m % y.h;
+    const int n = m / y.h;
+    const int ty = oy + before, tx = ox + before;
+    float acc = 0.f;
+    // contributing inputs i: 0 <= ty - i*f < k
+    for (int i = ty / f; i >= 0 && ty - i * f < k; --i) {
+      if (i >= x.h) continue;
+      const double wy = bil_w(ty - i * f, k);
+      for (int j = tx / f; j >= 0 && tx - j * f < k; --j) {
+        if (j >= x.w) continue;
+        const float wgt = (float)(wy * bil_w(tx - j * f, k));
+        acc += __bfloat162float(view_at(x, n, i, j)[c]) * wgt;
+      }
+    }
+    if (add.ptr) acc += __bfloat162float(view_at(add, n, oy, ox)[c]);
+    const int64_t off = n * y.sn + oy * y.sh + ox * y.sw + c;
+    if (y_f32)
+      reinterpret_cast<float*>(y.ptr)[off] = acc;
+    else
+      reinterpret_cast<bf16*>(y.ptr)[off] = __float2bfloat16(acc);
+  }
+}
+
+__global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view dx) {
+  const int k = 2 * f - (f & 1);
+  const int before = (k - f) / 2;
+  const int64_t total = (int64_t)dx.n * dx.h * dx.w * dx.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % dx.c;
+    int64_t m = idx / dx.c;
+    const int j = m % dx.w;
+    m /= dx.w;
+    const int i = m % dx.h;
+    const int n = m / dx.h;
+    float acc = 0.f;
+    for (int a = 0; a < k; ++a) {
+      const int oy = i * f + a - before;
+      if (oy < 0 || oy >= dy.h) continue;
+      const double wy = bil_w(a, k);
+      for (int b = 0; b < k; ++b) {
+        const int ox = j * f + b - before;
+        if (ox < 0 || ox >= dy.w) continue;
+        const float wgt = (float)(wy * bil_w(b, k));
+        const int64_t off = n * dy.sn + oy * dy.sh + ox * dy.sw + c;
+        const float g = dy_f32 ? reinterpret_cast<const float*>(dy.ptr)[off]
+                               : __bfloat162float(reinterpret_cast<const bf16*>(dy.ptr)[off]);
+        acc += g * wgt;
+      }
+    }
+    view_at_mut(dx, n, i, j)[c] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------- tf.image.resize_bilinear legacy
+__device__ __forceinline__ void legacy_src(int o, float scale, int n_in, int& lo, int& hi,
+                                           float& frac) {
+  const float src = (float)o * scale;
+  lo = (int)floorf(src);
+  hi = min((int)ceilf(src), n_in - 1);
+  frac = src - (float)lo;
+}
+
+__global__ void resize_bilinear_fwd_kernel(seg_view x, seg_view y) {
+  const float sy = (float)x.h / (float)y.h, sx = (float)x.w / (float)y.w;
+  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % y.c;
+    int64_t m = idx / y.c;
+    const int ox = m % y.w;
+    m /= y.w;
+    const int oy = m % y.h;
+    const int n = m / y.h;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    legacy_src(oy, sy, x.h, y0, y1, ly);
+    legacy_src(ox, sx, x.w, x0, x1, lx);
+    const float tl = __bfloat162float(view_at(x, n, y0, x0)[c]);
+    const float tr = __bfloat162float(view_at(x, n, y0, x1)[c]);
+    const float bl = __bfloat162float(view_at(x, n, y1, x0)[c]);
+    const float br = __bfloat162float(view_at(x, n, y1, x1)[c]);
+    const float top = tl + (tr - tl) * lx;
+    const float bot = bl + (br - bl) * lx;
+    view_at_mut(y, n, oy, ox)[c] = __float2bfloat16(top + (bot - top) * ly);
+  }
+}
+
+// gather form of ResizeBilinearGrad: each input pixel sums the outputs that read it
+__global__ void resize_bilinear_bwd_kernel(seg_view dy, seg_view dx) {
+  const float sy = (float)dx.h / (float)dy.h, sx = (float)dx.w / (float)dy.w;
+  const int64_t total = (int64_t)dx.n * dx.h * dx.w * dx.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % dx.c;
+    int64_t m = idx / dx.c;
+    const int ix = m % dx.w;
+    m /= dx.w;
+    const int iy = m % dx.h;
+    const int n = m / dx.h;
+    const int oy_lo = max(0, (int)floorf((float)(iy - 1) / sy) - 1);
+    const int oy_hi = min(dy.h - 1, (int)ceilf((float)(iy + 1) / sy) + 1);
+    const int ox_lo = max(0, (int)floorf((float)(ix - 1) / sx) - 1);
+    const int ox_hi = min(dy.w - 1, (int)ceilf((float)(ix + 1) / sx) + 1);
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1;
+      float ly;
+      legacy_src(oy, sy, dx.h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1;
+        float lx;
+        legacy_src(ox, sx, dx.w, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        acc += __bfloat162float(view_at(dy, n, oy, ox)[c]) * wy * wx;
+      }
+    }
+    view_at_mut(dx, n, iy, ix)[c] = __float2bfloat16(acc);
+  }
+}
+
+// -------------------------------------------------------------- batch-norm
+// per-channel partial sums: thread t owns channel (t % C) when C <= blockDim.
+__global__ void channel_reduce2_kernel(seg_view a, seg_view b, const float* mean,
+                                       const float* rstd, int mode, float* out0, float* out1) {
+  // mode 0: out0 += sum a, out1 += sum a^2
+  // mode 1: out0 += sum a (dy), out1 += sum a * xhat(b)
+  // mode 2: out0 += sum a           (bias grad)
+  extern __shared__ float sh[];
+  const int C = a.c;
+  const int64_t pixels = (int64_t)a.n * a.h * a.w;
+  const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;   // pixel lanes per block
+  const int c = threadIdx.x % C;
+  const int pl = threadIdx.x / C;
+  float s0 = 0.f, s1 = 0.f;
+  if (pl < lanes && threadIdx.x < lanes * C) {
+    for (int cc = c; cc < C; cc += (C > (int)blockDim.x ? blockDim.x : C)) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int64_t m = (int64_t)blockIdx.x * lanes + pl; m < pixels;
+           m += (int64_t)gridDim.x * lanes) {
+        const int xx = m % a.w;
+        const int64_t t = m / a.w;
+        const int yy = t % a.h;
+        const int n = t / a.h;
+        const float av = __bfloat162float(view_at(a, n, yy, xx)[cc]);
+        t0 += av;
+        if (mode == 0)
+          t1 += av * av;
+        else if (mode == 1)
+          t1 += av * ((__bfloat162float(view_at(b, n, yy, xx)[cc]) - mean[cc]) * rstd[cc]);
+      }
+      if (C > (int)blockDim.x) {   // one thread owns several channels: flush directly
+        atomicAdd(out0 + cc, t0);
+        if (mode != 2) atomicAdd(out1 + cc, t1);
+      } else {
+        s0 = t0;
+        s1 = t1;
+      }
+    }
+  }
+  if (C <= (int)blockDim.x) {
+    sh[threadIdx.x] = s0;
+    sh[blockDim.x + threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float r0 = 0.f, r1 = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        r0 += sh[l * C + threadIdx.x];
+        r1 += sh[blockDim.x + l * C + threadIdx.x];
+      }
+      atomicAdd(out0 + threadIdx.x, r0);
+      if (mode != 2) atomicAdd(out1 + threadIdx.x, r1);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, float inv_count, int C,
+                                   float eps, float decay, float* mean, float* rstd,
+                                   float* mmean, float* mvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = sum[c] * inv_count;
+  const float var = fmaxf(sumsq[c] * inv_count - mu * mu, 0.f);
+  mean[c] = mu;
+  rstd[c] = rsqrtf(var + eps);
+  if (mmean) mmean[c] = mmean[c] * decay + mu * (1.f - decay);
+  if (mvar) mvar[c] = mvar[c] * decay + var * (1.f - decay);
+}
+
+__global__ void bn_apply_kernel(seg_view x, const float* mean, const float* rstd_or_var, float eps,
+                                int is_var, const float* beta, seg_view y) {
+  const int64_t total = (int64_t)x.n * x.h * x.w * x.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % x.c;
+    int64_t m = idx / x.c;
+    const int xx = m % x.w;
+    m /= x.w;
+    const int yy = m % x.h;
+    const int n = m / x.h;
+    const float r = is_var ? rsqrtf(rstd_or_var[c] + eps) : rstd_or_var[c];
+    const float v = (__bfloat162float(view_at(x, n, yy, xx)[c]) - mean[c]) * r + beta[c];
+    view_at_mut(y, n, yy, xx)[c] = __float2bfloat16(v);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(seg_view dy, seg_view x, const float* mean, const float* rstd,
+                                    const float* dbeta, const float* dxhat, float inv_count,
+                                    int relu_mask, seg_view dx) {
+  const int64_t total = (int64_t)x.n * x.h * x.w * x.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % x.c;
+    int64_t m = idx / x.c;
+    const int xx = m % x.w;
+    m /= x.w;
+    const int yy = m % x.h;
+    const int n = m / x.h;
+    const float xv = __bfloat162float(view_at(x, n, yy, xx)[c]);
+    const float xh = (xv - mean[c]) * rstd[c];
+    const float g = __bfloat162float(view_at(dy, n, yy, xx)[c]);
+    float v = rstd[c] * (g - dbeta[c] * inv_count - xh * dxhat[c] * inv_count);
+    if (relu_mask && !(xv > 0.f)) v = 0.f;
+    view_at_mut(dx, n, yy, xx)[c] = __float2bfloat16(v);
+  }
+}
+
+// ----------------------------------------------------------------- dropout
+struct Philox4 { uint32_t v[4]; };
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox4 r;
+  r.v[0] = c0; r.v[1] = c1; r.v[2] = c2; r.v[3] = c3;
+  return r;
+}
+
+// x, y dense with identical geometry; element index e is the dense NHWC index.
+__global__ void dropout_kernel(const bf16* x, bf16* y, int64_t numel, uint32_t seed_lo,
+                               uint32_t seed_hi, uint32_t stream_id, float keep, float inv_keep) {
+  const int64_t nq = (numel + 3) / 4;
+  GRID_STRIDE(qi, nq) {
+    const Philox4 r = philox4x32_10((uint32_t)qi, (uint32_t)((uint64_t)qi >> 32), stream_id, 0u,
+                                    seed_lo, seed_hi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = qi * 4 + j;
+      if (e >= numel) break;
+      const float u = (float)(r.v[j] >> 8) * 5.9604644775390625e-8f;   // 2^-24
+      const float v = __bfloat162float(x[e]);
+      y[e] = __float2bfloat16(u < keep ? v * inv_keep : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------ loss / heads
+// one thread per pixel, C <= 64 channels held in registers chunk-wise
+__global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* loss_sum,
+                                    seg_view dlogits, float inv_pixels) {
+  const int C = logits.c;
+  const int64_t pixels = (int64_t)logits.n * logits.h * logits.w;
+  float local = 0.f;
+  GRID_STRIDE(m, pixels) {
+    const int xx = m % logits.w;
+    const int64_t t = m / logits.w;
+    const int yy = t % logits.h;
+    const int n = t / logits.h;
+    const float* lp =
+        reinterpret_cast<const float*>(logits.ptr) + n * logits.sn + yy * logits.sh + xx * logits.sw;
+    const int lab = reinterpret_cast<const uint8_t*>(labels.ptr)[n * labels.sn + yy * labels.sh +
+                                                                 xx * labels.sw];
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, lp[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(lp[c] - mx);
+    const float lse = mx + logf(se);
+    const float picked = lab < C ? lp[lab] : 0.f;
+    local += lse - picked;
+    if (dlogits.ptr) {
+      bf16* dp = view_at_mut(dlogits, n, yy, xx);
+      const float inv_se = 1.f / se;
+      for (int c = 0; c < dlogits.c; ++c) {
+        float g = 0.f;
+        if (c < C) g = (expf(lp[c] - mx) * inv_se - (c == lab ? 1.f : 0.f)) * inv_pixels;
+        dp[c] = __float2bfloat16(g);
+      }
+    }
+  }
+  local = warp_sum(local);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
+__global__ void sigmoid_argmax_kernel(seg_view logits, float* probs, float* labelmap) {
+  const int C = logits.c;
+  const int64_t pixels = (int64_t)logits.n * logits.h * logits.w;
+  GRID_STRIDE(m, pixels) {
+    const int xx = m % logits.w;
+    const int64_t t = m / logits.w;
+    const int yy = t % logits.h;
+    const int n = t / logits.h;
+    const float* lp =
+        reinterpret_cast<const float*>(logits.ptr) + n * logits.sn + yy * logits.sh + xx * logits.sw;
+    float best = -1.f;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+      // fp32 sigmoid, saturating to exactly 1.0f for large logits like TF's
+      const float sg = 1.f / (1.f + expf(-lp[c]));
+      probs[m * C + c] = sg;
+      if (sg > best) { best = sg; bi = c; }   // strict >: first index on ties
+    }
+    labelmap[m] = (float)bi;
+  }
+}
+
+__global__ void mc_mean_var_kernel(const float* probs, int T, int64_t count, float* mean,
+                                   float* var) {
+  GRID_STRIDE(i, count) {
+    float mu = 0.f, m2 = 0.f;
+    for (int t = 0; t < T; ++t) {       // Welford
+      const float v = probs[(int64_t)t * count + i];
+      const float d = v - mu;
+      mu += d / (float)(t + 1);
+      m2 += d * (v - mu);
+    }
+    mean[i] = mu;
+    var[i] = m2 / (float)T;
+  }
+}
+
+// -------------------------------------------------------------------- Adam
+__global__ void adam_multi_kernel(float* param, float* grad, float* m, float* v, bf16* shadow,
+                                  const int32_t* seg, const int64_t* shadow_off, int nseg,
+                                  int64_t numel, float lr_t, float b1, float b2, float eps,
+                                  float gscale) {
+  GRID_STRIDE(i, numel) {
+    const float g = grad[i] * gscale;
+    grad[i] = 0.f;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    const float p = param[i] - lr_t * mi / (sqrtf(vi) + eps);
+    m[i] = mi;
+    v[i] = vi;
+    param[i] = p;
+    // locate the segment (sorted by master offset) -> padded bf16 shadow index
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int64_t)seg[mid * 6] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int64_t so = shadow_off[lo];
+    if (so >= 0) {
+      const int32_t* s = seg + lo * 6;
+      const int64_t e = i - s[0];
+      const int inner = s[2], inner_pad = s[3], mid = s[4], mid_pad = s[5];
+      const int64_t in_i = e % inner;
+      const int64_t mid_i = (e / inner) % mid;
+      const int64_t outer = e / ((int64_t)inner * mid);
+      shadow[so + (outer * mid_pad + mid_i) * inner_pad + in_i] = __float2bfloat16(p);
+    }
+  }
+}
+
+// ----------------------------------------------------------------- layout
+__global__ void pack_input_kernel(const float* x, int C, seg_view y) {
+  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % y.c;
+    int64_t m = idx / y.c;
+    const int xx = m % y.w;
+    m /= y.w;
+    const int yy = m % y.h;
+    const int n = m / y.h;
+    const float v = c < C ? x[(((int64_t)n * y.h + yy) * y.w + xx) * C + c] : 0.f;
+    view_at_mut(y, n, yy, xx)[c] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace segb
+
+using namespace segb;
+
+// =========================================================================
+// C ABI
+// =========================================================================
+extern "C" {
+
+SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const seg_view* y,
+                        uint8_t* argmax, void* stream) {
+  SEG_REQUIRE(x && y && argmax, SEG_E_BAD_SHAPE, "maxpool_fwd: null argument");
+  SEG_REQUIRE(k >= 1 && s >= 1 && y->h == (x->h - k) / s + 1 && y->w == (x->w - k) / s + 1 &&
+                  y->c == x->c && y->n == x->n,
+              SEG_E_BAD_SHAPE, "maxpool_fwd: bad geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v8 = vec8_ok(*x) && vec8_ok(*y) && (reinterpret_cast<uintptr_t>(argmax) % 8) == 0;
+  const int64_t total = (int64_t)y->n * y->h * y->w * (v8 ? y->c / 8 : y->c);
+  if (v8)
+    maxpool_fwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*x, k, s, *y, argmax);
+  else
+    maxpool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*x, k, s, *y, argmax);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                        const seg_view* add, int32_t add_y0, int32_t add_x0,
+                        const seg_view* mask_src, const seg_view* dx, void* stream) {
+  SEG_REQUIRE(dy && argmax && dx, SEG_E_BAD_SHAPE, "maxpool_bwd: null argument");
+  SEG_REQUIRE(k == s, SEG_E_UNSUPPORTED, "maxpool_bwd: only non-overlapping windows (k == s)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const seg_view a = add ? *add : null_view();
+  const seg_view mk = mask_src ? *mask_src : null_view();
+  const bool v8 = vec8_ok(*dx) && (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
+  const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
+  if (v8)
+    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, argmax, k, s, a, add_y0,
+                                                               add_x0, mk, *dx);
+  else
+    maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, argmax, k, s, a, add_y0,
+                                                               add_x0, mk, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_bilinear_upsample_fwd(const seg_view* x, int32_t factor, const seg_view* add,
+                                  const seg_view* y, int32_t y_is_f32, void* stream) {
+  SEG_REQUIRE(x && y && factor >= 1, SEG_E_BAD_SHAPE, "bilinear_upsample_fwd: bad argument");
+  SEG_REQUIRE(y->h == x->h * factor && y->w == x->w * factor && y->c == x->c, SEG_E_BAD_SHAPE,
+              "bilinear_upsample_fwd: y must be x scaled by factor");
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  bilinear_up_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      *x, factor, add ? *add : null_view(), *y, y_is_f32);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32, int32_t factor,
+                                  const seg_view* dx, void* stream) {
+  SEG_REQUIRE(dy && dx && factor >= 1, SEG_E_BAD_SHAPE, "bilinear_upsample_bwd: bad argument");
+  const int64_t total = (int64_t)dx->n * dx->h * dx->w * dx->c;
+  bilinear_up_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*dy, dy_is_f32,
+                                                                                 factor, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_resize_bilinear_fwd(const seg_view* x, const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && x->c == y->c && x->n == y->n, SEG_E_BAD_SHAPE, "resize_bilinear_fwd");
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  resize_bilinear_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_resize_bilinear_bwd(const seg_view* dy, const seg_view* dx, void* stream) {
+  SEG_REQUIRE(dy && dx && dx->c == dy->c && dx->n == dy->n, SEG_E_BAD_SHAPE, "resize_bilinear_bwd");
+  const int64_t total = (int64_t)dx->n * dx->h * dx->w * dx->c;
+  resize_bilinear_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*dy, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+static int launch_channel_reduce(const seg_view& a, const seg_view& b, const float* mean,
+                                 const float* rstd, int mode, float* o0, float* o1,
+                                 cudaStream_t st) {
+  const int64_t pixels = (int64_t)a.n * a.h * a.w;
+  const int block = 256;
+  const int lanes = block / a.c > 0 ? block / a.c : 1;
+  int64_t g = ceil_div64(pixels, (int64_t)lanes * 64);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  channel_reduce2_kernel<<<(int)g, block, 2 * block * sizeof(float), st>>>(a, b, mean, rstd, mode,
+                                                                           o0, o1);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_bias_grad(const seg_view* dz, float* db, void* stream) {
+  SEG_REQUIRE(dz && db, SEG_E_BAD_SHAPE, "bias_grad: null argument");
+  return launch_channel_reduce(*dz, null_view(), nullptr, nullptr, 2, db, nullptr,
+                               (cudaStream_t)stream);
+}
+
+SEG_API int32_t seg_batchnorm_stats(const seg_view* x, float* sum, float* sumsq, void* stream) {
+  SEG_REQUIRE(x && sum && sumsq, SEG_E_BAD_SHAPE, "batchnorm_stats: null argument");
+  return launch_channel_reduce(*x, null_view(), nullptr, nullptr, 0, sum, sumsq,
+                               (cudaStream_t)stream);
+}
+
+SEG_API int32_t seg_batchnorm_finalize(const float* sum, const float* sumsq, int64_t count, int32_t c,
+                               float eps, float decay, float* mean, float* rstd,
+                               float* moving_mean, float* moving_var, void* stream) {
+  SEG_REQUIRE(sum && sumsq && mean && rstd && count > 0, SEG_E_BAD_SHAPE, "batchnorm_finalize");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sum, sumsq, 1.f / (float)count, c, eps, decay, mean, rstd, moving_mean, moving_var);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_batchnorm_apply(const seg_view* x, const float* mean, const float* rstd,
+                            const float* beta, const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && mean && rstd && beta, SEG_E_BAD_SHAPE, "batchnorm_apply");
+  const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, mean, rstd, 0.f, 0,
+                                                                          beta, *y);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_batchnorm_infer(const seg_view* x, const float* moving_mean, const float* moving_var,
+                            float eps, const float* beta, const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && moving_mean && moving_var && beta, SEG_E_BAD_SHAPE, "batchnorm_infer");
+  const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      *x, moving_mean, moving_var, eps, 1, beta, *y);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_batchnorm_bwd_reduce(const seg_view* dy, const seg_view* x, const float* mean,
+                                 const float* rstd, float* dbeta, float* dxhat, void* stream) {
+  SEG_REQUIRE(dy && x && mean && rstd && dbeta && dxhat, SEG_E_BAD_SHAPE, "batchnorm_bwd_reduce");
+  return launch_channel_reduce(*dy, *x, mean, rstd, 1, dbeta, dxhat, (cudaStream_t)stream);
+}
+
+SEG_API int32_t seg_batchnorm_bwd_apply(const seg_view* dy, const seg_view* x, const float* mean,
+                                const float* rstd, const float* dbeta, const float* dxhat,
+                                int64_t count, int32_t relu_mask, const seg_view* dx,
+                                void* stream) {
+  SEG_REQUIRE(dy && x && dx && count > 0, SEG_E_BAD_SHAPE, "batchnorm_bwd_apply");
+  const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      *dy, *x, mean, rstd, dbeta, dxhat, 1.f / (float)count, relu_mask, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_dropout(const seg_view* x, uint64_t seed, uint32_t stream_id, float keep_prob,
+                    const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && view_dense(*x) && view_dense(*y), SEG_E_BAD_SHAPE,
+              "dropout: dense views required");
+  const int64_t numel = (int64_t)x->n * x->h * x->w * x->c;
+  dropout_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x->ptr), reinterpret_cast<bf16*>(y->ptr), numel,
+      (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32), stream_id, keep_prob,
+      1.f / keep_prob);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view* labels, float* loss_sum,
+                                 const seg_view* dlogits, void* stream) {
+  SEG_REQUIRE(logits && labels && loss_sum, SEG_E_BAD_SHAPE, "softmax_xent: null argument");
+  SEG_REQUIRE(labels->h == logits->h && labels->w == logits->w && labels->n == logits->n,
+              SEG_E_BAD_SHAPE, "softmax_xent: labels must match logits spatially");
+  const int64_t pixels = (int64_t)logits->n * logits->h * logits->w;
+  softmax_xent_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(
+      *logits, *labels, loss_sum, dlogits ? *dlogits : null_view(), 1.f / (float)pixels);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* labelmap, void* stream) {
+  SEG_REQUIRE(logits && probs && labelmap, SEG_E_BAD_SHAPE, "sigmoid_argmax: null argument");
+  const int64_t pixels = (int64_t)logits->n * logits->h * logits->w;
+  sigmoid_argmax_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(*logits, probs,
+                                                                                 labelmap);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, float* mean, float* var,
+                        void* stream) {
+  SEG_REQUIRE(probs && mean && var && t >= 1, SEG_E_BAD_SHAPE, "mc_mean_var: bad argument");
+  mc_mean_var_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(probs, t, count, mean,
+                                                                             var);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, void* shadow_bf16,
+                       const int32_t* segments, const int64_t* shadow_offsets, int32_t nseg,
+                       int64_t numel, float lr_t, float beta1, float beta2, float eps,
+                       float grad_scale, void* stream) {
+  SEG_REQUIRE(param && grad && m && v && segments && shadow_offsets && nseg > 0, SEG_E_BAD_SHAPE,
+              "adam_multi: null argument");
+  adam_multi_kernel<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, m, v, reinterpret_cast<bf16*>(shadow_bf16), segments, shadow_offsets, nseg,
+      numel, lr_t, beta1, beta2, eps, grad_scale);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && c <= y->c, SEG_E_BAD_SHAPE, "pack_input: bad argument");
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, *y);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_fill_zero(void* ptr, int64_t bytes, void* stream) {
+  SEG_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+  return SEG_OK;
+}
+
+}  // extern "C"

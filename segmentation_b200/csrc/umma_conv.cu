@@ -1,0 +1,513 @@
+// Host side of the tcgen05 implicit-GEMM kernels: tensor-map construction (tiled
+// and im2col), tile-shape selection and launches.
+#include "umma_conv.cuh"
+
+#include <mutex>
+
+namespace segb {
+
+// ---------------------------------------------------------------------------
+// driver entry points (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_encoders() {
+  static std::once_flag once;
+  static int status = SEG_OK;
+  std::call_once(once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) !=
+            cudaSuccess || !fn) {
+      status = SEG_E_CUDA;
+      return;
+    }
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) !=
+            cudaSuccess || !fn) {
+      status = SEG_E_CUDA;
+      return;
+    }
+    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    cudaDriverGetVersion(&g_driver_version);
+  });
+  if (status != SEG_OK) set_error("cuTensorMapEncode* driver entry points unavailable");
+  return status;
+}
+
+static CUtensorMapSwizzle swizzle_enum(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                       : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// 2-D row-major bf16 matrix [rows][cols] with row pitch `ld` elements.
+static int make_tmap_2d(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t rows, int64_t ld,
+                        int box_cols, int box_rows, int swizzle_bytes) {
+  SEG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, SEG_E_ALIGN,
+              "tensor map: base/pitch must be 16-byte aligned (ptr=%p ld=%lld)", ptr,
+              (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                              gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_enum(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEG_REQUIRE(r == CUDA_SUCCESS, SEG_E_CUDA,
+              "cuTensorMapEncodeTiled failed (%d) cols=%lld rows=%lld ld=%lld box=%dx%d sw=%d",
+              (int)r, (long long)cols, (long long)rows, (long long)ld, box_cols, box_rows,
+              swizzle_bytes);
+  return SEG_OK;
+}
+
+// im2col map over an NHWC view seen as (C, W, H, N).
+static int make_tmap_im2col(CUtensorMap* tm, const seg_view& v, int low_w, int low_h, int up_w,
+                            int up_h, int stride, int channels, int pixels, int swizzle_bytes) {
+  SEG_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && (v.sw * 2) % 16 == 0 &&
+                  (v.sh * 2) % 16 == 0 && (v.sn * 2) % 16 == 0,
+              SEG_E_ALIGN, "im2col tensor map: view must be 16-byte aligned in every stride");
+  SEG_REQUIRE(low_w >= -128 && low_w <= 127 && low_h >= -128 && low_h <= 127 && up_w >= -128 &&
+                  up_w <= 127 && up_h >= -128 && up_h <= 127,
+              SEG_E_UNSUPPORTED, "im2col corners out of range");
+  cuuint64_t gdim[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  int lower[2] = {low_w, low_h};
+  int upper[2] = {up_w, up_h};
+  cuuint32_t est[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, gdim, gstr, lower,
+                               upper, (cuuint32_t)channels, (cuuint32_t)pixels, est,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(swizzle_bytes),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEG_REQUIRE(r == CUDA_SUCCESS, SEG_E_CUDA,
+              "cuTensorMapEncodeIm2col failed (%d) c=%d w=%d h=%d n=%d low=(%d,%d) up=(%d,%d) "
+              "st=%d ch=%d px=%d sw=%d",
+              (int)r, v.c, v.w, v.h, v.n, low_w, low_h, up_w, up_h, stride, channels, pixels,
+              swizzle_bytes);
+  // Drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB
+  // (bit 21 of the second descriptor word must be cleared); same fix-up as the one
+  // NVIDIA's own conv templates apply after cuTensorMapEncodeIm2col.
+  if (g_driver_version <= 13010) {
+    const int64_t span = (int64_t)(v.n - 1) * v.sn + (int64_t)(v.h - 1) * v.sh +
+                         (int64_t)(v.w - 1) * v.sw + v.c;
+    if (span * 2 < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+  return SEG_OK;
+}
+
+static int pick_chunk(int c1, int c2) {
+  const int cands[3] = {64, 32, 16};
+  for (int k : cands)
+    if (c1 % k == 0 && c2 % k == 0 && c1 >= k) return k;
+  return 0;
+}
+
+static bool pixel_dense(const seg_view& v) {
+  return v.sh == (int64_t)v.w * v.sw && v.sn == (int64_t)v.h * v.sh;
+}
+
+static EpiDest make_dest(const seg_view* v, const seg_view* mask) {
+  EpiDest d;
+  memset(&d, 0, sizeof(d));
+  if (v && v->ptr) {
+    d.ptr = v->ptr;
+    d.sn = v->sn; d.sh = v->sh; d.sw = v->sw;
+    d.cols = v->c;
+  }
+  if (mask && mask->ptr) {
+    d.mask = reinterpret_cast<const bf16*>(mask->ptr);
+    d.msn = mask->sn; d.msh = mask->sh; d.msw = mask->sw;
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// igemm launch
+// ---------------------------------------------------------------------------
+struct IgemmJob {
+  seg_view a1, a2;             // activation sources (a2.ptr == null: none)
+  int kh, kw, stride;
+  int low_h, low_w, up_h, up_w;
+  int Ho, Wo, batch;           // base-pixel grid
+  const void* w;               // 2-D bf16 weight matrix
+  int w_rows, w_cols;
+  bool b_mn;
+  int b_rows_per_tap;
+  bool tap_flip;
+  int N_total;
+  int max_bn;                  // BN must divide this (tile may not straddle taps / dests)
+  EpiDest d0, d1;
+  int split_n;
+  const float* bias;
+  int flags;
+  int ps_k, ps_cout;
+  bool a_tiled2d;
+};
+
+template <int KC, int BN, bool B_MN>
+static int launch_igemm_t(const IgemmJob& J, cudaStream_t st) {
+  using Cfg = IgemmCfg<KC, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<KC, BN, B_MN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc;
+  if (J.a_tiled2d) {
+    const int64_t rows = (int64_t)J.batch * J.Ho * J.Wo;
+    rc = make_tmap_2d(&tmA1, J.a1.ptr, J.a1.c, rows, J.a1.sw, KC, kBlockM, KC * 2);
+    if (rc) return rc;
+    tmA2 = tmA1;
+  } else {
+    rc = make_tmap_im2col(&tmA1, J.a1, J.low_w, J.low_h, J.up_w, J.up_h, J.stride, KC, kBlockM,
+                          KC * 2);
+    if (rc) return rc;
+    if (J.a2.ptr) {
+      rc = make_tmap_im2col(&tmA2, J.a2, J.low_w, J.low_h, J.up_w, J.up_h, J.stride, KC, kBlockM,
+                            KC * 2);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA1;
+    }
+  }
+  if (B_MN)
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, Cfg::kAtomN, KC, Cfg::kAtomN * 2);
+  else
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN, KC * 2);
+  if (rc) return rc;
+
+  IgemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.a_tiled2d = J.a_tiled2d ? 1 : 0;
+  P.M_total = J.batch * J.Ho * J.Wo;
+  P.Ho = J.Ho; P.Wo = J.Wo;
+  P.stride = J.stride;
+  P.base_h = J.low_h; P.base_w = J.low_w;
+  P.kh = J.kh; P.kw = J.kw;
+  P.chunks1 = J.a1.c / KC;
+  P.chunks2 = J.a2.ptr ? J.a2.c / KC : 0;
+  P.tap_flip = J.tap_flip ? 1 : 0;
+  P.b_rows_per_tap = J.b_rows_per_tap;
+  P.N_total = J.N_total;
+  P.d0 = J.d0; P.d1 = J.d1; P.split_n = J.split_n;
+  P.bias = J.bias;
+  P.flags = J.flags;
+  P.ps_k = J.ps_k; P.ps_cout = J.ps_cout;
+  const int m_tiles = (P.M_total + kBlockM - 1) / kBlockM;
+  const int tiles = m_tiles * (J.N_total / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  igemm_kernel<KC, BN, B_MN><<<grid, kIgemmThreads, Cfg::kSmemBytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+template <int KC, bool B_MN>
+static int launch_igemm_bn(const IgemmJob& J, int BN, cudaStream_t st) {
+  switch (BN) {
+    case 256: return launch_igemm_t<KC, 256, B_MN>(J, st);
+    case 128: return launch_igemm_t<KC, 128, B_MN>(J, st);
+    case 64: return launch_igemm_t<KC, 64, B_MN>(J, st);
+    case 32: return launch_igemm_t<KC, 32, B_MN>(J, st);
+    case 16: return launch_igemm_t<KC, 16, B_MN>(J, st);
+  }
+  set_error("igemm: unsupported BN %d", BN);
+  return SEG_E_UNSUPPORTED;
+}
+
+static int launch_igemm(const IgemmJob& J, cudaStream_t st) {
+  int rc = load_encoders();
+  if (rc) return rc;
+  const int KC = pick_chunk(J.a1.c, J.a2.ptr ? J.a2.c : 0);
+  SEG_REQUIRE(KC != 0, SEG_E_UNSUPPORTED, "igemm: channel counts (%d,%d) not multiples of 16",
+              J.a1.c, J.a2.ptr ? J.a2.c : 0);
+  // BN: largest of {256..16} dividing max_bn; shrink while the grid underfills the SMs.
+  int BN = 0;
+  for (int c = 256; c >= 16; c >>= 1)
+    if (J.max_bn % c == 0) { BN = c; break; }
+  SEG_REQUIRE(BN != 0 && J.N_total % BN == 0, SEG_E_UNSUPPORTED,
+              "igemm: N=%d (tile bound %d) not a multiple of 16", J.N_total, J.max_bn);
+  const int64_t m_tiles = ceil_div64((int64_t)J.batch * J.Ho * J.Wo, kBlockM);
+  while (BN > 64 && m_tiles * (J.N_total / BN) < num_sms()) BN >>= 1;
+  if (J.b_mn) {
+    switch (KC) {
+      case 64: return launch_igemm_bn<64, true>(J, BN, st);
+      case 32: return launch_igemm_bn<32, true>(J, BN, st);
+      default: return launch_igemm_bn<16, true>(J, BN, st);
+    }
+  }
+  switch (KC) {
+    case 64: return launch_igemm_bn<64, false>(J, BN, st);
+    case 32: return launch_igemm_bn<32, false>(J, BN, st);
+    default: return launch_igemm_bn<16, false>(J, BN, st);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad launch
+// ---------------------------------------------------------------------------
+struct WgradJob {
+  seg_view big, big2, small_;
+  int kh, kw, stride, low_h, low_w, up_h, up_w;
+  int BC, SC;
+  float* dw;
+};
+
+template <int AW, int BN>
+static int launch_wgrad_t(const WgradJob& J, cudaStream_t st) {
+  using Cfg = WgradCfg<AW, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<AW, BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc = make_tmap_im2col(&tmA1, J.big, J.low_w, J.low_h, J.up_w, J.up_h, J.stride, AW,
+                            kWgradPK, AW * 2);
+  if (rc) return rc;
+  if (J.big2.ptr) {
+    rc = make_tmap_im2col(&tmA2, J.big2, J.low_w, J.low_h, J.up_w, J.up_h, J.stride, AW, kWgradPK,
+                          AW * 2);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA1;
+  }
+  const int64_t M = (int64_t)J.small_.n * J.small_.h * J.small_.w;
+  rc = make_tmap_2d(&tmB, J.small_.ptr, J.small_.c, M, J.small_.sw, Cfg::kAtomN, kWgradPK,
+                    Cfg::kAtomN * 2);
+  if (rc) return rc;
+
+  WgradUmmaParams P;
+  memset(&P, 0, sizeof(P));
+  P.M_total = (int)M;
+  P.Ho = J.small_.h; P.Wo = J.small_.w;
+  P.stride = J.stride;
+  P.base_h = J.low_h; P.base_w = J.low_w;
+  P.kh = J.kh; P.kw = J.kw;
+  P.chunks1 = J.big.c / AW;
+  P.chunks2 = J.big2.ptr ? J.big2.c / AW : 0;
+  P.total_atoms = J.kh * J.kw * (P.chunks1 + P.chunks2);
+  P.n_tiles = J.small_.c / BN;
+  P.BC = J.BC; P.SC = J.SC;
+  P.dw = J.dw;
+  const int groups = (P.total_atoms + Cfg::kNA - 1) / Cfg::kNA;
+  const int base_ctas = groups * P.n_tiles;
+  const int total_kb = (int)ceil_div64(M, kWgradPK);
+  int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
+  if (splits > total_kb) splits = total_kb;
+  if (splits < 1) splits = 1;
+  P.kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
+  dim3 grid(base_ctas, splits);
+  wgrad_kernel<AW, BN><<<grid, kIgemmThreads, Cfg::kSmemBytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+template <int AW>
+static int launch_wgrad_bn(const WgradJob& J, int BN, cudaStream_t st) {
+  switch (BN) {
+    case 256: return launch_wgrad_t<AW, 256>(J, st);
+    case 128: return launch_wgrad_t<AW, 128>(J, st);
+    case 64: return launch_wgrad_t<AW, 64>(J, st);
+    case 32: return launch_wgrad_t<AW, 32>(J, st);
+    case 16: return launch_wgrad_t<AW, 16>(J, st);
+  }
+  set_error("wgrad: unsupported BN %d", BN);
+  return SEG_E_UNSUPPORTED;
+}
+
+static int launch_wgrad(const WgradJob& J, cudaStream_t st) {
+  int rc = load_encoders();
+  if (rc) return rc;
+  const int AW = pick_chunk(J.big.c, J.big2.ptr ? J.big2.c : 0);
+  SEG_REQUIRE(AW != 0, SEG_E_UNSUPPORTED, "wgrad: channel counts not multiples of 16");
+  SEG_REQUIRE(pixel_dense(J.small_) && J.small_.sw == J.small_.c, SEG_E_UNSUPPORTED,
+              "wgrad: dz must be a dense NHWC tensor");
+  int BN = 0;
+  for (int c = 256; c >= 16; c >>= 1)
+    if (J.small_.c % c == 0) { BN = c; break; }
+  SEG_REQUIRE(BN != 0, SEG_E_UNSUPPORTED, "wgrad: N=%d not a multiple of 16", J.small_.c);
+  switch (AW) {
+    case 64: return launch_wgrad_bn<64>(J, BN, st);
+    case 32: return launch_wgrad_bn<32>(J, BN, st);
+    default: return launch_wgrad_bn<16>(J, BN, st);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// op-level entry points used by api.cu
+// ---------------------------------------------------------------------------
+int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
+                  const float* bias, const seg_view& y, cudaStream_t st) {
+  IgemmJob J;
+  memset(&J, 0, sizeof(J));
+  J.a1 = x;
+  J.a2 = x2 ? *x2 : null_view();
+  SEG_REQUIRE(x.c + J.a2.c == d.cin_pad, SEG_E_BAD_SHAPE,
+              "conv_fwd: input channels %d+%d != cin_pad %d", x.c, J.a2.c, d.cin_pad);
+  J.kh = d.kh; J.kw = d.kw; J.stride = d.stride;
+  J.low_h = -d.pad_t; J.low_w = -d.pad_l;
+  J.up_h = d.pad_b - (d.kh - 1); J.up_w = d.pad_r - (d.kw - 1);
+  J.Ho = y.h; J.Wo = y.w; J.batch = y.n;
+  J.w = w; J.w_rows = d.kh * d.kw * d.cin_pad; J.w_cols = d.cout_pad;
+  J.b_mn = true; J.b_rows_per_tap = d.cin_pad; J.tap_flip = false;
+  J.N_total = d.cout_pad; J.max_bn = d.cout_pad;
+  J.d0 = make_dest(&y, nullptr);
+  J.bias = bias; J.flags = d.flags;
+  return launch_igemm(J, st);
+}
+
+int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, const seg_view& dx,
+                    const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
+                    cudaStream_t st) {
+  SEG_REQUIRE(d.stride == 1, SEG_E_UNSUPPORTED, "umma conv_dgrad: stride 1 only");
+  SEG_REQUIRE(dz.c == d.cout_pad, SEG_E_BAD_SHAPE, "conv_dgrad: dz.c %d != cout_pad %d", dz.c,
+              d.cout_pad);
+  IgemmJob J;
+  memset(&J, 0, sizeof(J));
+  J.a1 = dz;
+  J.a2 = null_view();
+  J.kh = d.kh; J.kw = d.kw; J.stride = 1;
+  J.low_h = -(d.kh - 1 - d.pad_t); J.low_w = -(d.kw - 1 - d.pad_l);
+  J.up_h = dx.h - dz.h + J.low_h; J.up_w = dx.w - dz.w + J.low_w;
+  J.Ho = dx.h; J.Wo = dx.w; J.batch = dx.n;
+  J.w = w; J.w_rows = d.kh * d.kw * d.cin_pad; J.w_cols = d.cout_pad;
+  J.b_mn = false; J.b_rows_per_tap = d.cin_pad; J.tap_flip = true;
+  J.N_total = d.cin_pad;
+  J.d0 = make_dest(&dx, mask);
+  if (dx2 && dx2->ptr) {
+    J.d1 = make_dest(dx2, mask2);
+    J.split_n = dx.c;
+    J.max_bn = dx.c;
+    for (int c = 256; c >= 16; c >>= 1)
+      if (dx.c % c == 0 && dx2->c % c == 0) { J.max_bn = c; break; }
+    SEG_REQUIRE(dx.c + dx2->c == d.cin_pad, SEG_E_BAD_SHAPE, "conv_dgrad: dx channels mismatch");
+  } else {
+    J.max_bn = d.cin_pad;
+  }
+  J.flags = d.flags & (SEG_EPI_RELU_MASK);
+  return launch_igemm(J, st);
+}
+
+int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
+                    const seg_view& dz, float* dw, cudaStream_t st) {
+  WgradJob J;
+  memset(&J, 0, sizeof(J));
+  J.big = x;
+  J.big2 = x2 ? *x2 : null_view();
+  J.small_ = dz;
+  J.kh = d.kh; J.kw = d.kw; J.stride = d.stride;
+  J.low_h = -d.pad_t; J.low_w = -d.pad_l;
+  J.up_h = d.pad_b - (d.kh - 1); J.up_w = d.pad_r - (d.kw - 1);
+  J.BC = d.cin; J.SC = d.cout;
+  J.dw = dw;
+  return launch_wgrad(J, st);
+}
+
+// transposed conv with k == stride, VALID: GEMM + pixel shuffle
+int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
+                    const seg_view& y, cudaStream_t st) {
+  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_fwd: k == stride, VALID only");
+  IgemmJob J;
+  memset(&J, 0, sizeof(J));
+  J.a1 = x;
+  J.a2 = null_view();
+  SEG_REQUIRE(x.c == d.cin_pad, SEG_E_BAD_SHAPE, "deconv_fwd: x.c != cin_pad");
+  J.kh = 1; J.kw = 1; J.stride = 1;
+  J.Ho = x.h; J.Wo = x.w; J.batch = x.n;
+  J.w = w; J.w_rows = d.kh * d.kw * d.cout_pad; J.w_cols = d.cin_pad;
+  J.b_mn = false; J.b_rows_per_tap = 0; J.tap_flip = false;
+  J.N_total = d.kh * d.kw * d.cout_pad; J.max_bn = d.cout_pad;
+  J.d0 = make_dest(&y, nullptr);
+  J.bias = bias; J.flags = d.flags;
+  J.ps_k = d.stride; J.ps_cout = d.cout_pad;
+  return launch_igemm(J, st);
+}
+
+int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
+                      const seg_view& dx, const seg_view* mask, cudaStream_t st) {
+  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_dgrad: k == stride, VALID only");
+  SEG_REQUIRE(dz.c == d.cout_pad, SEG_E_BAD_SHAPE, "deconv_dgrad: dz.c != cout_pad");
+  IgemmJob J;
+  memset(&J, 0, sizeof(J));
+  J.a1 = dz;
+  J.a2 = null_view();
+  J.kh = d.kh; J.kw = d.kw; J.stride = d.stride;
+  J.low_h = 0; J.low_w = 0;
+  J.up_h = -(d.kh - 1); J.up_w = -(d.kw - 1);
+  J.Ho = dx.h; J.Wo = dx.w; J.batch = dx.n;
+  J.w = w; J.w_rows = d.kh * d.kw * d.cout_pad; J.w_cols = d.cin_pad;
+  J.b_mn = true; J.b_rows_per_tap = d.cout_pad; J.tap_flip = false;
+  J.N_total = d.cin_pad; J.max_bn = d.cin_pad;
+  J.d0 = make_dest(&dx, mask);
+  J.flags = d.flags & (SEG_EPI_RELU_MASK);
+  return launch_igemm(J, st);
+}
+
+int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
+                      cudaStream_t st) {
+  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_wgrad: k == stride, VALID only");
+  WgradJob J;
+  memset(&J, 0, sizeof(J));
+  J.big = dz;
+  J.big2 = null_view();
+  J.small_ = x;
+  J.kh = d.kh; J.kw = d.kw; J.stride = d.stride;
+  J.low_h = 0; J.low_w = 0;
+  J.up_h = -(d.kh - 1); J.up_w = -(d.kw - 1);
+  J.BC = d.cout; J.SC = d.cin;
+  J.dw = dw;
+  return launch_wgrad(J, st);
+}
+
+// probe: D[M][N] (fp32) = A[M][K] * B, A K-major bf16; mode bit0: B is [K][N] (MN-major)
+// instead of [N][K] (K-major).  Exercises descriptors without im2col.
+int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, float* dptr,
+               cudaStream_t st) {
+  IgemmJob J;
+  memset(&J, 0, sizeof(J));
+  J.a_tiled2d = true;
+  J.a1.ptr = const_cast<void*>(a);
+  J.a1.n = 1; J.a1.h = 1; J.a1.w = M; J.a1.c = K;
+  J.a1.sw = K; J.a1.sh = (int64_t)M * K; J.a1.sn = (int64_t)M * K;
+  J.a2 = null_view();
+  J.kh = 1; J.kw = 1; J.stride = 1;
+  J.Ho = 1; J.Wo = M; J.batch = 1;
+  J.w = b;
+  J.b_mn = (mode & 1) != 0;
+  if (J.b_mn) { J.w_rows = K; J.w_cols = N; } else { J.w_rows = N; J.w_cols = K; }
+  J.b_rows_per_tap = 0;
+  J.N_total = N; J.max_bn = N;
+  seg_view dv;
+  dv.ptr = dptr; dv.n = 1; dv.h = 1; dv.w = M; dv.c = N;
+  dv.sw = N; dv.sh = (int64_t)M * N; dv.sn = (int64_t)M * N;
+  J.d0 = make_dest(&dv, nullptr);
+  J.flags = SEG_EPI_OUT_F32;
+  return launch_igemm(J, st);
+}
+
+}  // namespace segb

@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — U-Net 256x256 training throughput (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+forward + softmax-xent + backward + Adam of UNetModel(n_kernels=32, 3->2 ch) at
+256x256, 16 images per GPU (BASELINE.json configs[2] at N GPUs; weak scaling,
+data-parallel gradient all-reduce over NCCL for N>1).
+
+  value : img/s, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e   : img/s through UNetModel.train_step(batch) with HOST (pinned) batches:
+          H2D of images+masks and D2H of the loss inside the timed region
+  roofline     : the single heaviest kernel launch of the step (tensor bound)
+  cpu_baseline : the oracle (torch-CPU fp32 restatement of the reference graph —
+                 the reference's TensorFlow path cannot run) on
+                 the host cores, BASELINE configs[0] (batch 4), bounded sample
+  --impl reference : that same CPU restatement as the reference arm
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRAIN_GFLOP_PER_IMG = 23.360      # BASELINE.md §3 (fwd + dgrad + wgrad, conv1_1 has no dgrad)
+S, NK, NCLS, BATCH = 256, 32, 2, 16
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'tf_burst': p['bf16_tflops'],
+                'tf_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
+
+
+class SyntheticDataSet(object):
+    """images fp32 [B,256,256,3] ~ U[0,1), masks uint8 [B,256,256,1] ~ Bernoulli(.5)
+    (reference utils/datasets.py:174-190 tensor contract); a small pool of pinned
+    host batches is cycled."""
+    use_feed, has_masks = False, True
+
+    def __init__(self, batch_size, seed, pool=4, pinned=True):
+        import numpy as np
+        import torch
+        self.batch_size = batch_size
+        g = np.random.default_rng(seed)
+        self.pool = []
+        for _ in range(pool):
+            x = torch.from_numpy(g.random((batch_size, S, S, 3), dtype=np.float32))
+            y = torch.from_numpy(g.integers(0, 2, (batch_size, S, S, 1)).astype(np.uint8))
+            if pinned:
+                x, y = x.pin_memory(), y.pin_memory()
+            self.pool.append((x, y))
+        self.i = 0
+
+    def set_tf_sess(self, sess):
+        pass
+
+    def next_batch(self):
+        b = self.pool[self.i % len(self.pool)]
+        self.i += 1
+        return b
+
+
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out['sm_max_mhz'] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), r[5:9]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            # median of the upper half = clocks under load (idle samples sit at the bottom)
+            upper = sm[len(sm) // 2:]
+            out['sm_mhz'] = upper[len(upper) // 2]
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def cpu_oracle_rate(steps, warmup, batch=4):
+    """Oracle U-Net train steps on the host cores -> (img/s, cores, sample text)."""
+    import numpy as np
+    import torch
+    from oracle import nets
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = nets.unet_params(n_kernels=NK, n_classes=NCLS, seed=0)
+    st = nets.AdamState(p)
+    g = np.random.default_rng(0)
+    x = torch.from_numpy(g.random((batch, S, S, 3), dtype=np.float32))
+    y = torch.from_numpy(g.integers(0, 2, (batch, S, S, 1)).astype(np.uint8))
+    fwd = lambda q, xx: nets.unet_forward(q, xx)
+    for _ in range(warmup):
+        nets.train_step(fwd, p, st, x, y, lr=1e-4)
+    times = []
+    for _ in range(steps):
+        t0 = time.time()
+        nets.train_step(fwd, p, st, x, y, lr=1e-4)
+        times.append(time.time() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    sample = ('%d warm-up + %d timed fp32 train steps (fwd+bwd+Adam) of U-Net 256x256 nk32 at '
+              'batch %d, torch-CPU restatement of the reference graph (not TensorFlow), median'
+              % (warmup, steps, batch))
+    return batch / med, cores, sample, med
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    rate, cores, sample, med = cpu_oracle_rate(steps, 1)
+    line = {
+        'impl': 'reference', 'metric': 'U-Net train img/s (256x256, bs16/GPU)', 'value': rate,
+        'unit': 'img/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+        'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'U-Net 256x256 nk32 3->2ch train step (fwd+bwd+Adam), CPU sample at '
+                               'batch 4 of the bs16/GPU workload'},
+        'cpu_baseline': {'value': rate, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': rate, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from segmentation_b200 import native as N
+    from segmentation_b200.models.unet import UNetModel
+    from segmentation_b200 import parallel
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    ds = SyntheticDataSet(BATCH, seed=1000 + rank)
+    model = UNetModel(dataset=ds, n_classes=NCLS, input_dims=S, n_kernels=NK, learning_rate=1e-4,
+                      load_snapshot=False, save_dir=None, seed=0)
+    if world > 1:
+        parallel.DataParallel(model)
+    ex = model._get_exec(BATCH, True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W, K = max(3, args.warmup), args.steps
+    dev_batches = [(x.to(dev), y.to(dev)) for x, y in ds.pool]
+
+    # ---- launches per step (eager first step), then graph capture in warm-up
+    before = N.LAUNCHES
+    model.train_step(dev_batches[0])
+    launches_per_step = N.LAUNCHES - before
+    for i in range(1, W):
+        model.train_step(dev_batches[i % len(dev_batches)])
+
+    # ---- value: inputs resident in HBM
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        model.train_step(dev_batches[i % len(dev_batches)])
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- e2e: pinned host batches, H2D inside, loss read back every step
+    for i in range(2):
+        model.train_step(ds.next_batch())
+    barrier()
+    e0.record()
+    loss = 0.0
+    for i in range(K):
+        model.train_step(ds.next_batch())
+        loss = model.seg_loss_op                 # D2H read of the step's loss
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if clocks is not None else None
+
+    # ---- per-launch timeline (un-captured pass) -> dominant kernel roofline
+    roof = None
+    if rank == 0:
+        ex.use_graph = False
+        saved = ex.graph
+        ex.graph = None
+        N.TIMELINE = []
+        ex.stage(*dev_batches[0])
+        for _ in range(3):                       # fwd + loss + bwd only: parameters untouched
+            N.TIMELINE.clear()
+            ex.forward()
+            ex.loss(True)
+            ex.backward()
+            model.store.grad.zero_()
+        torch.cuda.synchronize()
+        tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
+        N.TIMELINE = None
+        ex.graph, ex.use_graph = saved, True
+        roof = dominant_kernel(tl, model, ex)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    imgs = BATCH * world * K
+    value = imgs / (ms_dev * 1e-3)
+    e2e = imgs / (ms_e2e * 1e-3)
+    h2d = BATCH * S * S * 3 * 4 + BATCH * S * S
+    cpu_rate, cores, sample, _ = cpu_oracle_rate(2, 1)
+    line = {
+        'metric': 'U-Net train img/s (256x256, bs16/GPU)', 'value': value, 'unit': 'img/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_dev / K,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic',
+        'config': {'workload': 'U-Net (models/unet.py graph) 256x256 RGB, 2 classes, n_kernels 32, '
+                               'batch 16/GPU, fwd+xent+bwd+Adam, bf16 compute fp32 accumulate',
+                   'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
+                   'l2': 'per-step working set (>1 GB activations+gradients) exceeds the 126 MB L2; '
+                         '4 distinct input batches cycled',
+                   'impl': 'umma' if model.impl == 0 else 'simt', 'cuda_graph': True},
+        'e2e': {'value': e2e, 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K},
+        'gpu_launches': launches_per_step * K,
+        'launches_per_step': launches_per_step,
+        'conv_tensor_frac': {'of_burst': value / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk['tf_burst'],
+                             'of_sustained': value / world * TRAIN_GFLOP_PER_IMG / 1e3 /
+                             pk['tf_sustained'], 'peaks': pk['src']},
+        'roofline': roof,
+        'cpu_baseline': {'value': cpu_rate, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'clocks': clk,
+        'loss': loss,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_flops(layer, x_shape, y_shape, which):
+    """Algorithmic FLOPs of one launch: 2*N*Ho*Wo*Cout*Cin*kh*kw for a
+    conv, 2*N*Hi*Wi*Cin*Cout*kh*kw for a transposed conv."""
+    k = layer.k
+    if layer.kind == 'conv':
+        n, ho, wo = y_shape[0], y_shape[1], y_shape[2]
+    else:
+        n, ho, wo = x_shape[0], x_shape[1], x_shape[2]
+    return 2.0 * n * ho * wo * layer.cout * layer.cin * k * k
+
+
+def dominant_kernel(timeline, model, ex):
+    """Pick the conv-family launch with the largest duration and report its
+    achieved TFLOP/s against the measured bf16 peak."""
+    pk = peaks()
+    shapes = {}
+    A = ex.act
+    for name, layer in model.layers.items():
+        if name == 'output':
+            shapes[name] = (A['conv9_2'].shape, ex.logits.shape)
+        elif name.startswith('upconv'):
+            j = int(name[-1])
+            below = 'conv%d_2' % (4 + j) if j > 1 else 'conv5_2'
+            shapes[name] = (A[below].shape, A[name].shape)
+        elif name == 'conv1_2':
+            shapes[name] = (A['conv1_1'].shape, A['conv1_2'].shape)
+        else:
+            shapes[name] = (None, A[name].shape)
+    kind_of = {'seg_conv2d_fwd': 'fwd', 'seg_conv2d_dgrad': 'dgrad', 'seg_conv2d_wgrad': 'wgrad',
+               'seg_deconv2d_fwd': 'fwd', 'seg_deconv2d_dgrad': 'dgrad',
+               'seg_deconv2d_wgrad': 'wgrad'}
+    total = sum(t for _, _, t in timeline)
+    best = None
+    per = []
+    for fn, tag, ms in timeline:
+        if fn not in kind_of or tag not in model.layers:
+            continue
+        xs, ys = shapes[tag]
+        fl = conv_flops(model.layers[tag], xs if xs is not None else ys, ys, kind_of[fn])
+        if tag == 'conv1_2' and kind_of[fn] != 'fwd':
+            # backward runs on the 72x72 skip crop only (exact: gradient is zero outside)
+            y0, x0, h, w = ex.crop[4]
+            fl = 2.0 * ys[0] * h * w * model.layers[tag].cout * model.layers[tag].cin * 9
+        per.append((tag, kind_of[fn], ms, fl))
+        if best is None or ms > best[2]:
+            best = (tag, kind_of[fn], ms, fl)
+    if best is None:
+        return None
+    tag, kind, ms, fl = best
+    achieved = fl / (ms * 1e-3) / 1e12
+    conv_ms = sum(p[2] for p in per)
+    return {'bound': 'tensor', 'kernel': '%s %s' % (tag, kind), 'achieved': achieved,
+            'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tf_burst'],
+            'traffic': None, 'launch_ms': ms, 'peak_source': pk['src'] + ' burst',
+            'share_of_step': ms / total if total > 0 else None,
+            'conv_family_share_of_step': conv_ms / total if total > 0 else None,
+            'top5': [{'kernel': '%s %s' % (p[0], p[1]), 'ms': p[2],
+                      'tflops': p[3] / (p[2] * 1e-3) / 1e12}
+                     for p in sorted(per, key=lambda q: -q[2])[:5]]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -189,11 +189,14 @@ SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, fl
  * outside the bias correction.  One launch over a flat fp32 parameter buffer.
  * `segments` (device, int32[6*nseg]) maps master elements to the padded bf16
  * shadow: {master_off, numel, inner(=last dim), inner_pad, mid(=dim -2), mid_pad}.
- * grad is scaled by grad_scale (1/world_size for data-parallel) and zeroed. */
+ * grad is scaled by grad_scale (1/world_size for data-parallel) and zeroed.
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is read from the device scalar lr_t_dev
+ * when non-null (so a captured CUDA graph can be replayed with a new value),
+ * else taken from the host argument lr_t. */
 SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, void* shadow_bf16,
                        const int32_t* segments, const int64_t* shadow_offsets, int32_t nseg,
-                       int64_t numel, float lr_t, float beta1, float beta2, float eps,
-                       float grad_scale, void* stream);
+                       int64_t numel, float lr_t, const float* lr_t_dev, float beta1,
+                       float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- layout helpers */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with channels zero-padded to y.c */

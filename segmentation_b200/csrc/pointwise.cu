@@ -498,8 +498,9 @@ __global__ void mc_mean_var_kernel(const float* probs, int T, int64_t count, flo
 // -------------------------------------------------------------------- Adam
 __global__ void adam_multi_kernel(float* param, float* grad, float* m, float* v, bf16* shadow,
                                   const int32_t* seg, const int64_t* shadow_off, int nseg,
-                                  int64_t numel, float lr_t, float b1, float b2, float eps,
-                                  float gscale) {
+                                  int64_t numel, float lr_t, const float* lr_t_dev, float b1,
+                                  float b2, float eps, float gscale) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   GRID_STRIDE(i, numel) {
     const float g = grad[i] * gscale;
     grad[i] = 0.f;
@@ -748,13 +749,13 @@ SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, fl
 
 SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, void* shadow_bf16,
                        const int32_t* segments, const int64_t* shadow_offsets, int32_t nseg,
-                       int64_t numel, float lr_t, float beta1, float beta2, float eps,
-                       float grad_scale, void* stream) {
+                       int64_t numel, float lr_t, const float* lr_t_dev, float beta1,
+                       float beta2, float eps, float grad_scale, void* stream) {
   SEG_REQUIRE(param && grad && m && v && segments && shadow_offsets && nseg > 0, SEG_E_BAD_SHAPE,
               "adam_multi: null argument");
   adam_multi_kernel<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(
       param, grad, m, v, reinterpret_cast<bf16*>(shadow_bf16), segments, shadow_offsets, nseg,
-      numel, lr_t, beta1, beta2, eps, grad_scale);
+      numel, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

@@ -56,11 +56,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a descriptor/barrier bug must not hang the GPU box (a hang is a
-// strike).  ~2^28 polls is seconds; then trap so the launch fails loudly.
+// strike).  ~2^24 polls is seconds; then trap so the launch fails loudly.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
+    if (++spins > (1u << 24)) {
       printf("segb200: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x,
              parity);
       __trap();

@@ -239,7 +239,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < W; ++j) {
             v[j] = __uint_as_float(r[j]);
-            if (P.flags & SEG_EPI_BIAS) v[j] += __ldg(P.bias + (P.ps_k ? ncol : n0 + cc) + j);
+            // bias is indexed by the destination column (logical channel); padded
+            // columns are never stored, so never read a bias for them either
+            if ((P.flags & SEG_EPI_BIAS) && ncol + j < D.cols) v[j] += __ldg(P.bias + ncol + j);
             if (P.flags & SEG_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
           }
           if ((P.flags & SEG_EPI_RELU_MASK) && D.mask) {

@@ -1,0 +1,369 @@
+"""Host-side execution engine: parameter store + layer-level wrappers over the
+C ABI (include/segb200.h).  The three model classes build explicit forward and
+backward schedules out of these wrappers (no torch.autograd on the hot path);
+a whole train step is a fixed kernel sequence that is captured into a CUDA graph.
+
+What the pieces replace in the reference:
+  * ParamStore  <- the slim variables + `tf.train.AdamOptimizer` slots
+                   (/root/reference/models/basemodel.py:321,366)
+  * ConvLayer   <- slim.convolution2d / slim.convolution2d_transpose call sites
+"""
+import ctypes
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import native as N
+
+BF16 = torch.bfloat16
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def same_pad(n, k, s):
+    """TF SAME padding (extra goes bottom/right)."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+def xavier_uniform(shape, gen):
+    """tf.contrib.layers.xavier_initializer() (uniform), slim's default
+    weights_initializer for convolution2d / convolution2d_transpose."""
+    rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    fan_in, fan_out = rf * shape[-2], rf * shape[-1]
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (gen.random(shape, dtype=np.float32) * 2 - 1) * np.float32(limit)
+
+
+class Param(object):
+    __slots__ = ('name', 'shape', 'offset', 'numel', 'shadow_offset', 'shadow_shape',
+                 'trainable', 'store')
+
+    def value(self):
+        return self.store.master[self.offset:self.offset + self.numel].view(self.shape)
+
+    def grad(self):
+        return self.store.grad[self.offset:self.offset + self.numel].view(self.shape)
+
+    def shadow(self):
+        n = int(np.prod(self.shadow_shape))
+        return self.store.shadow[self.shadow_offset:self.shadow_offset + n].view(self.shadow_shape)
+
+
+class ParamStore(object):
+    """Flat fp32 master / grad / Adam-slot buffers in TF variable order, plus a
+    flat bf16 shadow with channel-padded weight copies.  Non-trainable state
+    (BN moving statistics) lives in a separate flat buffer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.params = OrderedDict()
+        self.state = OrderedDict()      # name -> fp32 tensor (non-trainable)
+        self._n = 0
+        self._ns = 0
+        self.finalized = False
+
+    def add(self, name, shape, shadow_shape=None):
+        assert not self.finalized
+        p = Param()
+        p.name, p.shape, p.store = name, tuple(shape), self
+        p.offset, p.numel = self._n, int(np.prod(shape))
+        p.trainable = True
+        self._n += p.numel
+        if shadow_shape is not None:
+            p.shadow_shape = tuple(shadow_shape)
+            p.shadow_offset = self._ns
+            self._ns += int(np.prod(shadow_shape))
+            self._ns = (self._ns + 127) // 128 * 128      # keep 256-byte alignment
+        else:
+            p.shadow_shape, p.shadow_offset = None, -1
+        self.params[name] = p
+        return p
+
+    def add_state(self, name, init):
+        self.state[name] = init.to(self.device, torch.float32).clone()
+        return self.state[name]
+
+    def finalize(self):
+        dev = self.device
+        n = max(self._n, 1)
+        self.master = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(max(self._ns, 1), dtype=BF16, device=dev)
+        seg, soff = [], []
+        for p in self.params.values():
+            if p.shadow_shape is not None:
+                inner, mid = p.shape[-1], p.shape[-2]
+                inner_pad, mid_pad = p.shadow_shape[-1], p.shadow_shape[-2]
+            else:
+                inner = inner_pad = p.shape[-1]
+                mid = mid_pad = 1
+            seg += [p.offset, p.numel, inner, inner_pad, mid, mid_pad]
+            soff.append(p.shadow_offset)
+        self.segments = torch.tensor(seg, dtype=torch.int32, device=dev)
+        self.shadow_offsets = torch.tensor(soff, dtype=torch.int64, device=dev)
+        self.numel = self._n
+        self.step = 0
+        self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.finalized = True
+
+    # -- host <-> device parameter exchange (TF names / TF layouts) ---------
+    def load_state_dict(self, sd):
+        for name, p in self.params.items():
+            if name in sd:
+                t = torch.as_tensor(np.asarray(sd[name]), dtype=torch.float32).reshape(p.shape)
+                p.value().copy_(t.to(self.device))
+        for name in self.state:
+            if name in sd:
+                self.state[name].copy_(torch.as_tensor(np.asarray(sd[name]),
+                                                       dtype=torch.float32).to(self.device))
+        self.refresh_shadow()
+
+    def state_dict(self):
+        out = OrderedDict()
+        for name, p in self.params.items():
+            out[name] = p.value().detach().cpu().numpy().copy()
+        for name, t in self.state.items():
+            out[name] = t.detach().cpu().numpy().copy()
+        return out
+
+    def refresh_shadow(self):
+        """Re-derive every bf16 shadow from its fp32 master (init / load)."""
+        for p in self.params.values():
+            if p.shadow_shape is None:
+                continue
+            sh = p.shadow()
+            sh.zero_()
+            idx = tuple(slice(0, s) for s in p.shape)
+            sh[idx] = p.value().to(BF16)
+
+    def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        """tf.train.AdamOptimizer update over the flat buffer (one launch); also
+        rewrites the bf16 shadows and zeroes the gradient buffer."""
+        self.adam_launch(self.next_lr_t(lr, beta1, beta2), beta1, beta2, eps, grad_scale)
+
+    def next_lr_t(self, lr, beta1=0.9, beta2=0.999):
+        """Advance the step counter; returns lr*sqrt(1-b2^t)/(1-b1^t)."""
+        self.step += 1
+        return lr * math.sqrt(1.0 - beta2 ** self.step) / (1.0 - beta1 ** self.step)
+
+    def adam_launch(self, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
+                    from_device=False):
+        """from_device=True reads lr_t from self.lr_t_dev (CUDA-graph replay)."""
+        N.call('seg_adam_multi', N.ptr(self.master), N.ptr(self.grad), N.ptr(self.m),
+               N.ptr(self.v), N.ptr(self.shadow), N.ptr(self.segments),
+               N.ptr(self.shadow_offsets), len(self.params), self.numel, lr_t,
+               N.ptr(self.lr_t_dev) if from_device else None, beta1, beta2,
+               eps, grad_scale, N.stream_ptr())
+
+
+class ConvLayer(object):
+    """One slim.convolution2d (kind='conv', weights HWIO) or
+    slim.convolution2d_transpose (kind='deconv', weights HWOI) call site."""
+
+    def __init__(self, store, name, kind, k, stride, padding, cin, cout, relu=True, gen=None,
+                 in_pad=None):
+        self.name, self.kind, self.k, self.stride, self.padding = name, kind, k, stride, padding
+        self.cin, self.cout, self.relu = cin, cout, relu
+        self.cin_pad = in_pad if in_pad is not None else pad16(cin)
+        self.cout_pad = pad16(cout)
+        if kind == 'conv':
+            shape, sshape = (k, k, cin, cout), (k, k, self.cin_pad, self.cout_pad)
+        else:
+            shape, sshape = (k, k, cout, cin), (k, k, self.cout_pad, self.cin_pad)
+        self.w = store.add(name + '/weights', shape, sshape)
+        self.b = store.add(name + '/biases', (cout,))
+        self._init = xavier_uniform(shape, gen) if gen is not None else None
+
+    def init_values(self):
+        if self._init is not None:
+            self.w.value().copy_(torch.from_numpy(self._init).to(self.w.store.device))
+            self._init = None
+
+    def out_hw(self, h, w):
+        k, s = self.k, self.stride
+        if self.kind == 'conv':
+            if self.padding == 'SAME':
+                return -(-h // s), -(-w // s)
+            return (h - k) // s + 1, (w - k) // s + 1
+        if self.padding == 'SAME':
+            return h * s, w * s
+        return h * s + max(k - s, 0), w * s + max(k - s, 0)
+
+    def desc(self, in_h, in_w, flags, impl):
+        """seg_conv_desc.  For 'conv', (in_h,in_w) is the conv input size; for
+        'deconv' it is the size of the LARGE side (the deconv output), whose
+        SAME crop plays the role of the padding."""
+        k, s = self.k, self.stride
+        if self.padding == 'SAME':
+            if self.kind == 'conv':
+                pt, pb = same_pad(in_h, k, s)
+                pl, pr = same_pad(in_w, k, s)
+            else:
+                tot = max(k - s, 0)
+                pt = pl = tot // 2
+                pb = pr = tot - tot // 2
+        else:
+            pt = pb = pl = pr = 0
+        return N.SegConvDesc(k, k, s, pt, pl, pb, pr, self.cin, self.cout, self.cin_pad,
+                             self.cout_pad, flags, impl)
+
+    def epi_flags(self, out_f32=False):
+        f = N.EPI_BIAS
+        if self.relu:
+            f |= N.EPI_RELU
+        if out_f32:
+            f |= N.EPI_OUT_F32
+        return f
+
+    # ---- forward -----------------------------------------------------------
+    def forward(self, x, y, x2=None, impl=N.IMPL_UMMA, out_f32=False):
+        st = N.stream_ptr()
+        N.set_tag(self.name)
+        if self.kind == 'conv':
+            d = self.desc(x.shape[1], x.shape[2], self.epi_flags(out_f32), impl)
+            N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x), N.vref(x2),
+                   N.ptr(self.w.shadow()), N.ptr(self.b.value()), N.vref(y), st)
+        else:
+            d = self.desc(y.shape[1], y.shape[2], self.epi_flags(out_f32), impl)
+            N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(x), N.ptr(self.w.shadow()),
+                   N.ptr(self.b.value()), N.vref(y), st)
+
+    # ---- backward ----------------------------------------------------------
+    def backward(self, x, dz, dx=None, x2=None, dx2=None, mask=None, mask2=None,
+                 impl=N.IMPL_UMMA, y_hw=None, dz_bias=None):
+        """Accumulates dW, db into the grad buffer; writes dx (/dx2) if given.
+        `dz` is the gradient w.r.t. this layer's pre-activation output (channels
+        padded to cout_pad).  `mask`/`mask2` = forward tensors whose ReluGrad is
+        applied to dx/dx2.  `dz_bias`: view of dz restricted to the real cout
+        channels when cout_pad != cout."""
+        st = N.stream_ptr()
+        N.set_tag(self.name)
+        dzb = dz_bias if dz_bias is not None else (dz if dz.shape[3] == self.cout
+                                                   else dz[..., :self.cout])
+        N.call('seg_bias_grad', N.vref(dzb), N.ptr(self.b.grad()), st)
+        if self.kind == 'conv':
+            d = self.desc(x.shape[1], x.shape[2], 0, impl)
+            N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(x2), N.vref(dz),
+                   N.ptr(self.w.grad()), st)
+            if dx is not None:
+                N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
+                       N.vref(dx), N.vref(dx2), N.vref(mask), N.vref(mask2), st)
+        else:
+            d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
+            N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(dz),
+                   N.ptr(self.w.grad()), st)
+            if dx is not None:
+                N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz),
+                       N.ptr(self.w.shadow()), N.vref(dx), N.vref(mask), st)
+
+
+# ---------------------------------------------------------------------------
+# thin op wrappers
+# ---------------------------------------------------------------------------
+def pack_input(x_f32, y):
+    N.call('seg_pack_input', N.ptr(x_f32), x_f32.shape[3], N.vref(y), N.stream_ptr())
+
+
+def maxpool_fwd(x, y, argmax, k=2, s=2):
+    N.call('seg_maxpool_fwd', N.vref(x), k, s, N.vref(y), N.ptr(argmax), N.stream_ptr())
+
+
+def maxpool_bwd(dy, argmax, dx, k=2, s=2, add=None, add_y0=0, add_x0=0, mask=None):
+    N.call('seg_maxpool_bwd', N.vref(dy), N.ptr(argmax), k, s, N.vref(add), add_y0, add_x0,
+           N.vref(mask), N.vref(dx), N.stream_ptr())
+
+
+def softmax_xent(logits, labels, loss_sum, dlogits=None):
+    N.call('seg_softmax_xent_fwd_bwd', N.vref(logits), N.vref(labels), N.ptr(loss_sum),
+           N.vref(dlogits), N.stream_ptr())
+
+
+def sigmoid_argmax(logits, probs, labelmap):
+    N.call('seg_sigmoid_argmax', N.vref(logits), N.ptr(probs), N.ptr(labelmap), N.stream_ptr())
+
+
+def fill_zero(t):
+    N.call('seg_fill_zero', N.ptr(t), t.numel() * t.element_size(), N.stream_ptr())
+
+
+def bilinear_upsample_fwd(x, factor, y, add=None):
+    N.call('seg_bilinear_upsample_fwd', N.vref(x), factor, N.vref(add), N.vref(y),
+           1 if y.dtype == torch.float32 else 0, N.stream_ptr())
+
+
+def bilinear_upsample_bwd(dy, factor, dx):
+    N.call('seg_bilinear_upsample_bwd', N.vref(dy), 1 if dy.dtype == torch.float32 else 0,
+           factor, N.vref(dx), N.stream_ptr())
+
+
+def resize_bilinear_fwd(x, y):
+    N.call('seg_resize_bilinear_fwd', N.vref(x), N.vref(y), N.stream_ptr())
+
+
+def resize_bilinear_bwd(dy, dx):
+    N.call('seg_resize_bilinear_bwd', N.vref(dy), N.vref(dx), N.stream_ptr())
+
+
+def dropout(x, y, seed, stream_id, keep_prob=0.5):
+    N.call('seg_dropout', N.vref(x), seed, stream_id, keep_prob, N.vref(y), N.stream_ptr())
+
+
+def mc_mean_var(probs, mean, var):
+    t = probs.shape[0]
+    N.call('seg_mc_mean_var', N.ptr(probs), t, probs[0].numel(), N.ptr(mean), N.ptr(var),
+           N.stream_ptr())
+
+
+class BatchNorm(object):
+    """slim.batch_norm with slim defaults (decay .999, eps 1e-3, center only),
+    applied AFTER the ReLU of the producing layer
+    (/root/reference/models/deconvolution.py:116)."""
+
+    def __init__(self, store, name, c, decay=0.999, eps=1e-3):
+        self.name, self.c, self.decay, self.eps = name, c, decay, eps
+        self.beta = store.add(name + '/beta', (c,))
+        self.moving_mean = store.add_state(name + '/moving_mean', torch.zeros(c))
+        self.moving_var = store.add_state(name + '/moving_variance', torch.ones(c))
+        dev = store.device
+        self.scratch = torch.zeros(6, c, dtype=torch.float32, device=dev)
+
+    def forward(self, x, y, training=True):
+        st = N.stream_ptr()
+        xs = x[..., :self.c]
+        if training:
+            s = self.scratch
+            fill_zero(s[0:2])
+            N.call('seg_batchnorm_stats', N.vref(xs), N.ptr(s[0]), N.ptr(s[1]), st)
+            count = x.shape[0] * x.shape[1] * x.shape[2]
+            N.call('seg_batchnorm_finalize', N.ptr(s[0]), N.ptr(s[1]), count, self.c, self.eps,
+                   self.decay, N.ptr(s[2]), N.ptr(s[3]), N.ptr(self.moving_mean),
+                   N.ptr(self.moving_var), st)
+            N.call('seg_batchnorm_apply', N.vref(xs), N.ptr(s[2]), N.ptr(s[3]),
+                   N.ptr(self.beta.value()), N.vref(y[..., :self.c]), st)
+        else:
+            N.call('seg_batchnorm_infer', N.vref(xs), N.ptr(self.moving_mean),
+                   N.ptr(self.moving_var), self.eps, N.ptr(self.beta.value()),
+                   N.vref(y[..., :self.c]), st)
+
+    def backward(self, dy, x, dx, relu_mask=True):
+        """dx = BN-grad(dy) masked by the ReluGrad of the layer that produced x;
+        dbeta accumulated into the grad buffer."""
+        st = N.stream_ptr()
+        s = self.scratch
+        fill_zero(s[5])
+        c = self.c
+        dbeta = self.beta.grad()       # zero at step start (Adam zeroes the grad buffer)
+        N.call('seg_batchnorm_bwd_reduce', N.vref(dy[..., :c]), N.vref(x[..., :c]), N.ptr(s[2]),
+               N.ptr(s[3]), N.ptr(dbeta), N.ptr(s[5]), st)
+        count = x.shape[0] * x.shape[1] * x.shape[2]
+        N.call('seg_batchnorm_bwd_apply', N.vref(dy[..., :c]), N.vref(x[..., :c]), N.ptr(s[2]),
+               N.ptr(s[3]), N.ptr(dbeta), N.ptr(s[5]), count, 1 if relu_mask else 0,
+               N.vref(dx[..., :c]), st)

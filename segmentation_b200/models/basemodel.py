@@ -1,0 +1,238 @@
+"""BaseModel — host-side mirror of /root/reference/models/basemodel.py.
+
+Same constructor kwargs, modes ('TRAINING' / 'INFERENCE'), methods
+(`train_step`, `infer`, `test`, `snapshot`) and attributes (`y_hat`,
+`y_hat_sig`, `output`, `inference_ops`, `seg_loss_op`, `global_step`,
+`batch_size`, `n_kernels`, `model_name`) as the reference, but `sess.run` is
+replaced by an explicit kernel schedule over the C ABI (include/segb200.h),
+captured into a CUDA graph.  Evident intent is implemented where the
+reference is broken at HEAD (SURVEY.md §7 "Reference defects"):
+
+  * `train_step()` (raises at reference `basemodel.py:477-478`; intended body
+    in the comments at `:480-489`): one Adam step on
+    mean softmax-cross-entropy (`:59-70`, `:194`, `:360`), `global_step += 1`.
+  * `infer(imgs)` (`:527-531`): `[sigmoid(y_hat), float32(argmax(...)[..., None])]`.
+  * INFERENCE mode accepts `dataset=None` (reference dereferences it at `:39`).
+
+Dataset duck-type consumed (reference `:39,95,159-169`): `.batch_size`,
+`.use_feed`, `.has_masks`, `.set_tf_sess(sess)`; the TF queue ops
+`.image_op/.mask_op` become `.next_batch()` -> (images fp32 [B,H,W,C] in
+[0,1], masks uint8 [B,H,W,1]) as numpy arrays or torch tensors.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import engine as E
+from .. import native as N
+
+
+class BaseModel(object):
+    def __init__(self,
+                 sess,
+                 mode='TRAINING',
+                 log_dir='./logs',
+                 dataset=None,
+                 test_dataset=None,
+                 bayesian=False,
+                 save_dir='./snapshot',
+                 n_classes=None,
+                 input_dims=None,
+                 input_channel=3,
+                 autoencoder=False,
+                 load_snapshot=True,
+                 learning_rate=1e-3,
+                 load_snapshot_from=None,
+                 adversarial_training=False):
+        self.mode = mode
+        self.log_dir = log_dir
+        self.dataset = dataset
+        self.test_dataset = test_dataset
+        self.save_dir = save_dir
+        self.bayesian = bayesian
+        self.n_classes = n_classes
+        if isinstance(input_dims, int):          # reference default is an int (unet.py:32)
+            input_dims = [input_dims, input_dims]
+        self.input_dims = list(input_dims)
+        self.autoencoder = autoencoder
+        self.learning_rate = learning_rate
+        self.input_channel = input_channel
+        self.adversarial_training = adversarial_training
+        if adversarial_training:
+            raise Exception('adversarial_training is outside the B200 hot path (SURVEY.md §8 N3)')
+        if mode not in ('TRAINING', 'INFERENCE'):
+            raise Exception('mode must be TRAINING or INFERENCE')
+        self.batch_size = self.dataset.batch_size if self.dataset is not None else None
+        if mode == 'TRAINING' and self.dataset is None:
+            raise Exception('TRAINING mode needs a dataset')
+
+        self.IN_OUT_EQUAL = False
+        self.IN_OUT_CROP = False
+        self.IN_OUT_RATIO = False
+
+        self.load_snapshot = load_snapshot if load_snapshot else False
+        if self.mode == 'INFERENCE':
+            self.load_snapshot = True
+        self.load_snapshot_from = load_snapshot_from if load_snapshot_from else False
+        self.summary_iter = 25
+
+        # ---- device / library
+        self.sess = sess                          # opaque, ignored
+        N.load()
+        N.check(N.load().seg_device_check(), 'seg_device_check')
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.impl = N.IMPL_SIMT if os.environ.get('SEGB200_IMPL', 'umma') == 'simt' else N.IMPL_UMMA
+        self.global_step = 0
+        self.store = E.ParamStore(self.device)
+        self._exec = {}                           # (B, training) -> executor
+        self._loss_sum = None
+        self._last_pixels = 1
+        self.mc_seed = 0
+        self.world_size = 1
+        self._grad_hook = None                    # set by parallel.DataParallel
+        self._bucket_done = None
+        if self.dataset is not None and hasattr(self.dataset, 'set_tf_sess'):
+            self.dataset.set_tf_sess(self.sess)
+
+    # ------------------------------------------------------------ child API
+    def _build_layers(self, gen):
+        raise NotImplementedError
+
+    def _make_exec(self, batch, training):
+        raise NotImplementedError
+
+    def _finish_init(self, seed=0):
+        """Called by the child constructor after it set its hyper-parameters:
+        creates parameters (xavier-uniform weights, zero biases), loads a
+        snapshot if asked to."""
+        gen = np.random.default_rng(seed)
+        self._build_layers(gen)
+        self.store.finalize()
+        for layer in self.layers.values():
+            if hasattr(layer, 'init_values'):
+                layer.init_values()
+        self.store.refresh_shadow()
+        self._init_saver(self.model_name)
+
+    # ----------------------------------------------------------- snapshots
+    def _init_saver(self, name='model'):
+        self.save_path = None
+        if self.save_dir is not None:
+            if not os.path.exists(self.save_dir):
+                os.makedirs(self.save_dir)
+            self.save_path = os.path.join(self.save_dir, '{}.ckpt'.format(name))
+        if not self.load_snapshot:
+            return
+        try:
+            path = self.load_snapshot_from if self.load_snapshot_from else self._latest_checkpoint()
+            if path is None:
+                raise IOError('no checkpoint')
+            sd = dict(np.load(path, allow_pickle=False))
+            self.global_step = int(sd.pop('global_step', 0))
+            self.store.step = int(sd.pop('adam_step', self.global_step))
+            self.store.load_state_dict(sd)
+            for k, buf in (('segAdam', self.store.m), ('segAdam_1', self.store.v)):
+                if ('__flat__/' + k) in sd:
+                    buf.copy_(torch.from_numpy(sd['__flat__/' + k]).to(self.device))
+            print('Success! Resuming from global step {}'.format(self.global_step))
+        except Exception:
+            print('Failed to load snapshot; proceed with training')
+
+    def _latest_checkpoint(self):
+        if self.save_dir is None or not os.path.isdir(self.save_dir):
+            return None
+        best, best_gs = None, -1
+        for f in os.listdir(self.save_dir):
+            if f.startswith(self.model_name + '.ckpt-') and f.endswith('.npz'):
+                gs = int(f[len(self.model_name) + 6:-4])
+                if gs > best_gs:
+                    best, best_gs = os.path.join(self.save_dir, f), gs
+        return best
+
+    def snapshot(self):
+        """`saver.save(sess, save_path, global_step=gs)` (reference :494-501);
+        variables keep their TF names and layouts."""
+        if self.mode == 'INFERENCE':
+            print('snapshot() with INFERENCE mode invalid')
+            return
+        sd = self.store.state_dict()
+        sd['global_step'] = np.int64(self.global_step)
+        sd['adam_step'] = np.int64(self.store.step)
+        sd['__flat__/segAdam'] = self.store.m.cpu().numpy()
+        sd['__flat__/segAdam_1'] = self.store.v.cpu().numpy()
+        path = '{}-{}.npz'.format(self.save_path, self.global_step)
+        np.savez(path, **sd)
+        for f in os.listdir(self.save_dir):       # max_to_keep=1
+            full = os.path.join(self.save_dir, f)
+            if f.startswith(self.model_name + '.ckpt-') and full != path:
+                os.remove(full)
+        print('Global step {}, snapshotting to {}'.format(self.global_step, path))
+        return path
+
+    # -------------------------------------------------------------- helpers
+    def _get_exec(self, batch, training):
+        key = (batch, training)
+        if key not in self._exec:
+            self._exec[key] = self._make_exec(batch, training)
+        return self._exec[key]
+
+    def _to_device(self, arr, dtype):
+        if isinstance(arr, np.ndarray):
+            arr = torch.from_numpy(np.ascontiguousarray(arr))
+        return arr.to(self.device, dtype, non_blocking=True).contiguous()
+
+    def load_weights(self, state_dict):
+        """Inject parameters given under their TF variable names / layouts."""
+        self.store.load_state_dict(state_dict)
+
+    # ----------------------------------------------------------- train_step
+    def train_step(self, batch=None):
+        """One optimizer step (`sess.run(self.train_op_list)`, reference
+        :484/:488): forward, mean softmax x-entropy, backward, Adam, global_step+1."""
+        if self.mode == 'INFERENCE':
+            raise Exception('train_step() with INFERENCE mode invalid')
+        if batch is None:
+            batch = self.dataset.next_batch()
+        imgs, masks = batch
+        # host (pinned or pageable) or device tensors: staged straight into the
+        # executor's static input buffers (H2D on the compute stream)
+        x = torch.from_numpy(imgs) if isinstance(imgs, np.ndarray) else imgs
+        y = torch.from_numpy(masks) if isinstance(masks, np.ndarray) else masks
+        ex = self._get_exec(x.shape[0], True)
+        ex.train_step(x, y)
+        self.global_step += 1
+
+    @property
+    def seg_loss_op(self):
+        """Mean cross-entropy of the most recent train_step (host float)."""
+        ex = self._exec.get((self.batch_size, True))
+        if ex is None:
+            return float('nan')
+        return float(ex.loss_sum.item()) / ex.loss_pixels
+
+    # ---------------------------------------------------------------- infer
+    def infer(self, imgs):
+        """`sess.run(self.inference_ops, {input_x: imgs})` (reference :527-531).
+        imgs: fp32 [B,H,W,C] in [0,1].  Returns [probs [B,H',W',n_classes],
+        labelmap [B,H',W',1]] as float32 numpy arrays."""
+        x = self._to_device(imgs, torch.float32)
+        ex = self._get_exec(x.shape[0], False)
+        probs, labels = ex.infer(x)
+        torch.cuda.current_stream().synchronize()
+        return [probs.cpu().numpy(), labels.cpu().numpy()]
+
+    def test(self):
+        """Loss on one batch of `test_dataset` through the weight-sharing tower
+        (reference :506-518, :397-436) without touching the parameters."""
+        if self.mode == 'INFERENCE':
+            print('test() with INFERENCE mode invalid')
+            return None
+        ds = self.test_dataset if self.test_dataset is not None else self.dataset
+        imgs, masks = ds.next_batch()
+        x = self._to_device(imgs, torch.float32)
+        y = self._to_device(masks, torch.uint8)
+        ex = self._get_exec(x.shape[0], False)
+        loss = ex.eval_loss(x, y)
+        print('TEST LOSS', loss, self.global_step)
+        return loss

@@ -1,0 +1,346 @@
+"""UNetModel — mirror of /root/reference/models/unet.py (Ronneberger et al. 2015
+as the reference wires it), executed by hand-written sm_100a kernels.
+
+Graph (reference `models/unet.py:109-175`): 18x (3x3 VALID conv + bias + ReLU),
+4x 2x2/2 max-pool, 4x learned 2x2/2 transposed conv (+ReLU, slim default),
+4x centre-crop + concat [skip_crop, upconv], 1x1 head without activation.
+Load-bearing quirks kept: pool1 consumes conv1_1 (not conv1_2, `:118-120`),
+conv1_2 feeds only the last skip (`:161`).
+
+Crops and concats cost no kernel: the consumer conv reads two TMA descriptors
+(skip crop view | upconv output) and its dgrad writes two destinations.  The
+gradient of conv1_2's output is zero outside the 72x72 skip crop, so conv1_2's
+backward runs on that crop only (exact, not an approximation).
+"""
+import numpy as np
+import torch
+
+from .. import engine as E
+from .. import native as N
+from .basemodel import BaseModel
+
+BF16 = torch.bfloat16
+
+
+class UNetModel(BaseModel):
+    def __init__(self,
+                 sess=None,
+                 n_classes=2,
+                 log_dir=None,
+                 dataset=None,
+                 save_dir=None,
+                 bayesian=False,
+                 input_dims=512,
+                 mode='TRAINING',
+                 input_channel=3,
+                 test_dataset=None,
+                 learning_rate=1e-4,
+                 load_snapshot=None,
+                 load_snapshot_from=None,
+                 n_kernels=32,
+                 adversarial_training=False,
+                 seed=0):
+        super(UNetModel, self).__init__(
+            sess=sess, mode=mode, log_dir=log_dir, dataset=dataset, bayesian=bayesian,
+            save_dir=save_dir, n_classes=n_classes, input_dims=input_dims,
+            test_dataset=test_dataset, input_channel=input_channel, load_snapshot=load_snapshot,
+            learning_rate=learning_rate, load_snapshot_from=load_snapshot_from,
+            adversarial_training=adversarial_training)
+        self.model_name = 'unet'
+        self.IN_OUT_CROP = True
+        self.n_kernels = n_kernels
+        self._finish_init(seed)
+        self.y_hat = None          # logits of the most recent forward (device fp32 tensor)
+        self.y_hat_sig = None
+        self.output = None
+        self.inference_ops = ['y_hat_sig', 'output']
+
+    # ---------------------------------------------------------------- layers
+    def _build_layers(self, gen):
+        nk, st = self.n_kernels, self.store
+        L = self.layers = {}
+
+        def conv(name, cin, cout, k=3, relu=True):
+            L[name] = E.ConvLayer(st, name, 'conv', k, 1, 'VALID', cin, cout, relu, gen)
+
+        def up(name, cin, cout):
+            L[name] = E.ConvLayer(st, name, 'deconv', 2, 2, 'VALID', cin, cout, True, gen)
+
+        conv('conv1_1', self.input_channel, nk); conv('conv1_2', nk, nk)
+        conv('conv2_1', nk, nk * 2); conv('conv2_2', nk * 2, nk * 2)
+        conv('conv3_1', nk * 2, nk * 4); conv('conv3_2', nk * 4, nk * 4)
+        conv('conv4_1', nk * 4, nk * 8); conv('conv4_2', nk * 8, nk * 8)
+        conv('conv5_1', nk * 8, nk * 16); conv('conv5_2', nk * 16, nk * 16)
+        up('upconv1', nk * 16, nk * 8)
+        conv('conv6_1', nk * 16, nk * 8); conv('conv6_2', nk * 8, nk * 8)
+        up('upconv2', nk * 8, nk * 4)
+        conv('conv7_1', nk * 8, nk * 4); conv('conv7_2', nk * 4, nk * 4)
+        up('upconv3', nk * 4, nk * 2)
+        conv('conv8_1', nk * 4, nk * 2); conv('conv8_2', nk * 2, nk * 2)
+        up('upconv4', nk * 2, nk)
+        conv('conv9_1', nk * 2, nk); conv('conv9_2', nk, nk)
+        conv('output', nk, self.n_classes, k=1, relu=False)
+
+    def _make_exec(self, batch, training):
+        return _UNetExec(self, batch, training)
+
+    def model(self, input_op, reuse=False):
+        """Forward graph on a fp32 NHWC batch (numpy or torch); returns the
+        logits as a device fp32 tensor [B,H',W',n_classes]."""
+        x = self._to_device(input_op, torch.float32)
+        ex = self._get_exec(x.shape[0], False)
+        ex.stage(x, None)
+        ex.forward()
+        return ex.logits
+
+    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0):
+        """Bayesian mode (BASELINE config 5): `passes` stochastic forward passes of
+        ONE tile executed as one batch, MC-dropout (keep .5) after conv2_2,
+        conv4_2, conv6_2 (build-defined placement — the reference's UNetModel
+        accepts `bayesian` but never reads it, `models/unet.py:31`), then mean
+        and variance of the sigmoid probabilities over the passes.
+        Returns [mean [H',W',C], var [H',W',C], probs [T,H',W',C]]."""
+        x = self._to_device(imgs, torch.float32)
+        assert x.shape[0] == 1, 'infer_mc takes one tile'
+        ex = self._get_exec(passes, False)
+        ex.stage(x.expand(passes, -1, -1, -1), None)
+        ex.forward(dropout=(self.mc_seed if seed is None else seed, pass_offset))
+        probs, _ = ex.head()
+        mean = torch.empty_like(probs[0])
+        var = torch.empty_like(probs[0])
+        E.mc_mean_var(probs, mean, var)
+        torch.cuda.current_stream().synchronize()
+        return [mean.cpu().numpy(), var.cpu().numpy(), probs.cpu().numpy()]
+
+
+class _UNetExec(object):
+    """Buffers + kernel schedule for one (batch size, mode)."""
+
+    MC_SITES = {'conv2_2': 0, 'conv4_2': 1, 'conv6_2': 2}
+
+    def __init__(self, model, B, training):
+        self.m, self.B, self.training = model, B, training
+        dev, nk = model.device, model.n_kernels
+        H, W = model.input_dims
+        self.H, self.W = H, W
+        L = model.layers
+        self.act = {}
+        self.amax = {}
+
+        def buf(name, h, w, c, dtype=BF16):
+            self.act[name] = torch.zeros(B, h, w, c, dtype=dtype, device=dev)
+            return self.act[name]
+
+        self.x_f32 = torch.zeros(B, H, W, model.input_channel, dtype=torch.float32, device=dev)
+        self.mask = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
+        buf('x', H, W, L['conv1_1'].cin_pad)
+        # ---- encoder geometry
+        h, w = H - 2, W - 2
+        buf('conv1_1', h, w, nk)
+        buf('conv1_2', h - 2, w - 2, nk)
+        ph, pw = h // 2, w // 2
+        buf('pool1', ph, pw, nk)
+        self.amax['pool1'] = torch.zeros(B, ph, pw, nk, dtype=torch.uint8, device=dev)
+        for i in range(2, 6):
+            c = nk * 2 ** (i - 1)
+            h, w = ph - 2, pw - 2
+            buf('conv%d_1' % i, h, w, c)
+            buf('conv%d_2' % i, h - 2, w - 2, c)
+            if i < 5:
+                ph, pw = (h - 2) // 2, (w - 2) // 2
+                buf('pool%d' % i, ph, pw, c)
+                self.amax['pool%d' % i] = torch.zeros(B, ph, pw, c, dtype=torch.uint8, device=dev)
+        # ---- decoder geometry
+        self.skip_of = {1: 'conv4_2', 2: 'conv3_2', 3: 'conv2_2', 4: 'conv1_2'}
+        self.crop = {}
+        below = self.act['conv5_2']
+        for j in range(1, 5):
+            c = nk * 2 ** (4 - j)
+            uh, uw = below.shape[1] * 2, below.shape[2] * 2
+            buf('upconv%d' % j, uh, uw, c)
+            sk = self.act[self.skip_of[j]]
+            self.crop[j] = ((sk.shape[1] - uh) // 2, (sk.shape[2] - uw) // 2, uh, uw)
+            buf('conv%d_1' % (5 + j), uh - 2, uw - 2, c)
+            below = buf('conv%d_2' % (5 + j), uh - 4, uw - 4, c)
+        self.oh, self.ow = below.shape[1], below.shape[2]
+        self.logits = torch.zeros(B, self.oh, self.ow, model.n_classes, dtype=torch.float32,
+                                  device=dev)
+        self.probs = torch.zeros(B, self.oh, self.ow, model.n_classes, dtype=torch.float32,
+                                 device=dev)
+        self.labelmap = torch.zeros(B, self.oh, self.ow, 1, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_pixels = B * self.oh * self.ow
+        # mask centre crop (reference models/unet.py:71-72)
+        self.my0, self.mx0 = (H - self.oh) // 2, (W - self.ow) // 2
+        self.graph = None
+        self.calls = 0
+        self.use_graph = True
+        if training:
+            self._alloc_grads()
+
+    # ------------------------------------------------------------- buffers
+    def skip_view(self, j):
+        y0, x0, h, w = self.crop[j]
+        return self.act[self.skip_of[j]][:, y0:y0 + h, x0:x0 + w, :]
+
+    def _alloc_grads(self):
+        dev, B = self.m.device, self.B
+        self.g = {}
+
+        def gbuf(name, like=None, shape=None):
+            shp = tuple(like.shape) if like is not None else shape
+            self.g[name] = torch.zeros(shp, dtype=BF16, device=dev)
+            return self.g[name]
+
+        L = self.m.layers
+        gbuf('logits', shape=(B, self.oh, self.ow, L['output'].cout_pad))
+        for name, t in self.act.items():
+            if name in ('x', 'conv1_2'):
+                continue
+            gbuf(name, like=t)
+        for j in range(1, 5):
+            y0, x0, h, w = self.crop[j]
+            gbuf('skip%d' % j, shape=(B, h, w, self.act[self.skip_of[j]].shape[3]))
+        y0, x0, h, w = self.crop[4]
+        gbuf('conv1_1_part', shape=(B, h + 2, w + 2, self.act['conv1_1'].shape[3]))
+
+    # ------------------------------------------------------------- staging
+    def stage(self, x, mask):
+        self.x_f32.copy_(x, non_blocking=True)
+        if mask is not None:
+            self.mask.copy_(mask, non_blocking=True)
+
+    # ------------------------------------------------------------- forward
+    def forward(self, dropout=None):
+        m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl
+        E.pack_input(self.x_f32, A['x'])
+
+        def conv(name, src, x2=None):
+            L[name].forward(src, A[name], x2=x2, impl=impl)
+            if dropout is not None and name in self.MC_SITES:
+                seed, off = dropout
+                for t in range(self.B):       # one Philox stream per MC pass
+                    E.dropout(A[name][t:t + 1], A[name][t:t + 1], seed,
+                              (off + t) * 8 + self.MC_SITES[name])
+
+        conv('conv1_1', A['x'])
+        conv('conv1_2', A['conv1_1'])
+        E.maxpool_fwd(A['conv1_1'], A['pool1'], self.amax['pool1'])
+        for i in range(2, 6):
+            conv('conv%d_1' % i, A['pool%d' % (i - 1)])
+            conv('conv%d_2' % i, A['conv%d_1' % i])
+            if i < 5:
+                E.maxpool_fwd(A['conv%d_2' % i], A['pool%d' % i], self.amax['pool%d' % i])
+        below = A['conv5_2']
+        for j in range(1, 5):
+            up = 'upconv%d' % j
+            L[up].forward(below, A[up], impl=impl)
+            conv('conv%d_1' % (5 + j), self.skip_view(j), x2=A[up])
+            conv('conv%d_2' % (5 + j), A['conv%d_1' % (5 + j)])
+            below = A['conv%d_2' % (5 + j)]
+        L['output'].forward(below, self.logits, impl=impl, out_f32=True)
+        m.y_hat = self.logits
+
+    def head(self):
+        E.sigmoid_argmax(self.logits, self.probs, self.labelmap)
+        self.m.y_hat_sig, self.m.output = self.probs, self.labelmap
+        return self.probs, self.labelmap
+
+    def mask_view(self):
+        return self.mask[:, self.my0:self.my0 + self.oh, self.mx0:self.mx0 + self.ow, :]
+
+    def loss(self, with_grad):
+        E.fill_zero(self.loss_sum)
+        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum,
+                       self.g['logits'] if with_grad else None)
+
+    # ------------------------------------------------------------ backward
+    def backward(self):
+        L, A, G, impl = self.m.layers, self.act, self.g, self.m.impl
+        nc = self.m.n_classes
+        hook = self.m._bucket_done
+
+        def done(name):            # data-parallel: a gradient bucket may be complete
+            if hook is not None:
+                hook(name)
+        # head (no activation): dz = dlogits
+        L['output'].backward(A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],
+                             impl=impl, dz_bias=G['logits'][..., :nc])
+        done('output')
+        for j in range(4, 0, -1):
+            c1, c2, up = 'conv%d_1' % (5 + j), 'conv%d_2' % (5 + j), 'upconv%d' % j
+            below = 'conv%d_2' % (4 + j) if j > 1 else 'conv5_2'
+            L[c2].backward(A[c1], G[c2], dx=G[c1], mask=A[c1], impl=impl)
+            done(c2)
+            # conv over the virtual concat [skip_crop | upconv]: two dgrad destinations.
+            # The skip gradient is ReLU-masked later by the pool backward that merges
+            # it (j<4); for j==4 conv1_2 has no other consumer, so mask it here.
+            sk = self.skip_view(j)
+            L[c1].backward(sk, G[c1], dx=G['skip%d' % j], x2=A[up], dx2=G[up],
+                           mask=sk if j == 4 else None, mask2=A[up], impl=impl)
+            done(c1)
+            L[up].backward(A[below], G[up], dx=G[below], mask=A[below], impl=impl)
+            done(up)
+        # encoder
+        L['conv5_2'].backward(A['conv5_1'], G['conv5_2'], dx=G['conv5_1'], mask=A['conv5_1'],
+                              impl=impl)
+        done('conv5_2')
+        for i in range(5, 1, -1):
+            c1, c2, pool = 'conv%d_1' % i, 'conv%d_2' % i, 'pool%d' % (i - 1)
+            if i < 5:
+                # dZ(conv i_2) = relu_mask(pool_i backward + skip gradient at the crop)
+                j = 5 - i
+                y0, x0, _, _ = self.crop[j]
+                E.maxpool_bwd(G['pool%d' % i], self.amax['pool%d' % i], G[c2],
+                              add=G['skip%d' % j], add_y0=y0, add_x0=x0, mask=A[c2])
+                L[c2].backward(A[c1], G[c2], dx=G[c1], mask=A[c1], impl=impl)
+                done(c2)
+            L[c1].backward(A[pool], G[c1], dx=G[pool], impl=impl)
+            done(c1)
+        # conv1_2: output gradient lives only on the skip crop -> run on the crop
+        y0, x0, h, w = self.crop[4]
+        x_win = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
+        L['conv1_2'].backward(x_win, G['skip4'], dx=G['conv1_1_part'], impl=impl)
+        done('conv1_2')
+        E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['conv1_1'], add=G['conv1_1_part'],
+                      add_y0=y0, add_x0=x0, mask=A['conv1_1'])
+        L['conv1_1'].backward(A['x'], G['conv1_1'], dx=None, impl=impl)
+        done('conv1_1')
+
+    # ---------------------------------------------------------------- steps
+    def _step_body(self):
+        self.forward()
+        self.loss(True)
+        self.backward()
+        if self.m._grad_hook is not None:
+            self.m._grad_hook()
+        self.m.store.adam_launch(0.0, grad_scale=1.0 / self.m.world_size, from_device=True)
+
+    def train_step(self, x, mask):
+        m = self.m
+        self.stage(x, mask)
+        lr_t = m.store.next_lr_t(m.learning_rate)
+        m.store.lr_t_dev.fill_(lr_t)
+        if self.use_graph and self.graph is None and self.calls >= 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self.graph = g
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.calls += 1
+
+    def infer(self, x):
+        self.stage(x, None)
+        self.forward()
+        return self.head()
+
+    def eval_loss(self, x, mask):
+        self.stage(x, mask)
+        self.forward()
+        E.fill_zero(self.loss_sum)
+        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum, None)
+        return float(self.loss_sum.item()) / self.loss_pixels

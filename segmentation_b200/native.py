@@ -1,0 +1,148 @@
+"""ctypes binding of libsegb200.so (the C ABI declared in include/segb200.h).
+
+PyTorch is used only for device memory (`tensor.data_ptr()`) and streams
+(`torch.cuda.current_stream().cuda_stream`); no torch types cross the ABI.
+There is NO fallback: if the library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsegb200.so')
+
+IMPL_UMMA, IMPL_SIMT = 0, 1
+EPI_BIAS, EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK = 1, 2, 4, 8
+
+
+class SegError(RuntimeError):
+    pass
+
+
+class SegView(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p),
+                ('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32),
+                ('c', ctypes.c_int32),
+                ('sn', ctypes.c_int64), ('sh', ctypes.c_int64), ('sw', ctypes.c_int64)]
+
+
+class SegConvDesc(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in
+                ('kh', 'kw', 'stride', 'pad_t', 'pad_l', 'pad_b', 'pad_r', 'cin', 'cout',
+                 'cin_pad', 'cout_pad', 'flags', 'impl')]
+
+
+_VP = ctypes.POINTER(SegView)
+_DP = ctypes.POINTER(SegConvDesc)
+_P = ctypes.c_void_p
+_I32, _I64, _U32, _U64, _F = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
+                              ctypes.c_float)
+
+# name -> argtypes; every function returns int32 status unless noted
+SIGNATURES = {
+    'seg_version': [],
+    'seg_device_check': [],
+    'seg_conv2d_fwd': [_DP, _VP, _VP, _P, _P, _VP, _P],
+    'seg_conv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _VP, _VP, _P],
+    'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P],
+    'seg_deconv2d_fwd': [_DP, _VP, _P, _P, _VP, _P],
+    'seg_deconv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _P],
+    'seg_deconv2d_wgrad': [_DP, _VP, _VP, _P, _P],
+    'seg_bias_grad': [_VP, _P, _P],
+    'seg_maxpool_fwd': [_VP, _I32, _I32, _VP, _P, _P],
+    'seg_maxpool_bwd': [_VP, _P, _I32, _I32, _VP, _I32, _I32, _VP, _VP, _P],
+    'seg_bilinear_upsample_fwd': [_VP, _I32, _VP, _VP, _I32, _P],
+    'seg_bilinear_upsample_bwd': [_VP, _I32, _I32, _VP, _P],
+    'seg_resize_bilinear_fwd': [_VP, _VP, _P],
+    'seg_resize_bilinear_bwd': [_VP, _VP, _P],
+    'seg_batchnorm_stats': [_VP, _P, _P, _P],
+    'seg_batchnorm_finalize': [_P, _P, _I64, _I32, _F, _F, _P, _P, _P, _P, _P],
+    'seg_batchnorm_apply': [_VP, _P, _P, _P, _VP, _P],
+    'seg_batchnorm_infer': [_VP, _P, _P, _F, _P, _VP, _P],
+    'seg_batchnorm_bwd_reduce': [_VP, _VP, _P, _P, _P, _P, _P],
+    'seg_batchnorm_bwd_apply': [_VP, _VP, _P, _P, _P, _P, _I64, _I32, _VP, _P],
+    'seg_dropout': [_VP, _U64, _U32, _F, _VP, _P],
+    'seg_softmax_xent_fwd_bwd': [_VP, _VP, _P, _VP, _P],
+    'seg_sigmoid_argmax': [_VP, _P, _P, _P],
+    'seg_mc_mean_var': [_P, _I32, _I64, _P, _P, _P],
+    'seg_adam_multi': [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _F, _P, _F, _F, _F, _F, _P],
+    'seg_pack_input': [_P, _I32, _VP, _P],
+    'seg_fill_zero': [_P, _I64, _P],
+    'seg_probe_umma': [_I32, _I32, _I32, _I32, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library.  Fails loudly — there is no CPU/eager fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SegError('%s not found: build it with `python -m segmentation_b200.build` '
+                       '(or __graft_entry__.build()); there is no fallback path' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int32
+    lib.seg_last_error_string.argtypes = []
+    lib.seg_last_error_string.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().seg_last_error_string()
+        raise SegError('%s failed (status %d): %s' % (what, status,
+                                                      msg.decode() if msg else ''))
+
+
+LAUNCHES = 0          # number of kernel-enqueueing C-ABI calls made so far
+TIMELINE = None       # set to a list to record (name, tag, start_event, end_event) per call
+_TAG = ['']
+
+
+def set_tag(tag):
+    _TAG[0] = tag
+
+
+def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    if TIMELINE is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(getattr(load(), name)(*args), name)
+    e1.record()
+    TIMELINE.append((name, _TAG[0], e0, e1))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def view(t):
+    """SegView of a 4-D NHWC torch tensor (any strides, channel stride 1).
+    Slicing the tensor in torch (crops, channel slices) yields the crop / concat
+    views the C ABI understands."""
+    if t is None:
+        return None
+    assert t.dim() == 4, 'NHWC tensor expected'
+    assert t.stride(3) == 1 or t.shape[3] == 1, 'channel stride must be 1'
+    return SegView(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3],
+                   t.stride(0), t.stride(1), t.stride(2))
+
+
+def vref(t):
+    return ctypes.byref(view(t)) if t is not None else None

@@ -1,0 +1,93 @@
+"""Data-parallel training over one 8xB200 box: one process per GPU, batch
+partitioned across ranks, gradients summed with NCCL all-reduce over
+NVLink/NVSwitch, bucketed in reverse layer order and overlapped with the rest
+of the backward pass.  The reference has no distributed code at all
+(SURVEY.md §2.1); images are independent in U-Net / FCN (no batch-coupled op),
+and the loss is a mean over N*H*W (reference models/basemodel.py:360), so with
+equal per-rank batches grad_global = (1/W) * sum_r grad_r: the 1/W is folded
+into the Adam kernel (`grad_scale`).
+
+The flat gradient buffer is laid out in TF variable order (forward order);
+backward completes it from the back, so buckets are contiguous slices that
+become ready one after the other.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets(object):
+    """Contiguous slices of a flat gradient buffer, all-reduced asynchronously
+    as they become ready, joined before the optimizer."""
+
+    def __init__(self, flat_grad, boundaries, group=None):
+        """boundaries: ascending element offsets [0, b1, ..., numel]."""
+        assert boundaries[0] == 0 and boundaries[-1] == flat_grad.numel()
+        self.flat = flat_grad
+        self.slices = [flat_grad[a:b] for a, b in zip(boundaries[:-1], boundaries[1:])]
+        self.group = group
+        self.pending = []
+
+    def launch(self, idx):
+        """All-reduce (sum) bucket idx; returns immediately."""
+        w = dist.all_reduce(self.slices[idx], op=dist.ReduceOp.SUM, group=self.group,
+                            async_op=True)
+        self.pending.append(w)
+
+    def join(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+    def allreduce_all(self):
+        for i in reversed(range(len(self.slices))):
+            self.launch(i)
+        self.join()
+
+
+def bucket_boundaries(store, first_layers):
+    """Offsets that split the flat buffer at the first parameter of each named
+    layer (in TF order)."""
+    offs = [0]
+    for name in first_layers:
+        o = store.params[name + '/weights'].offset
+        if o > offs[-1]:
+            offs.append(o)
+    offs.append(store.numel)
+    return offs
+
+
+class DataParallel(object):
+    """Wraps a model: identical initial parameters on every rank, world_size for
+    the Adam grad_scale, bucketed gradient all-reduce hooks."""
+
+    # U-Net: encoder (conv1..4) | bottleneck conv5_* (61 % of the bytes) | decoder
+    UNET_SPLITS = ('conv5_1', 'upconv1')
+
+    def __init__(self, model, splits=None, group=None):
+        self.model = model
+        self.world = dist.get_world_size(group)
+        model.world_size = self.world
+        st = model.store
+        dist.broadcast(st.master, src=0, group=group)
+        for t in st.state.values():
+            dist.broadcast(t, src=0, group=group)
+        st.refresh_shadow()
+        if splits is None:
+            splits = self.UNET_SPLITS if model.model_name == 'unet' else ()
+        self.buckets = GradBuckets(st.grad, bucket_boundaries(st, splits), group)
+        # layer whose backward completes bucket i (buckets are in forward order)
+        self.ready_after = {}
+        names = list(model.layers)
+        first = [0] + [names.index(s) for s in splits if s in names]
+        for i, start in enumerate(first):
+            self.ready_after[names[start]] = i
+        model._bucket_done = self.on_layer_done
+        model._grad_hook = self.buckets.join
+
+    def on_layer_done(self, layer_name):
+        """Called by the backward schedule after `layer_name`'s wgrad was enqueued:
+        launches the all-reduce of a bucket once its LAST gradient (the first layer
+        of the bucket in forward order) is complete."""
+        i = self.ready_after.get(layer_name)
+        if i is not None:
+            self.buckets.launch(i)

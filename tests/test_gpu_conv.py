@@ -1,0 +1,255 @@
+"""-m gpu parity tests for the convolution family: tcgen05 implicit-GEMM (UMMA)
+and CUDA-core (SIMT) paths against the CPU oracle, through the C ABI.
+
+Tolerance: operands are rounded to bf16 on both sides and accumulated in fp32,
+so the only difference is summation order -> rel-L2 <= 2e-3 for bf16 outputs
+(one bf16 rounding of the result, 2^-9 relative), 1e-4 for fp32 outputs.
+"""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from segmentation_b200 import native as N
+
+from gpu_util import (bfr, conv_pads, desc, dev_bf16, pad16, rel_l2, report, shadow_conv,
+                      shadow_deconv, sync)
+
+pytestmark = pytest.mark.gpu
+IMPLS = [('simt', N.IMPL_SIMT), ('umma', N.IMPL_UMMA)]
+TOL_BF16 = 4e-3
+TOL_F32 = 2e-4
+
+
+def _gen(seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g
+
+
+# ---------------------------------------------------------------------------
+# descriptor probes: plain GEMMs through the igemm kernel (no im2col)
+# ---------------------------------------------------------------------------
+PROBE_SHAPES = [
+    # M, N, K           (K picks KC: 64 | 32 | 16; N picks BN / swizzle of MN-major B)
+    (128, 64, 64), (128, 128, 128), (384, 256, 192), (200, 128, 64),
+    (128, 32, 32), (256, 64, 96), (130, 32, 160),
+    (128, 16, 16), (256, 16, 48), (128, 32, 16), (128, 64, 16), (192, 128, 48),
+    (128, 16, 64), (128, 256, 32),
+]
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_probe_umma_gemm(cuda, mode):
+    g = _gen(1)
+    fails = []
+    for (M, Nn, K) in PROBE_SHAPES:
+        a = bfr(torch.randn(M, K, generator=g))
+        b = bfr(torch.randn(Nn, K, generator=g))           # [N][K]
+        ref = a @ b.t()
+        a_d = a.to(torch.bfloat16).cuda()
+        b_d = (b.t().contiguous() if mode == 1 else b).to(torch.bfloat16).cuda()
+        d = torch.full((M, Nn), float('nan'), dtype=torch.float32, device='cuda')
+        N.call('seg_probe_umma', mode, M, Nn, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d),
+               N.stream_ptr())
+        sync()
+        err = rel_l2(d.cpu(), ref)
+        report('probe', {'mode': mode, 'M': M, 'N': Nn, 'K': K, 'err': err})
+        if not (err < TOL_F32):
+            fails.append((M, Nn, K, err))
+    assert not fails, 'probe failures (M,N,K,err): %s' % fails
+
+
+# ---------------------------------------------------------------------------
+# conv forward
+# ---------------------------------------------------------------------------
+CONV_CASES = [
+    # name, N, H, W, C1, C2, Cout, k, stride, padding, relu, out_f32
+    ('v3_32_64', 2, 20, 18, 32, 0, 64, 3, 1, 'VALID', True, False),
+    ('v3_64_128', 1, 17, 23, 64, 0, 128, 3, 1, 'VALID', True, False),
+    ('v3_128_256', 1, 12, 12, 128, 0, 256, 3, 1, 'VALID', True, False),
+    ('v3_rgb', 2, 30, 26, 3, 0, 32, 3, 1, 'VALID', True, False),
+    ('s3_32_32', 2, 16, 16, 32, 0, 32, 3, 1, 'SAME', True, False),
+    ('s3_rgb_odd', 1, 15, 17, 3, 0, 32, 3, 1, 'SAME', True, False),
+    ('concat', 2, 14, 14, 64, 64, 64, 3, 1, 'VALID', True, False),
+    ('concat32', 1, 20, 20, 32, 32, 32, 3, 1, 'VALID', True, False),
+    ('head1x1', 2, 12, 12, 32, 0, 2, 1, 1, 'VALID', False, True),
+    ('p1x1_21', 1, 16, 16, 128, 0, 21, 1, 1, 'SAME', True, False),
+    ('s5s2_rgb', 1, 32, 32, 3, 0, 32, 5, 2, 'SAME', True, False),
+    ('bigM', 3, 40, 40, 32, 0, 32, 3, 1, 'VALID', True, False),
+    ('c512', 1, 10, 10, 256, 0, 512, 3, 1, 'VALID', True, False),
+]
+
+
+def _conv_inputs(case, seed=0):
+    name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
+    g = _gen(seed)
+    x = bfr(torch.rand(Nb, H, W, C1 + C2, generator=g) - 0.3)
+    w = bfr(torch.randn(k, k, C1 + C2, Co, generator=g) * 0.1)
+    b = torch.randn(Co, generator=g) * 0.1
+    return x, w, b
+
+
+@pytest.mark.parametrize('impl_name,impl', IMPLS)
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_fwd(cuda, case, impl_name, impl):
+    name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
+    x, w, b = _conv_inputs(case)
+    ref = T.conv2d(x, w, b, s, padding)
+    if relu:
+        ref = torch.relu(ref)
+    cin, cin_pad, cout_pad = C1 + C2, pad16(C1 + C2), pad16(Co)
+    if C2:
+        x1_d, x2_d = dev_bf16(x[..., :C1]), dev_bf16(x[..., C1:])
+    else:
+        x1_d, x2_d = dev_bf16(x, cin_pad), None
+    w_d = shadow_conv(w, cin_pad, cout_pad)
+    b_d = b.cuda()
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    y_d = torch.full((Nb, Ho, Wo, Co), float('nan'),
+                     dtype=torch.float32 if f32 else torch.bfloat16, device='cuda')
+    flags = N.EPI_BIAS | (N.EPI_RELU if relu else 0) | (N.EPI_OUT_F32 if f32 else 0)
+    d = desc(k, s, conv_pads(H, W, k, s, padding), cin, Co, cin_pad, cout_pad, flags, impl)
+    N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x1_d), N.vref(x2_d), N.ptr(w_d), N.ptr(b_d),
+           N.vref(y_d), N.stream_ptr())
+    sync()
+    err = rel_l2(y_d.float().cpu(), ref)
+    report('conv_fwd', {'case': name, 'impl': impl_name, 'err': err})
+    assert err < (TOL_F32 if f32 else TOL_BF16), (name, impl_name, err)
+
+
+# ---------------------------------------------------------------------------
+# conv dgrad / wgrad / bias grad
+# ---------------------------------------------------------------------------
+BWD_CASES = [c for c in CONV_CASES if c[0] not in ('s5s2_rgb',)]
+
+
+@pytest.mark.parametrize('impl_name,impl', IMPLS)
+@pytest.mark.parametrize('case', BWD_CASES, ids=[c[0] for c in BWD_CASES])
+def test_conv_bwd(cuda, case, impl_name, impl):
+    name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
+    x, w, b = _conv_inputs(case)
+    g = _gen(7)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    z = T.conv2d(xr, wr, None, s, padding)
+    dz = bfr(torch.randn(z.shape, generator=g) * 0.05)
+    dx_ref, dw_ref = torch.autograd.grad(z, [xr, wr], dz)
+    db_ref = dz.sum(dim=(0, 1, 2))
+    # the producer of x is a ReLU layer: mask where x <= 0
+    mask = (x > 0).float()
+    dx_ref = dx_ref * mask
+
+    cin, cin_pad, cout_pad = C1 + C2, pad16(C1 + C2), pad16(Co)
+    dz_d = dev_bf16(dz, cout_pad)
+    w_d = shadow_conv(w, cin_pad, cout_pad)
+    d = desc(k, s, conv_pads(H, W, k, s, padding), cin, Co, cin_pad, cout_pad, 0, impl)
+    if C2:
+        x1_d, x2_d = dev_bf16(x[..., :C1]), dev_bf16(x[..., C1:])
+        dx1 = torch.full((Nb, H, W, C1), float('nan'), dtype=torch.bfloat16, device='cuda')
+        dx2 = torch.full((Nb, H, W, C2), float('nan'), dtype=torch.bfloat16, device='cuda')
+    else:
+        x1_d, x2_d = dev_bf16(x, cin_pad), None
+        dx1 = torch.full((Nb, H, W, cin_pad), float('nan'), dtype=torch.bfloat16, device='cuda')
+        dx2 = None
+    dw_d = torch.zeros(k, k, cin, Co, dtype=torch.float32, device='cuda')
+    db_d = torch.zeros(Co, dtype=torch.float32, device='cuda')
+    st = N.stream_ptr()
+    N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x1_d), N.vref(x2_d), N.vref(dz_d),
+           N.ptr(dw_d), st)
+    N.call('seg_bias_grad', N.vref(dz_d[..., :Co]), N.ptr(db_d), st)
+    do_dgrad = cin >= 16          # the RGB layer never needs dgrad
+    if do_dgrad:
+        N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz_d), N.ptr(w_d), N.vref(dx1),
+               N.vref(dx2), N.vref(x1_d), N.vref(x2_d), st)
+    sync()
+    e_w = rel_l2(dw_d.cpu(), dw_ref)
+    e_b = rel_l2(db_d.cpu(), db_ref)
+    rec = {'case': name, 'impl': impl_name, 'dw': e_w, 'db': e_b}
+    ok = e_w < TOL_F32 * 5 and e_b < TOL_F32 * 5
+    if do_dgrad:
+        got = torch.cat([dx1.float().cpu()[..., :C1 if C2 else cin]] +
+                        ([dx2.float().cpu()] if C2 else []), dim=-1)
+        e_x = rel_l2(got, dx_ref)
+        rec['dx'] = e_x
+        ok = ok and e_x < TOL_BF16
+    report('conv_bwd', rec)
+    assert ok, rec
+
+
+# ---------------------------------------------------------------------------
+# transposed conv (slim.convolution2d_transpose)
+# ---------------------------------------------------------------------------
+DECONV_CASES = [
+    # name, N, H, W, Cin, Cout, k, stride, padding, impls
+    ('up2_64_32', 2, 8, 8, 64, 32, 2, 2, 'VALID', ('simt', 'umma')),
+    ('up2_512_256', 1, 8, 8, 512, 256, 2, 2, 'VALID', ('simt', 'umma')),
+    ('up2_32_2', 1, 10, 12, 32, 2, 2, 2, 'VALID', ('simt', 'umma')),
+    ('up2_odd', 3, 7, 9, 128, 64, 2, 2, 'VALID', ('simt', 'umma')),
+    ('k5s2', 1, 11, 11, 64, 32, 5, 2, 'VALID', ('simt',)),
+    ('k4s2_same', 1, 9, 9, 32, 16, 4, 2, 'SAME', ('simt',)),
+]
+
+
+@pytest.mark.parametrize('case', DECONV_CASES, ids=[c[0] for c in DECONV_CASES])
+def test_deconv_fwd_bwd(cuda, case):
+    name, Nb, H, W, Ci, Co, k, s, padding, impls = case
+    g = _gen(3)
+    x = bfr(torch.rand(Nb, H, W, Ci, generator=g) - 0.3)
+    w = bfr(torch.randn(k, k, Co, Ci, generator=g) * 0.1)
+    b = torch.randn(Co, generator=g) * 0.1
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    z = T.conv2d_transpose(xr, wr, b, s, padding)
+    y_ref = torch.relu(z)
+    dz = bfr(torch.randn(z.shape, generator=g) * 0.05)
+    dx_ref, dw_ref = torch.autograd.grad(z, [xr, wr], dz)
+    dx_ref = dx_ref * (x > 0).float()
+    OH, OW = z.shape[1], z.shape[2]
+    cin_pad, cout_pad = pad16(Ci), pad16(Co)
+    tot = max(k - s, 0) if padding == 'SAME' else 0
+    pads = (tot // 2, tot // 2, tot - tot // 2, tot - tot // 2)
+    for impl_name in impls:
+        impl = dict(IMPLS)[impl_name]
+        x_d = dev_bf16(x, cin_pad)
+        w_d = shadow_deconv(w, cin_pad, cout_pad)
+        b_d = b.cuda()
+        y_d = torch.full((Nb, OH, OW, Co), float('nan'), dtype=torch.bfloat16, device='cuda')
+        d = desc(k, s, pads, Ci, Co, cin_pad, cout_pad, N.EPI_BIAS | N.EPI_RELU, impl)
+        st = N.stream_ptr()
+        N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(x_d), N.ptr(w_d), N.ptr(b_d),
+               N.vref(y_d), st)
+        dz_d = dev_bf16(dz, cout_pad)
+        dx_d = torch.full((Nb, H, W, cin_pad), float('nan'), dtype=torch.bfloat16, device='cuda')
+        dw_d = torch.zeros(k, k, Co, Ci, dtype=torch.float32, device='cuda')
+        N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz_d), N.ptr(w_d), N.vref(dx_d),
+               N.vref(x_d), st)
+        N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x_d), N.vref(dz_d), N.ptr(dw_d), st)
+        sync()
+        rec = {'case': name, 'impl': impl_name,
+               'y': rel_l2(y_d.float().cpu(), y_ref),
+               'dx': rel_l2(dx_d.float().cpu()[..., :Ci], dx_ref),
+               'dw': rel_l2(dw_d.cpu(), dw_ref)}
+        report('deconv', rec)
+        assert rec['y'] < TOL_BF16 and rec['dx'] < TOL_BF16 and rec['dw'] < TOL_F32 * 5, rec
+
+
+def test_conv_crop_view_and_slice_output(cuda):
+    """Crop views as inputs (tf.image.resize_image_with_crop_or_pad as a TMA base
+    offset) and channel-slice outputs."""
+    g = _gen(11)
+    big = bfr(torch.rand(2, 24, 24, 32, generator=g) - 0.3)
+    w = bfr(torch.randn(3, 3, 32, 32, generator=g) * 0.1)
+    b = torch.zeros(32)
+    crop = T.crop_or_pad(big, 16, 16)
+    ref = torch.relu(T.conv2d(crop, w, b, 1, 'VALID'))
+    for impl_name, impl in IMPLS:
+        big_d = dev_bf16(big)
+        view = big_d[:, 4:20, 4:20, :]
+        out = torch.zeros(2, 14, 14, 64, dtype=torch.bfloat16, device='cuda')
+        d = desc(3, 1, (0, 0, 0, 0), 32, 32, 32, 32, N.EPI_BIAS | N.EPI_RELU, impl)
+        N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(view), None, N.ptr(shadow_conv(w, 32, 32)),
+               N.ptr(b.cuda()), N.vref(out[..., 32:]), N.stream_ptr())
+        sync()
+        assert rel_l2(out[..., 32:].float().cpu(), ref) < TOL_BF16, impl_name
+        assert float(out[..., :32].abs().max()) == 0.0

@@ -1,0 +1,224 @@
+"""-m gpu parity tests for the memory-bound kernels against the CPU oracle.
+
+Bit-exact: max-pool values + argmax slots (first max, row-major window scan),
+dropout keep-masks, label maps.  Tolerances for floating point are stated at
+each assert."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from segmentation_b200 import engine as E
+from segmentation_b200 import native as N
+
+from gpu_util import bfr, dev_bf16, rel_l2, report, sync
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+def _gen(seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g
+
+
+@pytest.mark.parametrize('shape,k', [((2, 9, 11, 32), 2), ((1, 14, 14, 64), 2), ((2, 10, 13, 32), 3),
+                                     ((1, 7, 7, 5), 2), ((1, 254, 254, 32), 2)])
+def test_maxpool_fwd_bwd_bit_exact(cuda, shape, k):
+    g = _gen(5)
+    x = bfr(torch.randn(shape, generator=g))
+    # force ties: quantise + ReLU-like zeros (all-zero windows are the common tie)
+    x = torch.relu(torch.round(x * 2) / 2)
+    y_ref, slot_ref = T.max_pool_with_argmax(x, k, k)
+    x_d = dev_bf16(x)
+    Nb, H, W, C = shape
+    Ho, Wo = y_ref.shape[1], y_ref.shape[2]
+    y_d = torch.zeros(Nb, Ho, Wo, C, dtype=BF16, device='cuda')
+    am = torch.zeros(Nb, Ho, Wo, C, dtype=torch.uint8, device='cuda')
+    E.maxpool_fwd(x_d, y_d, am, k, k)
+    sync()
+    assert torch.equal(y_d.float().cpu(), y_ref)                 # bit-exact values
+    assert torch.equal(am.cpu(), slot_ref)                       # bit-exact argmax
+    # backward: gather by argmax + skip add + relu mask
+    dy = bfr(torch.randn(y_ref.shape, generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = T.max_pool(xr, k, k)
+    (dx_ref,) = torch.autograd.grad(yr, xr, dy)
+    add = bfr(torch.randn(Nb, H - 2, W - 2, C, generator=g))
+    addp = torch.zeros(shape)
+    addp[:, 1:H - 1, 1:W - 1] = add
+    ref = bfr((dx_ref + addp) * (x > 0).float())
+    dx_d = torch.zeros(shape, dtype=BF16, device='cuda')
+    E.maxpool_bwd(dev_bf16(dy), am, dx_d, k, k, add=dev_bf16(add), add_y0=1, add_x0=1, mask=x_d)
+    sync()
+    assert torch.equal(dx_d.float().cpu(), ref)
+
+
+def test_softmax_xent_and_head(cuda):
+    g = _gen(2)
+    for C, cpad in ((2, 16), (21, 32), (5, 16)):
+        logits = torch.randn(2, 9, 7, C, generator=g) * 3
+        labels = torch.randint(0, C, (2, 13, 11, 1), generator=g).to(torch.uint8)
+        lab_crop = T.crop_or_pad(labels, 9, 7)
+        lr = logits.clone().requires_grad_(True)
+        loss_ref = T.softmax_xent_mean(lr, lab_crop)
+        (dl_ref,) = torch.autograd.grad(loss_ref, lr)
+        lg_d = logits.cuda()
+        lab_d = labels.cuda()
+        view = lab_d[:, 2:11, 2:9, :]
+        loss_sum = torch.zeros(1, device='cuda')
+        dl = torch.full((2, 9, 7, cpad), float('nan'), dtype=BF16, device='cuda')
+        E.softmax_xent(lg_d, view, loss_sum, dl)
+        probs = torch.zeros(2, 9, 7, C, device='cuda')
+        lm = torch.zeros(2, 9, 7, 1, device='cuda')
+        E.sigmoid_argmax(lg_d, probs, lm)
+        sync()
+        loss = float(loss_sum.item()) / (2 * 9 * 7)
+        assert abs(loss - float(loss_ref)) < 1e-5 * max(1.0, abs(float(loss_ref)))
+        assert rel_l2(dl.float().cpu()[..., :C], dl_ref) < 4e-3         # one bf16 rounding
+        assert float(dl.float().cpu()[..., C:].abs().max()) == 0.0
+        sig_ref, lab_ref = T.sigmoid_argmax(logits)
+        assert torch.allclose(probs.cpu(), sig_ref, atol=2e-7, rtol=1e-6)
+        assert torch.equal(lm.cpu(), lab_ref)                           # bit-exact label map
+
+
+def test_sigmoid_argmax_saturation_ties(cuda):
+    """fp32 sigmoid saturates to 1.0 -> argmax(sigmoid) ties resolve to index 0
+    (reference applies argmax to y_hat_sig, models/unet.py:76-77)."""
+    logits = torch.tensor([[[[20.0, 30.0], [30.0, 20.0], [-1.0, 2.0], [2.0, 2.0]]]])
+    probs = torch.zeros(1, 1, 4, 2, device='cuda')
+    lm = torch.zeros(1, 1, 4, 1, device='cuda')
+    E.sigmoid_argmax(logits.cuda(), probs, lm)
+    sync()
+    _, lab_ref = T.sigmoid_argmax(logits)
+    assert torch.equal(lm.cpu(), lab_ref)
+    assert lm.cpu().flatten().tolist() == [0.0, 0.0, 1.0, 0.0]
+
+
+def test_dropout_mask_bit_exact(cuda):
+    g = _gen(9)
+    x = bfr(torch.randn(1, 13, 11, 16, generator=g))
+    for seed, stream in ((0, 0), (1234567891011, 17), (2 ** 40 + 5, 3)):
+        ref = bfr(T.dropout(x, seed, stream))
+        x_d = dev_bf16(x)
+        y_d = torch.zeros_like(x_d)
+        E.dropout(x_d, y_d, seed, stream)
+        sync()
+        assert torch.equal(y_d.float().cpu(), ref)
+
+
+def test_bilinear_upsample(cuda):
+    g = _gen(4)
+    for f, C, H in ((2, 21, 8), (8, 21, 6), (2, 3, 5), (16, 2, 3), (32, 2, 2)):
+        x = bfr(torch.randn(2, H, H + 1, C, generator=g))
+        add = bfr(torch.randn(2, H * f, (H + 1) * f, C, generator=g))
+        xr = x.clone().requires_grad_(True)
+        up = T.bilinear_upsample(xr, f)
+        ref = up + add
+        x_d = dev_bf16(x)
+        y32 = torch.zeros(ref.shape, device='cuda')
+        E.bilinear_upsample_fwd(x_d, f, y32, add=dev_bf16(add))
+        sync()
+        assert torch.allclose(y32.cpu(), ref.detach(), atol=1e-5, rtol=1e-5), f
+        dy = torch.randn(ref.shape, generator=g)
+        (dx_ref,) = torch.autograd.grad(up, xr, dy)
+        dx_d = torch.zeros(x.shape, dtype=BF16, device='cuda')
+        E.bilinear_upsample_bwd(dy.cuda(), f, dx_d)
+        sync()
+        assert rel_l2(dx_d.float().cpu(), dx_ref) < 4e-3, f
+
+
+def test_resize_bilinear(cuda):
+    g = _gen(6)
+    for (H, W, oh, ow) in ((11, 11, 25, 25), (221 // 4, 50, 128, 128), (16, 16, 8, 8), (7, 9, 7, 9)):
+        x = bfr(torch.randn(2, H, W, 8, generator=g))
+        xr = x.clone().requires_grad_(True)
+        ref = T.resize_bilinear(xr, oh, ow)
+        y_d = torch.zeros(2, oh, ow, 8, dtype=BF16, device='cuda')
+        E.resize_bilinear_fwd(dev_bf16(x), y_d)
+        dy = bfr(torch.randn(ref.shape, generator=g))
+        (dx_ref,) = torch.autograd.grad(ref, xr, dy)
+        dx_d = torch.zeros(x.shape, dtype=BF16, device='cuda')
+        E.resize_bilinear_bwd(dev_bf16(dy), dx_d)
+        sync()
+        assert rel_l2(y_d.float().cpu(), ref.detach()) < 4e-3
+        assert rel_l2(dx_d.float().cpu(), dx_ref) < 4e-3
+
+
+def test_batchnorm(cuda):
+    g = _gen(8)
+    for C in (32, 64, 2, 256):
+        x = bfr(torch.relu(torch.randn(2, 9, 10, C, generator=g)))
+        store = E.ParamStore(torch.device('cuda'))
+        bn = E.BatchNorm(store, 'bn', C)
+        store.finalize()
+        beta = torch.randn(C, generator=g) * 0.1
+        bn.beta.value().copy_(beta.cuda())
+        xr = x.clone().requires_grad_(True)
+        y_ref, m_ref, v_ref = T.batch_norm(xr, beta, torch.zeros(C), torch.ones(C), True)
+        cp = E.pad16(C)
+        x_d = dev_bf16(x, cp)
+        y_d = torch.zeros(2, 9, 10, cp, dtype=BF16, device='cuda')
+        bn.forward(x_d, y_d, training=True)
+        dy = bfr(torch.randn(y_ref.shape, generator=g))
+        (dx_ref,) = torch.autograd.grad(y_ref, xr, dy)
+        dx_ref = dx_ref * (x > 0).float()
+        dx_d = torch.zeros_like(y_d)
+        bn.backward(dev_bf16(dy, cp), x_d, dx_d)
+        sync()
+        assert rel_l2(y_d.float().cpu()[..., :C], y_ref.detach()) < 4e-3
+        assert torch.allclose(bn.moving_mean.cpu(), m_ref, atol=1e-6)
+        assert torch.allclose(bn.moving_var.cpu(), v_ref, atol=1e-6)
+        assert rel_l2(dx_d.float().cpu()[..., :C], dx_ref) < 6e-3
+        assert rel_l2(bn.beta.grad().cpu(), dy.sum(dim=(0, 1, 2))) < 1e-4
+        # inference form uses the moving statistics
+        y_inf, _, _ = T.batch_norm(x, beta, m_ref, v_ref, False)
+        bn.forward(x_d, y_d, training=False)
+        sync()
+        assert rel_l2(y_d.float().cpu()[..., :C], y_inf) < 4e-3
+
+
+def test_adam_matches_tf_formula(cuda):
+    g = _gen(10)
+    store = E.ParamStore(torch.device('cuda'))
+    gen = np.random.default_rng(0)
+    lay = E.ConvLayer(store, 'c', 'conv', 3, 1, 'VALID', 3, 20, True, gen)
+    lay2 = E.ConvLayer(store, 'd', 'deconv', 2, 2, 'VALID', 20, 5, True, gen)
+    store.finalize()
+    lay.init_values(); lay2.init_values()
+    store.refresh_shadow()
+    p = store.master.cpu().clone()
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(p.shape, generator=g) * 0.01
+        store.grad.copy_(grad.cuda())
+        store.adam_step(1e-3, grad_scale=0.5)
+        p, m, v = T.adam_update(p, grad * 0.5, m, v, step, 1e-3)
+        sync()
+        assert torch.allclose(store.master.cpu(), p, atol=1e-7, rtol=1e-5)
+        assert float(store.grad.abs().max()) == 0.0          # zeroed for the next step
+    # bf16 shadows follow the masters, with zero channel padding
+    w = lay.w.value().cpu(); sh = lay.w.shadow().float().cpu()
+    assert torch.equal(sh[:, :, :3, :20], bfr(w))
+    assert float(sh[:, :, 3:, :].abs().max()) == 0.0 and float(sh[:, :, :, 20:].abs().max()) == 0.0
+    w2 = lay2.w.value().cpu(); sh2 = lay2.w.shadow().float().cpu()
+    assert torch.equal(sh2[:, :, :5, :20], bfr(w2))
+
+
+def test_mc_mean_var_and_pack(cuda):
+    g = _gen(12)
+    probs = torch.rand(16, 5, 6, 2, generator=g)
+    mean = torch.zeros(5, 6, 2, device='cuda'); var = torch.zeros(5, 6, 2, device='cuda')
+    E.mc_mean_var(probs.cuda(), mean, var)
+    x = torch.rand(2, 6, 7, 3, generator=g)
+    y = torch.full((2, 6, 7, 16), float('nan'), dtype=BF16, device='cuda')
+    E.pack_input(x.cuda(), y)
+    sync()
+    assert torch.allclose(mean.cpu(), probs.mean(0), atol=1e-6)
+    assert torch.allclose(var.cpu(), probs.var(0, unbiased=False), atol=1e-6)
+    assert torch.equal(y.float().cpu()[..., :3], bfr(x))
+    assert float(y.float().cpu()[..., 3:].abs().max()) == 0.0

@@ -1,0 +1,148 @@
+"""-m gpu whole-network parity: UNetModel (C-ABI kernels) vs the CPU oracle's
+restatement of /root/reference/models/unet.py:109-175 + loss + Adam.
+
+Tolerances (bf16 storage, fp32 accumulate; stated per SURVEY §7):
+  * vs the bf16-emulating oracle: activations / logits rel-L2 <= 1e-2,
+    parameter gradients rel-L2 <= 3e-2, loss |d| <= 2e-3;
+  * label maps: compared on pixels whose top-2 logit margin exceeds the logit
+    tolerance; mismatches elsewhere are counted and reported.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, tf_ops as T
+from segmentation_b200 import native as N
+from segmentation_b200.models.unet import UNetModel
+
+from gpu_util import rel_l2, report, sync
+
+pytestmark = pytest.mark.gpu
+
+
+class FeedDataSet(object):
+    """Minimal dataset duck-type (reference utils/datasets.py:94-196 contract:
+    images fp32 [B,H,W,3] in [0,1], masks uint8 [B,H,W,1] in {0,1})."""
+    use_feed = False
+    has_masks = True
+
+    def __init__(self, batch_size, h, w, c=3, n_classes=2, seed=0):
+        self.batch_size = batch_size
+        self.shape = (batch_size, h, w, c)
+        self.n_classes = n_classes
+        self.gen = np.random.default_rng(seed)
+
+    def set_tf_sess(self, sess):
+        pass
+
+    def next_batch(self):
+        x = self.gen.random(self.shape, dtype=np.float32)
+        y = self.gen.integers(0, self.n_classes, self.shape[:3] + (1,)).astype(np.uint8)
+        return x, y
+
+
+def _make(impl, B=2, S=188, nk=16, lr=1e-4):
+    import os
+    os.environ['SEGB200_IMPL'] = impl
+    ds = FeedDataSet(B, S, S)
+    model = UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=nk, learning_rate=lr,
+                      load_snapshot=False, save_dir=None)
+    p = nets.unet_params(n_kernels=nk, n_classes=2, seed=3)
+    gen = np.random.default_rng(5)
+    for k in p:
+        if k.endswith('/biases'):       # non-zero biases so bias paths are exercised
+            p[k] = torch.from_numpy(gen.normal(0, 0.05, p[k].shape).astype(np.float32))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    return model, ds, p
+
+
+@pytest.mark.parametrize('impl', ['simt', 'umma'])
+def test_unet_forward_backward_parity(cuda, impl):
+    model, ds, p = _make(impl)
+    x, y = ds.next_batch()
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    ex = model._get_exec(2, True)
+    ex.use_graph = False
+    ex.stage(xt.cuda(), yt.cuda())
+    ex.forward()
+    ex.loss(True)
+    ex.backward()
+    sync()
+    taps = {}
+    fwd = lambda q, xx: nets.unet_forward(q, xx, prec=T.BF16, taps=taps)
+    loss_ref, logits_ref, grads_ref = nets.loss_and_grads(fwd, p, xt, yt)
+    rec = {'impl': impl}
+    worst_act = 0.0
+    for name, t in taps.items():
+        if name == 'output':
+            continue
+        e = rel_l2(ex.act[name].float().cpu(), t.detach())
+        rec['act/' + name] = e
+        worst_act = max(worst_act, e)
+    e_logits = rel_l2(ex.logits.cpu(), logits_ref)
+    loss = float(ex.loss_sum.item()) / ex.loss_pixels
+    rec.update({'logits': e_logits, 'loss': loss, 'loss_ref': float(loss_ref)})
+    worst_g = 0.0
+    for name, gref in grads_ref.items():
+        e = rel_l2(model.store.params[name].grad().cpu(), gref)
+        rec['grad/' + name] = e
+        worst_g = max(worst_g, e)
+    report('unet_parity', rec)
+    assert worst_act < 1e-2, rec
+    assert e_logits < 1e-2, rec
+    assert abs(loss - float(loss_ref)) < 2e-3, rec
+    assert worst_g < 3e-2, rec
+    # label map: bit-exact where the logit margin exceeds the logit error
+    probs, lab = ex.head()
+    sync()
+    _, lab_ref = T.sigmoid_argmax(logits_ref)
+    margin = (logits_ref[..., 0] - logits_ref[..., 1]).abs()
+    tol = 4 * float((ex.logits.cpu() - logits_ref).abs().max())
+    safe = margin > tol
+    assert torch.equal(lab.cpu()[..., 0][safe], lab_ref[..., 0][safe])
+    mism = int((lab.cpu() != lab_ref).sum())
+    report('unet_labelmap', {'impl': impl, 'mismatch_pixels': mism, 'pixels': int(lab_ref.numel()),
+                             'unsafe_pixels': int((~safe).sum())})
+
+
+def test_unet_train_steps_match_oracle(cuda):
+    """3 train_step() calls (eager, graph capture, graph replay) == 3 oracle
+    Adam steps on the same batches; global_step advances."""
+    model, ds, p = _make('umma', lr=1e-3)
+    state = nets.AdamState(p)
+    ds_ref = FeedDataSet(2, 188, 188)
+    fwd = lambda q, xx: nets.unet_forward(q, xx, prec=T.BF16)
+    losses, losses_ref = [], []
+    for it in range(3):
+        model.train_step()
+        losses.append(model.seg_loss_op)
+        x, y = ds_ref.next_batch()
+        losses_ref.append(nets.train_step(fwd, p, state, torch.from_numpy(x),
+                                          torch.from_numpy(y), lr=1e-3))
+    assert model.global_step == 3
+    report('unet_train', {'loss': losses, 'loss_ref': losses_ref})
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) < 5e-3, (losses, losses_ref)
+    sd = model.store.state_dict()
+    worst = max(rel_l2(torch.from_numpy(sd[k]), p[k]) for k in nets.trainable_names(p))
+    report('unet_train_params', {'worst_param_rel_l2': worst})
+    assert worst < 2e-3
+
+
+def test_unet_infer_api(cuda):
+    """infer(imgs) returns [probs, labelmap] float32 numpy like
+    /root/reference/models/basemodel.py:527-531 + models/unet.py:76-79."""
+    import os
+    os.environ['SEGB200_IMPL'] = 'umma'
+    model = UNetModel(mode='INFERENCE', n_classes=2, input_dims=188, n_kernels=16,
+                      load_snapshot=False, save_dir=None)
+    p = nets.unet_params(n_kernels=16, n_classes=2, seed=3)
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x = np.random.default_rng(1).random((3, 188, 188, 3), dtype=np.float32)
+    out = model.infer(x)
+    assert isinstance(out, list) and len(out) == 2
+    assert out[0].shape == (3, 4, 4, 2) and out[0].dtype == np.float32
+    assert out[1].shape == (3, 4, 4, 1) and out[1].dtype == np.float32
+    ref = nets.infer(lambda q, xx: nets.unet_forward(q, xx, prec=T.BF16), p, torch.from_numpy(x))
+    assert np.allclose(out[0], ref[0], atol=5e-3)
+    assert set(np.unique(out[1])).issubset({0.0, 1.0})

@@ -243,13 +243,14 @@ def test_conv_crop_view_and_slice_output(cuda):
     b = torch.zeros(32)
     crop = T.crop_or_pad(big, 16, 16)
     ref = torch.relu(T.conv2d(crop, w, b, 1, 'VALID'))
+    w_d, b_d = shadow_conv(w, 32, 32), b.cuda()      # keep alive across the async launch
     for impl_name, impl in IMPLS:
         big_d = dev_bf16(big)
         view = big_d[:, 4:20, 4:20, :]
         out = torch.zeros(2, 14, 14, 64, dtype=torch.bfloat16, device='cuda')
         d = desc(3, 1, (0, 0, 0, 0), 32, 32, 32, 32, N.EPI_BIAS | N.EPI_RELU, impl)
-        N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(view), None, N.ptr(shadow_conv(w, 32, 32)),
-               N.ptr(b.cuda()), N.vref(out[..., 32:]), N.stream_ptr())
+        N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(view), None, N.ptr(w_d),
+               N.ptr(b_d), N.vref(out[..., 32:]), N.stream_ptr())
         sync()
         assert rel_l2(out[..., 32:].float().cpu(), ref) < TOL_BF16, impl_name
         assert float(out[..., :32].abs().max()) == 0.0

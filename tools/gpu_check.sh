@@ -8,7 +8,7 @@ rm -f gpurun_out/diag.jsonl
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 run() {  # name, timeout, pytest args...
   local name=$1; shift; local to=$1; shift
-  timeout "$to" python -m pytest -m gpu -q -x --no-header -p no:cacheprovider "$@" > "gpurun_out/$name.log" 2>&1
+  timeout "$to" python -m pytest -m gpu -q --no-header -p no:cacheprovider "$@" > "gpurun_out/$name.log" 2>&1
   echo "$name exit=$?" | tee -a gpurun_out/summary.txt
   tail -n 4 "gpurun_out/$name.log"
 }
@@ -21,4 +21,5 @@ run conv_umma_fwd 600 tests/test_gpu_conv.py -k "umma and fwd"
 run conv_umma_bwd 600 tests/test_gpu_conv.py -k "umma and bwd"
 run unet_simt 900 tests/test_gpu_unet.py -k "simt"
 run unet_umma 900 tests/test_gpu_unet.py -k "umma or train or infer"
+run unet_full 900 tests/test_gpu_unet.py -k "config1"
 cat gpurun_out/summary.txt

@@ -254,6 +254,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
         N.TIMELINE = None
+        out_dir = os.path.join(ROOT, 'gpurun_out')
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, 'timeline.json'), 'w') as f:
+                json.dump(tl, f)
         ex.graph, ex.use_graph = saved, True
         roof = dominant_kernel(tl, model, ex)
 
@@ -266,7 +270,10 @@ def run_ours(args):
     value = imgs / (ms_dev * 1e-3)
     e2e = imgs / (ms_e2e * 1e-3)
     h2d = BATCH * S * S * 3 * 4 + BATCH * S * S
-    cpu_rate, cores, sample, _ = cpu_oracle_rate(2, 1)
+    if args.skip_cpu:
+        cpu_rate, cores, sample = None, 0, 'skipped (--skip-cpu)'
+    else:
+        cpu_rate, cores, sample, _ = cpu_oracle_rate(2, 1)
     line = {
         'metric': 'U-Net train img/s (256x256, bs16/GPU)', 'value': value, 'unit': 'img/s',
         'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_dev / K,
@@ -363,6 +370,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--skip-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -93,9 +93,11 @@ SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const 
 SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
                          const seg_view* dx, const seg_view* dx2, const seg_view* mask_src,
                          const seg_view* mask_src2, void* stream);
-/* dw (fp32, master layout [kh][kw][cin][cout]) += x^T * dz;  caller zeroes dw. */
+/* dw (fp32, master layout [kh][kw][cin][cout]) += x^T * dz;  caller zeroes dw.
+ * db (nullable, fp32 [cout]) += sum over pixels of dz (BiasAddGrad), fused: on the
+ * tcgen05 path it is one extra all-ones A-atom of the same GEMM. */
 SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
-                         const seg_view* dz, float* dw, void* stream);
+                         const seg_view* dz, float* dw, float* db, void* stream);
 
 /* ---- transposed convolution: replaces Conv2DBackpropInput (+BiasAdd+Relu) and
  * its gradients for slim.convolution2d_transpose (models/unet.py:138,145,152,159;

@@ -23,7 +23,7 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
                     const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
                     cudaStream_t st);
 int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
-                    const seg_view& dz, float* dw, cudaStream_t st);
+                    const seg_view& dz, float* dw, float* db, cudaStream_t st);
 int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
                     const seg_view& y, cudaStream_t st);
 int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
@@ -107,10 +107,16 @@ SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, con
 }
 
 SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
-                         const seg_view* dz, float* dw, void* stream) {
+                         const seg_view* dz, float* dw, float* db, void* stream) {
   SEG_REQUIRE(desc_ok(d) && x && dz && dw, SEG_E_BAD_SHAPE, "conv2d_wgrad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->impl == SEG_IMPL_UMMA) return umma_conv_wgrad(*d, *x, x2, *dz, dw, st);
+  if (d->impl == SEG_IMPL_UMMA) return umma_conv_wgrad(*d, *x, x2, *dz, dw, db, st);
+  if (db) {
+    seg_view dzb = *dz;
+    dzb.c = d->cout;
+    int rc = seg_bias_grad(&dzb, db, stream);
+    if (rc) return rc;
+  }
   WgradParams P;
   memset(&P, 0, sizeof(P));
   P.big = *x;

@@ -544,6 +544,75 @@ __global__ void pack_input_kernel(const float* x, int C, seg_view y) {
   }
 }
 
+// dense RGB(A) fp32 -> 16-channel bf16: one thread per pixel, two 16-byte stores
+__global__ void pack_input16_kernel(const float* __restrict__ x, int C, bf16* __restrict__ y,
+                                    int64_t pixels) {
+  GRID_STRIDE(m, pixels) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) v[c] = __ldg(x + m * C + c);
+    uint4 lo, hi;
+    lo.x = pack_bf16x2(v[0], v[1]);
+    lo.y = pack_bf16x2(v[2], v[3]);
+    lo.z = lo.w = 0u;
+    hi.x = hi.y = hi.z = hi.w = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(y + m * 16);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+}
+
+// per-channel sums with 16-byte loads: thread = (pixel lane, 8-channel group)
+template <int MODE>   // 0: sum + sumsq   2: sum only
+__global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
+  extern __shared__ float sh[];
+  const int C = a.c;
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  const int64_t pixels = (int64_t)a.n * a.h * a.w;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  if (pl < lanes) {
+    for (int64_t m = (int64_t)blockIdx.x * lanes + pl; m < pixels; m += (int64_t)gridDim.x * lanes) {
+      const int xx = m % a.w;
+      const int64_t t = m / a.w;
+      const int yy = t % a.h;
+      const int n = t / a.h;
+      const uint4 u = *reinterpret_cast<const uint4*>(view_at(a, n, yy, xx) + g * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+        s0[2 * j] += lo;
+        s0[2 * j + 1] += hi;
+        if (MODE == 0) { s1[2 * j] += lo * lo; s1[2 * j + 1] += hi * hi; }
+      }
+    }
+  }
+  // block reduce over pixel lanes through shared memory: sh[lane][C]
+  float* sh0 = sh;
+  float* sh1 = sh + blockDim.x * 8;
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sh0[pl * C + g * 8 + j] = s0[j];
+      if (MODE == 0) sh1[pl * C + g * 8 + j] = s1[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float r0 = 0.f, r1 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      r0 += sh0[l * C + c];
+      if (MODE == 0) r1 += sh1[l * C + c];
+    }
+    atomicAdd(out0 + c, r0);
+    if (MODE == 0) atomicAdd(out1 + c, r1);
+  }
+}
+
 }  // namespace segb
 
 using namespace segb;
@@ -633,6 +702,20 @@ static int launch_channel_reduce(const seg_view& a, const seg_view& b, const flo
                                  cudaStream_t st) {
   const int64_t pixels = (int64_t)a.n * a.h * a.w;
   const int block = 256;
+  if ((mode == 0 || mode == 2) && vec8_ok(a) && a.c / 8 <= block) {
+    const int lanes_v = block / (a.c / 8);
+    int64_t gv = ceil_div64(pixels, (int64_t)lanes_v * 8);
+    const int64_t capv = (int64_t)num_sms() * 4;
+    if (gv > capv) gv = capv;
+    if (gv < 1) gv = 1;
+    const size_t shb = (size_t)2 * block * 8 * sizeof(float);
+    if (mode == 0)
+      channel_sum_vec8_kernel<0><<<(int)gv, block, shb, st>>>(a, o0, o1);
+    else
+      channel_sum_vec8_kernel<2><<<(int)gv, block, shb, st>>>(a, o0, o1);
+    SEG_LAUNCH_CHECK();
+    return SEG_OK;
+  }
   const int lanes = block / a.c > 0 ? block / a.c : 1;
   int64_t g = ceil_div64(pixels, (int64_t)lanes * 64);
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -763,7 +846,13 @@ SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, vo
 SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, void* stream) {
   SEG_REQUIRE(x && y && c <= y->c, SEG_E_BAD_SHAPE, "pack_input: bad argument");
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
-  pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, *y);
+  if (y->c == 16 && c <= 4 && view_dense(*y) && (reinterpret_cast<uintptr_t>(y->ptr) % 16) == 0) {
+    const int64_t pixels = (int64_t)y->n * y->h * y->w;
+    pack_input16_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, c, reinterpret_cast<bf16*>(y->ptr), pixels);
+  } else {
+    pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, *y);
+  }
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

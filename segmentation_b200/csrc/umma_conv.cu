@@ -269,6 +269,7 @@ struct WgradJob {
   int kh, kw, stride, low_h, low_w, up_h, up_w;
   int BC, SC;
   float* dw;
+  float* db;
 };
 
 template <int AW, int BN>
@@ -310,7 +311,8 @@ static int launch_wgrad_t(const WgradJob& J, cudaStream_t st) {
   P.n_tiles = J.small_.c / BN;
   P.BC = J.BC; P.SC = J.SC;
   P.dw = J.dw;
-  const int groups = (P.total_atoms + Cfg::kNA - 1) / Cfg::kNA;
+  P.db = J.db;
+  const int groups = (P.total_atoms + (J.db ? 1 : 0) + Cfg::kNA - 1) / Cfg::kNA;
   const int base_ctas = groups * P.n_tiles;
   const int total_kb = (int)ceil_div64(M, kWgradPK);
   int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
@@ -411,7 +413,7 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
 }
 
 int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
-                    const seg_view& dz, float* dw, cudaStream_t st) {
+                    const seg_view& dz, float* dw, float* db, cudaStream_t st) {
   WgradJob J;
   memset(&J, 0, sizeof(J));
   J.big = x;
@@ -422,6 +424,7 @@ int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x
   J.up_h = d.pad_b - (d.kh - 1); J.up_w = d.pad_r - (d.kw - 1);
   J.BC = d.cin; J.SC = d.cout;
   J.dw = dw;
+  J.db = db;
   return launch_wgrad(J, st);
 }
 

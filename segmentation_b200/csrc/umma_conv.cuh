@@ -61,12 +61,13 @@ struct IgemmCfg {
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  // enough bytes in flight to cover the TMA latency even when a stage is only a few KB
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 24 ? 24 : kStagesRaw;
   static constexpr int kAtomN = BN < 64 ? BN : 64;           // MN-major B atom width
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                                    : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 template <int KC, int BN, bool B_MN>
@@ -310,6 +311,10 @@ struct WgradUmmaParams {
   int kb_per_split;       // k-blocks (PK pixels each) per CTA
   int BC, SC;             // logical channel counts of dW [taps][BC][SC]
   float* dw;
+  // Bias gradient on the tensor core: the A-atom slot with index == total_atoms is
+  // filled with ones (never loaded), so its first accumulator row is
+  // sum_pixels small[pixel, :] = BiasAddGrad when `small` is dz.  Null: disabled.
+  float* db;
 };
 
 constexpr int kWgradPK = 64;   // pixels per pipeline stage
@@ -324,10 +329,10 @@ struct WgradCfg {
   static constexpr int kAtomBytesB = kWgradPK * kAtomN * 2;
   static constexpr int kBBytes = kNB * kAtomBytesB;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
 };
 
 template <int AW, int BN>
@@ -367,6 +372,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  // A-atom slots that hold no real (tap, channel-chunk) atom are filled with 1.0 once,
+  // in every stage (all-ones is invariant under the smem swizzle).
+  int real_atoms = P.total_atoms - group * Cfg::kNA;
+  real_atoms = real_atoms < 0 ? 0 : (real_atoms > Cfg::kNA ? Cfg::kNA : real_atoms);
+  if (real_atoms < Cfg::kNA) {
+    const int words_per_atom = Cfg::kAtomBytesA / 4;
+    for (int st = 0; st < S; ++st)
+      for (int a = real_atoms; a < Cfg::kNA; ++a) {
+        uint32_t* dst =
+            reinterpret_cast<uint32_t*>(smem + st * Cfg::kStageBytes + a * Cfg::kAtomBytesA);
+        for (int i = threadIdx.x; i < words_per_atom; i += blockDim.x) dst[i] = 0x3F803F80u;
+      }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -377,6 +396,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        const uint32_t tx_bytes = real_atoms * Cfg::kAtomBytesA + Cfg::kBBytes;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int m0 = kb * kWgradPK;
           const int q0 = m0 % P.Wo;
@@ -387,11 +407,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          mbar_expect_tx(&full[stage], tx_bytes);
 #pragma unroll
           for (int a = 0; a < Cfg::kNA; ++a) {
-            int atom = group * Cfg::kNA + a;
-            if (atom >= P.total_atoms) atom = 0;       // dummy rows: never stored
+            const int atom = group * Cfg::kNA + a;
+            if (atom >= P.total_atoms) break;          // ones-filled slots: no load
             const int t = atom / chunks;
             const int j = atom - t * chunks;
             const int r = t / P.kw, s = t - r * P.kw;
@@ -439,8 +459,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       const bool atom_ok = atom < P.total_atoms;
       const int t = atom_ok ? atom / chunks : 0;
       const int bc = atom_ok ? (atom - t * chunks) * AW + chn : 0;
-      const bool row_ok = atom_ok && bc < P.BC;
+      bool row_ok = atom_ok && bc < P.BC;
       float* dst = P.dw + ((int64_t)t * P.BC + bc) * P.SC;
+      if (P.db != nullptr && atom == P.total_atoms && chn == 0) {   // ones-atom: bias grad
+        row_ok = true;
+        dst = P.db;
+      }
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
 #pragma unroll 1

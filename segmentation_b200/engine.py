@@ -246,17 +246,18 @@ class ConvLayer(object):
         channels when cout_pad != cout."""
         st = N.stream_ptr()
         N.set_tag(self.name)
-        dzb = dz_bias if dz_bias is not None else (dz if dz.shape[3] == self.cout
-                                                   else dz[..., :self.cout])
-        N.call('seg_bias_grad', N.vref(dzb), N.ptr(self.b.grad()), st)
         if self.kind == 'conv':
+            # BiasAddGrad is fused into the wgrad GEMM (all-ones A-atom)
             d = self.desc(x.shape[1], x.shape[2], 0, impl)
             N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(x2), N.vref(dz),
-                   N.ptr(self.w.grad()), st)
+                   N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
             if dx is not None:
                 N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
                        N.vref(dx), N.vref(dx2), N.vref(mask), N.vref(mask2), st)
         else:
+            dzb = dz_bias if dz_bias is not None else (dz if dz.shape[3] == self.cout
+                                                       else dz[..., :self.cout])
+            N.call('seg_bias_grad', N.vref(dzb), N.ptr(self.b.grad()), st)
             d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
             N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(dz),
                    N.ptr(self.w.grad()), st)

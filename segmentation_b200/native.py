@@ -45,7 +45,7 @@ SIGNATURES = {
     'seg_device_check': [],
     'seg_conv2d_fwd': [_DP, _VP, _VP, _P, _P, _VP, _P],
     'seg_conv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _VP, _VP, _P],
-    'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P],
+    'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P, _P],
     'seg_deconv2d_fwd': [_DP, _VP, _P, _P, _VP, _P],
     'seg_deconv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _P],
     'seg_deconv2d_wgrad': [_DP, _VP, _VP, _P, _P],

@@ -157,8 +157,7 @@ def test_conv_bwd(cuda, case, impl_name, impl):
     db_d = torch.zeros(Co, dtype=torch.float32, device='cuda')
     st = N.stream_ptr()
     N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x1_d), N.vref(x2_d), N.vref(dz_d),
-           N.ptr(dw_d), st)
-    N.call('seg_bias_grad', N.vref(dz_d[..., :Co]), N.ptr(db_d), st)
+           N.ptr(dw_d), N.ptr(db_d), st)                 # BiasAddGrad fused
     do_dgrad = cin >= 16          # the RGB layer never needs dgrad
     if do_dgrad:
         N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz_d), N.ptr(w_d), N.vref(dx1),

@@ -126,6 +126,14 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
 SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
                         const seg_view* add, int32_t add_y0, int32_t add_x0,
                         const seg_view* mask_src, const seg_view* dx, void* stream);
+/* same with two incoming pool-output gradients (dy + dy2): the pooled tensor has
+ * two consumers (FCN pool3/pool4 feed the next conv AND a score conv,
+ * models/fcn.py:192-195). */
+SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                         int32_t k, int32_t s, const seg_view* mask_src, const seg_view* dx,
+                         void* stream);
+/* ReluGrad as a copy: dz = (y > 0) ? dy : 0 (dy, y, dz same geometry). */
+SEG_API int32_t seg_relu_grad(const seg_view* dy, const seg_view* y, const seg_view* dz, void* stream);
 
 /* ---- depthwise bilinear x f upsample: replaces tf.nn.conv2d_transpose with the
  * constant diagonal filter bank of utils/upsampling.py:27-46 (models/fcn.py:142,
@@ -133,8 +141,9 @@ SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32
  * (models/fcn.py:204,212).  out = up(x) + add (add nullable).  fp32 or bf16 out. */
 SEG_API int32_t seg_bilinear_upsample_fwd(const seg_view* x, int32_t factor, const seg_view* add,
                                   const seg_view* y, int32_t y_is_f32, void* stream);
+/* mask_src (nullable): ReluGrad of the layer that produced x is applied to dx. */
 SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32, int32_t factor,
-                                  const seg_view* dx, void* stream);
+                                  const seg_view* mask_src, const seg_view* dx, void* stream);
 
 /* ---- tf.image.resize_bilinear legacy (models/deconvolution.py:163) */
 SEG_API int32_t seg_resize_bilinear_fwd(const seg_view* x, const seg_view* y, void* stream);

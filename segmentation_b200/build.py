@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsegb200.so')
-SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu']
+SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu', 'probe.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']

@@ -75,8 +75,9 @@ __global__ void maxpool_fwd_kernel(seg_view x, int k, int s, seg_view y, uint8_t
 
 // dx = relu_mask(route(dy, argmax) + add).  Non-overlapping windows (k == s).
 template <int VEC>
-__global__ void maxpool_bwd_kernel(seg_view dy, const uint8_t* argmax, int k, int s, seg_view add,
-                                   int add_y0, int add_x0, seg_view mask, seg_view dx) {
+__global__ void maxpool_bwd_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k, int s,
+                                   seg_view add, int add_y0, int add_x0, seg_view mask,
+                                   seg_view dx) {
   const int cv = dx.c / VEC;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * cv;
   GRID_STRIDE(idx, total) {
@@ -97,6 +98,12 @@ __global__ void maxpool_bwd_kernel(seg_view dy, const uint8_t* argmax, int k, in
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
         if (ap[j] == me) g[j] = __bfloat162float(gp[j]);
+      if (dy2.ptr) {
+        const bf16* gp2 = view_at(dy2, n, p, q) + c0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (ap[j] == me) g[j] += __bfloat162float(gp2[j]);
+      }
     }
     if (add.ptr) {
       const int ay = yy - add_y0, ax = xx - add_x0;
@@ -124,6 +131,21 @@ __global__ void maxpool_bwd_kernel(seg_view dy, const uint8_t* argmax, int k, in
 #pragma unroll
       for (int j = 0; j < VEC; ++j) op[j] = __float2bfloat16(g[j]);
     }
+  }
+}
+
+__global__ void relu_grad_kernel(seg_view dy, seg_view y, seg_view dz) {
+  const int64_t total = (int64_t)dz.n * dz.h * dz.w * dz.c;
+  GRID_STRIDE(idx, total) {
+    const int c = idx % dz.c;
+    int64_t m = idx / dz.c;
+    const int xx = m % dz.w;
+    m /= dz.w;
+    const int yy = m % dz.h;
+    const int n = m / dz.h;
+    const float g = __bfloat162float(view_at(dy, n, yy, xx)[c]);
+    const float a = __bfloat162float(view_at(y, n, yy, xx)[c]);
+    view_at_mut(dz, n, yy, xx)[c] = __float2bfloat16(a > 0.f ? g : 0.f);
   }
 }
 
@@ -172,7 +194,7 @@ __global__ void bilinear_up_fwd_kernel(seg_view x, int f, seg_view add, seg_view
   }
 }
 
-__global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view dx) {
+__global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view mask, seg_view dx) {
   const int k = 2 * f - (f & 1);
   const int before = (k - f) / 2;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * dx.c;
@@ -198,6 +220,7 @@ __global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view 
         acc += g * wgt;
       }
     }
+    if (mask.ptr && !(__bfloat162float(view_at(mask, n, i, j)[c]) > 0.f)) acc = 0.f;
     view_at_mut(dx, n, i, j)[c] = __float2bfloat16(acc);
   }
 }
@@ -650,11 +673,38 @@ SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32
   const bool v8 = vec8_ok(*dx) && (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
-    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, argmax, k, s, a, add_y0,
-                                                               add_x0, mk, *dx);
+    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
+                                                               add_y0, add_x0, mk, *dx);
   else
-    maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, argmax, k, s, a, add_y0,
-                                                               add_x0, mk, *dx);
+    maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
+                                                               add_y0, add_x0, mk, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                         int32_t k, int32_t s, const seg_view* mask_src, const seg_view* dx,
+                         void* stream) {
+  SEG_REQUIRE(dy && dy2 && argmax && dx, SEG_E_BAD_SHAPE, "maxpool_bwd2: null argument");
+  SEG_REQUIRE(k == s, SEG_E_UNSUPPORTED, "maxpool_bwd2: only non-overlapping windows (k == s)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const seg_view mk = mask_src ? *mask_src : null_view();
+  const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && vec8_ok(*dy2) && (!mask_src || vec8_ok(mk));
+  const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
+  if (v8)
+    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,
+                                                               null_view(), 0, 0, mk, *dx);
+  else
+    maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,
+                                                               null_view(), 0, 0, mk, *dx);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_relu_grad(const seg_view* dy, const seg_view* y, const seg_view* dz, void* stream) {
+  SEG_REQUIRE(dy && y && dz, SEG_E_BAD_SHAPE, "relu_grad: null argument");
+  const int64_t total = (int64_t)dz->n * dz->h * dz->w * dz->c;
+  relu_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*dy, *y, *dz);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -672,11 +722,11 @@ SEG_API int32_t seg_bilinear_upsample_fwd(const seg_view* x, int32_t factor, con
 }
 
 SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32, int32_t factor,
-                                  const seg_view* dx, void* stream) {
+                                  const seg_view* mask_src, const seg_view* dx, void* stream) {
   SEG_REQUIRE(dy && dx && factor >= 1, SEG_E_BAD_SHAPE, "bilinear_upsample_bwd: bad argument");
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * dx->c;
-  bilinear_up_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*dy, dy_is_f32,
-                                                                                 factor, *dx);
+  bilinear_up_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      *dy, dy_is_f32, factor, mask_src ? *mask_src : null_view(), *dx);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

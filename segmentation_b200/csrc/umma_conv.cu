@@ -111,6 +111,13 @@ static int make_tmap_im2col(CUtensorMap* tm, const seg_view& v, int low_w, int l
   return SEG_OK;
 }
 
+int make_probe_tmap(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t rows, int box_cols,
+                    int box_rows, int swizzle_bytes) {
+  int rc = load_encoders();
+  if (rc) return rc;
+  return make_tmap_2d(tm, ptr, cols, rows, cols, box_cols, box_rows, swizzle_bytes);
+}
+
 static int pick_chunk(int c1, int c2) {
   const int cands[3] = {64, 32, 16};
   for (int k : cands)

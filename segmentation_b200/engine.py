@@ -300,9 +300,18 @@ def bilinear_upsample_fwd(x, factor, y, add=None):
            1 if y.dtype == torch.float32 else 0, N.stream_ptr())
 
 
-def bilinear_upsample_bwd(dy, factor, dx):
+def bilinear_upsample_bwd(dy, factor, dx, mask=None):
     N.call('seg_bilinear_upsample_bwd', N.vref(dy), 1 if dy.dtype == torch.float32 else 0,
-           factor, N.vref(dx), N.stream_ptr())
+           factor, N.vref(mask), N.vref(dx), N.stream_ptr())
+
+
+def maxpool_bwd2(dy, dy2, argmax, dx, k=2, s=2, mask=None):
+    N.call('seg_maxpool_bwd2', N.vref(dy), N.vref(dy2), N.ptr(argmax), k, s, N.vref(mask),
+           N.vref(dx), N.stream_ptr())
+
+
+def relu_grad(dy, y, dz):
+    N.call('seg_relu_grad', N.vref(dy), N.vref(y), N.vref(dz), N.stream_ptr())
 
 
 def resize_bilinear_fwd(x, y):

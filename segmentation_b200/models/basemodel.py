@@ -236,3 +236,86 @@ class BaseModel(object):
         loss = ex.eval_loss(x, y)
         print('TEST LOSS', loss, self.global_step)
         return loss
+
+
+class ExecBase(object):
+    """Buffers + kernel schedule of one model for one (batch size, mode).
+    Children allocate activations / gradients and implement forward() and
+    backward(); this base owns input staging, loss, head, the CUDA-graph
+    captured train step and inference."""
+
+    def _init_io(self, model, B, H, W, oh, ow, n_out, dlogits_pad, training):
+        dev = model.device
+        self.m, self.B, self.training = model, B, training
+        self.H, self.W, self.oh, self.ow = H, W, oh, ow
+        self.x_f32 = torch.zeros(B, H, W, model.input_channel, dtype=torch.float32, device=dev)
+        self.mask = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
+        self.logits = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
+        self.probs = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
+        self.labelmap = torch.zeros(B, oh, ow, 1, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_pixels = B * oh * ow
+        # mask centre crop when the logits are smaller than the input (unet.py:71-72)
+        self.my0, self.mx0 = (H - oh) // 2, (W - ow) // 2
+        self.dlogits = (torch.zeros(B, oh, ow, dlogits_pad, dtype=torch.bfloat16, device=dev)
+                        if training else None)
+        self.graph = None
+        self.calls = 0
+        self.use_graph = os.environ.get('SEGB200_NO_GRAPH', '0') != '1'
+
+    # ------------------------------------------------------------- staging
+    def stage(self, x, mask):
+        self.x_f32.copy_(x, non_blocking=True)
+        if mask is not None:
+            self.mask.copy_(mask, non_blocking=True)
+
+    def mask_view(self):
+        return self.mask[:, self.my0:self.my0 + self.oh, self.mx0:self.mx0 + self.ow, :]
+
+    def head(self):
+        E.sigmoid_argmax(self.logits, self.probs, self.labelmap)
+        self.m.y_hat_sig, self.m.output = self.probs, self.labelmap
+        return self.probs, self.labelmap
+
+    def loss(self, with_grad):
+        E.fill_zero(self.loss_sum)
+        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum,
+                       self.dlogits if with_grad else None)
+
+    # ---------------------------------------------------------------- steps
+    def _step_body(self):
+        self.forward()
+        self.loss(True)
+        self.backward()
+        if self.m._grad_hook is not None:
+            self.m._grad_hook()
+        self.m.store.adam_launch(0.0, grad_scale=1.0 / self.m.world_size, from_device=True)
+
+    def train_step(self, x, mask):
+        m = self.m
+        self.stage(x, mask)
+        lr_t = m.store.next_lr_t(m.learning_rate)
+        m.store.lr_t_dev.fill_(lr_t)
+        if self.use_graph and self.graph is None and self.calls >= 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self.graph = g
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.calls += 1
+
+    def infer(self, x):
+        self.stage(x, None)
+        self.forward()
+        return self.head()
+
+    def eval_loss(self, x, mask):
+        self.stage(x, mask)
+        self.forward()
+        E.fill_zero(self.loss_sum)
+        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum, None)
+        return float(self.loss_sum.item()) / self.loss_pixels

@@ -1,0 +1,240 @@
+"""DeconvModel — mirror of /root/reference/models/deconvolution.py (generic
+conv / batch-norm / pool encoder + transposed-conv / batch-norm decoder with a
+bilinear resize in the middle), executed by hand-written sm_100a kernels.
+
+Graph (reference `models/deconvolution.py:101-178`):
+  conv5x5/s2 SAME -> bn1 -> pool2/2 -> conv3 VALID -> bn2 -> [drop] -> pool3/3 ->
+  conv3 -> bn3 -> pool3/3 -> conv3 -> bn4 -> [drop] -> deconv5/s2 -> bn5 -> [drop] ->
+  deconv5/s2 -> bn6 -> deconv5/s2 -> bn7 -> resize_bilinear(H/2) -> deconv2/s2 ->
+  bn8 -> crop_or_pad(H) -> conv3 SAME (no activation).
+Quirks kept: every conv / transposed conv keeps slim's default ReLU (incl.
+deconv3_0, `:166`), BN comes AFTER the ReLU and has no gamma (`:116`), dropout
+(`bayesian=True`) is active in training AND inference (`:128-129,143-144,153-154`:
+slim.dropout without is_training).
+
+This is the only reference model whose MC-dropout placement is reference-defined;
+`infer_mc` runs T stochastic passes of one tile as one batch and returns the
+mean / variance maps (BASELINE config 5).
+"""
+import torch
+
+from .. import engine as E
+from .. import native as N
+from .basemodel import BaseModel, ExecBase
+
+BF16 = torch.bfloat16
+
+
+class DeconvModel(BaseModel):
+    def __init__(self,
+                 sess=None,
+                 n_classes=2,
+                 log_dir=None,
+                 dataset=None,
+                 save_dir=None,
+                 bayesian=False,
+                 input_dims=512,
+                 mode='TRAINING',
+                 input_channel=3,
+                 test_dataset=None,
+                 learning_rate=1e-4,
+                 load_snapshot=None,
+                 load_snapshot_from=None,
+                 n_kernels=32,
+                 autoencoder=False,
+                 adversarial_training=False,
+                 seed=0):
+        super(DeconvModel, self).__init__(
+            sess=sess, mode=mode, log_dir=log_dir, dataset=dataset, bayesian=bayesian,
+            save_dir=save_dir, n_classes=n_classes, input_dims=input_dims,
+            autoencoder=autoencoder, test_dataset=test_dataset, input_channel=input_channel,
+            load_snapshot=load_snapshot, learning_rate=learning_rate,
+            load_snapshot_from=load_snapshot_from, adversarial_training=adversarial_training)
+        if autoencoder:
+            raise Exception('autoencoder mode is outside the segmentation hot path (SURVEY §2 #7)')
+        self.model_name = 'deconvolution'
+        self.n_kernels = n_kernels
+        if self.input_dims[0] % 2 or self.input_dims[1] % 2:
+            raise Exception('DeconvModel: input_dims must be even')
+        self._finish_init(seed)
+        self.y_hat = self.y_hat_sig = self.output = None
+        self.inference_ops = ['y_hat_sig', 'output']
+
+    def _build_layers(self, gen):
+        nk, st, nc = self.n_kernels, self.store, self.n_classes
+        L = self.layers = {}
+
+        def conv(name, k, s, padding, cin, cout, relu=True):
+            L[name] = E.ConvLayer(st, name, 'conv', k, s, padding, cin, cout, relu, gen)
+
+        def deconv(name, k, cin, cout):
+            L[name] = E.ConvLayer(st, name, 'deconv', k, 2, 'VALID', cin, cout, True, gen)
+
+        def bn(name, c):
+            L[name] = E.BatchNorm(st, name, c)
+
+        conv('conv1_0', 5, 2, 'SAME', self.input_channel, nk); bn('bn1', nk)
+        conv('conv2_0', 3, 1, 'VALID', nk, nk * 2); bn('bn2', nk * 2)
+        conv('conv3_0', 3, 1, 'VALID', nk * 2, nk * 4); bn('bn3', nk * 4)
+        conv('conv4_0', 3, 1, 'VALID', nk * 4, nk * 8); bn('bn4', nk * 8)
+        deconv('deconv1_0', 5, nk * 8, nk * 2); bn('bn5', nk * 2)
+        deconv('deconv2_0', 5, nk * 2, nk); bn('bn6', nk)
+        deconv('deconv2_1', 5, nk, nk); bn('bn7', nk)
+        deconv('deconv3_0', 2, nk, nc); bn('bn8', nc)
+        conv('conv_out', 3, 1, 'SAME', nc, nc, relu=False)
+
+    def _make_exec(self, batch, training):
+        return _DeconvExec(self, batch, training)
+
+    def model(self, input_op, reuse=False, training=True):
+        """Forward graph; `training` selects batch statistics vs moving statistics
+        in the batch-norm layers (reference `models/deconvolution.py:101,116`)."""
+        x = self._to_device(input_op, torch.float32)
+        ex = self._get_exec(x.shape[0], False)
+        ex.stage(x, None)
+        ex.forward(bn_training=training)
+        return ex.logits
+
+    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0):
+        """T stochastic passes of one tile as one batch (dropout sites of the
+        reference graph, Philox stream (pass_offset+t)*8+site), mean / variance of
+        the sigmoid probabilities.  Returns [mean, var, probs[T]]."""
+        x = self._to_device(imgs, torch.float32)
+        assert x.shape[0] == 1, 'infer_mc takes one tile'
+        ex = self._get_exec(passes, False)
+        ex.stage(x.expand(passes, -1, -1, -1), None)
+        ex.forward(dropout=(self.mc_seed if seed is None else seed, pass_offset), per_image=True)
+        probs, _ = ex.head()
+        mean = torch.empty_like(probs[0])
+        var = torch.empty_like(probs[0])
+        E.mc_mean_var(probs, mean, var)
+        torch.cuda.current_stream().synchronize()
+        return [mean.cpu().numpy(), var.cpu().numpy(), probs.cpu().numpy()]
+
+
+class _DeconvExec(ExecBase):
+    SITES = {'bn2': 0, 'bn4': 1, 'bn5': 2}
+
+    def __init__(self, model, B, training):
+        dev, nk, nc = model.device, model.n_kernels, model.n_classes
+        H, W = model.input_dims
+        L = model.layers
+        self.act, self.amax = {}, {}
+        self.ncp = L['deconv3_0'].cout_pad
+
+        def buf(name, h, w, c):
+            self.act[name] = torch.zeros(B, h, w, c, dtype=BF16, device=dev)
+            return self.act[name]
+
+        def pair(conv, bn, h, w, c):
+            buf(conv, h, w, c)
+            buf(bn, h, w, c)
+            return h, w
+
+        def pool(name, src, k):
+            t = self.act[src]
+            h, w = (t.shape[1] - k) // k + 1, (t.shape[2] - k) // k + 1
+            buf(name, h, w, t.shape[3])
+            self.amax[name] = torch.zeros(B, h, w, t.shape[3], dtype=torch.uint8, device=dev)
+            return h, w
+
+        buf('x', H, W, L['conv1_0'].cin_pad)
+        h, w = L['conv1_0'].out_hw(H, W)
+        pair('conv1_0', 'bn1', h, w, nk)
+        h, w = pool('pool1', 'bn1', 2)
+        h, w = pair('conv2_0', 'bn2', h - 2, w - 2, nk * 2)
+        h, w = pool('pool2', 'bn2', 3)
+        h, w = pair('conv3_0', 'bn3', h - 2, w - 2, nk * 4)
+        h, w = pool('pool3', 'bn3', 3)
+        h, w = pair('conv4_0', 'bn4', h - 2, w - 2, nk * 8)
+        h, w = pair('deconv1_0', 'bn5', *L['deconv1_0'].out_hw(h, w), nk * 2)
+        h, w = pair('deconv2_0', 'bn6', *L['deconv2_0'].out_hw(h, w), nk)
+        h, w = pair('deconv2_1', 'bn7', *L['deconv2_1'].out_hw(h, w), nk)
+        buf('resize', H // 2, W // 2, nk)
+        pair('deconv3_0', 'bn8', H, W, self.ncp)
+        self._init_io(model, B, H, W, H, W, nc, L['conv_out'].cout_pad, training)
+        if training:
+            self.g = {name: torch.zeros_like(t) for name, t in self.act.items() if name != 'x'}
+            self.g['logits'] = self.dlogits
+        self.step_seed = 0
+
+    def forward(self, bn_training=None, dropout=None, per_image=False):
+        m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl
+        if bn_training is None:
+            bn_training = self.training
+        if dropout is None and m.bayesian:
+            dropout = (m.mc_seed, m.global_step)          # fresh masks every step
+        self._dropout = dropout
+        self._per_image = per_image
+
+        def bn(name, src):
+            L[name].forward(A[src], A[name], training=bn_training)
+            if dropout is not None and name in self.SITES:
+                self._drop(A[name], self.SITES[name])
+
+        E.pack_input(self.x_f32, A['x'])
+        L['conv1_0'].forward(A['x'], A['conv1_0'], impl=impl); bn('bn1', 'conv1_0')
+        E.maxpool_fwd(A['bn1'], A['pool1'], self.amax['pool1'], 2, 2)
+        L['conv2_0'].forward(A['pool1'], A['conv2_0'], impl=impl); bn('bn2', 'conv2_0')
+        E.maxpool_fwd(A['bn2'], A['pool2'], self.amax['pool2'], 3, 3)
+        L['conv3_0'].forward(A['pool2'], A['conv3_0'], impl=impl); bn('bn3', 'conv3_0')
+        E.maxpool_fwd(A['bn3'], A['pool3'], self.amax['pool3'], 3, 3)
+        L['conv4_0'].forward(A['pool3'], A['conv4_0'], impl=impl); bn('bn4', 'conv4_0')
+        # 5x5 stride-2 transposed convs: overlapping taps -> CUDA-core gather kernel
+        L['deconv1_0'].forward(A['bn4'], A['deconv1_0'], impl=N.IMPL_SIMT); bn('bn5', 'deconv1_0')
+        L['deconv2_0'].forward(A['bn5'], A['deconv2_0'], impl=N.IMPL_SIMT); bn('bn6', 'deconv2_0')
+        L['deconv2_1'].forward(A['bn6'], A['deconv2_1'], impl=N.IMPL_SIMT); bn('bn7', 'deconv2_1')
+        E.resize_bilinear_fwd(A['bn7'], A['resize'])
+        nc = m.n_classes
+        L['deconv3_0'].forward(A['resize'], A['deconv3_0'][..., :nc], impl=impl)
+        bn('bn8', 'deconv3_0')
+        L['conv_out'].forward(A['bn8'], self.logits, impl=impl, out_f32=True)
+        m.y_hat = self.logits
+
+    def _drop(self, t, site):
+        seed, off = self._dropout
+        if self._per_image:
+            for i in range(self.B):
+                E.dropout(t[i:i + 1], t[i:i + 1], seed, (off + i) * 8 + site)
+        else:
+            E.dropout(t, t, seed, off * 8 + site)
+
+    def backward(self):
+        m, L, A, G, impl = self.m, self.m.layers, self.act, self.g, self.m.impl
+        nc = m.n_classes
+        S = N.IMPL_SIMT
+
+        def bn_bwd(name, src):
+            if self._dropout is not None and name in self.SITES:
+                self._drop(G[name], self.SITES[name])         # same mask on the gradient
+            L[name].backward(G[name], A[src], G[src], relu_mask=True)
+
+        L['conv_out'].backward(A['bn8'], G['logits'], dx=G['bn8'], impl=impl)
+        bn_bwd('bn8', 'deconv3_0')
+        L['deconv3_0'].backward(A['resize'], G['deconv3_0'], dx=G['resize'], impl=impl,
+                                dz_bias=G['deconv3_0'][..., :nc])
+        E.resize_bilinear_bwd(G['resize'], G['bn7'])
+        bn_bwd('bn7', 'deconv2_1')
+        L['deconv2_1'].backward(A['bn6'], G['deconv2_1'], dx=G['bn6'], impl=S)
+        bn_bwd('bn6', 'deconv2_0')
+        L['deconv2_0'].backward(A['bn5'], G['deconv2_0'], dx=G['bn5'], impl=S)
+        bn_bwd('bn5', 'deconv1_0')
+        L['deconv1_0'].backward(A['bn4'], G['deconv1_0'], dx=G['bn4'], impl=S)
+        bn_bwd('bn4', 'conv4_0')
+        L['conv4_0'].backward(A['pool3'], G['conv4_0'], dx=G['pool3'], impl=impl)
+        E.maxpool_bwd(G['pool3'], self.amax['pool3'], G['bn3'], 3, 3)
+        bn_bwd('bn3', 'conv3_0')
+        L['conv3_0'].backward(A['pool2'], G['conv3_0'], dx=G['pool2'], impl=impl)
+        E.maxpool_bwd(G['pool2'], self.amax['pool2'], G['bn2'], 3, 3)
+        bn_bwd('bn2', 'conv2_0')
+        L['conv2_0'].backward(A['pool1'], G['conv2_0'], dx=G['pool1'], impl=impl)
+        E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['bn1'], 2, 2)
+        bn_bwd('bn1', 'conv1_0')
+        # strided 5x5 wgrad: CUDA-core correlation kernel (the tcgen05 wgrad covers
+        # stride 1 and k == stride)
+        L['conv1_0'].backward(A['x'], G['conv1_0'], dx=None, impl=S)
+
+    def train_step(self, x, mask):
+        if self.m.bayesian:
+            self.use_graph = False       # dropout streams change every step
+        ExecBase.train_step(self, x, mask)

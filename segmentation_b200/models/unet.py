@@ -17,7 +17,7 @@ import torch
 
 from .. import engine as E
 from .. import native as N
-from .basemodel import BaseModel
+from .basemodel import BaseModel, ExecBase
 
 BF16 = torch.bfloat16
 
@@ -113,7 +113,7 @@ class UNetModel(BaseModel):
         return [mean.cpu().numpy(), var.cpu().numpy(), probs.cpu().numpy()]
 
 
-class _UNetExec(object):
+class _UNetExec(ExecBase):
     """Buffers + kernel schedule for one (batch size, mode)."""
 
     MC_SITES = {'conv2_2': 0, 'conv4_2': 1, 'conv6_2': 2}
@@ -131,8 +131,6 @@ class _UNetExec(object):
             self.act[name] = torch.zeros(B, h, w, c, dtype=dtype, device=dev)
             return self.act[name]
 
-        self.x_f32 = torch.zeros(B, H, W, model.input_channel, dtype=torch.float32, device=dev)
-        self.mask = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
         buf('x', H, W, L['conv1_1'].cin_pad)
         # ---- encoder geometry
         h, w = H - 2, W - 2
@@ -162,19 +160,8 @@ class _UNetExec(object):
             self.crop[j] = ((sk.shape[1] - uh) // 2, (sk.shape[2] - uw) // 2, uh, uw)
             buf('conv%d_1' % (5 + j), uh - 2, uw - 2, c)
             below = buf('conv%d_2' % (5 + j), uh - 4, uw - 4, c)
-        self.oh, self.ow = below.shape[1], below.shape[2]
-        self.logits = torch.zeros(B, self.oh, self.ow, model.n_classes, dtype=torch.float32,
-                                  device=dev)
-        self.probs = torch.zeros(B, self.oh, self.ow, model.n_classes, dtype=torch.float32,
-                                 device=dev)
-        self.labelmap = torch.zeros(B, self.oh, self.ow, 1, dtype=torch.float32, device=dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.loss_pixels = B * self.oh * self.ow
-        # mask centre crop (reference models/unet.py:71-72)
-        self.my0, self.mx0 = (H - self.oh) // 2, (W - self.ow) // 2
-        self.graph = None
-        self.calls = 0
-        self.use_graph = True
+        oh, ow = below.shape[1], below.shape[2]
+        self._init_io(model, B, H, W, oh, ow, model.n_classes, L['output'].cout_pad, training)
         if training:
             self._alloc_grads()
 
@@ -192,8 +179,7 @@ class _UNetExec(object):
             self.g[name] = torch.zeros(shp, dtype=BF16, device=dev)
             return self.g[name]
 
-        L = self.m.layers
-        gbuf('logits', shape=(B, self.oh, self.ow, L['output'].cout_pad))
+        self.g['logits'] = self.dlogits
         for name, t in self.act.items():
             if name in ('x', 'conv1_2'):
                 continue
@@ -203,12 +189,6 @@ class _UNetExec(object):
             gbuf('skip%d' % j, shape=(B, h, w, self.act[self.skip_of[j]].shape[3]))
         y0, x0, h, w = self.crop[4]
         gbuf('conv1_1_part', shape=(B, h + 2, w + 2, self.act['conv1_1'].shape[3]))
-
-    # ------------------------------------------------------------- staging
-    def stage(self, x, mask):
-        self.x_f32.copy_(x, non_blocking=True)
-        if mask is not None:
-            self.mask.copy_(mask, non_blocking=True)
 
     # ------------------------------------------------------------- forward
     def forward(self, dropout=None):
@@ -240,19 +220,6 @@ class _UNetExec(object):
             below = A['conv%d_2' % (5 + j)]
         L['output'].forward(below, self.logits, impl=impl, out_f32=True)
         m.y_hat = self.logits
-
-    def head(self):
-        E.sigmoid_argmax(self.logits, self.probs, self.labelmap)
-        self.m.y_hat_sig, self.m.output = self.probs, self.labelmap
-        return self.probs, self.labelmap
-
-    def mask_view(self):
-        return self.mask[:, self.my0:self.my0 + self.oh, self.mx0:self.mx0 + self.ow, :]
-
-    def loss(self, with_grad):
-        E.fill_zero(self.loss_sum)
-        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum,
-                       self.g['logits'] if with_grad else None)
 
     # ------------------------------------------------------------ backward
     def backward(self):
@@ -306,41 +273,3 @@ class _UNetExec(object):
                       add_y0=y0, add_x0=x0, mask=A['conv1_1'])
         L['conv1_1'].backward(A['x'], G['conv1_1'], dx=None, impl=impl)
         done('conv1_1')
-
-    # ---------------------------------------------------------------- steps
-    def _step_body(self):
-        self.forward()
-        self.loss(True)
-        self.backward()
-        if self.m._grad_hook is not None:
-            self.m._grad_hook()
-        self.m.store.adam_launch(0.0, grad_scale=1.0 / self.m.world_size, from_device=True)
-
-    def train_step(self, x, mask):
-        m = self.m
-        self.stage(x, mask)
-        lr_t = m.store.next_lr_t(m.learning_rate)
-        m.store.lr_t_dev.fill_(lr_t)
-        if self.use_graph and self.graph is None and self.calls >= 1:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_body()
-            self.graph = g
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._step_body()
-        self.calls += 1
-
-    def infer(self, x):
-        self.stage(x, None)
-        self.forward()
-        return self.head()
-
-    def eval_loss(self, x, mask):
-        self.stage(x, mask)
-        self.forward()
-        E.fill_zero(self.loss_sum)
-        E.softmax_xent(self.logits, self.mask_view(), self.loss_sum, None)
-        return float(self.loss_sum.item()) / self.loss_pixels

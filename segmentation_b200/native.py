@@ -53,7 +53,9 @@ SIGNATURES = {
     'seg_maxpool_fwd': [_VP, _I32, _I32, _VP, _P, _P],
     'seg_maxpool_bwd': [_VP, _P, _I32, _I32, _VP, _I32, _I32, _VP, _VP, _P],
     'seg_bilinear_upsample_fwd': [_VP, _I32, _VP, _VP, _I32, _P],
-    'seg_bilinear_upsample_bwd': [_VP, _I32, _I32, _VP, _P],
+    'seg_bilinear_upsample_bwd': [_VP, _I32, _I32, _VP, _VP, _P],
+    'seg_maxpool_bwd2': [_VP, _VP, _P, _I32, _I32, _VP, _VP, _P],
+    'seg_relu_grad': [_VP, _VP, _VP, _P],
     'seg_resize_bilinear_fwd': [_VP, _VP, _P],
     'seg_resize_bilinear_bwd': [_VP, _VP, _P],
     'seg_batchnorm_stats': [_VP, _P, _P, _P],

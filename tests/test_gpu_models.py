@@ -1,0 +1,240 @@
+"""-m gpu whole-network parity for FCNModel, DeconvModel (incl. Bayesian MC mode) and
+the utils/ops.py helpers against the CPU oracle.  Gradient tolerances are anchored
+to the oracle's own bf16 noise floor (see test_gpu_unet.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, tf_ops as T
+
+from gpu_util import bfr, rel_l2, report, sync
+from test_gpu_unet import FeedDataSet
+
+pytestmark = pytest.mark.gpu
+
+
+def noise_floor(fwd, p, xt, yt, grads_ref, crop_mask):
+    c32, d32 = T.conv2d, T.conv2d_transpose
+
+    def c64(x, w, b=None, stride=1, padding='SAME'):
+        return c32(x.double(), w.double(), None if b is None else b.double(), stride,
+                   padding).float()
+
+    def d64(x, w, b=None, stride=2, padding='VALID'):
+        return d32(x.double(), w.double(), None if b is None else b.double(), stride,
+                   padding).float()
+
+    T.conv2d, T.conv2d_transpose = c64, d64
+    try:
+        _, _, g64 = nets.loss_and_grads(fwd, p, xt, yt, crop_mask)
+    finally:
+        T.conv2d, T.conv2d_transpose = c32, d32
+    return {k: rel_l2(g64[k], grads_ref[k]) for k in grads_ref}
+
+
+def _nonzero_biases(p, seed=5, suffixes=('/biases', '/beta')):
+    gen = np.random.default_rng(seed)
+    for k in p:
+        if k.endswith(suffixes):
+            p[k] = torch.from_numpy(gen.normal(0, 0.05, p[k].shape).astype(np.float32))
+    return p
+
+
+def _run_fwd_bwd(model, B, xt, yt):
+    ex = model._get_exec(B, True)
+    ex.use_graph = False
+    ex.stage(xt.cuda(), yt.cuda())
+    ex.forward()
+    ex.loss(True)
+    ex.backward()
+    sync()
+    return ex
+
+
+def _check_grads(model, grads_ref, floor, slack, tag):
+    rec, bad = {}, []
+    for name, gref in grads_ref.items():
+        e = rel_l2(model.store.params[name].grad().cpu(), gref)
+        rec[name] = [e, floor[name]]
+        if not e <= 3 * floor[name] + slack:
+            bad.append((name, e, floor[name]))
+    report(tag, rec)
+    return bad
+
+
+@pytest.mark.parametrize('fcn_type', ['8s', '16s', '32s'])
+def test_fcn_forward_backward_parity(cuda, fcn_type):
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.fcn import FCNModel
+    B, S, nk, nc = 2, 64, 16, 5
+    ds = FeedDataSet(B, S, S, n_classes=nc)
+    model = FCNModel(dataset=ds, n_classes=nc, input_dims=S, n_kernels=nk, fcn_type=fcn_type,
+                     load_snapshot=False, save_dir=None)
+    p = _nonzero_biases(nets.fcn_params(n_kernels=nk, n_classes=nc, fcn_type=fcn_type, seed=2))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x, y = ds.next_batch()
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    ex = _run_fwd_bwd(model, B, xt, yt)
+    taps = {}
+    fwd = lambda q, xx: nets.fcn_forward(q, xx, fcn_type=fcn_type, prec=T.BF16, taps=taps)
+    loss_ref, logits_ref, grads_ref = nets.loss_and_grads(fwd, p, xt, yt, crop_mask=False)
+    e_logits = rel_l2(ex.logits.cpu(), logits_ref)
+    loss = float(ex.loss_sum.item()) / ex.loss_pixels
+    acts = {k: rel_l2(ex.act[k].float().cpu()[..., :t.shape[-1]], t.detach())
+            for k, t in taps.items() if k in ex.act}
+    report('fcn_parity', {'type': fcn_type, 'logits': e_logits, 'loss': loss,
+                          'loss_ref': float(loss_ref), 'acts': acts})
+    assert tuple(ex.logits.shape) == (B, S, S, nc)
+    assert max(acts.values()) < 1e-2, acts
+    assert e_logits < 1e-2 and abs(loss - float(loss_ref)) < 2e-3
+    floor = noise_floor(lambda q, xx: nets.fcn_forward(q, xx, fcn_type=fcn_type, prec=T.BF16),
+                        p, xt, yt, grads_ref, False)
+    bad = _check_grads(model, grads_ref, floor, 1.5e-2, 'fcn_grads_' + fcn_type)
+    assert not bad, bad
+    # label map, first-index argmax over 5 classes, compared where the margin is safe
+    probs, lab = ex.head()
+    sync()
+    _, lab_ref = T.sigmoid_argmax(logits_ref)
+    top2 = torch.topk(logits_ref, 2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 4 * float((ex.logits.cpu() - logits_ref).abs().max())
+    assert torch.equal(lab.cpu()[..., 0][safe], lab_ref[..., 0][safe])
+
+
+def test_fcn_train_step_runs_and_tracks_oracle_loss(cuda):
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.fcn import FCNModel
+    B, S, nk, nc = 2, 64, 16, 21
+    ds = FeedDataSet(B, S, S, n_classes=nc)
+    model = FCNModel(dataset=ds, n_classes=nc, input_dims=S, n_kernels=nk, fcn_type='8s',
+                     learning_rate=1e-3, load_snapshot=False, save_dir=None)
+    p = nets.fcn_params(n_kernels=nk, n_classes=nc, fcn_type='8s', seed=2)
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    state = nets.AdamState(p)
+    ds_ref = FeedDataSet(B, S, S, n_classes=nc)
+    fwd = lambda q, xx: nets.fcn_forward(q, xx, fcn_type='8s', prec=T.BF16)
+    for it in range(3):
+        model.train_step()
+        x, y = ds_ref.next_batch()
+        ref = nets.train_step(fwd, p, state, torch.from_numpy(x), torch.from_numpy(y), lr=1e-3,
+                              crop_mask=False)
+        assert abs(model.seg_loss_op - ref) < 5e-3, (it, model.seg_loss_op, ref)
+    assert model.global_step == 3
+
+
+def _deconv_model(bayesian, mode='TRAINING', B=2, S=256, nk=16):
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.deconvolution import DeconvModel
+    ds = FeedDataSet(B, S, S) if mode == 'TRAINING' else None
+    model = DeconvModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=nk, bayesian=bayesian,
+                        mode=mode, load_snapshot=False, save_dir=None)
+    p = _nonzero_biases(nets.deconv_params(n_kernels=nk, n_classes=2, seed=4))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    return model, ds, p
+
+
+@pytest.mark.parametrize('bayesian', [False, True])
+def test_deconv_forward_backward_parity(cuda, bayesian):
+    model, ds, p = _deconv_model(bayesian)
+    x, y = ds.next_batch()
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    ex = _run_fwd_bwd(model, 2, xt, yt)
+    taps, stats = {}, {}
+    kw = dict(training=True, bayesian=bayesian, prec=T.BF16, dropout=(0, 0))
+    fwd = lambda q, xx: nets.deconv_forward(q, xx, taps=taps, new_stats=stats, **kw)
+    loss_ref, logits_ref, grads_ref = nets.loss_and_grads(fwd, p, xt, yt, crop_mask=False)
+    # with dropout the model drops the bn2/bn4/bn5 buffers in place, the oracle taps
+    # hold the pre-dropout tensors: skip those three (their consumers are compared)
+    skip = ('bn2', 'bn4', 'bn5') if bayesian else ()
+    acts = {k: rel_l2(ex.act[k].float().cpu()[..., :t.shape[-1]], t.detach())
+            for k, t in taps.items() if k in ex.act and k not in skip}
+    e_logits = rel_l2(ex.logits.cpu(), logits_ref)
+    loss = float(ex.loss_sum.item()) / ex.loss_pixels
+    report('deconv_parity', {'bayesian': bayesian, 'logits': e_logits, 'loss': loss,
+                             'loss_ref': float(loss_ref), 'acts': acts})
+    assert tuple(ex.logits.shape) == (2, 256, 256, 2)
+    assert max(acts.values()) < 2e-2, acts
+    assert e_logits < 2e-2 and abs(loss - float(loss_ref)) < 3e-3
+    # moving statistics updated like slim (decay .999)
+    for name in ('bn1', 'bn4', 'bn8'):
+        mm = model.store.state[name + '/moving_mean'].cpu()
+        mv = model.store.state[name + '/moving_variance'].cpu()
+        assert torch.allclose(mm, stats[name + '/moving_mean'], atol=2e-5)
+        assert torch.allclose(mv, stats[name + '/moving_variance'], atol=2e-5)
+    floor = noise_floor(lambda q, xx: nets.deconv_forward(q, xx, **kw), p, xt, yt, grads_ref, False)
+    bad = _check_grads(model, grads_ref, floor, 2e-2, 'deconv_grads_%s' % bayesian)
+    assert not bad, bad
+
+
+def test_deconv_inference_uses_moving_stats_and_mc_dropout(cuda):
+    model, _, p = _deconv_model(True, mode='INFERENCE', S=256)
+    g = np.random.default_rng(3)
+    # non-trivial moving statistics
+    for k in p:
+        if k.endswith('moving_mean'):
+            p[k] = torch.from_numpy(g.normal(0.2, 0.05, p[k].shape).astype(np.float32))
+        if k.endswith('moving_variance'):
+            p[k] = torch.from_numpy(g.uniform(0.05, 0.3, p[k].shape).astype(np.float32))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x = g.random((1, 256, 256, 3), dtype=np.float32)
+    T_passes = 4
+    mean, var, probs = model.infer_mc(x, passes=T_passes, seed=7, pass_offset=3)
+    assert mean.shape == (256, 256, 2) and var.shape == (256, 256, 2)
+    ref = []
+    for t in range(T_passes):
+        lg = nets.deconv_forward(p, torch.from_numpy(x), training=False, bayesian=True, prec=T.BF16,
+                                 dropout=(7, 3 + t))
+        ref.append(torch.sigmoid(lg)[0])
+    ref = torch.stack(ref)
+    e = rel_l2(torch.from_numpy(probs), ref)
+    report('deconv_mc', {'probs': e})
+    assert e < 1e-2
+    assert np.allclose(mean, probs.mean(0), atol=1e-6)
+    assert np.allclose(var, probs.var(0), atol=1e-6)
+    assert float(var.max()) > 0          # passes differ: dropout is live at inference
+
+
+def test_unet_mc_dropout_mean_variance(cuda):
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.unet import UNetModel
+    model = UNetModel(mode='INFERENCE', n_classes=2, input_dims=188, n_kernels=16, bayesian=True,
+                      load_snapshot=False, save_dir=None)
+    p = nets.unet_params(n_kernels=16, n_classes=2, seed=3)
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x = np.random.default_rng(1).random((1, 188, 188, 3), dtype=np.float32)
+    mean, var, probs = model.infer_mc(x, passes=3, seed=11, pass_offset=0)
+    ref = torch.stack([torch.sigmoid(nets.unet_forward(p, torch.from_numpy(x), prec=T.BF16,
+                                                       dropout=(11, t)))[0] for t in range(3)])
+    assert rel_l2(torch.from_numpy(probs), ref) < 1e-2
+    assert np.allclose(mean, probs.mean(0), atol=1e-6) and np.allclose(var, probs.var(0), atol=1e-6)
+
+
+def test_ops_helpers(cuda):
+    """utils/ops.py mirror: conv2d / deconv2d / linear / batch_norm / lrelu / concat."""
+    from segmentation_b200.utils import ops
+    ops.reset_variables(0)
+    g = torch.Generator().manual_seed(0)
+    x = bfr(torch.randn(2, 12, 12, 8, generator=g))
+    y = ops.conv2d(x.cuda(), 24, name='d_h0_conv')
+    w, b = ops.get_variable('d_h0_conv/w').cpu(), ops.get_variable('d_h0_conv/biases').cpu()
+    assert tuple(w.shape) == (5, 5, 8, 24) and float(w.abs().max()) <= 0.04 + 1e-6
+    ref = T.conv2d(x, bfr(w), b, 2, 'SAME')
+    assert tuple(y.shape) == (2, 6, 6, 24) and rel_l2(y.float().cpu(), ref) < 4e-3
+    y2 = ops.conv2d(x.cuda(), 24, name='d_h0_conv')                  # reuse
+    assert torch.equal(y2, y)
+    d, dw, db = ops.deconv2d(y, [2, 12, 12, 16], name='g_h1', with_w=True)
+    ref = T.conv2d_transpose(bfr(y.float().cpu()), bfr(dw.cpu()), db.cpu(), 2, 'SAME')
+    assert tuple(d.shape) == (2, 12, 12, 16) and rel_l2(d.float().cpu(), ref) < 4e-3
+    z = bfr(torch.randn(4, 40, generator=g))
+    out, M, bias = ops.linear(z.cuda(), 10, 'g_h0_lin', with_w=True)
+    assert rel_l2(out.cpu(), z @ bfr(M.cpu()) + bias.cpu()) < 1e-4
+    bn = ops.batch_norm(name='g_bn0')
+    yb = bn(x.cuda(), train=True)
+    ref, m_ref, v_ref = T.batch_norm(x, torch.zeros(8), torch.zeros(8), torch.ones(8), True,
+                                     decay=0.9, eps=1e-5, gamma=torch.ones(8))
+    assert rel_l2(yb.float().cpu(), ref) < 4e-3
+    assert torch.allclose(ops.get_variable('g_bn0/moving_mean').cpu(), m_ref, atol=1e-5)
+    assert torch.equal(ops.lrelu(torch.tensor([-1.0, 2.0])), torch.tensor([-0.2, 2.0]))
+    cc = ops.conv_cond_concat(x.cuda(), torch.ones(2, 1, 1, 3).cuda())
+    assert tuple(cc.shape) == (2, 12, 12, 11)

@@ -22,4 +22,5 @@ run conv_umma_bwd 600 tests/test_gpu_conv.py -k "umma and bwd"
 run unet_simt 900 tests/test_gpu_unet.py -k "simt"
 run unet_umma 900 tests/test_gpu_unet.py -k "umma or train or infer"
 run unet_full 900 tests/test_gpu_unet.py -k "config1"
+run models 1200 tests/test_gpu_models.py
 cat gpurun_out/summary.txt

@@ -519,12 +519,39 @@ __global__ void mc_mean_var_kernel(const float* probs, int T, int64_t count, flo
 }
 
 // -------------------------------------------------------------------- Adam
-__global__ void adam_multi_kernel(float* param, float* grad, float* m, float* v, bf16* shadow,
-                                  const int32_t* seg, const int64_t* shadow_off, int nseg,
-                                  int64_t numel, float lr_t, const float* lr_t_dev, float b1,
-                                  float b2, float eps, float gscale) {
+// One block per chunk; a chunk is a contiguous run of <= kAdamChunk master elements
+// inside ONE segment (parameter tensor), so no per-element search.  Segments whose
+// shadow needs no channel padding take the identity-mapping fast path.
+constexpr int kAdamChunk = 2048;
+__global__ void adam_multi_kernel(float* __restrict__ param, float* __restrict__ grad,
+                                  float* __restrict__ m, float* __restrict__ v,
+                                  bf16* __restrict__ shadow, const int32_t* __restrict__ seg,
+                                  const int64_t* __restrict__ shadow_off, int nseg, float lr_t,
+                                  const float* lr_t_dev, float b1, float b2, float eps,
+                                  float gscale) {
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
-  GRID_STRIDE(i, numel) {
+  // locate (segment, chunk-in-segment) of this block: segments are few (<= ~100)
+  __shared__ int s_seg, s_begin;
+  if (threadIdx.x == 0) {
+    int blk = blockIdx.x, sidx = 0;
+    for (; sidx < nseg; ++sidx) {
+      const int nchunks = (seg[sidx * 6 + 1] + kAdamChunk - 1) / kAdamChunk;
+      if (blk < nchunks) break;
+      blk -= nchunks;
+    }
+    s_seg = sidx;
+    s_begin = blk * kAdamChunk;
+  }
+  __syncthreads();
+  if (s_seg >= nseg) return;
+  const int32_t* s = seg + s_seg * 6;
+  const int64_t base = s[0];
+  const int numel = s[1], inner = s[2], inner_pad = s[3], mid = s[4], mid_pad = s[5];
+  const int64_t so = shadow_off[s_seg];
+  const bool identity = inner == inner_pad && mid == mid_pad;
+  const int end = min(numel, s_begin + kAdamChunk);
+  for (int e = s_begin + threadIdx.x; e < end; e += blockDim.x) {
+    const int64_t i = base + e;
     const float g = grad[i] * gscale;
     grad[i] = 0.f;
     const float mi = b1 * m[i] + (1.f - b1) * g;
@@ -533,21 +560,18 @@ __global__ void adam_multi_kernel(float* param, float* grad, float* m, float* v,
     m[i] = mi;
     v[i] = vi;
     param[i] = p;
-    // locate the segment (sorted by master offset) -> padded bf16 shadow index
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if ((int64_t)seg[mid * 6] <= i) lo = mid; else hi = mid - 1;
-    }
-    const int64_t so = shadow_off[lo];
     if (so >= 0) {
-      const int32_t* s = seg + lo * 6;
-      const int64_t e = i - s[0];
-      const int inner = s[2], inner_pad = s[3], mid = s[4], mid_pad = s[5];
-      const int64_t in_i = e % inner;
-      const int64_t mid_i = (e / inner) % mid;
-      const int64_t outer = e / ((int64_t)inner * mid);
-      shadow[so + (outer * mid_pad + mid_i) * inner_pad + in_i] = __float2bfloat16(p);
+      int64_t si;
+      if (identity) {
+        si = so + e;
+      } else {
+        const int in_i = e % inner;
+        const int t = e / inner;
+        const int mid_i = t % mid;
+        const int outer = t / mid;
+        si = so + ((int64_t)outer * mid_pad + mid_i) * inner_pad + in_i;
+      }
+      shadow[si] = __float2bfloat16(p);
     }
   }
 }
@@ -886,9 +910,12 @@ SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, vo
                        float beta2, float eps, float grad_scale, void* stream) {
   SEG_REQUIRE(param && grad && m && v && segments && shadow_offsets && nseg > 0, SEG_E_BAD_SHAPE,
               "adam_multi: null argument");
-  adam_multi_kernel<<<grid_for(numel, 256), 256, 0, (cudaStream_t)stream>>>(
+  // upper bound on the chunk count without reading the device table: every segment adds
+  // at most one partial chunk
+  const int64_t blocks = numel / kAdamChunk + nseg;
+  adam_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       param, grad, m, v, reinterpret_cast<bf16*>(shadow_bf16), segments, shadow_offsets, nseg,
-      numel, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale);
+      lr_t, lr_t_dev, beta1, beta2, eps, grad_scale);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

@@ -243,6 +243,10 @@ def run_ours(args):
         ex.use_graph = False
         saved = ex.graph
         ex.graph = None
+        # single-rank pass: no collectives may be issued here (the other ranks are not
+        # participating), so the data-parallel bucket hooks are detached
+        saved_hooks = (model._bucket_done, model._grad_hook)
+        model._bucket_done, model._grad_hook = None, None
         N.TIMELINE = []
         ex.stage(*dev_batches[0])
         for _ in range(3):                       # fwd + loss + bwd only: parameters untouched
@@ -254,6 +258,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
         N.TIMELINE = None
+        model._bucket_done, model._grad_hook = saved_hooks
         out_dir = os.path.join(ROOT, 'gpurun_out')
         if os.path.isdir(out_dir):
             with open(os.path.join(out_dir, 'timeline.json'), 'w') as f:
@@ -261,9 +266,10 @@ def run_ours(args):
         ex.graph, ex.use_graph = saved, True
         roof = dominant_kernel(tl, model, ex)
 
+    if world > 1:
+        dist.barrier()                           # every rank is done with its GPU work
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
     pk = peaks()
     imgs = BATCH * world * K
@@ -364,7 +370,22 @@ def dominant_kernel(timeline, model, ex):
                      for p in sorted(per, key=lambda q: -q[2])[:5]]}
 
 
+def _watchdog(seconds):
+    """A hung collective must not hold the GPU box: hard-exit after `seconds`."""
+    import threading
+
+    def _kill():
+        sys.stderr.write('bench.py watchdog: exceeded %d s, aborting\n' % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(seconds, _kill)
+    t.daemon = True
+    t.start()
+
+
 def main():
+    _watchdog(int(os.environ.get('SEGB200_BENCH_WATCHDOG', '420')))
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

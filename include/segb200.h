@@ -81,6 +81,10 @@ SEG_API int32_t seg_version(void);
 /* 0 iff the current device is compute capability 10.0 (sm_100a kernels). */
 SEG_API int32_t seg_device_check(void);
 SEG_API const char* seg_last_error_string(void);
+/* Tuning / test switches (process-wide).  key 1: use the halo-tile tcgen05 conv kernel
+ * where it applies (default 1; 0 forces the TMA-im2col kernel).  key 2: smem row
+ * alignment of the halo kernel's row staging in pixels (0 = natural, 8 = swizzle repeat). */
+SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 
 /* ---- convolution: replaces Conv2D(+BiasAdd+Relu), Conv2DBackpropInput,
  * Conv2DBackpropFilter emitted for slim.convolution2d

@@ -32,8 +32,11 @@ int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view&
                       cudaStream_t st);
 int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, float* d,
                cudaStream_t st);
-int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, float* d,
-                     cudaStream_t st);
+int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, int split,
+                     float* d, cudaStream_t st);
+
+void hconv_set_row_align(int a);
+void hconv_enable(int on);
 
 static bool desc_ok(const seg_conv_desc* d) {
   return d && d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->cin >= 1 && d->cout >= 1 &&
@@ -50,6 +53,15 @@ extern "C" {
 SEG_API int32_t seg_version(void) { return 100; }
 
 SEG_API const char* seg_last_error_string(void) { return g_err; }
+
+SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
+  switch (key) {
+    case 1: hconv_enable(value); return SEG_OK;
+    case 2: hconv_set_row_align(value); return SEG_OK;
+  }
+  set_error("seg_set_option: unknown key %d", key);
+  return SEG_E_BAD_SHAPE;
+}
 
 SEG_API int32_t seg_device_check(void) {
   int dev = 0;
@@ -193,8 +205,10 @@ SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, co
                        const void* b, float* d, void* stream) {
   SEG_REQUIRE(a && b && d && m > 0 && n % 16 == 0 && k % 16 == 0, SEG_E_BAD_SHAPE,
               "probe_umma: bad argument");
-  if (mode & 0x100)   // row-shift experiment: bits 16.. = shift, bit 9 = base_offset field
-    return umma_probe_shift(k, a, b, (mode >> 16) & 0xff, (mode >> 9) & 1, d, (cudaStream_t)stream);
+  if (mode & 0x100)   // row-shift experiment: bits 16..23 = shift, bit 9 = base_offset field,
+                      // bits 24..31 = split row of a two-box load (0 = single box)
+    return umma_probe_shift(k, a, b, (mode >> 16) & 0xff, (mode >> 9) & 1, (mode >> 24) & 0xff, d,
+                            (cudaStream_t)stream);
   return umma_probe(mode, m, n, k, a, b, d, (cudaStream_t)stream);
 }
 

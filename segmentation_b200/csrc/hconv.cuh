@@ -1,0 +1,287 @@
+// Halo-tile tcgen05 convolution (stride 1): ONE staged input tile per channel chunk
+// serves every filter tap.
+//
+// Position space: the (virtually padded) input is a grid of Hp x Wp positions per
+// image; position m = (img*Hp + yp)*Wp + xp.  The output pixel (img, yp, xp) — valid
+// iff yp < Ho, xp < Wo — is  sum_{r,s,c} in[m + r*Wp + s, c] * w[r,s,c,:]:  for a tile of
+// 128 consecutive positions every tap is the SAME staged rows shifted by r*Wp+s rows,
+// i.e. the same K-major UMMA descriptor with its start address advanced by
+// (r*Wp+s)*row_bytes (the smem swizzle is a function of the absolute address, see
+// tools/probe_shift.py).  A is therefore fetched from L2 once per (tile, chunk)
+// instead of once per tap; junk positions (xp >= Wo or yp >= Ho) are computed and
+// dropped (efficiency Ho*Wo/(Hp*Wp)).
+//
+// Staging modes:  flat — dense unpadded input: 2-D TMA boxes over [N*H*W][C];
+//                 rows — any NHWC view / zero padding: one 4-D TMA box per padded
+//                        input row (out-of-bounds coordinates are zero-filled).
+// B (weights) streams through its own smem ring, one (chunk, tap) tile per stage, or
+// stays resident for the whole kernel when all tiles of the CTA's N-slice fit.
+#pragma once
+#include "umma_conv.cuh"
+
+namespace segb {
+
+struct HconvParams {
+  int Wp;                    // position-space row pitch (>= row_px; smem rows per padded row)
+  int row_px;                // pixels per padded input row actually loaded (rows mode box width)
+  int Hp, batch, Ho, Wo;
+  int P_total;               // batch*Hp*Wp
+  int kh, kw;
+  int flat, box_rows, nboxes;
+  int pad_t, pad_l;
+  int a_stage_bytes;
+  int chunks1, chunks2;
+  int tap_flip, b_rows_per_tap;
+  int N_total;
+  int SA, SB;
+  int b_resident;
+  EpiDest d0, d1;
+  int split_n;
+  const float* bias;
+  int flags;
+};
+
+constexpr int kHconvMaxSA = 8;
+constexpr int kHconvMaxSB = 40;
+
+template <int KC, int BN, bool B_MN>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmB, const HconvParams P) {
+  constexpr int SWZ = KC * 2;
+  constexpr int kBBytes = BN * KC * 2;
+  constexpr int kAtomN = BN < 64 ? BN : 64;
+  constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                            : 2 * BN <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem + P.SA * P.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P.SB * kBBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kHconvMaxSA;
+  uint64_t* b_full = bars + 2 * kHconvMaxSA;
+  uint64_t* b_empty = b_full + kHconvMaxSB;
+  uint64_t* tfull = b_empty + kHconvMaxSB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = P.kh * P.kw;
+  const int chunks = P.chunks1 + P.chunks2;
+  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
+  const int n_tiles = P.N_total / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int halo = (P.kh - 1) * P.Wp + P.kw - 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM;
+        const int n0 = (tile % n_tiles) * BN;
+        const int g0 = m0 / P.Wp;                          // first padded row (global)
+        const int g1 = (m0 + kBlockM - 1 + halo) / P.Wp;   // last padded row needed
+        for (int j = 0; j < chunks; ++j) {
+          const bool second = j >= P.chunks1;
+          const CUtensorMap* tm = second ? &tmA2 : &tmA1;
+          const int c0 = (second ? j - P.chunks1 : j) * KC;
+          mbar_wait(&a_empty[sa], pa ^ 1u);
+          uint8_t* dst = smem + sa * P.a_stage_bytes;
+          if (P.flat) {
+            mbar_expect_tx(&a_full[sa], (uint32_t)(P.nboxes * P.box_rows) * SWZ);
+            for (int b = 0; b < P.nboxes; ++b)
+              tma_load_2d(tm, &a_full[sa], dst + b * P.box_rows * SWZ, c0, m0 + b * P.box_rows);
+          } else {
+            mbar_expect_tx(&a_full[sa], (uint32_t)((g1 - g0 + 1) * P.row_px) * SWZ);
+            for (int g = g0; g <= g1; ++g) {
+              const int img = g / P.Hp;
+              const int yp = g - img * P.Hp;
+              tma_load_4d(tm, &a_full[sa], dst + (g - g0) * P.Wp * SWZ, c0, -P.pad_l,
+                          yp - P.pad_t, img);
+            }
+          }
+          if (++sa == P.SA) { sa = 0; pa ^= 1u; }
+          if (!P.b_resident || first_tile) {
+            for (int t = 0; t < taps; ++t) {
+              const int bt = P.tap_flip ? taps - 1 - t : t;
+              mbar_wait(&b_empty[sb], pb ^ 1u);
+              uint8_t* sbp = smem_b + sb * kBBytes;
+              mbar_expect_tx(&b_full[sb], kBBytes);
+              if (B_MN) {
+                const int row = bt * P.b_rows_per_tap + j * KC;
+#pragma unroll
+                for (int a = 0; a < BN / kAtomN; ++a)
+                  tma_load_2d(&tmB, &b_full[sb], sbp + a * (KC * kAtomN * 2), n0 + a * kAtomN, row);
+              } else {
+                tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, bt * P.b_rows_per_tap + n0);
+              }
+              if (++sb == P.SB) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+        first_tile = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, B_MN ? 1 : 0);
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM;
+        const int a_off = P.flat ? 0 : m0 - (m0 / P.Wp) * P.Wp;
+        mbar_wait(&tempty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        if (P.b_resident) sb = 0;
+        for (int j = 0; j < chunks; ++j) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + sa * P.a_stage_bytes);
+          for (int t = 0; t < taps; ++t) {
+            const int r = t / P.kw, s = t - r * P.kw;
+            if (!P.b_resident || first_tile) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+            }
+            const uint32_t a_tap = a_base + (uint32_t)(a_off + r * P.Wp + s) * SWZ;
+            const uint32_t b_base = smem_u32(smem_b + sb * kBBytes);
+#pragma unroll
+            for (int kk = 0; kk < KC / 16; ++kk) {
+              const uint64_t da = umma_smem_desc(a_tap + kk * 32, 0, 8 * SWZ, SWZ);
+              uint64_t db;
+              if (B_MN) {
+                constexpr int atom_bytes = kAtomN * 2;
+                db = umma_smem_desc(b_base + kk * 16 * atom_bytes, KC * atom_bytes,
+                                    8 * atom_bytes, atom_bytes);
+              } else {
+                db = umma_smem_desc(b_base + kk * 32, 0, 8 * SWZ, SWZ);
+              }
+              umma_f16(tmem_d, da, db, idesc, (j | t | kk) ? 1u : 0u);
+            }
+            if (!P.b_resident) umma_commit(&b_empty[sb]);
+            if (++sb == P.SB) { sb = 0; pb ^= 1u; }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == P.SA) { sa = 0; pa ^= 1u; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        first_tile = false;
+      }
+    }
+  } else {
+    // ============================= epilogue =============================
+    const int quad = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const int img_stride = P.Hp * P.Wp;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kBlockM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int m = m0 + quad * 32 + lane;
+      const int img = m / img_stride;
+      const int rem = m - img * img_stride;
+      const int yp = rem / P.Wp;
+      const int xp = rem - yp * P.Wp;
+      const bool row_ok = img < P.batch && yp < P.Ho && xp < P.Wo;
+      const bool second = P.d1.ptr != nullptr && n0 >= P.split_n;
+      const EpiDest& D = second ? P.d1 : P.d0;
+      const int nl0 = second ? n0 - P.split_n : n0;
+      const int64_t off = row_ok ? img * D.sn + yp * D.sh + xp * D.sw : 0;
+      const int64_t moff = row_ok ? img * D.msn + yp * D.msh + xp * D.msw : 0;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += (BN >= 32 ? 32 : 16)) {
+        constexpr int W = BN >= 32 ? 32 : 16;
+        uint32_t r[W];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + cc;
+        if (W == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int ncol = nl0 + cc;
+          float v[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            v[j] = __uint_as_float(r[j]);
+            if ((P.flags & SEG_EPI_BIAS) && ncol + j < D.cols) v[j] += __ldg(P.bias + ncol + j);
+            if (P.flags & SEG_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+          }
+          if ((P.flags & SEG_EPI_RELU_MASK) && D.mask) {
+            const bf16* mp = D.mask + moff + ncol;
+            if (ncol + W <= D.cols) {
+#pragma unroll
+              for (int j = 0; j < W; j += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(mp + j);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(w4[e]) > 0.f)) v[j + 2 * e] = 0.f;
+                  if (!(bf16_hi(w4[e]) > 0.f)) v[j + 2 * e + 1] = 0.f;
+                }
+              }
+            } else {
+              for (int j = 0; j < W && ncol + j < D.cols; ++j)
+                if (!(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
+            }
+          }
+          if (P.flags & SEG_EPI_OUT_F32) {
+            float* op = reinterpret_cast<float*>(D.ptr) + off + ncol;
+            for (int j = 0; j < W && ncol + j < D.cols; ++j) op[j] = v[j];
+          } else {
+            bf16* op = reinterpret_cast<bf16*>(D.ptr) + off + ncol;
+            if (ncol + W <= D.cols) {
+#pragma unroll
+              for (int j = 0; j < W; j += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]);
+                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(op + j) = o;
+              }
+            } else {
+              for (int j = 0; j < W && ncol + j < D.cols; ++j) op[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace segb

@@ -12,7 +12,8 @@ int make_probe_tmap(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t rows
 template <int KC>
 __global__ void __launch_bounds__(128, 1)
 probe_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   int shift, int use_base_offset, float* d_out) {
+                   const __grid_constant__ CUtensorMap tmA2, int split, int shift,
+                   int use_base_offset, float* d_out) {
   constexpr int ROWS = 160;            // staged A rows (>= 128 + max shift)
   constexpr int BN = 64;
   constexpr int SWZ = KC * 2;
@@ -36,7 +37,14 @@ probe_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bars[0], ROWS * SWZ + BN * SWZ);
-    tma_load_2d(&tmA, &bars[0], sa, 0, 0);
+    if (split > 0) {
+      // two boxes: the second one lands at a smem address that is NOT aligned to the
+      // swizzle repeat -> tests whether TMA's swizzle is a function of the smem address
+      tma_load_2d(&tmA, &bars[0], sa, 0, 0);
+      tma_load_2d(&tmA2, &bars[0], sa + split * SWZ, 0, split);
+    } else {
+      tma_load_2d(&tmA, &bars[0], sa, 0, 0);
+    }
     tma_load_2d(&tmB, &bars[0], sb, 0, 0);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
@@ -74,29 +82,31 @@ probe_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 template <int KC>
-static int run_probe_shift(const void* a, const void* b, int shift, int use_bo, float* d,
-                           cudaStream_t st) {
-  CUtensorMap tmA, tmB;
-  int rc = make_probe_tmap(&tmA, a, KC, 160, KC, 160, KC * 2);
+static int run_probe_shift(const void* a, const void* b, int shift, int use_bo, int split,
+                           float* d, cudaStream_t st) {
+  CUtensorMap tmA, tmB, tmA2;
+  int rc = make_probe_tmap(&tmA, a, KC, 160, KC, split > 0 ? split : 160, KC * 2);
+  if (rc) return rc;
+  rc = make_probe_tmap(&tmA2, a, KC, 160, KC, split > 0 ? 160 - split : 160, KC * 2);
   if (rc) return rc;
   rc = make_probe_tmap(&tmB, b, KC, 64, KC, 64, KC * 2);
   if (rc) return rc;
   const int smem = 160 * KC * 2 + 64 * KC * 2 + 4096;
   SEG_CHECK_CUDA(cudaFuncSetAttribute(probe_shift_kernel<KC>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_shift_kernel<KC><<<1, 128, smem, st>>>(tmA, tmB, shift, use_bo, d);
+  probe_shift_kernel<KC><<<1, 128, smem, st>>>(tmA, tmB, tmA2, split, shift, use_bo, d);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
 
 // a: [160][K] bf16, b: [64][K] bf16 (K-major), d: [128][64] fp32 = a[shift:shift+128] @ b^T
-int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, float* d,
-                     cudaStream_t st) {
+int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, int split,
+                     float* d, cudaStream_t st) {
   SEG_REQUIRE(shift >= 0 && shift <= 32, SEG_E_BAD_SHAPE, "probe_shift: shift out of range");
   switch (K) {
-    case 64: return run_probe_shift<64>(a, b, shift, use_bo, d, st);
-    case 32: return run_probe_shift<32>(a, b, shift, use_bo, d, st);
-    case 16: return run_probe_shift<16>(a, b, shift, use_bo, d, st);
+    case 64: return run_probe_shift<64>(a, b, shift, use_bo, split, d, st);
+    case 32: return run_probe_shift<32>(a, b, shift, use_bo, split, d, st);
+    case 16: return run_probe_shift<16>(a, b, shift, use_bo, split, d, st);
   }
   set_error("probe_shift: K must be 16, 32 or 64");
   return SEG_E_UNSUPPORTED;

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 implicit-GEMM kernels: tensor-map construction (tiled
 // and im2col), tile-shape selection and launches.
 #include "umma_conv.cuh"
+#include "hconv.cuh"
 
 #include <mutex>
 
@@ -116,6 +117,26 @@ int make_probe_tmap(CUtensorMap* tm, const void* ptr, int64_t cols, int64_t rows
   int rc = load_encoders();
   if (rc) return rc;
   return make_tmap_2d(tm, ptr, cols, rows, cols, box_cols, box_rows, swizzle_bytes);
+}
+
+// tiled 4-D map over an NHWC view seen as (C, W, H, N); box = {channels, width, 1, 1}
+static int make_tmap_rows(CUtensorMap* tm, const seg_view& v, int channels, int width,
+                          int swizzle_bytes) {
+  SEG_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && (v.sw * 2) % 16 == 0 &&
+                  (v.sh * 2) % 16 == 0 && (v.sn * 2) % 16 == 0,
+              SEG_E_ALIGN, "row tensor map: view must be 16-byte aligned in every stride");
+  cuuint64_t gdim[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)channels, (cuuint32_t)width, 1, 1};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, gdim, gstr, box, est,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(swizzle_bytes),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEG_REQUIRE(r == CUDA_SUCCESS, SEG_E_CUDA,
+              "cuTensorMapEncodeTiled(4d rows) failed (%d) c=%d w=%d h=%d n=%d box=%dx%d sw=%d",
+              (int)r, v.c, v.w, v.h, v.n, channels, width, swizzle_bytes);
+  return SEG_OK;
 }
 
 static int pick_chunk(int c1, int c2) {
@@ -364,6 +385,195 @@ static int launch_wgrad(const WgradJob& J, cudaStream_t st) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// halo-tile convolution (hconv.cuh): launch
+// ---------------------------------------------------------------------------
+struct HconvJob {
+  seg_view a1, a2;
+  int kh, kw;
+  int pad_t, pad_l;            // padded-position (0,0) = tensor coordinate (-pad_t, -pad_l)
+  int Hp, Wp_logical;          // padded grid per image
+  int Ho, Wo, batch;
+  const void* w;
+  int w_rows, w_cols;
+  bool b_mn;
+  int b_rows_per_tap;
+  bool tap_flip;
+  int N_total, max_bn;
+  EpiDest d0, d1;
+  int split_n;
+  const float* bias;
+  int flags;
+};
+
+static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
+
+template <int KC, int BN, bool B_MN>
+static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_bytes,
+                          cudaStream_t st) {
+  static int attr_smem = 0;
+  if (attr_smem < smem_bytes) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_smem = 227 * 1024;
+  }
+  constexpr int kAtomN = BN < 64 ? BN : 64;
+  HconvParams P = P0;
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc;
+  if (P.flat) {
+    rc = make_tmap_2d(&tmA1, J.a1.ptr, J.a1.c, (int64_t)J.batch * P.Hp * P.Wp, J.a1.sw, KC,
+                      P.box_rows, KC * 2);
+    if (rc) return rc;
+    if (J.a2.ptr) {
+      rc = make_tmap_2d(&tmA2, J.a2.ptr, J.a2.c, (int64_t)J.batch * P.Hp * P.Wp, J.a2.sw, KC,
+                        P.box_rows, KC * 2);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA1;
+    }
+  } else {
+    rc = make_tmap_rows(&tmA1, J.a1, KC, P.row_px, KC * 2);
+    if (rc) return rc;
+    if (J.a2.ptr) {
+      rc = make_tmap_rows(&tmA2, J.a2, KC, P.row_px, KC * 2);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA1;
+    }
+  }
+  if (B_MN)
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, kAtomN, KC, kAtomN * 2);
+  else
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN, KC * 2);
+  if (rc) return rc;
+  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
+  const int n_tiles = J.N_total / BN;
+  const int tiles = m_tiles * n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (P.b_resident && n_tiles > 1) {
+    grid -= grid % n_tiles;           // every CTA must keep one N-slice for its lifetime
+    if (grid < n_tiles) P.b_resident = 0, grid = tiles < num_sms() ? tiles : num_sms();
+  }
+  hconv_kernel<KC, BN, B_MN><<<grid, kIgemmThreads, smem_bytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+template <int KC, bool B_MN>
+static int launch_hconv_bn(const HconvJob& J, const HconvParams& P, int BN, int smem,
+                           cudaStream_t st) {
+  switch (BN) {
+    case 256: return launch_hconv_t<KC, 256, B_MN>(J, P, smem, st);
+    case 128: return launch_hconv_t<KC, 128, B_MN>(J, P, smem, st);
+    case 64: return launch_hconv_t<KC, 64, B_MN>(J, P, smem, st);
+    case 32: return launch_hconv_t<KC, 32, B_MN>(J, P, smem, st);
+    case 16: return launch_hconv_t<KC, 16, B_MN>(J, P, smem, st);
+  }
+  return SEG_E_UNSUPPORTED;
+}
+
+// Returns SEG_E_UNSUPPORTED (without setting up anything) when the shape does not fit the
+// halo kernel; the caller then uses the im2col kernel.
+static int launch_hconv(const HconvJob& J, cudaStream_t st) {
+  int rc = load_encoders();
+  if (rc) return rc;
+  const int c2 = J.a2.ptr ? J.a2.c : 0;
+  const int KC = pick_chunk(J.a1.c, c2);
+  if (KC == 0) return SEG_E_UNSUPPORTED;
+  const int SWZ = KC * 2;
+  int BN = 0;
+  for (int c = 256; c >= 16; c >>= 1)
+    if (J.max_bn % c == 0) { BN = c; break; }
+  if (BN == 0 || J.N_total % BN) return SEG_E_UNSUPPORTED;
+
+  HconvParams P;
+  memset(&P, 0, sizeof(P));
+  const bool dense = view_dense(J.a1) && (!J.a2.ptr || view_dense(J.a2));
+  const bool nopad = J.pad_t == 0 && J.pad_l == 0 && J.Hp == J.a1.h && J.Wp_logical == J.a1.w;
+  P.flat = (dense && nopad) ? 1 : 0;
+  P.row_px = J.Wp_logical;
+  if (P.flat) {
+    P.Wp = J.Wp_logical;
+    const int need = kBlockM + (J.kh - 1) * P.Wp + J.kw - 1;
+    P.box_rows = need <= 256 ? ((need + 7) / 8) * 8 : 128;
+    P.nboxes = (need + P.box_rows - 1) / P.box_rows;
+    P.a_stage_bytes = P.nboxes * P.box_rows * SWZ;
+  } else {
+    if (J.Wp_logical > 256) return SEG_E_UNSUPPORTED;
+    int align = 128 / SWZ;                       // TMA smem destinations: 128-byte aligned
+    if (g_hconv_row_align > align) align = g_hconv_row_align;
+    P.Wp = ((J.Wp_logical + align - 1) / align) * align;
+    const int nrows = (P.Wp - 1 + kBlockM - 1 + (J.kh - 1) * P.Wp + J.kw - 1) / P.Wp + 1;
+    P.a_stage_bytes = nrows * P.Wp * SWZ;
+  }
+  P.a_stage_bytes = ((P.a_stage_bytes + 1023) / 1024) * 1024;
+  if (P.a_stage_bytes > 72 * 1024) return SEG_E_UNSUPPORTED;
+  P.Hp = J.Hp; P.batch = J.batch; P.Ho = J.Ho; P.Wo = J.Wo;
+  P.P_total = J.batch * J.Hp * P.Wp;
+  P.kh = J.kh; P.kw = J.kw;
+  P.pad_t = J.pad_t; P.pad_l = J.pad_l;
+  P.chunks1 = J.a1.c / KC;
+  P.chunks2 = c2 / KC;
+  P.tap_flip = J.tap_flip ? 1 : 0;
+  P.b_rows_per_tap = J.b_rows_per_tap;
+  P.N_total = J.N_total;
+  P.d0 = J.d0; P.d1 = J.d1; P.split_n = J.split_n;
+  P.bias = J.bias; P.flags = J.flags;
+
+  // shared-memory budget: B resident if every (chunk, tap) tile of one N-slice fits next
+  // to >= 2 A stages, else a B ring of a few stages.
+  const int budget = 222 * 1024 - 2048;
+  const int taps = J.kh * J.kw;
+  const int chunks = P.chunks1 + P.chunks2;
+  auto plan = [&](int bn, int* sa, int* sb, int* resident) {
+    const int bbytes = bn * KC * 2;
+    const int all_b = taps * chunks * bbytes;
+    if (taps * chunks <= kHconvMaxSB && all_b + 2 * P.a_stage_bytes <= budget) {
+      *resident = 1;
+      *sb = taps * chunks;
+    } else {
+      *resident = 0;
+      int s = (64 * 1024) / bbytes;
+      *sb = s < 2 ? 2 : (s > 12 ? 12 : s);
+    }
+    int a = (budget - *sb * bbytes) / P.a_stage_bytes;
+    *sa = a > kHconvMaxSA ? kHconvMaxSA : a;
+    return *sa >= 1;
+  };
+  int SA = 0, SB = 0, res = 0;
+  while (!plan(BN, &SA, &SB, &res) || (SA < 2 && BN > 32)) {
+    if (BN <= 16) return SEG_E_UNSUPPORTED;
+    BN >>= 1;
+  }
+  // fill the machine: halve BN while there are fewer tiles than SMs (not below 64)
+  const int64_t m_tiles = ceil_div64(P.P_total, kBlockM);
+  while (BN > 64 && m_tiles * (J.N_total / BN) < num_sms()) {
+    BN >>= 1;
+    plan(BN, &SA, &SB, &res);
+  }
+  P.SA = SA; P.SB = SB; P.b_resident = res;
+  const int smem = SA * P.a_stage_bytes + SB * BN * KC * 2 + 2048;
+  if (J.b_mn) {
+    switch (KC) {
+      case 64: return launch_hconv_bn<64, true>(J, P, BN, smem, st);
+      case 32: return launch_hconv_bn<32, true>(J, P, BN, smem, st);
+      default: return launch_hconv_bn<16, true>(J, P, BN, smem, st);
+    }
+  }
+  switch (KC) {
+    case 64: return launch_hconv_bn<64, false>(J, P, BN, smem, st);
+    case 32: return launch_hconv_bn<32, false>(J, P, BN, smem, st);
+    default: return launch_hconv_bn<16, false>(J, P, BN, smem, st);
+  }
+}
+
+void hconv_set_row_align(int a) { g_hconv_row_align = a; }
+
+static bool g_use_hconv = true;
+void hconv_enable(int on) { g_use_hconv = on != 0; }
+
 // ---------------------------------------------------------------------------
 // op-level entry points used by api.cu
 // ---------------------------------------------------------------------------
@@ -384,6 +594,21 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
   J.N_total = d.cout_pad; J.max_bn = d.cout_pad;
   J.d0 = make_dest(&y, nullptr);
   J.bias = bias; J.flags = d.flags;
+  if (g_use_hconv && d.stride == 1 && d.kh * d.kw > 1) {
+    HconvJob H;
+    memset(&H, 0, sizeof(H));
+    H.a1 = J.a1; H.a2 = J.a2;
+    H.kh = d.kh; H.kw = d.kw;
+    H.pad_t = d.pad_t; H.pad_l = d.pad_l;
+    H.Hp = x.h + d.pad_t + d.pad_b; H.Wp_logical = x.w + d.pad_l + d.pad_r;
+    H.Ho = y.h; H.Wo = y.w; H.batch = y.n;
+    H.w = J.w; H.w_rows = J.w_rows; H.w_cols = J.w_cols;
+    H.b_mn = true; H.b_rows_per_tap = J.b_rows_per_tap; H.tap_flip = false;
+    H.N_total = J.N_total; H.max_bn = J.max_bn;
+    H.d0 = J.d0; H.bias = bias; H.flags = d.flags;
+    const int rc = launch_hconv(H, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+  }
   return launch_igemm(J, st);
 }
 
@@ -416,6 +641,21 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
     J.max_bn = d.cin_pad;
   }
   J.flags = d.flags & (SEG_EPI_RELU_MASK);
+  if (g_use_hconv && d.kh * d.kw > 1) {
+    HconvJob H;
+    memset(&H, 0, sizeof(H));
+    H.a1 = dz; H.a2 = null_view();
+    H.kh = d.kh; H.kw = d.kw;
+    H.pad_t = d.kh - 1 - d.pad_t; H.pad_l = d.kw - 1 - d.pad_l;
+    H.Hp = dx.h + d.kh - 1; H.Wp_logical = dx.w + d.kw - 1;
+    H.Ho = dx.h; H.Wo = dx.w; H.batch = dx.n;
+    H.w = J.w; H.w_rows = J.w_rows; H.w_cols = J.w_cols;
+    H.b_mn = false; H.b_rows_per_tap = J.b_rows_per_tap; H.tap_flip = true;
+    H.N_total = J.N_total; H.max_bn = J.max_bn;
+    H.d0 = J.d0; H.d1 = J.d1; H.split_n = J.split_n; H.flags = J.flags;
+    const int rc = launch_hconv(H, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+  }
   return launch_igemm(J, st);
 }
 

@@ -43,6 +43,7 @@ _I32, _I64, _U32, _U64, _F = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, c
 SIGNATURES = {
     'seg_version': [],
     'seg_device_check': [],
+    'seg_set_option': [_I32, _I32],
     'seg_conv2d_fwd': [_DP, _VP, _VP, _P, _P, _VP, _P],
     'seg_conv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _VP, _VP, _P],
     'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P, _P],
@@ -110,6 +111,13 @@ _TAG = ['']
 
 def set_tag(tag):
     _TAG[0] = tag
+
+
+OPT_HALO_CONV, OPT_HALO_ROW_ALIGN = 1, 2
+
+
+def set_option(key, value):
+    check(load().seg_set_option(key, value), 'seg_set_option')
 
 
 def call(name, *args):

@@ -17,8 +17,9 @@ run pointwise 600 tests/test_gpu_pointwise.py
 run conv_simt 600 tests/test_gpu_conv.py -k "simt or deconv or crop"
 run probe0 300 tests/test_gpu_conv.py -k "probe and 0"
 run probe1 300 tests/test_gpu_conv.py -k "probe and 1"
-run conv_umma_fwd 600 tests/test_gpu_conv.py -k "umma and fwd"
-run conv_umma_bwd 600 tests/test_gpu_conv.py -k "umma and bwd"
+run conv_umma_fwd 600 tests/test_gpu_conv.py -k "umma and fwd and not im2col"
+run conv_umma_bwd 600 tests/test_gpu_conv.py -k "umma and bwd and not im2col"
+run conv_im2col 600 tests/test_gpu_conv.py -k "im2col"
 run unet_simt 900 tests/test_gpu_unet.py -k "simt"
 run unet_umma 900 tests/test_gpu_unet.py -k "umma or train or infer"
 run unet_full 900 tests/test_gpu_unet.py -k "config1"

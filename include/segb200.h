@@ -85,6 +85,9 @@ SEG_API const char* seg_last_error_string(void);
  * where it applies (default 1; 0 forces the TMA-im2col kernel).  key 2: smem row
  * alignment of the halo kernel's row staging in pixels (0 = natural, 8 = swizzle repeat). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
+/* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
+ * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */
+SEG_API int32_t seg_debug_prof_buffer(void* device_buf);
 
 /* ---- convolution: replaces Conv2D(+BiasAdd+Relu), Conv2DBackpropInput,
  * Conv2DBackpropFilter emitted for slim.convolution2d

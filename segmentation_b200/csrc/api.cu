@@ -36,6 +36,7 @@ int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo,
                      float* d, cudaStream_t st);
 
 void hconv_set_row_align(int a);
+void hconv_set_prof(void* p);
 void hconv_enable(int on);
 
 static bool desc_ok(const seg_conv_desc* d) {
@@ -53,6 +54,11 @@ extern "C" {
 SEG_API int32_t seg_version(void) { return 100; }
 
 SEG_API const char* seg_last_error_string(void) { return g_err; }
+
+SEG_API int32_t seg_debug_prof_buffer(void* device_buf) {
+  hconv_set_prof(device_buf);
+  return SEG_OK;
+}
 
 SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
   switch (key) {

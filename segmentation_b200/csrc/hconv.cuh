@@ -39,9 +39,15 @@ struct HconvParams {
   int split_n;
   const float* bias;
   int flags;
+  long long* prof;           // optional in-kernel timeline of CTA 0 (test hook), else null
 };
 
 constexpr int kHconvMaxSA = 8;
+constexpr int kProfTiles = 16;     // tiles recorded per role; 4 events each
+__device__ __forceinline__ void prof_mark(long long* prof, int role, int tile_i, int ev) {
+  if (prof != nullptr && blockIdx.x == 0 && tile_i < kProfTiles)
+    prof[(role * kProfTiles + tile_i) * 4 + ev] = clock64();
+}
 constexpr int kHconvMaxSB = 40;
 
 template <int KC, int BN, bool B_MN>
@@ -92,13 +98,16 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // whole warp runs the (uniform) control flow; one elected lane issues the copies
+    {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int m0 = (tile / n_tiles) * kBlockM;
         const int n0 = (tile % n_tiles) * BN;
+        if (lane == 0) prof_mark(P.prof, 0, ti, 0);
         const int g0 = m0 / P.Wp;                          // first padded row (global)
         const int g1 = (m0 + kBlockM - 1 + halo) / P.Wp;   // last padded row needed
         for (int j = 0; j < chunks; ++j) {
@@ -106,88 +115,116 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           const CUtensorMap* tm = second ? &tmA2 : &tmA1;
           const int c0 = (second ? j - P.chunks1 : j) * KC;
           mbar_wait(&a_empty[sa], pa ^ 1u);
+          if (j == 0 && lane == 0) prof_mark(P.prof, 0, ti, 1);
           uint8_t* dst = smem + sa * P.a_stage_bytes;
-          if (P.flat) {
-            mbar_expect_tx(&a_full[sa], (uint32_t)(P.nboxes * P.box_rows) * SWZ);
-            for (int b = 0; b < P.nboxes; ++b)
-              tma_load_2d(tm, &a_full[sa], dst + b * P.box_rows * SWZ, c0, m0 + b * P.box_rows);
-          } else {
-            mbar_expect_tx(&a_full[sa], (uint32_t)((g1 - g0 + 1) * P.row_px) * SWZ);
-            for (int g = g0; g <= g1; ++g) {
-              const int img = g / P.Hp;
-              const int yp = g - img * P.Hp;
-              tma_load_4d(tm, &a_full[sa], dst + (g - g0) * P.Wp * SWZ, c0, -P.pad_l,
-                          yp - P.pad_t, img);
+          if (elect_one()) {
+            if (P.flat) {
+              mbar_expect_tx(&a_full[sa], (uint32_t)(P.nboxes * P.box_rows) * SWZ);
+              for (int b = 0; b < P.nboxes; ++b)
+                tma_load_2d(tm, &a_full[sa], dst + b * P.box_rows * SWZ, c0, m0 + b * P.box_rows);
+            } else {
+              mbar_expect_tx(&a_full[sa], (uint32_t)((g1 - g0 + 1) * P.row_px) * SWZ);
+              int img = g0 / P.Hp;
+              int yp = g0 - img * P.Hp;
+              for (int g = g0; g <= g1; ++g) {
+                tma_load_4d(tm, &a_full[sa], dst + (g - g0) * P.Wp * SWZ, c0, -P.pad_l,
+                            yp - P.pad_t, img);
+                if (++yp == P.Hp) { yp = 0; ++img; }
+              }
             }
           }
+          __syncwarp();
           if (++sa == P.SA) { sa = 0; pa ^= 1u; }
           if (!P.b_resident || first_tile) {
+            int bt = P.tap_flip ? taps - 1 : 0;
             for (int t = 0; t < taps; ++t) {
-              const int bt = P.tap_flip ? taps - 1 - t : t;
               mbar_wait(&b_empty[sb], pb ^ 1u);
-              uint8_t* sbp = smem_b + sb * kBBytes;
-              mbar_expect_tx(&b_full[sb], kBBytes);
-              if (B_MN) {
-                const int row = bt * P.b_rows_per_tap + j * KC;
+              if (elect_one()) {
+                uint8_t* sbp = smem_b + sb * kBBytes;
+                mbar_expect_tx(&b_full[sb], kBBytes);
+                if (B_MN) {
+                  const int row = bt * P.b_rows_per_tap + j * KC;
 #pragma unroll
-                for (int a = 0; a < BN / kAtomN; ++a)
-                  tma_load_2d(&tmB, &b_full[sb], sbp + a * (KC * kAtomN * 2), n0 + a * kAtomN, row);
-              } else {
-                tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, bt * P.b_rows_per_tap + n0);
+                  for (int a = 0; a < BN / kAtomN; ++a)
+                    tma_load_2d(&tmB, &b_full[sb], sbp + a * (KC * kAtomN * 2), n0 + a * kAtomN,
+                                row);
+                } else {
+                  tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, bt * P.b_rows_per_tap + n0);
+                }
               }
+              __syncwarp();
+              bt += P.tap_flip ? -1 : 1;
               if (++sb == P.SB) { sb = 0; pb ^= 1u; }
             }
           }
         }
         first_tile = false;
+        if (lane == 0) prof_mark(P.prof, 0, ti, 2);
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // warp-uniform control flow; descriptors advance by 32-bit adds on the low word;
+    // one elected lane issues tcgen05.mma / tcgen05.commit
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, B_MN ? 1 : 0);
+      constexpr uint32_t hiA = umma_desc_hi(8 * SWZ, SWZ);
+      constexpr int atom_bytes = kAtomN * 2;
+      constexpr uint32_t hiB = B_MN ? umma_desc_hi(8 * atom_bytes, atom_bytes)
+                                    : umma_desc_hi(8 * SWZ, SWZ);
+      constexpr uint32_t lboB = B_MN ? KC * atom_bytes : 0;
+      constexpr uint32_t kstepB = B_MN ? (16 * atom_bytes) >> 4 : 2;   // per UMMA_K, in 16-B units
+      const uint32_t row16 = SWZ >> 4;                                  // one A row, 16-B units
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, aphase = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int m0 = (tile / n_tiles) * kBlockM;
         const int a_off = P.flat ? 0 : m0 - (m0 / P.Wp) * P.Wp;
+        if (lane == 0) prof_mark(P.prof, 1, ti, 0);
         mbar_wait(&tempty[as], aphase ^ 1u);
         tc_fence_after();
+        if (lane == 0) prof_mark(P.prof, 1, ti, 1);
         const uint32_t tmem_d = tmem_base + as * BN;
         if (P.b_resident) sb = 0;
+        uint32_t acc = 0;
         for (int j = 0; j < chunks; ++j) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + sa * P.a_stage_bytes);
-          for (int t = 0; t < taps; ++t) {
-            const int r = t / P.kw, s = t - r * P.kw;
-            if (!P.b_resident || first_tile) {
-              mbar_wait(&b_full[sb], pb);
-              tc_fence_after();
-            }
-            const uint32_t a_tap = a_base + (uint32_t)(a_off + r * P.Wp + s) * SWZ;
-            const uint32_t b_base = smem_u32(smem_b + sb * kBBytes);
-#pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk) {
-              const uint64_t da = umma_smem_desc(a_tap + kk * 32, 0, 8 * SWZ, SWZ);
-              uint64_t db;
-              if (B_MN) {
-                constexpr int atom_bytes = kAtomN * 2;
-                db = umma_smem_desc(b_base + kk * 16 * atom_bytes, KC * atom_bytes,
-                                    8 * atom_bytes, atom_bytes);
-              } else {
-                db = umma_smem_desc(b_base + kk * 32, 0, 8 * SWZ, SWZ);
+          if (j == 0 && lane == 0) prof_mark(P.prof, 1, ti, 2);
+          const uint32_t a_lo0 =
+              umma_desc_lo(smem_u32(smem + sa * P.a_stage_bytes), 0) + (uint32_t)a_off * row16;
+          uint32_t a_row = a_lo0;                       // tap (r, 0)
+          for (int r = 0; r < P.kh; ++r, a_row += (uint32_t)P.Wp * row16) {
+            uint32_t a_tap = a_row;
+            for (int s = 0; s < P.kw; ++s, a_tap += row16) {
+              if (!P.b_resident || first_tile) {
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
               }
-              umma_f16(tmem_d, da, db, idesc, (j | t | kk) ? 1u : 0u);
+              const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b + sb * kBBytes), lboB);
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  umma_f16(tmem_d, umma_desc_pack(hiA, a_tap + kk * 2),
+                           umma_desc_pack(hiB, b_lo0 + kk * kstepB), idesc, acc);
+                  acc = 1;
+                }
+                if (!P.b_resident) umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              acc = 1;
+              if (++sb == P.SB) { sb = 0; pb ^= 1u; }
             }
-            if (!P.b_resident) umma_commit(&b_empty[sb]);
-            if (++sb == P.SB) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(&a_empty[sa]);
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
           if (++sa == P.SA) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(&tfull[as]);
+        if (elect_one()) umma_commit(&tfull[as]);
+        __syncwarp();
+        if (lane == 0) prof_mark(P.prof, 1, ti, 3);
         if (++as == 2) { as = 0; aphase ^= 1u; }
         first_tile = false;
       }
@@ -198,7 +235,9 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int as = 0;
     uint32_t aphase = 0;
     const int img_stride = P.Hp * P.Wp;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int ti = 0;
+    long long* eprof = (warp == 2 && lane == 0) ? P.prof : nullptr;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
       const int m = m0 + quad * 32 + lane;
@@ -212,8 +251,10 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       const int nl0 = second ? n0 - P.split_n : n0;
       const int64_t off = row_ok ? img * D.sn + yp * D.sh + xp * D.sw : 0;
       const int64_t moff = row_ok ? img * D.msn + yp * D.msh + xp * D.msw : 0;
+      prof_mark(eprof, 2, ti, 0);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      prof_mark(eprof, 2, ti, 1);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += (BN >= 32 ? 32 : 16)) {
         constexpr int W = BN >= 32 ? 32 : 16;
@@ -269,9 +310,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           }
         }
       }
+      prof_mark(eprof, 2, ti, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      prof_mark(eprof, 2, ti, 3);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }

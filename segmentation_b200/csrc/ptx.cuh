@@ -201,6 +201,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(umma_layout_code(swizzle_bytes)) << 61;
   return d;
 }
+// Split form for tight issue loops: the high word is constant per operand, the low word
+// is (start address >> 4) | (LBO >> 4) << 16 and advances by plain 32-bit adds.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, int swizzle_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (umma_layout_code(swizzle_bytes) << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c format (1 = f32)  [7,10) a format (1 = bf16)  [10,13) b format
 //   [15] a major (0 K, 1 MN)  [16] b major  [17,23) N>>3  [24,29) M>>4

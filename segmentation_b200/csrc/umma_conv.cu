@@ -407,6 +407,8 @@ struct HconvJob {
   int flags;
 };
 
+static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
+void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
 template <int KC, int BN, bool B_MN>
@@ -521,6 +523,7 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   P.N_total = J.N_total;
   P.d0 = J.d0; P.d1 = J.d1; P.split_n = J.split_n;
   P.bias = J.bias; P.flags = J.flags;
+  P.prof = g_prof_buf;
 
   // shared-memory budget: B resident if every (chunk, tap) tile of one N-slice fits next
   // to >= 2 A stages, else a B ring of a few stages.

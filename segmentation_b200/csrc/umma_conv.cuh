@@ -117,7 +117,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // warp-uniform control flow; one elected lane issues the copies
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -128,40 +129,47 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         const int img0 = m0 / (P.Wo * P.Ho);
         const int cw = q0 * P.stride + P.base_w;
         const int ch = p0 * P.stride + P.base_h;
+        int t = 0, j = 0, r = 0, s = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int t = kb / chunks;
-          const int j = kb - t * chunks;
           mbar_wait(&empty[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          const bool second = j >= P.chunks1;
-          const CUtensorMap* tm = second ? &tmA2 : &tmA1;
-          const int c0 = (second ? j - P.chunks1 : j) * KC;
-          if (P.a_tiled2d) {
-            tma_load_2d(tm, &full[stage], sa, c0, m0);
-          } else {
-            const int r = t / P.kw, s = t - r * P.kw;
-            tma_load_im2col_4d(tm, &full[stage], sa, c0, cw, ch, img0, (uint16_t)s, (uint16_t)r);
-          }
-          const int bt = P.tap_flip ? taps - 1 - t : t;
-          if (B_MN) {
-            const int row = bt * P.b_rows_per_tap + j * KC;
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            const bool second = j >= P.chunks1;
+            const CUtensorMap* tm = second ? &tmA2 : &tmA1;
+            const int c0 = (second ? j - P.chunks1 : j) * KC;
+            if (P.a_tiled2d)
+              tma_load_2d(tm, &full[stage], sa, c0, m0);
+            else
+              tma_load_im2col_4d(tm, &full[stage], sa, c0, cw, ch, img0, (uint16_t)s, (uint16_t)r);
+            const int bt = P.tap_flip ? taps - 1 - t : t;
+            if (B_MN) {
+              const int row = bt * P.b_rows_per_tap + j * KC;
 #pragma unroll
-            for (int a = 0; a < BN / Cfg::kAtomN; ++a)
-              tma_load_2d(&tmB, &full[stage], sb + a * (KC * Cfg::kAtomN * 2),
-                          n0 + a * Cfg::kAtomN, row);
-          } else {
-            tma_load_2d(&tmB, &full[stage], sb, j * KC, bt * P.b_rows_per_tap + n0);
+              for (int a = 0; a < BN / Cfg::kAtomN; ++a)
+                tma_load_2d(&tmB, &full[stage], sb + a * (KC * Cfg::kAtomN * 2),
+                            n0 + a * Cfg::kAtomN, row);
+            } else {
+              tma_load_2d(&tmB, &full[stage], sb, j * KC, bt * P.b_rows_per_tap + n0);
+            }
           }
+          __syncwarp();
+          if (++j == chunks) { j = 0; ++t; if (++s == P.kw) { s = 0; ++r; } }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, B_MN ? 1 : 0);
+      constexpr uint32_t hiA = umma_desc_hi(8 * Cfg::kSwzA, Cfg::kSwzA);
+      constexpr int atom_bytes = Cfg::kAtomN * 2;
+      constexpr uint32_t hiB = B_MN ? umma_desc_hi(8 * atom_bytes, atom_bytes)
+                                    : umma_desc_hi(8 * Cfg::kSwzA, Cfg::kSwzA);
+      constexpr uint32_t lboB = B_MN ? KC * atom_bytes : 0;
+      constexpr uint32_t kstepB = B_MN ? (16 * atom_bytes) >> 4 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -170,28 +178,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         mbar_wait(&tempty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t acc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t a_lo = umma_desc_lo(sa, 0);
+          const uint32_t b_lo = umma_desc_lo(sa + Cfg::kABytes, lboB);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk) {
-            const uint64_t da = umma_smem_desc(sa + kk * 32, 0, 8 * Cfg::kSwzA, Cfg::kSwzA);
-            uint64_t db;
-            if (B_MN) {
-              constexpr int atom_bytes = Cfg::kAtomN * 2;
-              db = umma_smem_desc(sb + kk * 16 * atom_bytes, KC * atom_bytes, 8 * atom_bytes,
-                                  atom_bytes);
-            } else {
-              db = umma_smem_desc(sb + kk * 32, 0, 8 * Cfg::kSwzA, Cfg::kSwzA);
+            for (int kk = 0; kk < KC / 16; ++kk) {
+              umma_f16(tmem_d, umma_desc_pack(hiA, a_lo + kk * 2),
+                       umma_desc_pack(hiB, b_lo + kk * kstepB), idesc, acc);
+              acc = 1;
             }
-            umma_f16(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
+          acc = 1;
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull[as]);
+        if (elect_one()) umma_commit(&tfull[as]);
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -393,18 +401,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   if (num_kb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        const uint32_t tx_bytes = real_atoms * Cfg::kAtomBytesA + Cfg::kBBytes;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          const int m0 = kb * kWgradPK;
-          const int q0 = m0 % P.Wo;
-          const int p0 = (m0 / P.Wo) % P.Ho;
-          const int img0 = m0 / (P.Wo * P.Ho);
-          const int cw = q0 * P.stride + P.base_w;
-          const int ch = p0 * P.stride + P.base_h;
-          mbar_wait(&empty[stage], phase ^ 1u);
+      // TMA producer: warp-uniform control flow, elected lane issues
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = real_atoms * Cfg::kAtomBytesA + Cfg::kBBytes;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int m0 = kb * kWgradPK;
+        const int q0 = m0 % P.Wo;
+        const int p0 = (m0 / P.Wo) % P.Ho;
+        const int img0 = m0 / (P.Wo * P.Ho);
+        const int cw = q0 * P.stride + P.base_w;
+        const int ch = p0 * P.stride + P.base_h;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full[stage], tx_bytes);
@@ -424,33 +433,39 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 #pragma unroll
           for (int b = 0; b < Cfg::kNB; ++b)
             tma_load_2d(&tmB, &full[stage], sb + b * Cfg::kAtomBytesB, n0 + b * Cfg::kAtomN, m0);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          constexpr int rowA = AW * 2, rowB = Cfg::kAtomN * 2;
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 1, 1);
+      constexpr int rowA = AW * 2, rowB = Cfg::kAtomN * 2;
+      constexpr uint32_t hiA = umma_desc_hi(8 * rowA, rowA);
+      constexpr uint32_t hiB = umma_desc_hi(8 * rowB, rowB);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t a_lo = umma_desc_lo(sa, Cfg::kAtomBytesA);
+        const uint32_t b_lo = umma_desc_lo(sa + Cfg::kABytes, Cfg::kAtomBytesB);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kWgradPK / 16; ++kk) {
-            const uint64_t da =
-                umma_smem_desc(sa + kk * 16 * rowA, Cfg::kAtomBytesA, 8 * rowA, rowA);
-            const uint64_t db =
-                umma_smem_desc(sb + kk * 16 * rowB, Cfg::kAtomBytesB, 8 * rowB, rowB);
-            umma_f16(tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
+            umma_f16(tmem_base, umma_desc_pack(hiA, a_lo + kk * ((16 * rowA) >> 4)),
+                     umma_desc_pack(hiB, b_lo + kk * ((16 * rowB) >> 4)), idesc, acc);
+            acc = 1;
           }
           umma_commit(&empty[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull[0]);
+        __syncwarp();
+        acc = 1;
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(&tfull[0]);
+      __syncwarp();
     } else {
       const int quad = warp & 3;
       const int L = quad * 32 + lane;                  // accumulator row = (atom, channel)

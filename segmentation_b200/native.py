@@ -44,6 +44,7 @@ SIGNATURES = {
     'seg_version': [],
     'seg_device_check': [],
     'seg_set_option': [_I32, _I32],
+    'seg_debug_prof_buffer': [_P],
     'seg_conv2d_fwd': [_DP, _VP, _VP, _P, _P, _VP, _P],
     'seg_conv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _VP, _VP, _P],
     'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P, _P],

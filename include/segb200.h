@@ -83,7 +83,10 @@ SEG_API int32_t seg_device_check(void);
 SEG_API const char* seg_last_error_string(void);
 /* Tuning / test switches (process-wide).  key 1: use the halo-tile tcgen05 conv kernel
  * where it applies (default 1; 0 forces the TMA-im2col kernel).  key 2: smem row
- * alignment of the halo kernel's row staging in pixels (0 = natural, 8 = swizzle repeat). */
+ * alignment of the halo kernel's row staging in pixels (0 = natural, 8 = swizzle repeat).
+ * key 3: use the spatial-tile tcgen05 conv kernel for 3x3 stride-1 fwd / dgrad (default 1).
+ * key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles below which that kernel
+ * declines a shape (default 70). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */
@@ -210,11 +213,16 @@ SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, fl
  * grad is scaled by grad_scale (1/world_size for data-parallel) and zeroed.
  * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is read from the device scalar lr_t_dev
  * when non-null (so a captured CUDA graph can be replayed with a new value),
- * else taken from the host argument lr_t. */
+ * else taken from the host argument lr_t.
+ * `chunks` (device, int32[2*nchunks]) is the launch plan the host builds once: one
+ * {segment index, first element inside the segment} pair per block, each block
+ * covering at most seg_adam_chunk_elems() elements of ONE segment. */
+SEG_API int32_t seg_adam_chunk_elems(void);
 SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, void* shadow_bf16,
-                       const int32_t* segments, const int64_t* shadow_offsets, int32_t nseg,
-                       int64_t numel, float lr_t, const float* lr_t_dev, float beta1,
-                       float beta2, float eps, float grad_scale, void* stream);
+                       const int32_t* segments, const int64_t* shadow_offsets,
+                       const int32_t* chunks, int32_t nchunks, float lr_t,
+                       const float* lr_t_dev, float beta1, float beta2, float eps,
+                       float grad_scale, void* stream);
 
 /* ---- layout helpers */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with channels zero-padded to y.c */
@@ -224,6 +232,10 @@ SEG_API int32_t seg_fill_zero(void* ptr, int64_t bytes, void* stream);
 /* ---- self-test hooks used by tests/ (tcgen05 descriptor probes) */
 SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, const void* a,
                        const void* b, float* d, void* stream);
+/* MMA issue/retire rate of `iters` x 9 taps x kc/16 tcgen05.mma (M=128, N=bn) per CTA;
+ * out[2*cta] = cycles to issue, out[2*cta+1] = cycles to retire (tools/probe_rate.py) */
+SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,
+                           int32_t iters, int32_t a_mn, int32_t ctas, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,9 +35,14 @@ int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, floa
 int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, int split,
                      float* d, cudaStream_t st);
 
+int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn, int ctas,
+                    long long* out, cudaStream_t st);
+
 void hconv_set_row_align(int a);
 void hconv_set_prof(void* p);
 void hconv_enable(int on);
+void tconv_enable(int on);
+void tconv_set_min_eff(int pct);
 
 static bool desc_ok(const seg_conv_desc* d) {
   return d && d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->cin >= 1 && d->cout >= 1 &&
@@ -64,6 +69,8 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
   switch (key) {
     case 1: hconv_enable(value); return SEG_OK;
     case 2: hconv_set_row_align(value); return SEG_OK;
+    case 3: tconv_enable(value); return SEG_OK;
+    case 4: tconv_set_min_eff(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;
@@ -216,6 +223,13 @@ SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, co
     return umma_probe_shift(k, a, b, (mode >> 16) & 0xff, (mode >> 9) & 1, (mode >> 24) & 0xff, d,
                             (cudaStream_t)stream);
   return umma_probe(mode, m, n, k, a, b, d, (cudaStream_t)stream);
+}
+
+SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,
+                           int32_t iters, int32_t a_mn, int32_t ctas, int64_t* out, void* stream) {
+  SEG_REQUIRE(out, SEG_E_BAD_SHAPE, "probe_mma_rate: null out");
+  return umma_probe_rate(kc, bn, b_mn, wp, shifted, iters, a_mn, ctas,
+                         reinterpret_cast<long long*>(out), (cudaStream_t)stream);
 }
 
 }  // extern "C"

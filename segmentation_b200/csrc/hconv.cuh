@@ -212,6 +212,9 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                   acc = 1;
                 }
                 if (!P.b_resident) umma_commit(&b_empty[sb]);
+                // per-tap issue timestamps of tiles 2 and 3 (role 3 of the timeline hook)
+                if (P.prof != nullptr && blockIdx.x == 0 && (ti == 2 || ti == 3) && j == 0)
+                  P.prof[3 * kProfTiles * 4 + (ti - 2) * 16 + r * P.kw + s] = clock64();
               }
               __syncwarp();
               acc = 1;

@@ -113,3 +113,225 @@ int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo,
 }
 
 }  // namespace segb
+
+// ---------------------------------------------------------------------------
+// MMA issue/execute rate experiment: one thread issues `iters` x 9 taps x KC/16
+// tcgen05.mma (M=128, N=bn) against zero-filled smem, with the A start address either
+// fixed (aligned) or shifted by (r*wp+s) rows per tap as the halo-tile conv does.
+// out[2*cta] = cycles until the last MMA was issued, out[2*cta+1] = until all retired.
+// ---------------------------------------------------------------------------
+namespace segb {
+
+__global__ void __launch_bounds__(128, 1)
+probe_rate_kernel(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn,
+                  long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int swz = kc * 2;
+  const int a_rows = 128 + 2 * wp + 2 + 8;
+  const int a_bytes = ((a_rows * swz + 1023) / 1024) * 1024;
+  const int b_bytes = bn * kc * 2;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + ((b_bytes + 1023) / 1024) * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  volatile uint32_t* done_flag = reinterpret_cast<volatile uint32_t*>(bars + 3);
+  uint8_t* sx = reinterpret_cast<uint8_t*>(bars) + 1024;     // 32 KB scratch for stress copies
+  const int flags = a_mn >> 4;                                // stress flags (see probe_rate.py)
+  a_mn &= 1;
+  long long* scratch = out + 2 * gridDim.x + (size_t)blockIdx.x * 8192;   // 64 KB per CTA
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += blockDim.x) {
+    uint32_t v = 0;
+    if (flags & 1) {   // pseudo-random bf16 pairs in about [-2, 2]
+      uint32_t h = (uint32_t)i * 2654435761u + 12345u;
+      h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+      v = (h & 0x807F807Fu) | 0x3F003F00u;
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    *done_flag = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    // warp-uniform branch, one elected lane issues (same shape as the production loops)
+    const uint32_t idesc = umma_idesc_bf16(128, bn, a_mn, b_mn);
+    const uint32_t hiA = umma_desc_hi(8 * swz, swz);
+    const int atom_n = bn < 64 ? bn : 64;
+    const int atom_bytes = atom_n * 2;
+    const uint32_t hiB = b_mn ? umma_desc_hi(8 * atom_bytes, atom_bytes) : umma_desc_hi(8 * swz, swz);
+    const uint32_t lboB = b_mn ? kc * atom_bytes : 0;
+    const uint32_t kstepB = b_mn ? (16 * atom_bytes) >> 4 : 2;
+    // a_mn: A is [K rows = pixels][M cols = channels], atom = swz bytes of M; LBO = one row
+    // (tap-shifted atoms), K step = 16 rows
+    const uint32_t lboA = a_mn ? swz : 0;
+    const uint32_t kstepA = a_mn ? (16 * swz) >> 4 : 2;
+    const uint32_t a0 = umma_desc_lo(smem_u32(sa), lboA);
+    const uint32_t b0 = umma_desc_lo(smem_u32(sb), lboB);
+    const uint32_t row16 = swz >> 4;
+    const uint32_t sh = shifted ? 1u : 0u;
+    const uint32_t d1 = sh * row16, dw = sh * (uint32_t)wp * row16;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      uint32_t acc = 0;
+      if (flags & 32) {
+        // rolled variant: the tap loop is NOT unrolled, so every tap re-writes the same
+        // uniform registers (as a generic runtime-kh/kw loop does)
+        for (int it = 0; it < iters; ++it) {
+          uint32_t a_row = a0;
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r, a_row += dw) {
+#pragma unroll 1
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t a_tap = a_row + s * d1;
+#pragma unroll 1
+              for (int kk = 0; kk < kc / 16; ++kk) {
+                umma_f16(tmem_base, umma_desc_pack(hiA, a_tap + kk * kstepA),
+                         umma_desc_pack(hiB, b0 + kk * kstepB), idesc, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+      } else if (flags & 64) {
+        // tap loop rolled, 4 k-steps unrolled (the production hconv loop shape)
+        for (int it = 0; it < iters; ++it) {
+          uint32_t a_row = a0;
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r, a_row += dw) {
+#pragma unroll 1
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t a_tap = a_row + s * d1;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < kc / 16) {
+                  umma_f16(tmem_base, umma_desc_pack(hiA, a_tap + kk * kstepA),
+                           umma_desc_pack(hiB, b0 + kk * kstepB), idesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+        }
+      } else {
+      for (int it = 0; it < iters; ++it) {
+          uint32_t a_row = a0;
+  #pragma unroll
+          for (int r = 0; r < 3; ++r, a_row += dw) {
+  #pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t a_tap = a_row + s * d1;
+              if (kc == 64) {
+  #pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  umma_f16(tmem_base, umma_desc_pack(hiA, a_tap + kk * kstepA),
+                           umma_desc_pack(hiB, b0 + kk * kstepB), idesc, acc);
+                  acc = 1;
+                }
+              } else if (kc == 32) {
+  #pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                  umma_f16(tmem_base, umma_desc_pack(hiA, a_tap + kk * kstepA),
+                           umma_desc_pack(hiB, b0 + kk * kstepB), idesc, acc);
+                  acc = 1;
+                }
+              } else {
+                umma_f16(tmem_base, umma_desc_pack(hiA, a_tap), umma_desc_pack(hiB, b0), idesc, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+      }
+      umma_commit(&bars[0]);
+      t1 = clock64();
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    t2 = clock64();
+    t0 = __shfl_sync(0xffffffffu, t0, 0) | 0;
+    if (t1 != 0) {
+      out[2 * blockIdx.x] = t1 - t0;
+      out[2 * blockIdx.x + 1] = t2 - t0;
+      *done_flag = 1;
+    }
+  } else if (warp == 1) {
+    if ((flags & 2) && lane == 0) {     // bulk global -> smem copies, 16 KB each, back to back
+      uint32_t ph = 0;
+      int slot = 0;
+      while (!*done_flag) {
+        mbar_expect_tx(&bars[1], 16384);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(sx + slot * 16384)), "l"(scratch), "r"(16384), "r"(smem_u32(&bars[1]))
+            : "memory");
+        mbar_wait(&bars[1], ph);
+        ph ^= 1u;
+        slot ^= 1;
+      }
+    }
+  } else {
+    if (flags & 4) {                    // epilogue-like TMEM reads of another accumulator stage
+      uint32_t r[32];
+      uint32_t sink = 0;
+      while (!*done_flag) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256, r);
+        tmem_ld_wait();
+        sink += r[lane & 31];
+      }
+      if (sink == 0x12345678u) scratch[lane] = sink;
+    }
+    if (flags & 8) {                    // row-strided 16-byte global stores (uncoalesced epilogue)
+      uint4* dst = reinterpret_cast<uint4*>(scratch) + (warp - 2) * 2048;
+      int k = 0;
+      while (!*done_flag) {
+        dst[lane * 8 + (k & 7)] = make_uint4(k, k, k, k);
+        ++k;
+      }
+    }
+    if (flags & 16) {                   // broadcast global loads (bias-style)
+      float acc = 0.f;
+      int k = 0;
+      while (!*done_flag) {
+        acc += __ldg(reinterpret_cast<const float*>(scratch) + (k & 63));
+        ++k;
+      }
+      if (acc == 1.2345f) scratch[lane] = 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn, int ctas,
+                    long long* out, cudaStream_t st) {
+  SEG_REQUIRE((kc == 16 || kc == 32 || kc == 64) && bn >= 16 && bn <= 256 && bn % 16 == 0 &&
+                  wp >= 1 && wp <= 256 && ctas >= 1,
+              SEG_E_BAD_SHAPE, "probe_rate: bad argument");
+  const int a_rows = 128 + 2 * wp + 2 + 8;
+  const int smem = ((a_rows * kc * 2 + 1023) / 1024) * 1024 + ((bn * kc * 2 + 1023) / 1024) * 1024 +
+                   2048 + 1024 + 32768;
+  SEG_CHECK_CUDA(cudaFuncSetAttribute(probe_rate_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  probe_rate_kernel<<<ctas, 128, smem, st>>>(kc, bn, b_mn, wp, shifted, iters, a_mn, out);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+}  // namespace segb

@@ -2,6 +2,7 @@
 // and im2col), tile-shape selection and launches.
 #include "umma_conv.cuh"
 #include "hconv.cuh"
+#include "tconv.cuh"
 
 #include <mutex>
 
@@ -572,6 +573,237 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// spatial-tile convolution (tconv.cuh): launch
+// ---------------------------------------------------------------------------
+// tiled 4-D map over an NHWC view seen as (C, W, H, N) with an arbitrary box
+static int make_tmap_box(CUtensorMap* tm, const seg_view& v, int box_c, int box_w, int box_h,
+                         int swizzle_bytes) {
+  SEG_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && (v.sw * 2) % 16 == 0 &&
+                  (v.sh * 2) % 16 == 0 && (v.sn * 2) % 16 == 0,
+              SEG_E_ALIGN, "box tensor map: view must be 16-byte aligned in every stride");
+  cuuint64_t gdim[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, gdim, gstr, box, est,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(swizzle_bytes),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEG_REQUIRE(r == CUDA_SUCCESS, SEG_E_CUDA,
+              "cuTensorMapEncodeTiled(4d box) failed (%d) c=%d w=%d h=%d n=%d box=%dx%dx%d sw=%d",
+              (int)r, v.c, v.w, v.h, v.n, box_c, box_w, box_h, swizzle_bytes);
+  return SEG_OK;
+}
+
+struct TconvJob {
+  seg_view a1, a2;             // input sources (a2.ptr == null: none)
+  int pad_t, pad_l;
+  seg_view d0, d1;             // destinations (d1.ptr == null: none); d0.h x d0.w = output grid
+  seg_view m0, m1;             // ReLU-grad mask sources (same geometry as d0 / d1), nullable
+  const void* w;
+  int w_rows, w_cols;
+  bool b_mn;
+  int b_rows_per_tap;
+  bool tap_flip;
+  int N_total, max_bn;
+  int split_n;
+  const float* bias;
+  int flags;
+};
+
+static int g_tconv_min_eff = 70;     // percent of computed output pixels that must be useful
+static bool g_use_tconv = true;
+void tconv_enable(int on) { g_use_tconv = on != 0; }
+void tconv_set_min_eff(int pct) { g_tconv_min_eff = pct; }
+
+struct TconvPlan {
+  int KC, BN, MT, SA, SB, resident, smem;
+  TconvParams P;
+};
+
+template <int KC, int BN, bool B_MN, int MT>
+static int launch_tconv_t(const TconvJob& J, const TconvPlan& L, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(tconv_kernel<KC, BN, B_MN, MT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  constexpr int kAtomN = BN < 64 ? BN : 64;
+  constexpr int BNH = BN < 64 ? BN : 64;
+  constexpr int PW = 8 * MT + 2, PH = kTconvTH + 2;
+  CUtensorMap tmA1, tmA2, tmB, tmD0, tmD1, tmM0, tmM1;
+  int rc = make_tmap_box(&tmA1, J.a1, KC, PW, PH, KC * 2);
+  if (rc) return rc;
+  if (J.a2.ptr) {
+    rc = make_tmap_box(&tmA2, J.a2, KC, PW, PH, KC * 2);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA1;
+  }
+  if (B_MN)
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, kAtomN, KC, kAtomN * 2);
+  else
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN, KC * 2);
+  if (rc) return rc;
+  rc = make_tmap_box(&tmD0, J.d0, BNH, 8, 4, BNH * 2);
+  if (rc) return rc;
+  if (J.d1.ptr) {
+    rc = make_tmap_box(&tmD1, J.d1, BNH, 8, 4, BNH * 2);
+    if (rc) return rc;
+  } else {
+    tmD1 = tmD0;
+  }
+  tmM0 = tmD0;
+  tmM1 = tmD1;
+  if (J.flags & SEG_EPI_RELU_MASK) {
+    rc = make_tmap_box(&tmM0, J.m0, BNH, 8, 4, BNH * 2);
+    if (rc) return rc;
+    if (J.d1.ptr) {
+      rc = make_tmap_box(&tmM1, J.m1, BNH, 8, 4, BNH * 2);
+      if (rc) return rc;
+    } else {
+      tmM1 = tmM0;
+    }
+  }
+  const TconvParams& P = L.P;
+  const int tiles = P.batch * P.tiles_y * P.tiles_x * P.n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (P.b_resident && P.n_tiles > 1) grid -= grid % P.n_tiles;   // fixed N-slice per CTA
+  tconv_kernel<KC, BN, B_MN, MT><<<grid, kIgemmThreads, L.smem, st>>>(tmA1, tmA2, tmB, tmD0, tmD1,
+                                                                     tmM0, tmM1, P);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+template <int KC, bool B_MN>
+static int launch_tconv_bn(const TconvJob& J, const TconvPlan& L, cudaStream_t st) {
+  if (L.MT == 2) {
+    switch (L.BN) {
+      case 128: return launch_tconv_t<KC, 128, B_MN, 2>(J, L, st);
+      case 64: return launch_tconv_t<KC, 64, B_MN, 2>(J, L, st);
+      case 32: return launch_tconv_t<KC, 32, B_MN, 2>(J, L, st);
+    }
+  } else {
+    switch (L.BN) {
+      case 128: return launch_tconv_t<KC, 128, B_MN, 1>(J, L, st);
+      case 64: return launch_tconv_t<KC, 64, B_MN, 1>(J, L, st);
+      case 32: return launch_tconv_t<KC, 32, B_MN, 1>(J, L, st);
+    }
+  }
+  return SEG_E_UNSUPPORTED;
+}
+
+// smem plan for (KC, BN, MT); false if it does not fit
+static bool tconv_plan(const TconvJob& J, int KC, int BN, int MT, int chunks, TconvPlan* L) {
+  const int budget = 227 * 1024 - 1024;                 // minus base-alignment slack
+  const int a_stage = (((8 * MT + 2) * (kTconvTH + 2) * KC * 2) + 1023) / 1024 * 1024;
+  const int bbytes = BN * KC * 2;
+  const int stg = 4 * 2 * (32 * BN * 2);
+  const int msk = (J.flags & SEG_EPI_RELU_MASK) ? 4 * MT * (32 * BN * 2) : 0;
+  const int fixed = stg + msk + 2048 /*bias*/ + 1024 /*barriers*/;
+  int SB, resident;
+  if (9 * chunks <= kTconvMaxSB && 9 * chunks * bbytes + 2 * a_stage + fixed <= budget) {
+    resident = 1;
+    SB = 9 * chunks;
+  } else {
+    resident = 0;
+    SB = (48 * 1024) / bbytes;
+    SB = SB < 3 ? 3 : (SB > 9 ? 9 : SB);
+  }
+  int SA = (budget - fixed - SB * bbytes) / a_stage;
+  if (SA > kTconvMaxSA) SA = kTconvMaxSA;
+  if (SA > 2 * chunks + 2) SA = 2 * chunks + 2;         // more stages than two tiles is waste
+  if (SA < 2) return false;
+  L->KC = KC; L->BN = BN; L->MT = MT; L->SA = SA; L->SB = SB; L->resident = resident;
+  TconvParams& P = L->P;
+  P.SA = SA; P.SB = SB; P.b_resident = resident;
+  P.a_stage_bytes = a_stage;
+  P.off_b = SA * a_stage;
+  P.off_stage = P.off_b + ((SB * bbytes + 1023) / 1024) * 1024;
+  P.off_mask = P.off_stage + stg;
+  P.off_bias = P.off_mask + msk;
+  P.off_bars = P.off_bias + 2048;
+  L->smem = P.off_bars + 1024 + 1024;
+  return L->smem <= 227 * 1024;
+}
+
+// Returns SEG_E_UNSUPPORTED (nothing launched) when the shape does not suit this kernel.
+static int launch_tconv(const TconvJob& J, cudaStream_t st) {
+  int rc = load_encoders();
+  if (rc) return rc;
+  if (J.flags & SEG_EPI_OUT_F32) return SEG_E_UNSUPPORTED;
+  const int c2 = J.a2.ptr ? J.a2.c : 0;
+  const int KC = pick_chunk(J.a1.c, c2);
+  if (KC == 0 || J.N_total > 512) return SEG_E_UNSUPPORTED;
+  int BN = 0;
+  for (int c = 128; c >= 32; c >>= 1)
+    if (J.max_bn % c == 0) { BN = c; break; }
+  if (BN == 0 || J.N_total % BN) return SEG_E_UNSUPPORTED;
+  const int Ho = J.d0.h, Wo = J.d0.w, batch = J.d0.n;
+  const int tiles_y = (Ho + kTconvTH - 1) / kTconvTH;
+  // column-block count: the one wasting fewer columns, wider on ties
+  const int w1 = (Wo + 7) / 8 * 8, w2 = (Wo + 15) / 16 * 16;
+  int MT = w2 <= w1 ? 2 : 1;
+  const int wcomp = MT == 2 ? w2 : w1;
+  if ((int64_t)Ho * Wo * 100 < (int64_t)g_tconv_min_eff * tiles_y * kTconvTH * wcomp)
+    return SEG_E_UNSUPPORTED;
+  const int chunks = (J.a1.c + c2) / KC;
+  TconvPlan L;
+  memset(&L, 0, sizeof(L));
+  // prefer a resident B; shrink BN (more N-slices re-reading A) before giving that up only
+  // when the slice count stays small, else stream B through a ring
+  bool ok = tconv_plan(J, KC, BN, MT, chunks, &L);
+  if (ok && !L.resident) {
+    TconvPlan L2;
+    memset(&L2, 0, sizeof(L2));
+    for (int bn = BN / 2; bn >= 32; bn >>= 1) {
+      if (J.N_total / bn > 4) break;
+      if (tconv_plan(J, KC, bn, MT, chunks, &L2) && L2.resident) { L = L2; BN = bn; break; }
+      if (MT == 2 && tconv_plan(J, KC, bn, 1, chunks, &L2) && L2.resident) {
+        L = L2; BN = bn; MT = 1; break;
+      }
+    }
+  }
+  while (!ok) {
+    if (MT == 2) MT = 1;
+    else if (BN > 32) BN >>= 1;
+    else return SEG_E_UNSUPPORTED;
+    ok = tconv_plan(J, KC, BN, MT, chunks, &L);
+  }
+  MT = L.MT; BN = L.BN;
+  TconvParams& P = L.P;
+  const int TW = 8 * MT;
+  P.tiles_x = (Wo + TW - 1) / TW;
+  P.tiles_y = tiles_y;
+  P.batch = batch;
+  P.n_tiles = J.N_total / BN;
+  P.chunks1 = J.a1.c / KC;
+  P.chunks2 = c2 / KC;
+  P.pad_t = J.pad_t; P.pad_l = J.pad_l;
+  P.tap_flip = J.tap_flip ? 1 : 0;
+  P.b_rows_per_tap = J.b_rows_per_tap;
+  P.split_n = J.d1.ptr ? J.split_n : 0;
+  P.bias = J.bias;
+  P.bias_cols = J.d0.c;
+  P.n_total = J.N_total;
+  P.flags = J.flags;
+  if (J.b_mn) {
+    switch (KC) {
+      case 64: return launch_tconv_bn<64, true>(J, L, st);
+      case 32: return launch_tconv_bn<32, true>(J, L, st);
+      default: return launch_tconv_bn<16, true>(J, L, st);
+    }
+  }
+  switch (KC) {
+    case 64: return launch_tconv_bn<64, false>(J, L, st);
+    case 32: return launch_tconv_bn<32, false>(J, L, st);
+    default: return launch_tconv_bn<16, false>(J, L, st);
+  }
+}
+
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
 
 static bool g_use_hconv = true;
@@ -597,6 +829,19 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
   J.N_total = d.cout_pad; J.max_bn = d.cout_pad;
   J.d0 = make_dest(&y, nullptr);
   J.bias = bias; J.flags = d.flags;
+  if (g_use_tconv && d.stride == 1 && d.kh == 3 && d.kw == 3) {
+    TconvJob T;
+    memset(&T, 0, sizeof(T));
+    T.a1 = J.a1; T.a2 = J.a2;
+    T.pad_t = d.pad_t; T.pad_l = d.pad_l;
+    T.d0 = y; T.d1 = null_view(); T.m0 = null_view(); T.m1 = null_view();
+    T.w = J.w; T.w_rows = J.w_rows; T.w_cols = J.w_cols;
+    T.b_mn = true; T.b_rows_per_tap = J.b_rows_per_tap; T.tap_flip = false;
+    T.N_total = J.N_total; T.max_bn = J.max_bn;
+    T.bias = bias; T.flags = d.flags;
+    const int rc = launch_tconv(T, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+  }
   if (g_use_hconv && d.stride == 1 && d.kh * d.kw > 1) {
     HconvJob H;
     memset(&H, 0, sizeof(H));
@@ -644,6 +889,27 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
     J.max_bn = d.cin_pad;
   }
   J.flags = d.flags & (SEG_EPI_RELU_MASK);
+  if (g_use_tconv && d.kh == 3 && d.kw == 3) {
+    TconvJob T;
+    memset(&T, 0, sizeof(T));
+    T.a1 = dz; T.a2 = null_view();
+    T.pad_t = d.kh - 1 - d.pad_t; T.pad_l = d.kw - 1 - d.pad_l;
+    T.d0 = dx;
+    T.d1 = (dx2 && dx2->ptr) ? *dx2 : null_view();
+    T.m0 = (mask && mask->ptr) ? *mask : null_view();
+    T.m1 = (mask2 && mask2->ptr) ? *mask2 : null_view();
+    T.w = J.w; T.w_rows = J.w_rows; T.w_cols = J.w_cols;
+    T.b_mn = false; T.b_rows_per_tap = J.b_rows_per_tap; T.tap_flip = true;
+    T.N_total = J.N_total; T.max_bn = J.max_bn; T.split_n = J.split_n;
+    T.flags = J.flags;
+    // a mask must cover every destination it is requested for
+    const bool mask_ok = !(J.flags & SEG_EPI_RELU_MASK) ||
+                         (T.m0.ptr && (!T.d1.ptr || T.m1.ptr));
+    if (mask_ok) {
+      const int rc = launch_tconv(T, st);
+      if (rc != SEG_E_UNSUPPORTED) return rc;
+    }
+  }
   if (g_use_hconv && d.kh * d.kw > 1) {
     HconvJob H;
     memset(&H, 0, sizeof(H));

@@ -107,6 +107,14 @@ class ParamStore(object):
                 mid = mid_pad = 1
             seg += [p.offset, p.numel, inner, inner_pad, mid, mid_pad]
             soff.append(p.shadow_offset)
+        # launch plan of the Adam kernel: one {segment, first element} pair per block
+        ce = N.load().seg_adam_chunk_elems()
+        chunks = []
+        for si, p in enumerate(self.params.values()):
+            for b in range(0, p.numel, ce):
+                chunks += [si, b]
+        self.nchunks = len(chunks) // 2
+        self.chunks = torch.tensor(chunks or [0, 0], dtype=torch.int32, device=dev)
         self.segments = torch.tensor(seg, dtype=torch.int32, device=dev)
         self.shadow_offsets = torch.tensor(soff, dtype=torch.int64, device=dev)
         self.numel = self._n
@@ -159,7 +167,7 @@ class ParamStore(object):
         """from_device=True reads lr_t from self.lr_t_dev (CUDA-graph replay)."""
         N.call('seg_adam_multi', N.ptr(self.master), N.ptr(self.grad), N.ptr(self.m),
                N.ptr(self.v), N.ptr(self.shadow), N.ptr(self.segments),
-               N.ptr(self.shadow_offsets), len(self.params), self.numel, lr_t,
+               N.ptr(self.shadow_offsets), N.ptr(self.chunks), self.nchunks, lr_t,
                N.ptr(self.lr_t_dev) if from_device else None, beta1, beta2,
                eps, grad_scale, N.stream_ptr())
 

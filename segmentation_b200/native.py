@@ -70,10 +70,12 @@ SIGNATURES = {
     'seg_softmax_xent_fwd_bwd': [_VP, _VP, _P, _VP, _P],
     'seg_sigmoid_argmax': [_VP, _P, _P, _P],
     'seg_mc_mean_var': [_P, _I32, _I64, _P, _P, _P],
-    'seg_adam_multi': [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _F, _P, _F, _F, _F, _F, _P],
+    'seg_adam_chunk_elems': [],
+    'seg_adam_multi': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P, _F, _F, _F, _F, _P],
     'seg_pack_input': [_P, _I32, _VP, _P],
     'seg_fill_zero': [_P, _I64, _P],
     'seg_probe_umma': [_I32, _I32, _I32, _I32, _P, _P, _P, _P],
+    'seg_probe_mma_rate': [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
 }
 
 _lib = None
@@ -114,7 +116,7 @@ def set_tag(tag):
     _TAG[0] = tag
 
 
-OPT_HALO_CONV, OPT_HALO_ROW_ALIGN = 1, 2
+OPT_HALO_CONV, OPT_HALO_ROW_ALIGN, OPT_TILE_CONV, OPT_TILE_CONV_MIN_EFF = 1, 2, 3, 4
 
 
 def set_option(key, value):

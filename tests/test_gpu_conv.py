@@ -17,18 +17,27 @@ from gpu_util import (bfr, conv_pads, desc, dev_bf16, pad16, rel_l2, report, sha
                       shadow_deconv, sync)
 
 pytestmark = pytest.mark.gpu
-IMPLS = [('simt', N.IMPL_SIMT), ('umma', N.IMPL_UMMA), ('umma_im2col', N.IMPL_UMMA)]
+IMPLS = [('simt', N.IMPL_SIMT), ('umma', N.IMPL_UMMA), ('umma_halo', N.IMPL_UMMA),
+         ('umma_im2col', N.IMPL_UMMA)]
 
 
 @pytest.fixture(autouse=True)
 def _halo_switch(request):
-    """'umma' = tcgen05 with the halo-tile conv kernel where it applies (default);
-    'umma_im2col' forces the TMA-im2col kernel for the same shapes."""
+    """'umma' = tcgen05 with the spatial-tile conv kernel wherever it structurally applies
+    (efficiency gate off, so the small test shapes exercise it); 'umma_halo' = the
+    position-space halo kernel instead; 'umma_im2col' forces the TMA-im2col kernel."""
     name = request.node.callspec.params.get('impl_name') if hasattr(request.node, 'callspec') else None
-    if name == 'umma_im2col':
+    if name == 'umma':
+        N.set_option(N.OPT_TILE_CONV_MIN_EFF, 0)
+    elif name == 'umma_halo':
+        N.set_option(N.OPT_TILE_CONV, 0)
+    elif name == 'umma_im2col':
+        N.set_option(N.OPT_TILE_CONV, 0)
         N.set_option(N.OPT_HALO_CONV, 0)
     yield
     N.set_option(N.OPT_HALO_CONV, 1)
+    N.set_option(N.OPT_TILE_CONV, 1)
+    N.set_option(N.OPT_TILE_CONV_MIN_EFF, 70)
 TOL_BF16 = 4e-3
 TOL_F32 = 2e-4
 

@@ -21,7 +21,7 @@ ex.forward(); ex.loss(True); ex.backward(); model.store.grad.zero_()
 torch.cuda.synchronize()
 L, A, G = model.layers, ex.act, ex.g
 want = sys.argv[1:] or ['conv1_2', 'conv2_2', 'conv3_2', 'conv9_2']
-prof = torch.zeros(3 * 16 * 4, dtype=torch.int64, device='cuda')
+prof = torch.zeros(4 * 16 * 4, dtype=torch.int64, device='cuda')
 src_of = {'conv1_2': 'conv1_1', 'conv2_2': 'conv2_1', 'conv3_2': 'conv3_1', 'conv9_2': 'conv9_1',
           'conv2_1': 'pool1', 'conv3_1': 'pool2', 'conv4_2': 'conv4_1', 'conv5_2': 'conv5_1'}
 out = {}
@@ -45,7 +45,9 @@ for name in want:
         prof.zero_()
         N.call('seg_debug_prof_buffer', N.ptr(prof)); fn(); torch.cuda.synchronize()
         N.call('seg_debug_prof_buffer', None)
-        p = prof.cpu().view(3, 16, 4)
+        pall = prof.cpu()
+        taps = pall[3 * 64:].view(4, 16)
+        p = pall[:3 * 64].view(3, 16, 4)
         t0 = int(p[p > 0].min()) if (p > 0).any() else 0
         rel = (p - t0).clamp(min=0)
         print('=== %s %s: %.1f us/launch' % (name, kind, us))
@@ -53,6 +55,10 @@ for name in want:
             print(' ', rn)
             for t in range(8):
                 print('    tile %d:' % t, [int(v) for v in rel[role, t]])
+        for ti in (0, 1):
+            tt = taps[ti][taps[ti] > 0]
+            if len(tt):
+                print('  tap issue stamps tile %d (rel. to first, diffs):' % (ti + 2), [int(v) for v in (tt - t0)], [int(v) for v in (tt[1:] - tt[:-1])])
         out['%s_%s' % (name, kind)] = {'us': us, 'prof': rel.tolist()}
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(out, open('gpurun_out/layer_prof.json', 'w'))

@@ -490,10 +490,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         if (W == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
         if (row_ok) {
+          if ((P.SC & 3) == 0 && (reinterpret_cast<uintptr_t>(P.dw) & 15) == 0 && dst != P.db) {
+            // 16-byte vector reductions (dW rows are SC floats, SC % 4 == 0 keeps alignment)
 #pragma unroll
-          for (int j = 0; j < W; ++j) {
-            const int sc = n0 + cc + j;
-            if (sc < P.SC) atomicAdd(dst + sc, __uint_as_float(r[j]));
+            for (int j = 0; j < W; j += 4) {
+              const int sc = n0 + cc + j;
+              if (sc < P.SC)
+                red_add_v4(dst + sc, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              const int sc = n0 + cc + j;
+              if (sc < P.SC) atomicAdd(dst + sc, __uint_as_float(r[j]));
+            }
           }
         }
       }

@@ -43,6 +43,8 @@ void hconv_set_prof(void* p);
 void hconv_enable(int on);
 void tconv_enable(int on);
 void tconv_set_min_eff(int pct);
+void twgrad_enable(int on);
+void twgrad_set_min_eff(int pct);
 
 static bool desc_ok(const seg_conv_desc* d) {
   return d && d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->cin >= 1 && d->cout >= 1 &&
@@ -71,6 +73,8 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 2: hconv_set_row_align(value); return SEG_OK;
     case 3: tconv_enable(value); return SEG_OK;
     case 4: tconv_set_min_eff(value); return SEG_OK;
+    case 5: twgrad_enable(value); return SEG_OK;
+    case 6: twgrad_set_min_eff(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

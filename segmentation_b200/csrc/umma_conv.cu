@@ -3,6 +3,7 @@
 #include "umma_conv.cuh"
 #include "hconv.cuh"
 #include "tconv.cuh"
+#include "twgrad.cuh"
 
 #include <mutex>
 
@@ -804,6 +805,99 @@ static int launch_tconv(const TconvJob& J, cudaStream_t st) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// spatial-tile weight gradient (twgrad.cuh): launch
+// ---------------------------------------------------------------------------
+static bool g_use_twgrad = true;
+static int g_twgrad_min_eff = 40;
+void twgrad_enable(int on) { g_use_twgrad = on != 0; }
+void twgrad_set_min_eff(int pct) { g_twgrad_min_eff = pct; }
+
+template <int AW, int BN>
+static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(twgrad_kernel<AW, BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  constexpr int kAtomN = BN < 64 ? BN : 64;
+  CUtensorMap tmX1, tmX2, tmZ;
+  int rc = make_tmap_box(&tmX1, J.big, AW, kTwPW, kTwPH, AW * 2);
+  if (rc) return rc;
+  if (J.big2.ptr) {
+    rc = make_tmap_box(&tmX2, J.big2, AW, kTwPW, kTwPH, AW * 2);
+    if (rc) return rc;
+  } else {
+    tmX2 = tmX1;
+  }
+  rc = make_tmap_box(&tmZ, J.small_, kAtomN, kTwTW, kTwTH, kAtomN * 2);
+  if (rc) return rc;
+  TwgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.tiles_x = (J.small_.w + kTwTW - 1) / kTwTW;
+  P.tiles_y = (J.small_.h + kTwTH - 1) / kTwTH;
+  P.batch = J.small_.n;
+  P.chunks1 = J.big.c / AW;
+  P.chunks2 = J.big2.ptr ? J.big2.c / AW : 0;
+  P.n_slices = J.small_.c / BN;
+  P.pad_t = -J.low_h; P.pad_l = -J.low_w;
+  P.BC = J.BC; P.SC = J.SC;
+  P.dw = J.dw; P.db = J.db;
+  const int combos = (P.chunks1 + P.chunks2) * P.n_slices;
+  const int tiles = P.batch * P.tiles_y * P.tiles_x;
+  int per = num_sms() / combos;
+  if (per < 1) per = 1;
+  if (per > tiles) per = tiles;
+  P.ctas_per_combo = per;
+  P.x_bytes = ((kTwPW * kTwPH * AW * 2) + 1023) / 1024 * 1024;
+  P.stage_bytes = P.x_bytes + kTwTH * kTwTW * BN * 2;
+  int stages = (227 * 1024 - 2048 - 1024) / P.stage_bytes;
+  if (stages > kTwMaxStages) stages = kTwMaxStages;
+  P.stages = stages;
+  P.off_bars = stages * P.stage_bytes;
+  const int smem = P.off_bars + 1024 + 1024;
+  twgrad_kernel<AW, BN><<<combos * per, kIgemmThreads, smem, st>>>(tmX1, tmX2, tmZ, P);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+// Returns SEG_E_UNSUPPORTED (nothing launched) when the shape does not suit this kernel.
+static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
+  if (!(J.kh == 3 && J.kw == 3 && J.stride == 1)) return SEG_E_UNSUPPORTED;
+  int rc = load_encoders();
+  if (rc) return rc;
+  const int AW = pick_chunk(J.big.c, J.big2.ptr ? J.big2.c : 0);
+  if (AW == 0) return SEG_E_UNSUPPORTED;
+  const int co = J.small_.c;
+  const int BN = co % 64 == 0 ? 64 : (co % 32 == 0 ? 32 : (co % 16 == 0 ? 16 : 0));
+  if (BN == 0) return SEG_E_UNSUPPORTED;
+  const int Ho = J.small_.h, Wo = J.small_.w;
+  const int64_t comp = (int64_t)((Ho + kTwTH - 1) / kTwTH * kTwTH) * ((Wo + kTwTW - 1) / kTwTW * kTwTW);
+  if ((int64_t)Ho * Wo * 100 < (int64_t)g_twgrad_min_eff * comp) return SEG_E_UNSUPPORTED;
+  switch (AW) {
+    case 64:
+      switch (BN) {
+        case 64: return launch_twgrad_t<64, 64>(J, st);
+        case 32: return launch_twgrad_t<64, 32>(J, st);
+        default: return launch_twgrad_t<64, 16>(J, st);
+      }
+    case 32:
+      switch (BN) {
+        case 64: return launch_twgrad_t<32, 64>(J, st);
+        case 32: return launch_twgrad_t<32, 32>(J, st);
+        default: return launch_twgrad_t<32, 16>(J, st);
+      }
+    default:
+      switch (BN) {
+        case 64: return launch_twgrad_t<16, 64>(J, st);
+        case 32: return launch_twgrad_t<16, 32>(J, st);
+        default: return launch_twgrad_t<16, 16>(J, st);
+      }
+  }
+}
+
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
 
 static bool g_use_hconv = true;
@@ -941,6 +1035,10 @@ int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x
   J.BC = d.cin; J.SC = d.cout;
   J.dw = dw;
   J.db = db;
+  if (g_use_twgrad) {
+    const int rc = launch_twgrad(J, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+  }
   return launch_wgrad(J, st);
 }
 

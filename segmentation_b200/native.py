@@ -117,6 +117,7 @@ def set_tag(tag):
 
 
 OPT_HALO_CONV, OPT_HALO_ROW_ALIGN, OPT_TILE_CONV, OPT_TILE_CONV_MIN_EFF = 1, 2, 3, 4
+OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
 
 
 def set_option(key, value):

@@ -29,15 +29,20 @@ def _halo_switch(request):
     name = request.node.callspec.params.get('impl_name') if hasattr(request.node, 'callspec') else None
     if name == 'umma':
         N.set_option(N.OPT_TILE_CONV_MIN_EFF, 0)
+        N.set_option(N.OPT_TILE_WGRAD_MIN_EFF, 0)
     elif name == 'umma_halo':
         N.set_option(N.OPT_TILE_CONV, 0)
+        N.set_option(N.OPT_TILE_WGRAD, 0)      # TMA-im2col weight-gradient kernel
     elif name == 'umma_im2col':
         N.set_option(N.OPT_TILE_CONV, 0)
         N.set_option(N.OPT_HALO_CONV, 0)
+        N.set_option(N.OPT_TILE_WGRAD, 0)
     yield
     N.set_option(N.OPT_HALO_CONV, 1)
     N.set_option(N.OPT_TILE_CONV, 1)
     N.set_option(N.OPT_TILE_CONV_MIN_EFF, 70)
+    N.set_option(N.OPT_TILE_WGRAD, 1)
+    N.set_option(N.OPT_TILE_WGRAD_MIN_EFF, 40)
 TOL_BF16 = 4e-3
 TOL_F32 = 2e-4
 

@@ -122,7 +122,7 @@ int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo,
 // ---------------------------------------------------------------------------
 namespace segb {
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(192, 1)
 probe_rate_kernel(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn,
                   long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -287,10 +287,31 @@ probe_rate_kernel(int kc, int bn, int b_mn, int wp, int shifted, int iters, int 
       uint32_t r[32];
       uint32_t sink = 0;
       while (!*done_flag) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256, r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256, r);
         tmem_ld_wait();
         sink += r[lane & 31];
       }
+      if (sink == 0x12345678u) scratch[lane] = sink;
+    }
+    if (flags & 128) {
+      // TMEM drain rate: every warp 2..5 (one per lane quadrant) performs 512 x32 loads
+      // (4 KB each), two in flight, and reports its cycles in out[2*cta + 64 + warp]
+      uint32_t r0[32], r1[32];
+      uint32_t sink = 0;
+      const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+      const long long c0 = clock64();
+      tmem_ld_32x32(ta, r0);
+      for (int k = 0; k < 256; ++k) {
+        tmem_ld_wait();
+        tmem_ld_32x32(ta + 32, r1);
+        sink += r0[k & 31];
+        tmem_ld_wait();
+        tmem_ld_32x32(ta, r0);
+        sink += r1[k & 31];
+      }
+      tmem_ld_wait();
+      const long long c1 = clock64();
+      if (lane == 0) out[2 * gridDim.x + 64 + warp] = c1 - c0;
       if (sink == 0x12345678u) scratch[lane] = sink;
     }
     if (flags & 8) {                    // row-strided 16-byte global stores (uncoalesced epilogue)
@@ -329,7 +350,7 @@ int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, in
                    2048 + 1024 + 32768;
   SEG_CHECK_CUDA(cudaFuncSetAttribute(probe_rate_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  probe_rate_kernel<<<ctas, 128, smem, st>>>(kc, bn, b_mn, wp, shifted, iters, a_mn, out);
+  probe_rate_kernel<<<ctas, 192, smem, st>>>(kc, bn, b_mn, wp, shifted, iters, a_mn, out);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

@@ -17,9 +17,12 @@
 // Epilogue: TMEM -> registers -> bias/ReLU (or ReLU-grad mask) -> bf16 -> swizzled
 // smem staging -> TMA tensor store, one [4 rows][8 cols][<=64 ch] box per epilogue warp;
 // the store clips at the tensor bounds, so ragged tiles and padded channels need no
-// predicates.  The ReLU-grad mask tile is fetched by TMA into the same layout.
+// predicates.  The ReLU-grad mask tile is fetched by TMA into the same layout.  (Plain
+// LSU stores — direct or smem-staged and coalesced — were measured to slow the
+// concurrent UMMA stream by ~50 %; TMA stores do not.)
 #pragma once
 #include "umma_conv.cuh"
+#include "hconv.cuh"
 
 namespace segb {
 
@@ -33,18 +36,21 @@ struct TconvParams {
   int a_stage_bytes;
   int off_b, off_stage, off_mask, off_bias, off_bars;   // byte offsets in the aligned smem
   int split_n;                 // columns >= split_n go to destination 1 (0: single destination)
+  int nstg;                    // staging boxes per epilogue warp (2..4)
   const float* bias;
   int bias_cols;
   int n_total;
   int flags;
+  long long* prof;             // optional in-kernel timeline of CTA 0 (test hook), else null
 };
 
 constexpr int kTconvMaxSA = 8;
 constexpr int kTconvMaxSB = 40;
 constexpr int kTconvTH = 16;
+constexpr int kTconvThreads = 320;        // producer, MMA issuer, 8 epilogue warps
 
 template <int KC, int BN, bool B_MN, int MT>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kTconvThreads, 1)
 tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD0,
              const __grid_constant__ CUtensorMap tmD1, const __grid_constant__ CUtensorMap tmM0,
@@ -78,7 +84,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint64_t* tfull = b_empty + kTconvMaxSB;
   uint64_t* tempty = tfull + 2;
   uint64_t* mask_bar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,10 +99,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD0);
     tma_prefetch_desc(&tmD1);
+    for (int i = 0; i < 8; ++i) mbar_init(&mask_bar[i], 1);
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    for (int i = 0; i < 4; ++i) mbar_init(&mask_bar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MT * (BN / 32) >= 2 ? 8 : 4); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -114,7 +120,9 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        prof_mark(P.prof, 0, ti, 0);
         const int n0 = (tile % P.n_tiles) * BN;
         int mt = tile / P.n_tiles;
         const int tx = mt % P.tiles_x;
@@ -128,6 +136,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           const CUtensorMap* tm = second ? &tmA2 : &tmA1;
           const int c0 = (second ? j - P.chunks1 : j) * KC;
           mbar_wait(&a_empty[sa], pa ^ 1u);
+          if (j == 0) prof_mark(P.prof, 0, ti, 1);
           mbar_expect_tx(&a_full[sa], kABoxBytes);
           tma_load_4d(tm, &a_full[sa], smem + sa * P.a_stage_bytes, c0, xin, yin, img);
           if (++sa == P.SA) { sa = 0; pa ^= 1u; }
@@ -151,6 +160,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           }
         }
         first_tile = false;
+        prof_mark(P.prof, 0, ti, 2);
       }
     }
   } else if (warp == 1) {
@@ -166,15 +176,37 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int sa = 0, sb = 0, as = 0;
       uint32_t pa = 0, pb = 0, aphase = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1u);
-        tc_fence_after();
+      // The barriers of the NEXT step (next chunk's A stage; at a tile boundary also the
+      // next accumulator stage) are waited for in the middle of the current step, while
+      // the tensor pipe still has queued work: a wait costs ~100-200 cycles even when the
+      // barrier is already complete, and the MMA queue is only a few instructions deep.
+      // With a streamed B ring the producer reaches the next A stage only after all nine
+      // B tiles of this chunk, which need this chunk's b_empty commits: pre-wait after the
+      // last tap there (after tap 4 would deadlock), mid-step when B is resident.
+      bool pre_a = false, pre_t = false;
+      const int pre_tap = P.b_resident ? 4 : 8;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        prof_mark(P.prof, 1, ti, 0);
+        if (!pre_t) {
+          mbar_wait(&tempty[as], aphase ^ 1u);
+          tc_fence_after();
+        }
+        prof_mark(P.prof, 1, ti, 1);
         const uint32_t tmem_d = tmem_base + as * kAccCols;
+        const bool more_tiles = tile + (int)gridDim.x < total_tiles;
         if (P.b_resident) sb = 0;
         for (int j = 0; j < chunks; ++j) {
-          mbar_wait(&a_full[sa], pa);
-          tc_fence_after();
+          if (!pre_a) {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+          }
+          pre_a = pre_t = false;
+          if (j == 0) prof_mark(P.prof, 1, ti, 2);
           const uint32_t a0 = umma_desc_lo(smem_u32(smem + sa * P.a_stage_bytes), 0);
+          int sa_n = sa + 1;
+          uint32_t pa_n = pa;
+          if (sa_n == P.SA) { sa_n = 0; pa_n ^= 1u; }
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -196,115 +228,168 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               }
               if (!P.b_resident) umma_commit(&b_empty[sb]);
               if (++sb == P.SB) { sb = 0; pb ^= 1u; }
+              if (r * 3 + s == pre_tap) {
+                if (j + 1 < chunks) {
+                  mbar_wait(&a_full[sa_n], pa_n);
+                  pre_a = true;
+                } else if (more_tiles) {
+                  mbar_wait(&tempty[as ^ 1], (as == 1 ? aphase ^ 1u : aphase) ^ 1u);
+                  mbar_wait(&a_full[sa_n], pa_n);
+                  pre_a = pre_t = true;
+                }
+                tc_fence_after();
+              }
             }
           }
           umma_commit(&a_empty[sa]);
-          if (++sa == P.SA) { sa = 0; pa ^= 1u; }
+          sa = sa_n;
+          pa = pa_n;
         }
         umma_commit(&tfull[as]);
+        prof_mark(P.prof, 1, ti, 3);
         if (++as == 2) { as = 0; aphase ^= 1u; }
         first_tile = false;
       }
     }
   } else {
     // ============================= epilogue =============================
+    // Everything that leaves or enters the SM here goes through the async proxy (TMA):
+    // LSU global stores issued next to a running UMMA stream were measured to slow the
+    // kernel, TMA traffic does not.  Eight warps, two per TMEM lane quadrant, take the
+    // 32-column chunks of a tile alternately (a single warp per scheduler issues only one
+    // instruction per ~5 cycles in this dependent code, the TMEM drain itself needs ~290
+    // cycles per chunk).  Each thread owns one output pixel (TMEM lane): bias (one column
+    // per lane, broadcast by shuffle), ReLU or ReLU-grad mask, bf16, then its four 16-byte
+    // chunks go to a swizzled [4][8][32] staging box that one lane hands to a TMA tensor
+    // store; kStg boxes per warp rotate so that a store's smem-read completion (~1000
+    // cycles behind its commit) is never waited for, and the TMEM load of the warp's next
+    // chunk is in flight while the current one is processed.
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    uint8_t* stg = smem + P.off_stage + quad * (2 * kStgBytes);
-    uint8_t* msk = smem + P.off_mask + quad * (MT * kStgBytes);
-    // swizzled byte offset of 16-byte chunk `ci` of this lane's pixel inside a store box
-    const uint32_t row_off = (uint32_t)lane * (BNH * 2);
-    const uint32_t xor_sel = BNH == 64 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
-    int as = 0, sbuf = 0;
-    uint32_t aphase = 0, mphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n0 = (tile % P.n_tiles) * BN;
-      int mt = tile / P.n_tiles;
-      const int tx = mt % P.tiles_x;
-      mt /= P.tiles_x;
-      const int ty = mt % P.tiles_y;
-      const int img = mt / P.tiles_y;
-      const int x0 = tx * TW;
-      const int yw = ty * kTconvTH + 4 * quad;       // first output row of this warp's boxes
-      const bool second = P.split_n > 0 && n0 >= P.split_n;
-      const CUtensorMap* tmD = second ? &tmD1 : &tmD0;
-      const CUtensorMap* tmM = second ? &tmM1 : &tmM0;
-      const int nl0 = second ? n0 - P.split_n : n0;  // column inside the destination
-      if (has_mask && lane == 0) {
-        mbar_expect_tx(&mask_bar[quad], MT * kStgBytes);
+    const int half = (warp - 2) >> 2;                // which warp of the quadrant's pair
+    constexpr int NCH = BN / 32;                     // 32-column chunks per column block
+    constexpr int NLD = MT * NCH;                    // chunks (TMEM loads) per tile
+    constexpr int kBoxBytes = 32 * 32 * 2;           // [4 rows][8 cols][32 ch] bf16
+    constexpr int kMyMax = (NLD + 1) / 2;            // chunks per warp per tile
+    if (half < NLD) {
+      uint8_t* stg = smem + P.off_stage + (warp - 2) * (P.nstg * kBoxBytes);
+      const uint32_t msk_u32 = smem_u32(smem + P.off_mask + (warp - 2) * (kMyMax * kBoxBytes));
+      // swizzled (64-byte rows) offset of this lane's pixel, 16-byte chunk q: ^ ((lane>>1)&3)
+      const uint32_t row_off = (uint32_t)lane * 64;
+      const uint32_t xor_sel = (uint32_t)((lane >> 1) & 3);
+      int as = 0, sbuf = 0;
+      uint32_t aphase = 0, mphase = 0;
+      int ti = 0;
+      long long* eprof = (warp == 2 && lane == 0) ? P.prof : nullptr;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        prof_mark(eprof, 2, ti, 0);
+        const int n0 = (tile % P.n_tiles) * BN;
+        int mt = tile / P.n_tiles;
+        const int tx = mt % P.tiles_x;
+        mt /= P.tiles_x;
+        const int ty = mt % P.tiles_y;
+        const int img = mt / P.tiles_y;
+        const int x0 = tx * TW;
+        const int yw = ty * kTconvTH + 4 * quad;     // first output row of this warp's boxes
+        const bool second = P.split_n > 0 && n0 >= P.split_n;
+        const CUtensorMap* tmD = second ? &tmD1 : &tmD0;
+        const CUtensorMap* tmM = second ? &tmM1 : &tmM0;
+        const int nl0 = second ? n0 - P.split_n : n0;   // column inside the destination
+        if (has_mask && lane == 0) {
+          int cnt = 0;
 #pragma unroll
-        for (int mb = 0; mb < MT; ++mb)
+          for (int i = 0; i < NLD; ++i)
+            if ((i & 1) == half) ++cnt;
+          mbar_expect_tx(&mask_bar[warp - 2], cnt * kBoxBytes);
 #pragma unroll
-          for (int h = 0; h < NH; ++h)
-            tma_load_4d(tmM, &mask_bar[quad], msk + mb * kStgBytes + h * kHalfBytes, nl0 + h * BNH,
-                        x0 + 8 * mb, yw, img);
-      }
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      if (has_mask) {
-        mbar_wait(&mask_bar[quad], mphase);
-        mphase ^= 1u;
-      }
-#pragma unroll 1
-      for (int mb = 0; mb < MT; ++mb) {
-        // the staging buffer about to be overwritten was read by the store issued two
-        // boxes ago: allow only the most recent group to be still reading
-        if (lane == 0) bulk_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* sbp = stg + sbuf * kStgBytes;
+          for (int i = 0; i < NLD; ++i)
+            if ((i & 1) == half)
+              tma_load_4d(tmM, &mask_bar[warp - 2], smem + P.off_mask +
+                              ((warp - 2) * kMyMax + (i >> 1)) * kBoxBytes,
+                          nl0 + 32 * (i % NCH), x0 + 8 * (i / NCH), yw, img);
+        }
+        // bias of this tile's columns: lane l holds column 32*c + l of chunk c
+        float bl[NCH];
 #pragma unroll
-        for (int cc = 0; cc < BN; cc += 32) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + mb * BN + cc, rr);
-          tmem_ld_wait();
-          const int h = cc / BNH;                    // store box (64-channel half)
-          const int ci0 = (cc % BNH) / 8;            // first 16-byte chunk inside the box row
+        for (int c = 0; c < NCH; ++c) bl[c] = lds32f(smem_u32(s_bias + n0 + 32 * c + lane));
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
+        prof_mark(eprof, 2, ti, 1);
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols;
+        uint32_t rr[2][32];
+        tmem_ld_32x32(tbase + (half / NCH) * BN + (half % NCH) * 32, rr[0]);
+        if (has_mask) {
+          mbar_wait(&mask_bar[warp - 2], mphase);
+          mphase ^= 1u;
+        }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + cc + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + cc + q * 8 + 4);
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[e] = __uint_as_float(rr[q * 8 + e]) + bv[e];
-              if (P.flags & SEG_EPI_RELU) v[e] = fmaxf(v[e], 0.f);
+        for (int i0 = 0; i0 < NLD; i0 += 2) {
+          const int i = i0 + half;                   // this warp's chunk (runtime: half)
+          if (i < NLD) {
+            const int mb = i / NCH, c = i % NCH;
+            // rotate to the next staging box; the store that last read it was committed
+            // nstg boxes ago: allow the nstg-1 most recent groups to be still reading
+            uint8_t* sbp = stg + sbuf * kBoxBytes;
+            if (lane == 0) {
+              if (P.nstg >= 4) bulk_wait_group_read<3>();
+              else if (P.nstg == 3) bulk_wait_group_read<2>();
+              else bulk_wait_group_read<1>();
             }
-            const uint32_t off = h * kHalfBytes + row_off + (((uint32_t)(ci0 + q) ^ xor_sel) << 4);
-            if (has_mask) {
-              const uint4 u = *reinterpret_cast<const uint4*>(msk + mb * kStgBytes + off);
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            __syncwarp();
+            tmem_ld_wait();
+            if (i + 2 < NLD)
+              tmem_ld_32x32(tbase + ((i + 2) / NCH) * BN + ((i + 2) % NCH) * 32, rr[((i0 >> 1) + 1) & 1]);
+            const uint32_t* r = rr[(i0 >> 1) & 1];
+            float bias_l = bl[0];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (!(bf16_lo(w4[e]) > 0.f)) v[2 * e] = 0.f;
-                if (!(bf16_hi(w4[e]) > 0.f)) v[2 * e + 1] = 0.f;
+            for (int cc = 1; cc < NCH; ++cc)
+              if (cc == c) bias_l = bl[cc];
+            const uint32_t sb32 = smem_u32(sbp) + row_off;
+            const uint32_t mk32 = msk_u32 + (i >> 1) * kBoxBytes + row_off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[e] = __uint_as_float(r[q * 8 + e]) + __shfl_sync(0xffffffffu, bias_l, q * 8 + e);
+                if (P.flags & SEG_EPI_RELU) v[e] = fmaxf(v[e], 0.f);
               }
+              const uint32_t off = ((uint32_t)q ^ xor_sel) << 4;
+              if (has_mask) {
+                const uint4 u = lds128(mk32 + off);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(w4[e]) > 0.f)) v[2 * e] = 0.f;
+                  if (!(bf16_hi(w4[e]) > 0.f)) v[2 * e + 1] = 0.f;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+              sts128(sb32 + off, o);
             }
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(sbp + off) = o;
+            if (i + 2 >= NLD) {                      // this warp's share of the stage is read
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[as]);
+              prof_mark(eprof, 2, ti, 2);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(tmD, sbp, nl0 + 32 * c, x0 + 8 * mb, yw, img);
+              bulk_commit_group();
+            }
+            if (++sbuf == P.nstg) sbuf = 0;
           }
         }
-        if (mb == MT - 1) {                          // accumulator stage fully read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int h = 0; h < NH; ++h)
-            tma_store_4d(tmD, sbp + h * kHalfBytes, nl0 + h * BNH, x0 + 8 * mb, yw, img);
-          bulk_commit_group();
-        }
-        sbuf ^= 1;
+        prof_mark(eprof, 2, ti, 3);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (lane == 0) bulk_wait_group<0>();
     }
-    if (lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();

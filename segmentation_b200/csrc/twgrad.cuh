@@ -174,12 +174,12 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
         uint32_t phase = 0;
         for (int it = 0; it < my_tiles; ++it) {
           mbar_wait(&full[stage], phase);
-          const uint8_t* sz = smem + stage * P.stage_bytes + P.x_bytes + atom * kZAtomBytes;
+          const uint32_t sz = smem_u32(smem + stage * P.stage_bytes + P.x_bytes + atom * kZAtomBytes);
 #pragma unroll 4
           for (int p = rg; p < 128; p += kRG) {
             const uint32_t sw = rowB == 128 ? (uint32_t)(p & 7) : rowB == 64 ? (uint32_t)((p >> 1) & 3)
                                                                              : (uint32_t)((p >> 2) & 1);
-            const uint4 u = *reinterpret_cast<const uint4*>(sz + p * rowB + (((uint32_t)q ^ sw) << 4));
+            const uint4 u = lds128(sz + p * rowB + (((uint32_t)q ^ sw) << 4));
             s[0] += bf16_lo(u.x); s[1] += bf16_hi(u.x);
             s[2] += bf16_lo(u.y); s[3] += bf16_hi(u.y);
             s[4] += bf16_lo(u.z); s[5] += bf16_hi(u.z);

@@ -633,7 +633,7 @@ static int launch_tconv_t(const TconvJob& J, const TconvPlan& L, cudaStream_t st
     attr_done = true;
   }
   constexpr int kAtomN = BN < 64 ? BN : 64;
-  constexpr int BNH = BN < 64 ? BN : 64;
+  constexpr int BNH = 32;               // channels per epilogue store / mask box
   constexpr int PW = 8 * MT + 2, PH = kTconvTH + 2;
   CUtensorMap tmA1, tmA2, tmB, tmD0, tmD1, tmM0, tmM1;
   int rc = make_tmap_box(&tmA1, J.a1, KC, PW, PH, KC * 2);
@@ -673,7 +673,7 @@ static int launch_tconv_t(const TconvJob& J, const TconvPlan& L, cudaStream_t st
   const int tiles = P.batch * P.tiles_y * P.tiles_x * P.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (P.b_resident && P.n_tiles > 1) grid -= grid % P.n_tiles;   // fixed N-slice per CTA
-  tconv_kernel<KC, BN, B_MN, MT><<<grid, kIgemmThreads, L.smem, st>>>(tmA1, tmA2, tmB, tmD0, tmD1,
+  tconv_kernel<KC, BN, B_MN, MT><<<grid, kTconvThreads, L.smem, st>>>(tmA1, tmA2, tmB, tmD0, tmD1,
                                                                      tmM0, tmM1, P);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
@@ -702,8 +702,14 @@ static bool tconv_plan(const TconvJob& J, int KC, int BN, int MT, int chunks, Tc
   const int budget = 227 * 1024 - 1024;                 // minus base-alignment slack
   const int a_stage = (((8 * MT + 2) * (kTconvTH + 2) * KC * 2) + 1023) / 1024 * 1024;
   const int bbytes = BN * KC * 2;
-  const int stg = 4 * 2 * (32 * BN * 2);
-  const int msk = (J.flags & SEG_EPI_RELU_MASK) ? 4 * MT * (32 * BN * 2) : 0;
+  const int box = 32 * 32 * 2;                          // one [4][8][32] staging / mask box
+  const int nld = MT * (BN / 32);
+  const int msk = (J.flags & SEG_EPI_RELU_MASK) ? 8 * ((nld + 1) / 2) * box : 0;
+  // staging boxes per epilogue warp: 4 if that still leaves room for a resident B and 3 A
+  // stages, else fewer
+  int nstg = 4;
+  while (nstg > 2 && 9 * chunks * bbytes + 3 * a_stage + 8 * nstg * box + msk + 3072 > budget) --nstg;
+  const int stg = 8 * nstg * box;
   const int fixed = stg + msk + 2048 /*bias*/ + 1024 /*barriers*/;
   int SB, resident;
   if (9 * chunks <= kTconvMaxSB && 9 * chunks * bbytes + 2 * a_stage + fixed <= budget) {
@@ -721,6 +727,7 @@ static bool tconv_plan(const TconvJob& J, int KC, int BN, int MT, int chunks, Tc
   L->KC = KC; L->BN = BN; L->MT = MT; L->SA = SA; L->SB = SB; L->resident = resident;
   TconvParams& P = L->P;
   P.SA = SA; P.SB = SB; P.b_resident = resident;
+  P.nstg = nstg;
   P.a_stage_bytes = a_stage;
   P.off_b = SA * a_stage;
   P.off_stage = P.off_b + ((SB * bbytes + 1023) / 1024) * 1024;
@@ -791,6 +798,10 @@ static int launch_tconv(const TconvJob& J, cudaStream_t st) {
   P.bias_cols = J.d0.c;
   P.n_total = J.N_total;
   P.flags = J.flags;
+  P.prof = g_prof_buf;
+  if (g_prof_buf)
+    fprintf(stderr, "tconv plan: KC=%d BN=%d MT=%d SA=%d SB=%d resident=%d nstg=%d smem=%d tiles=%dx%dx%dx%d\n",
+            KC, BN, MT, L.SA, L.SB, L.resident, P.nstg, L.smem, batch, P.tiles_y, P.tiles_x, P.n_tiles);
   if (J.b_mn) {
     switch (KC) {
       case 64: return launch_tconv_bn<64, true>(J, L, st);

@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 L, A, G = model.layers, ex.act, ex.g
 want = sys.argv[1:] or ['conv1_2', 'conv2_2', 'conv3_2', 'conv9_2']
 prof = torch.zeros(4 * 16 * 4, dtype=torch.int64, device='cuda')
-src_of = {'conv1_2': 'conv1_1', 'conv2_2': 'conv2_1', 'conv3_2': 'conv3_1', 'conv9_2': 'conv9_1',
+src_of = {'conv1_1': 'x16', 'conv1_2': 'conv1_1', 'conv2_2': 'conv2_1', 'conv3_2': 'conv3_1', 'conv9_2': 'conv9_1',
           'conv2_1': 'pool1', 'conv3_1': 'pool2', 'conv4_2': 'conv4_1', 'conv5_2': 'conv5_1'}
 out = {}
 for name in want:
@@ -51,14 +51,14 @@ for name in want:
         t0 = int(p[p > 0].min()) if (p > 0).any() else 0
         rel = (p - t0).clamp(min=0)
         print('=== %s %s: %.1f us/launch' % (name, kind, us))
-        for role, rn in enumerate(('producer[start,a_empty_ok,done]', 'mma[start,tempty_ok,a_full_ok,issued]', 'epilogue[start,tfull_ok,stored,arrived]')):
+        for role, rn in enumerate(('producer[start,a_empty_ok,done]', 'mma[start,tempty_ok,a_full_ok,issued]', 'epilogue[start,tfull_ok,tmem_read,stored]')):
             print(' ', rn)
             for t in range(8):
                 print('    tile %d:' % t, [int(v) for v in rel[role, t]])
-        for ti in (0, 1):
-            tt = taps[ti][taps[ti] > 0]
-            if len(tt):
-                print('  tap issue stamps tile %d (rel. to first, diffs):' % (ti + 2), [int(v) for v in (tt - t0)], [int(v) for v in (tt[1:] - tt[:-1])])
+        ee = pall[3 * 64:3 * 64 + 16]
+        if (ee > 0).any():
+            print('  epilogue tile 2, per TMEM load [buffer_free, ld_done, processed, stored]:',
+                  [[int(v - t0) for v in ee[i * 4:i * 4 + 4]] for i in range(4) if ee[i * 4] > 0])
         out['%s_%s' % (name, kind)] = {'us': us, 'prof': rel.tolist()}
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(out, open('gpurun_out/layer_prof.json', 'w'))

@@ -7,8 +7,9 @@ import torch
 from segmentation_b200 import native as N
 res = []
 ITERS = 40
-FLAGS = {'data': 1, 'tma': 2, 'tld': 4, 'stg': 8, 'ldg': 16, 'roll1': 32, 'roll4': 64}
+FLAGS = {'data': 1, 'tma': 2, 'tld': 4, 'stg': 8, 'ldg': 16, 'roll1': 32, 'roll4': 64, 'drain': 128}
 def run(kc, bn, b_mn, wp, shifted, a_mn=0, ctas=1, stress=()):
+    global ITERS
     out = torch.zeros(2 * ctas + 8192 * ctas + 64, dtype=torch.int64, device='cuda')
     fl = sum(FLAGS[s] for s in stress)
     for _ in range(2):
@@ -16,7 +17,8 @@ def run(kc, bn, b_mn, wp, shifted, a_mn=0, ctas=1, stress=()):
     torch.cuda.synchronize()
     o = out[:2 * ctas].cpu().view(ctas, 2).double()
     n_mma = ITERS * 9 * (kc // 16)
-    r = {'kc': kc, 'bn': bn, 'b_mn': b_mn, 'wp': wp, 'shifted': shifted, 'a_mn': a_mn, 'ctas': ctas, 'stress': '+'.join(stress),
+    drain = out[2 * ctas + 64 + 2:2 * ctas + 64 + 6].cpu().tolist()
+    r = {'drain_cyc_per_4KB_load': [d / 512.0 for d in drain] if 'drain' in stress else None, 'kc': kc, 'bn': bn, 'b_mn': b_mn, 'wp': wp, 'shifted': shifted, 'a_mn': a_mn, 'ctas': ctas, 'stress': '+'.join(stress),
          'issue_cyc_per_mma': float(o[:, 0].mean()) / n_mma, 'retire_cyc_per_mma': float(o[:, 1].mean()) / n_mma,
          'retire_max': float(o[:, 1].max()) / n_mma}
     res.append(r)
@@ -33,10 +35,18 @@ if 'stress' in sys.argv:
         run(kc, bn, 1, 125, 1, ctas=ctas)
         for st in (('data',), ('tma',), ('tld',), ('stg',), ('ldg',), ('data', 'tma', 'tld', 'stg', 'ldg')):
             run(kc, bn, 1, 125, 1, ctas=ctas, stress=st)
-for kc, bn in ((64, 64), (32, 32), (64, 128), (64, 256), (16, 32)):
+if 'roll' in sys.argv:
+  for kc, bn in ((64, 64), (32, 32), (64, 128), (64, 256), (16, 32)):
     run(kc, bn, 1, 125, 1)
     run(kc, bn, 1, 125, 1, stress=('roll1',))
     run(kc, bn, 1, 125, 1, stress=('roll4',))
     run(kc, bn, 1, 125, 1, stress=('roll4', 'tld', 'stg', 'ldg', 'tma'))
+# TMEM drain rate with the tensor pipe idle (ITERS tiny) and busy
+for kc, bn in ((64, 64), (32, 32), (64, 128), (64, 256)):
+    ITERS = 1
+    run(kc, bn, 1, 125, 1, stress=('drain',))
+    ITERS = 400
+    run(kc, bn, 1, 125, 1, stress=('drain',))
+    ITERS = 40
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(res, open('gpurun_out/probe_rate2.json', 'w'))

@@ -71,49 +71,91 @@ class SyntheticDataSet(object):
 
 
 class ClockSampler(object):
+    """SM clock + throttle reasons sampled DURING the timed regions by an in-process NVML
+    thread (a polling `nvidia-smi -lms` child was measured to stall the host-synchronous
+    e2e loop for milliseconds at a time); falls back to nvidia-smi if NVML is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period=0.02):
+        import threading
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.p = self.f = self.thread = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(('GPU-' + uuid).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown),
+                     ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for n, bit in names:
+                            if r & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    self._stop.wait(period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+            try:
+                self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                           '--format=csv,noheader,nounits', '-lms', '250'],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
-            if len(r) < 9:
-                continue
+        out = {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': [], 'samples': 0}
+        sm, reasons = self.sm, self.reasons
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            out['source'] = 'nvml thread'
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(r[1]))
-                out['sm_max_mhz'] = float(r[2])
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                                'sw_power_cap'), r[5:9]):
-                if v.strip().lower().startswith('active'):
-                    reasons.add(name)
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+            os.unlink(self.f.name)
+            for r in rows:
+                if len(r) < 9:
+                    continue
+                try:
+                    sm.append(float(r[1]))
+                    out['sm_max_mhz'] = float(r[2])
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                    'sw_power_cap'), r[5:9]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(name)
+            out['source'] = 'nvidia-smi -lms 250'
         if sm:
-            sm.sort()
+            s2 = sorted(sm)
+            out['samples'] = len(s2)
             # median of the upper half = clocks under load (idle samples sit at the bottom)
-            upper = sm[len(sm) // 2:]
+            upper = s2[len(s2) // 2:]
             out['sm_mhz'] = upper[len(upper) // 2]
         out['reasons'] = sorted(reasons)
         return out
@@ -223,14 +265,16 @@ def run_ours(args):
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- e2e: pinned host batches, H2D inside, loss read back every step
+    # ---- e2e: the reference's own call, train_step() with no arguments: the model pulls
+    # pinned host batches from the dataset; every step issues one batch's H2D copy (the
+    # next step's, on a copy stream behind this step's kernels) and reads the loss back
     for i in range(2):
-        model.train_step(ds.next_batch())
+        model.train_step()
     barrier()
     e0.record()
     loss = 0.0
     for i in range(K):
-        model.train_step(ds.next_batch())
+        model.train_step()
         loss = model.seg_loss_op                 # D2H read of the step's loss
     e1.record()
     barrier()
@@ -243,6 +287,7 @@ def run_ours(args):
         ex.use_graph = False
         saved = ex.graph
         ex.graph = None
+        saved_side, ex.use_side = ex.use_side, False    # one stream: clean per-launch times
         # single-rank pass: no collectives may be issued here (the other ranks are not
         # participating), so the data-parallel bucket hooks are detached
         saved_hooks = (model._bucket_done, model._grad_hook)
@@ -264,6 +309,7 @@ def run_ours(args):
             with open(os.path.join(out_dir, 'timeline.json'), 'w') as f:
                 json.dump(tl, f)
         ex.graph, ex.use_graph = saved, True
+        ex.use_side = saved_side
         roof = dominant_kernel(tl, model, ex)
 
     if world > 1:

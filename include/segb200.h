@@ -87,7 +87,10 @@ SEG_API const char* seg_last_error_string(void);
  * key 3: use the spatial-tile tcgen05 conv kernel for 3x3 stride-1 fwd / dgrad (default 1).
  * key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles below which that kernel
  * declines a shape (default 70).  key 5 / key 6: the same two switches for the spatial-tile
- * weight-gradient kernel (defaults 1 and 40). */
+ * weight-gradient kernel (defaults 1 and 40).  key 7: launch the hot-path kernels with
+ * programmatic stream serialization (PDL) so that a kernel's prologue overlaps its
+ * predecessor's tail (default 1); every such kernel executes griddepcontrol.wait before
+ * its first global-memory access. */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */

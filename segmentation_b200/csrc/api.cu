@@ -52,6 +52,8 @@ static bool desc_ok(const seg_conv_desc* d) {
          d->cout_pad % 8 == 0;
 }
 
+int g_pdl = 1;              // seg_set_option key 7
+
 }  // namespace segb
 
 using namespace segb;
@@ -75,6 +77,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 4: tconv_set_min_eff(value); return SEG_OK;
     case 5: twgrad_enable(value); return SEG_OK;
     case 6: twgrad_set_min_eff(value); return SEG_OK;
+    case 7: g_pdl = value != 0; return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/segb200.h"
 
@@ -33,6 +34,28 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 #define SEG_LAUNCH_CHECK() SEG_CHECK_CUDA(cudaGetLastError())
+
+// Launch with the programmatic-stream-serialization attribute (PDL) when enabled
+// (seg_set_option key 7): the kernel may start while its predecessor in the stream is
+// still running; every kernel launched through here calls pdl_wait() before it touches
+// global memory.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                   cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int num_sms() {

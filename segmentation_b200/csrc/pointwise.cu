@@ -20,6 +20,8 @@ static int grid_for(int64_t total, int block) {
 // ---------------------------------------------------------------- max-pool
 template <int VEC>
 __global__ void maxpool_fwd_kernel(seg_view x, int k, int s, seg_view y, uint8_t* argmax) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = y.c / VEC;
   const int64_t total = (int64_t)y.n * y.h * y.w * cv;
   GRID_STRIDE(idx, total) {
@@ -78,6 +80,8 @@ template <int VEC>
 __global__ void maxpool_bwd_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k, int s,
                                    seg_view add, int add_y0, int add_x0, seg_view mask,
                                    seg_view dx) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = dx.c / VEC;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * cv;
   GRID_STRIDE(idx, total) {
@@ -441,6 +445,8 @@ __global__ void dropout_kernel(const bf16* x, bf16* y, int64_t numel, uint32_t s
 // one thread per pixel, C <= 64 channels held in registers chunk-wise
 __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* loss_sum,
                                     seg_view dlogits, float inv_pixels) {
+  pdl_trigger();
+  pdl_wait();
   const int C = logits.c;
   const int64_t pixels = (int64_t)logits.n * logits.h * logits.w;
   float local = 0.f;
@@ -544,6 +550,8 @@ adam_multi_kernel(float* __restrict__ param, float* __restrict__ grad, float* __
                   const int32_t* __restrict__ seg, const int64_t* __restrict__ shadow_off,
                   const int32_t* __restrict__ chunks, float lr_t, const float* lr_t_dev, float b1,
                   float b2, float eps, float gscale) {
+  pdl_trigger();
+  pdl_wait();
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);
   const int sidx = __ldg(chunks + 2 * blockIdx.x);
   const int begin = __ldg(chunks + 2 * blockIdx.x + 1);
@@ -637,6 +645,8 @@ __global__ void pack_input_kernel(const float* x, int C, seg_view y) {
 // dense RGB(A) fp32 -> 16-channel bf16: one thread per pixel, two 16-byte stores
 __global__ void pack_input16_kernel(const float* __restrict__ x, int C, bf16* __restrict__ y,
                                     int64_t pixels) {
+  pdl_trigger();
+  pdl_wait();
   GRID_STRIDE(m, pixels) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < C; ++c) v[c] = __ldg(x + m * C + c);
@@ -654,6 +664,8 @@ __global__ void pack_input16_kernel(const float* __restrict__ x, int C, bf16* __
 // per-channel sums with 16-byte loads: thread = (pixel lane, 8-channel group)
 template <int MODE>   // 0: sum + sumsq   2: sum only
 __global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];
   const int C = a.c;
   const int groups = C / 8;
@@ -722,7 +734,7 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
   const bool v8 = vec8_ok(*x) && vec8_ok(*y) && (reinterpret_cast<uintptr_t>(argmax) % 8) == 0;
   const int64_t total = (int64_t)y->n * y->h * y->w * (v8 ? y->c / 8 : y->c);
   if (v8)
-    maxpool_fwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*x, k, s, *y, argmax);
+    SEG_CHECK_CUDA(launch_k(maxpool_fwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *x, k, s, *y, argmax));
   else
     maxpool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*x, k, s, *y, argmax);
   SEG_LAUNCH_CHECK();
@@ -740,8 +752,7 @@ SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32
   const bool v8 = vec8_ok(*dx) && (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
-    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
-                                                               add_y0, add_x0, mk, *dx);
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, s, a, add_y0, add_x0, mk, *dx));
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
                                                                add_y0, add_x0, mk, *dx);
@@ -759,8 +770,7 @@ SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const 
   const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && vec8_ok(*dy2) && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
-    maxpool_bwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,
-                                                               null_view(), 0, 0, mk, *dx);
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, s, null_view(), 0, 0, mk, *dx));
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,
                                                                null_view(), 0, 0, mk, *dx);
@@ -827,9 +837,9 @@ static int launch_channel_reduce(const seg_view& a, const seg_view& b, const flo
     if (gv < 1) gv = 1;
     const size_t shb = (size_t)2 * block * 8 * sizeof(float);
     if (mode == 0)
-      channel_sum_vec8_kernel<0><<<(int)gv, block, shb, st>>>(a, o0, o1);
+      SEG_CHECK_CUDA(launch_k(channel_sum_vec8_kernel<0>, dim3((int)gv), dim3(block), (size_t)(shb), st, a, o0, o1));
     else
-      channel_sum_vec8_kernel<2><<<(int)gv, block, shb, st>>>(a, o0, o1);
+      SEG_CHECK_CUDA(launch_k(channel_sum_vec8_kernel<2>, dim3((int)gv), dim3(block), (size_t)(shb), st, a, o0, o1));
     SEG_LAUNCH_CHECK();
     return SEG_OK;
   }
@@ -923,8 +933,7 @@ SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view*
   SEG_REQUIRE(labels->h == logits->h && labels->w == logits->w && labels->n == logits->n,
               SEG_E_BAD_SHAPE, "softmax_xent: labels must match logits spatially");
   const int64_t pixels = (int64_t)logits->n * logits->h * logits->w;
-  softmax_xent_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(
-      *logits, *labels, loss_sum, dlogits ? *dlogits : null_view(), 1.f / (float)pixels);
+  SEG_CHECK_CUDA(launch_k(softmax_xent_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *logits, *labels, loss_sum, dlogits ? *dlogits : null_view(), 1.f / (float)pixels));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -956,9 +965,7 @@ SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, vo
                        float grad_scale, void* stream) {
   SEG_REQUIRE(param && grad && m && v && segments && shadow_offsets && chunks && nchunks > 0,
               SEG_E_BAD_SHAPE, "adam_multi: null argument");
-  adam_multi_kernel<<<(unsigned)nchunks, kAdamThreads, 0, (cudaStream_t)stream>>>(
-      param, grad, m, v, reinterpret_cast<bf16*>(shadow_bf16), segments, shadow_offsets, chunks,
-      lr_t, lr_t_dev, beta1, beta2, eps, grad_scale);
+  SEG_CHECK_CUDA(launch_k(adam_multi_kernel, dim3((unsigned)nchunks), dim3(kAdamThreads), (size_t)(0), (cudaStream_t)stream, param, grad, m, v, reinterpret_cast<bf16*>(shadow_bf16), segments, shadow_offsets, chunks, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -968,8 +975,7 @@ SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, voi
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
   if (y->c == 16 && c <= 4 && view_dense(*y) && (reinterpret_cast<uintptr_t>(y->ptr) % 16) == 0) {
     const int64_t pixels = (int64_t)y->n * y->h * y->w;
-    pack_input16_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, c, reinterpret_cast<bf16*>(y->ptr), pixels);
+    SEG_CHECK_CUDA(launch_k(pack_input16_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, c, reinterpret_cast<bf16*>(y->ptr), pixels));
   } else {
     pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, *y);
   }

@@ -14,6 +14,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch.  pdl_trigger(): the next kernel in the stream may be
+// scheduled now (its prologue overlaps this kernel's body).  pdl_wait(): block until the
+// preceding kernel has completed and its writes are visible; everything that touches
+// global memory comes after it.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -71,6 +71,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   static_assert(2 * kAccCols <= 512, "accumulator stages exceed TMEM");
   static_assert(BN % 32 == 0, "BN must be a multiple of 32");
 
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -106,6 +107,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_wait();                 // everything above overlaps the previous kernel's tail
   // bias vector -> smem (zero beyond the valid columns)
   for (int i = threadIdx.x; i < P.n_total; i += blockDim.x)
     s_bias[i] = ((P.flags & SEG_EPI_BIAS) && i < P.bias_cols) ? __ldg(P.bias + i) : 0.f;

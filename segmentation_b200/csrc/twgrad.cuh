@@ -57,6 +57,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
                             : kCols <= 256 ? 256 : 512;
   static_assert(kCols <= 512, "accumulators exceed TMEM");
 
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -92,6 +93,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlaps the previous kernel's tail
 
   if (my_tiles > 0) {
     if (warp == 0) {

@@ -245,7 +245,7 @@ static int launch_igemm_t(const IgemmJob& J, cudaStream_t st) {
   const int m_tiles = (P.M_total + kBlockM - 1) / kBlockM;
   const int tiles = m_tiles * (J.N_total / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  igemm_kernel<KC, BN, B_MN><<<grid, kIgemmThreads, Cfg::kSmemBytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_CHECK_CUDA(launch_k(igemm_kernel<KC, BN, B_MN>, dim3(grid), dim3(kIgemmThreads), (size_t)(Cfg::kSmemBytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -351,7 +351,7 @@ static int launch_wgrad_t(const WgradJob& J, cudaStream_t st) {
   P.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
   dim3 grid(base_ctas, splits);
-  wgrad_kernel<AW, BN><<<grid, kIgemmThreads, Cfg::kSmemBytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_CHECK_CUDA(launch_k(wgrad_kernel<AW, BN>, dim3(grid), dim3(kIgemmThreads), (size_t)(Cfg::kSmemBytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -460,7 +460,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
     grid -= grid % n_tiles;           // every CTA must keep one N-slice for its lifetime
     if (grid < n_tiles) P.b_resident = 0, grid = tiles < num_sms() ? tiles : num_sms();
   }
-  hconv_kernel<KC, BN, B_MN><<<grid, kIgemmThreads, smem_bytes, st>>>(tmA1, tmA2, tmB, P);
+  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN>, dim3(grid), dim3(kIgemmThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -673,8 +673,7 @@ static int launch_tconv_t(const TconvJob& J, const TconvPlan& L, cudaStream_t st
   const int tiles = P.batch * P.tiles_y * P.tiles_x * P.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (P.b_resident && P.n_tiles > 1) grid -= grid % P.n_tiles;   // fixed N-slice per CTA
-  tconv_kernel<KC, BN, B_MN, MT><<<grid, kTconvThreads, L.smem, st>>>(tmA1, tmA2, tmB, tmD0, tmD1,
-                                                                     tmM0, tmM1, P);
+  SEG_CHECK_CUDA(launch_k(tconv_kernel<KC, BN, B_MN, MT>, dim3(grid), dim3(kTconvThreads), (size_t)(L.smem), st, tmA1, tmA2, tmB, tmD0, tmD1, tmM0, tmM1, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -869,7 +868,7 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   P.stages = stages;
   P.off_bars = stages * P.stage_bytes;
   const int smem = P.off_bars + 1024 + 1024;
-  twgrad_kernel<AW, BN><<<combos * per, kIgemmThreads, smem, st>>>(tmX1, tmX2, tmZ, P);
+  SEG_CHECK_CUDA(launch_k(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kIgemmThreads), (size_t)(smem), st, tmX1, tmX2, tmZ, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

@@ -76,6 +76,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tmB, const IgemmParams P) {
   using Cfg = IgemmCfg<KC, BN>;
   constexpr int S = Cfg::kStages;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -114,6 +115,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlaps the previous kernel's tail
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -349,6 +351,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tmB, const WgradUmmaParams P) {
   using Cfg = WgradCfg<AW, BN>;
   constexpr int S = Cfg::kStages;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -398,6 +401,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlaps the previous kernel's tail
 
   if (num_kb > 0) {
     if (warp == 0) {

@@ -246,22 +246,44 @@ class ConvLayer(object):
 
     # ---- backward ----------------------------------------------------------
     def backward(self, x, dz, dx=None, x2=None, dx2=None, mask=None, mask2=None,
-                 impl=N.IMPL_UMMA, y_hw=None, dz_bias=None):
+                 impl=N.IMPL_UMMA, y_hw=None, dz_bias=None, side=None, after=None):
         """Accumulates dW, db into the grad buffer; writes dx (/dx2) if given.
         `dz` is the gradient w.r.t. this layer's pre-activation output (channels
         padded to cout_pad).  `mask`/`mask2` = forward tensors whose ReluGrad is
         applied to dx/dx2.  `dz_bias`: view of dz restricted to the real cout
-        channels when cout_pad != cout."""
-        st = N.stream_ptr()
+        channels when cout_pad != cout.
+        `side`: a SideStream — the weight/bias gradient kernels are enqueued there (they
+        only feed the optimizer, so they run beside the input-gradient chain); `after()` is
+        called once they are enqueued (in the side stream's context)."""
         N.set_tag(self.name)
+        if side is not None:
+            with side.fork():
+                self._wgrad(x, dz, x2, impl, dz_bias)
+                if after is not None:
+                    after()
+        else:
+            self._wgrad(x, dz, x2, impl, dz_bias)
+            if after is not None:
+                after()
+        if dx is None:
+            return
+        st = N.stream_ptr()
         if self.kind == 'conv':
-            # BiasAddGrad is fused into the wgrad GEMM (all-ones A-atom)
+            d = self.desc(x.shape[1], x.shape[2], 0, impl)
+            N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
+                   N.vref(dx), N.vref(dx2), N.vref(mask), N.vref(mask2), st)
+        else:
+            d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
+            N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz),
+                   N.ptr(self.w.shadow()), N.vref(dx), N.vref(mask), st)
+
+    def _wgrad(self, x, dz, x2, impl, dz_bias):
+        st = N.stream_ptr()
+        if self.kind == 'conv':
+            # BiasAddGrad is fused into the wgrad GEMM
             d = self.desc(x.shape[1], x.shape[2], 0, impl)
             N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(x2), N.vref(dz),
                    N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
-            if dx is not None:
-                N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
-                       N.vref(dx), N.vref(dx2), N.vref(mask), N.vref(mask2), st)
         else:
             dzb = dz_bias if dz_bias is not None else (dz if dz.shape[3] == self.cout
                                                        else dz[..., :self.cout])
@@ -269,9 +291,32 @@ class ConvLayer(object):
             d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
             N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(dz),
                    N.ptr(self.w.grad()), st)
-            if dx is not None:
-                N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz),
-                       N.ptr(self.w.shadow()), N.vref(dx), N.vref(mask), st)
+
+
+class SideStream(object):
+    """A second stream for work that is off the critical path of a schedule (the weight
+    gradients of the backward pass).  fork(): the side stream first waits for everything
+    enqueued so far on the current stream; join(): the current stream waits for the side
+    stream.  Works inside CUDA-graph capture (fork/join become graph edges)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.used = False
+
+    def fork(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(ev)
+        self.used = True
+        return torch.cuda.stream(self.stream)
+
+    def join(self):
+        if not self.used:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        torch.cuda.current_stream().wait_event(ev)
+        self.used = False
 
 
 # ---------------------------------------------------------------------------

@@ -193,7 +193,14 @@ class BaseModel(object):
         if self.mode == 'INFERENCE':
             raise Exception('train_step() with INFERENCE mode invalid')
         if batch is None:
-            batch = self.dataset.next_batch()
+            # the reference's call: the batch comes from the dataset.  The NEXT batch's
+            # host->device copy is issued on a copy stream right behind this step's
+            # launch, so it overlaps the step's kernels (the reference's queue runners
+            # prefetch the same way, utils/datasets.py:94-196).
+            ex = self._get_exec(self.dataset.batch_size, True)
+            ex.train_step_from(self.dataset)
+            self.global_step += 1
+            return
         imgs, masks = batch
         # host (pinned or pageable) or device tensors: staged straight into the
         # executor's static input buffers (H2D on the compute stream)
@@ -248,8 +255,18 @@ class ExecBase(object):
         dev = model.device
         self.m, self.B, self.training = model, B, training
         self.H, self.W, self.oh, self.ow = H, W, oh, ow
+        # x_f32 / mask_in are the host->device landing buffers; the packed bf16 input
+        # (act['x']) and `mask` are what the kernels of a step read, so the next batch
+        # may land while a step is running
         self.x_f32 = torch.zeros(B, H, W, model.input_channel, dtype=torch.float32, device=dev)
+        self.mask_in = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
         self.mask = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_staged = torch.cuda.Event()
+        self.ev_consumed = torch.cuda.Event()
+        self._pf = None                # host batch whose copy into the landing buffers is in flight
+        self._pf_host = None           # host batch fetched from the dataset but not staged
+        self._prepacked = False
         self.logits = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
         self.probs = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
         self.labelmap = torch.zeros(B, oh, ow, 1, dtype=torch.float32, device=dev)
@@ -291,9 +308,67 @@ class ExecBase(object):
             self.m._grad_hook()
         self.m.store.adam_launch(0.0, grad_scale=1.0 / self.m.world_size, from_device=True)
 
+    def pack(self):
+        """fp32 [B,H,W,C] landing buffer -> bf16 input tensor with C padded to 16."""
+        if not self._prepacked:
+            E.pack_input(self.x_f32, self.act['x'])
+
+    def _stage_async(self, x, mask):
+        """Copy a batch into the landing buffers: host tensors go over the copy stream
+        (pinned memory makes this asynchronous), device tensors over the compute stream."""
+        cur = torch.cuda.current_stream()
+        if x.is_cuda:
+            cur.wait_event(self.ev_staged)           # a prefetch still landing there
+            self.x_f32.copy_(x, non_blocking=True)
+            self.mask_in.copy_(mask, non_blocking=True)
+            self.ev_staged.record(cur)
+            return
+        cs = self.copy_stream
+        cs.wait_event(self.ev_consumed)              # previous batch packed
+        with torch.cuda.stream(cs):
+            self.x_f32.copy_(x, non_blocking=True)
+            self.mask_in.copy_(mask, non_blocking=True)
+            self.ev_staged.record(cs)
+
+    def _prefetch(self, dataset):
+        batch = self._pf_host if self._pf_host is not None else dataset.next_batch()
+        self._pf_host = None
+        imgs, masks = batch
+        x = torch.from_numpy(imgs) if isinstance(imgs, np.ndarray) else imgs
+        y = torch.from_numpy(masks) if isinstance(masks, np.ndarray) else masks
+        self._stage_async(x, y)
+        self._pf = batch
+
+    def train_step_from(self, dataset):
+        """One step on the dataset's next batch; the following batch's H2D copy is
+        issued behind this step's kernels."""
+        if self._pf is None:
+            self._prefetch(dataset)
+        self._pf = None
+        self._launch_step()
+        self._prefetch(dataset)
+
     def train_step(self, x, mask):
+        if self._pf is not None:                     # keep the prefetched batch for later
+            self._pf_host, self._pf = self._pf, None
+        self._stage_async(x, mask)
+        self._launch_step()
+
+    def _launch_step(self):
         m = self.m
-        self.stage(x, mask)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ev_staged)
+        E.pack_input(self.x_f32, self.act['x'])
+        self.mask.copy_(self.mask_in, non_blocking=True)
+        self.ev_consumed.record(cur)
+        self._prepacked = True
+        try:
+            self._run_step()
+        finally:
+            self._prepacked = False
+
+    def _run_step(self):
+        m = self.m
         lr_t = m.store.next_lr_t(m.learning_rate)
         m.store.lr_t_dev.fill_(lr_t)
         if self.use_graph and self.graph is None and self.calls >= 1:

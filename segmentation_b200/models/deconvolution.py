@@ -172,7 +172,7 @@ class _DeconvExec(ExecBase):
             if dropout is not None and name in self.SITES:
                 self._drop(A[name], self.SITES[name])
 
-        E.pack_input(self.x_f32, A['x'])
+        self.pack()
         L['conv1_0'].forward(A['x'], A['conv1_0'], impl=impl); bn('bn1', 'conv1_0')
         E.maxpool_fwd(A['bn1'], A['pool1'], self.amax['pool1'], 2, 2)
         L['conv2_0'].forward(A['pool1'], A['conv2_0'], impl=impl); bn('bn2', 'conv2_0')

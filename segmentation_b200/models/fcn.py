@@ -137,7 +137,7 @@ class _FCNExec(ExecBase):
 
     def forward(self):
         m, L, A, impl, v = self.m, self.m.layers, self.act, self.m.impl, self.v
-        E.pack_input(self.x_f32, A['x'])
+        self.pack()
         src = A['x']
         for i in range(1, 6):
             L['conv%d' % i].forward(src, A['conv%d' % i], impl=impl)

@@ -12,6 +12,8 @@ Crops and concats cost no kernel: the consumer conv reads two TMA descriptors
 gradient of conv1_2's output is zero outside the 72x72 skip crop, so conv1_2's
 backward runs on that crop only (exact, not an approximation).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -164,6 +166,8 @@ class _UNetExec(ExecBase):
         self._init_io(model, B, H, W, oh, ow, model.n_classes, L['output'].cout_pad, training)
         if training:
             self._alloc_grads()
+        self.side = E.SideStream(dev)
+        self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
 
     # ------------------------------------------------------------- buffers
     def skip_view(self, j):
@@ -193,7 +197,7 @@ class _UNetExec(ExecBase):
     # ------------------------------------------------------------- forward
     def forward(self, dropout=None):
         m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl
-        E.pack_input(self.x_f32, A['x'])
+        self.pack()
 
         def conv(name, src, x2=None):
             L[name].forward(src, A[name], x2=x2, impl=impl)
@@ -226,32 +230,30 @@ class _UNetExec(ExecBase):
         L, A, G, impl = self.m.layers, self.act, self.g, self.m.impl
         nc = self.m.n_classes
         hook = self.m._bucket_done
+        side = self.side if self.use_side else None
 
-        def done(name):            # data-parallel: a gradient bucket may be complete
-            if hook is not None:
-                hook(name)
+        def bw(name, *args, **kw):
+            # weight gradients go to the side stream; data-parallel: a gradient bucket
+            # may be complete once this layer's are enqueued
+            L[name].backward(*args, impl=impl, side=side,
+                             after=(lambda: hook(name)) if hook is not None else None, **kw)
+
         # head (no activation): dz = dlogits
-        L['output'].backward(A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],
-                             impl=impl, dz_bias=G['logits'][..., :nc])
-        done('output')
+        bw('output', A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],
+           dz_bias=G['logits'][..., :nc])
         for j in range(4, 0, -1):
             c1, c2, up = 'conv%d_1' % (5 + j), 'conv%d_2' % (5 + j), 'upconv%d' % j
             below = 'conv%d_2' % (4 + j) if j > 1 else 'conv5_2'
-            L[c2].backward(A[c1], G[c2], dx=G[c1], mask=A[c1], impl=impl)
-            done(c2)
+            bw(c2, A[c1], G[c2], dx=G[c1], mask=A[c1])
             # conv over the virtual concat [skip_crop | upconv]: two dgrad destinations.
             # The skip gradient is ReLU-masked later by the pool backward that merges
             # it (j<4); for j==4 conv1_2 has no other consumer, so mask it here.
             sk = self.skip_view(j)
-            L[c1].backward(sk, G[c1], dx=G['skip%d' % j], x2=A[up], dx2=G[up],
-                           mask=sk if j == 4 else None, mask2=A[up], impl=impl)
-            done(c1)
-            L[up].backward(A[below], G[up], dx=G[below], mask=A[below], impl=impl)
-            done(up)
+            bw(c1, sk, G[c1], dx=G['skip%d' % j], x2=A[up], dx2=G[up],
+               mask=sk if j == 4 else None, mask2=A[up])
+            bw(up, A[below], G[up], dx=G[below], mask=A[below])
         # encoder
-        L['conv5_2'].backward(A['conv5_1'], G['conv5_2'], dx=G['conv5_1'], mask=A['conv5_1'],
-                              impl=impl)
-        done('conv5_2')
+        bw('conv5_2', A['conv5_1'], G['conv5_2'], dx=G['conv5_1'], mask=A['conv5_1'])
         for i in range(5, 1, -1):
             c1, c2, pool = 'conv%d_1' % i, 'conv%d_2' % i, 'pool%d' % (i - 1)
             if i < 5:
@@ -260,16 +262,14 @@ class _UNetExec(ExecBase):
                 y0, x0, _, _ = self.crop[j]
                 E.maxpool_bwd(G['pool%d' % i], self.amax['pool%d' % i], G[c2],
                               add=G['skip%d' % j], add_y0=y0, add_x0=x0, mask=A[c2])
-                L[c2].backward(A[c1], G[c2], dx=G[c1], mask=A[c1], impl=impl)
-                done(c2)
-            L[c1].backward(A[pool], G[c1], dx=G[pool], impl=impl)
-            done(c1)
+                bw(c2, A[c1], G[c2], dx=G[c1], mask=A[c1])
+            bw(c1, A[pool], G[c1], dx=G[pool])
         # conv1_2: output gradient lives only on the skip crop -> run on the crop
         y0, x0, h, w = self.crop[4]
         x_win = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
-        L['conv1_2'].backward(x_win, G['skip4'], dx=G['conv1_1_part'], impl=impl)
-        done('conv1_2')
+        bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
         E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['conv1_1'], add=G['conv1_1_part'],
                       add_y0=y0, add_x0=x0, mask=A['conv1_1'])
-        L['conv1_1'].backward(A['x'], G['conv1_1'], dx=None, impl=impl)
-        done('conv1_1')
+        bw('conv1_1', A['x'], G['conv1_1'], dx=None)
+        if side is not None:
+            side.join()

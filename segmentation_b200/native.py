@@ -97,6 +97,8 @@ def load():
     lib.seg_last_error_string.argtypes = []
     lib.seg_last_error_string.restype = ctypes.c_char_p
     _lib = lib
+    if os.environ.get('SEGB200_PDL', '1') == '0':
+        lib.seg_set_option(OPT_PDL, 0)
     return lib
 
 
@@ -118,6 +120,7 @@ def set_tag(tag):
 
 OPT_HALO_CONV, OPT_HALO_ROW_ALIGN, OPT_TILE_CONV, OPT_TILE_CONV_MIN_EFF = 1, 2, 3, 4
 OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
+OPT_PDL = 7           # programmatic dependent launch of the hot-path kernels (default on)
 
 
 def set_option(key, value):

@@ -288,10 +288,8 @@ def run_ours(args):
         saved = ex.graph
         ex.graph = None
         saved_side, ex.use_side = ex.use_side, False    # one stream: clean per-launch times
-        # single-rank pass: no collectives may be issued here (the other ranks are not
-        # participating), so the data-parallel bucket hooks are detached
-        saved_hooks = (model._bucket_done, model._grad_hook)
-        model._bucket_done, model._grad_hook = None, None
+        # single-rank pass: forward/loss/backward called directly issue neither collectives
+        # nor optimizer launches (those belong to the train step)
         N.TIMELINE = []
         ex.stage(*dev_batches[0])
         for _ in range(3):                       # fwd + loss + bwd only: parameters untouched
@@ -303,10 +301,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
         N.TIMELINE = None
-        model._bucket_done, model._grad_hook = saved_hooks
         out_dir = os.path.join(ROOT, 'gpurun_out')
         if os.path.isdir(out_dir):
-            with open(os.path.join(out_dir, 'timeline.json'), 'w') as f:
+            with open(os.path.join(out_dir, 'timeline%s.json' % os.environ.get('SEGB200_TAG', '')), 'w') as f:
                 json.dump(tl, f)
         ex.graph, ex.use_graph = saved, True
         ex.use_side = saved_side

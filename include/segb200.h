@@ -90,7 +90,11 @@ SEG_API const char* seg_last_error_string(void);
  * weight-gradient kernel (defaults 1 and 40).  key 7: launch the hot-path kernels with
  * programmatic stream serialization (PDL) so that a kernel's prologue overlaps its
  * predecessor's tail (default 1); every such kernel executes griddepcontrol.wait before
- * its first global-memory access. */
+ * its first global-memory access.  key 8: thread-block-cluster size (1, 2, 4 or 8;
+ * default 1 = off) over which the spatial-tile weight-gradient kernel sums its per-CTA partial
+ * results through distributed shared memory before the global fp32 reductions.  key 9: minimum
+ * number of 8x16 pixel tiles per CTA of that kernel (default 8): smaller layers use fewer
+ * CTAs (fewer partial sums to reduce, SMs left to the concurrent input-gradient stream). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */
@@ -240,6 +244,13 @@ SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, co
  * out[2*cta] = cycles to issue, out[2*cta+1] = cycles to retire (tools/probe_rate.py) */
 SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,
                            int32_t iters, int32_t a_mn, int32_t ctas, int64_t* out, void* stream);
+
+/* fp32 global-reduction rate: `ctas` CTAs each add `elems` floats from shared memory into
+ * dst + (cta % regions) * elems with red.global.v4 (mode 0 coalesced, 1 row-per-thread) or
+ * cp.reduce.async.bulk (mode 2: 256-byte rows, 3: op_bytes per operation); out[2*cta] /
+ * out[2*cta+1] = cycles to issue / to complete (tools/probe_red.py) */
+SEG_API int32_t seg_probe_red_rate(int32_t mode, int32_t ctas, int32_t elems, int32_t regions,
+                           int32_t op_bytes, float* dst, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,8 @@ int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, floa
 int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, int split,
                      float* d, cudaStream_t st);
 
+int probe_red_rate(int mode, int ctas, int elems, int regions, int op_bytes, float* dst,
+                   long long* out, cudaStream_t st);
 int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn, int ctas,
                     long long* out, cudaStream_t st);
 
@@ -45,6 +47,8 @@ void tconv_enable(int on);
 void tconv_set_min_eff(int pct);
 void twgrad_enable(int on);
 void twgrad_set_min_eff(int pct);
+void twgrad_set_cluster(int n);
+void twgrad_set_min_tiles(int n);
 
 static bool desc_ok(const seg_conv_desc* d) {
   return d && d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->cin >= 1 && d->cout >= 1 &&
@@ -78,6 +82,8 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 5: twgrad_enable(value); return SEG_OK;
     case 6: twgrad_set_min_eff(value); return SEG_OK;
     case 7: g_pdl = value != 0; return SEG_OK;
+    case 8: twgrad_set_cluster(value); return SEG_OK;
+    case 9: twgrad_set_min_tiles(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;
@@ -230,6 +236,13 @@ SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, co
     return umma_probe_shift(k, a, b, (mode >> 16) & 0xff, (mode >> 9) & 1, (mode >> 24) & 0xff, d,
                             (cudaStream_t)stream);
   return umma_probe(mode, m, n, k, a, b, d, (cudaStream_t)stream);
+}
+
+SEG_API int32_t seg_probe_red_rate(int32_t mode, int32_t ctas, int32_t elems, int32_t regions,
+                           int32_t op_bytes, float* dst, int64_t* out, void* stream) {
+  SEG_REQUIRE(dst && out, SEG_E_BAD_SHAPE, "probe_red_rate: null argument");
+  return probe_red_rate(mode, ctas, elems, regions, op_bytes, dst,
+                        reinterpret_cast<long long*>(out), (cudaStream_t)stream);
 }
 
 SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,

@@ -75,6 +75,84 @@ __global__ void maxpool_fwd_kernel(seg_view x, int k, int s, seg_view y, uint8_t
   }
 }
 
+// Vector form of the pool backward (8 channels per thread, k == s): one thread per pool
+// window reads its dy / argmax once (16 + 8 bytes) and produces the k*k input-gradient
+// pixels of the window, each with one 16-byte mask load, optional 16-byte add load and one
+// 16-byte store.  The window grid is extended by one row / column so that input pixels
+// beyond the last full window (VALID pooling drops them) still get add/mask/zero.
+__global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k,
+                                         seg_view add, int add_y0, int add_x0, seg_view mask,
+                                         seg_view dx) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = dx.c / 8;
+  const int ch = (dx.h + k - 1) / k, cw = (dx.w + k - 1) / k;
+  const int64_t total = (int64_t)dx.n * ch * cw * cv;
+  GRID_STRIDE(idx, total) {
+    const int c0 = (idx % cv) * 8;
+    int64_t m = idx / cv;
+    const int q = m % cw;
+    m /= cw;
+    const int p = m % ch;
+    const int n = m / ch;
+    float gsel[8];
+    uint32_t sl[8];
+    const bool in_pool = p < dy.h && q < dy.w;
+    if (in_pool) {
+      const uint4 u = *reinterpret_cast<const uint4*>(view_at(dy, n, p, q) + c0);
+      const uint2 a = *reinterpret_cast<const uint2*>(
+          argmax + (((int64_t)n * dy.h + p) * dy.w + q) * dy.c + c0);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { gsel[2 * j] = bf16_lo(w[j]); gsel[2 * j + 1] = bf16_hi(w[j]); }
+      if (dy2.ptr) {
+        const uint4 u2 = *reinterpret_cast<const uint4*>(view_at(dy2, n, p, q) + c0);
+        const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gsel[2 * j] += bf16_lo(w2[j]); gsel[2 * j + 1] += bf16_hi(w2[j]); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sl[j] = (a.x >> (8 * j)) & 0xffu; sl[4 + j] = (a.y >> (8 * j)) & 0xffu; }
+    }
+    for (int wy = 0; wy < k; ++wy) {
+      const int yy = p * k + wy;
+      if (yy >= dx.h) break;
+      for (int wx = 0; wx < k; ++wx) {
+        const int xx = q * k + wx;
+        if (xx >= dx.w) break;
+        const uint32_t me = (uint32_t)(wy * k + wx);
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = (in_pool && sl[j] == me) ? gsel[j] : 0.f;
+        if (add.ptr) {
+          const int ay = yy - add_y0, ax = xx - add_x0;
+          if (ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
+            const uint4 u = *reinterpret_cast<const uint4*>(view_at(add, n, ay, ax) + c0);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { g[2 * j] += bf16_lo(w[j]); g[2 * j + 1] += bf16_hi(w[j]); }
+          }
+        }
+        if (mask.ptr) {
+          const uint4 u = *reinterpret_cast<const uint4*>(view_at(mask, n, yy, xx) + c0);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(bf16_lo(w[j]) > 0.f)) g[2 * j] = 0.f;
+            if (!(bf16_hi(w[j]) > 0.f)) g[2 * j + 1] = 0.f;
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]);
+        o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]);
+        o.w = pack_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(view_at_mut(dx, n, yy, xx) + c0) = o;
+      }
+    }
+  }
+}
+
 // dx = relu_mask(route(dy, argmax) + add).  Non-overlapping windows (k == s).
 template <int VEC>
 __global__ void maxpool_bwd_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k, int s,
@@ -749,10 +827,14 @@ SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32
   cudaStream_t st = (cudaStream_t)stream;
   const seg_view a = add ? *add : null_view();
   const seg_view mk = mask_src ? *mask_src : null_view();
-  const bool v8 = vec8_ok(*dx) && (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
+  const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && (reinterpret_cast<uintptr_t>(argmax) % 8) == 0 &&
+                  (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, s, a, add_y0, add_x0, mk, *dx));
+  {
+    const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, a, add_y0, add_x0, mk, *dx));
+  }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
                                                                add_y0, add_x0, mk, *dx);
@@ -767,10 +849,14 @@ SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const 
   SEG_REQUIRE(k == s, SEG_E_UNSUPPORTED, "maxpool_bwd2: only non-overlapping windows (k == s)");
   cudaStream_t st = (cudaStream_t)stream;
   const seg_view mk = mask_src ? *mask_src : null_view();
-  const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && vec8_ok(*dy2) && (!mask_src || vec8_ok(mk));
+  const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && vec8_ok(*dy2) &&
+                  (reinterpret_cast<uintptr_t>(argmax) % 8) == 0 && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, s, null_view(), 0, 0, mk, *dx));
+  {
+    const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, *dx));
+  }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,
                                                                null_view(), 0, 0, mk, *dx);

@@ -355,4 +355,69 @@ int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, in
   return SEG_OK;
 }
 
+// ---------------------------------------------------------------------------
+// fp32 global-reduction rate probe (tools/probe_red.py): every CTA adds `elems` floats
+// (rows of 64) from shared memory into dst + (cta % regions) * elems.
+//   mode 0: red.global.add.v4.f32, warp-coalesced (512 contiguous bytes per instruction)
+//   mode 1: red.global.add.v4.f32, thread = row of 64 floats (the weight-gradient pattern)
+//   mode 2: cp.reduce.async.bulk .add.f32, one 256-byte row per operation, thread = row
+//   mode 3: cp.reduce.async.bulk .add.f32, `op_bytes` per operation, issued by warp 0
+// out[2*cta] = cycles until the last operation was issued, out[2*cta+1] = until complete
+// (bulk modes; the red modes cannot observe completion).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_red_kernel(int mode, int elems, int regions, int op_bytes, float* dst, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  float* S = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  for (int i = threadIdx.x; i < elems; i += blockDim.x) S[i] = 1.0f;
+  fence_proxy_async();
+  __syncthreads();
+  float* g = dst + (size_t)(blockIdx.x % regions) * elems;
+  const int rows = elems / 64;
+  const long long t0 = clock64();
+  if (mode == 0) {
+    for (int i = threadIdx.x * 4; i < elems; i += blockDim.x * 4)
+      red_add_v4(g + i, S[i], S[i + 1], S[i + 2], S[i + 3]);
+  } else if (mode == 1) {
+    for (int r = threadIdx.x; r < rows; r += blockDim.x)
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const int i = r * 64 + j;
+        red_add_v4(g + i, S[i], S[i + 1], S[i + 2], S[i + 3]);
+      }
+  } else if (mode == 2) {
+    for (int r = threadIdx.x; r < rows; r += blockDim.x)
+      bulk_reduce_add_f32(g + r * 64, smem_u32(S + r * 64), 256);
+    bulk_commit_group();
+  } else {
+    if (threadIdx.x < 32) {
+      const int ops = elems * 4 / op_bytes;
+      for (int o = threadIdx.x; o < ops; o += 32)
+        bulk_reduce_add_f32(g + (size_t)o * (op_bytes / 4), smem_u32(S) + o * op_bytes, op_bytes);
+      bulk_commit_group();
+    }
+  }
+  const long long t1 = clock64();
+  if (mode >= 2) bulk_wait_group<0>();
+  __syncthreads();
+  const long long t2 = clock64();
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = t2 - t0;
+  }
+}
+
+int probe_red_rate(int mode, int ctas, int elems, int regions, int op_bytes, float* dst,
+                   long long* out, cudaStream_t st) {
+  SEG_REQUIRE(ctas >= 1 && elems >= 64 && elems % 64 == 0 && elems * 4 <= 200 * 1024 &&
+                  regions >= 1 && op_bytes >= 16 && op_bytes % 16 == 0 && (elems * 4) % op_bytes == 0,
+              SEG_E_BAD_SHAPE, "probe_red_rate: bad argument");
+  SEG_CHECK_CUDA(cudaFuncSetAttribute(probe_red_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  probe_red_kernel<<<ctas, 128, elems * 4 + 256, st>>>(mode, elems, regions, op_bytes, dst, out);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
 }  // namespace segb
+

@@ -781,6 +781,35 @@ static int launch_tconv(const TconvJob& J, cudaStream_t st) {
     ok = tconv_plan(J, KC, BN, MT, chunks, &L);
   }
   MT = L.MT; BN = L.BN;
+  // Fill the machine: a layer with few pixels and many channels gives fewer tiles than
+  // SMs.  Narrower column blocks / N-slices multiply the tile count; estimate each
+  // candidate's time as waves x MMA cycles per tile (measured: 64 / 48 / 40 cycles per
+  // 128 x BN x 16 MMA for BN = 128 / 64 / 32) and keep the cheapest.
+  {
+    auto tiles_of = [&](int mt, int bn) {
+      return (int64_t)batch * tiles_y * ((Wo + 8 * mt - 1) / (8 * mt)) * (J.N_total / bn);
+    };
+    auto cost_of = [&](const TconvPlan& C) {
+      const int64_t t = tiles_of(C.MT, C.BN);
+      const int64_t waves = (t + num_sms() - 1) / num_sms();
+      const int mma = C.BN >= 128 ? 64 : (C.BN == 64 ? 48 : 40);
+      double c = (double)waves * (C.MT * mma * 9.0 * chunks * (KC / 16) + C.MT * (C.BN / 32) * 150.0);
+      return C.resident ? c : c * 1.25;
+    };
+    if (tiles_of(MT, BN) < num_sms()) {
+      double best = cost_of(L);
+      for (int mt = MT; mt >= 1; --mt)
+        for (int bn = BN; bn >= 32; bn >>= 1) {
+          if (mt == MT && bn == BN) continue;
+          TconvPlan C;
+          memset(&C, 0, sizeof(C));
+          if (J.N_total % bn || !tconv_plan(J, KC, bn, mt, chunks, &C)) continue;
+          const double c = cost_of(C);
+          if (c < best * 0.9) { best = c; L = C; }
+        }
+      MT = L.MT; BN = L.BN;
+    }
+  }
   TconvParams& P = L.P;
   const int TW = 8 * MT;
   P.tiles_x = (Wo + TW - 1) / TW;
@@ -821,6 +850,10 @@ static int launch_tconv(const TconvJob& J, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 static bool g_use_twgrad = true;
 static int g_twgrad_min_eff = 40;
+static int g_twgrad_min_tiles = 8;   // pixel tiles per CTA below which the grid is narrowed
+void twgrad_set_min_tiles(int n) { g_twgrad_min_tiles = n < 1 ? 1 : n; }
+static int g_twgrad_cluster = 1;     // CTAs per cluster for the partial-sum reduction (1: off)
+void twgrad_set_cluster(int n) { g_twgrad_cluster = n >= 8 ? 8 : (n >= 4 ? 4 : (n >= 2 ? 2 : 1)); }
 void twgrad_enable(int on) { g_use_twgrad = on != 0; }
 void twgrad_set_min_eff(int pct) { g_twgrad_min_eff = pct; }
 
@@ -860,7 +893,14 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   int per = num_sms() / combos;
   if (per < 1) per = 1;
   if (per > tiles) per = tiles;
-  P.ctas_per_combo = per;
+  // Every CTA ends with a full-size partial sum for the global reduction (~25k cycles of
+  // epilogue and L2 reduction traffic that does not shrink with its share of the pixels),
+  // and these kernels run beside the input-gradient chain on a second stream: give a CTA
+  // at least g_twgrad_min_tiles pixel tiles, leaving the other SMs to the main stream.
+  if (per > 1 && tiles / per < g_twgrad_min_tiles) {
+    per = tiles / g_twgrad_min_tiles;
+    if (per < 1) per = 1;
+  }
   P.x_bytes = ((kTwPW * kTwPH * AW * 2) + 1023) / 1024 * 1024;
   P.stage_bytes = P.x_bytes + kTwTH * kTwTW * BN * 2;
   int stages = (227 * 1024 - 2048 - 1024) / P.stage_bytes;
@@ -868,8 +908,47 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   P.stages = stages;
   P.off_bars = stages * P.stage_bytes;
   const int smem = P.off_bars + 1024 + 1024;
-  SEG_CHECK_CUDA(launch_k(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kIgemmThreads), (size_t)(smem), st, tmX1, tmX2, tmZ, P));
-  SEG_LAUNCH_CHECK();
+  // Cluster of CTAs of one combo: reduce the partial sums through distributed shared
+  // memory before they go to L2 (twgrad.cuh).  The cluster size must divide the CTAs per
+  // combo, split the accumulator columns into multiples of 4, the staged accumulators
+  // must fit into the pipeline stages, and the whole grid must be co-resident.
+  constexpr int kCols = (AW == 64 ? 5 : 3) * BN;
+  int cs = g_twgrad_cluster;
+  while (cs > 1 && (cs > per || kCols % (4 * cs) != 0)) cs >>= 1;
+  P.staged_ok = 128 * (kCols + 4) * 4 <= stages * P.stage_bytes ? 1 : 0;
+  if (!P.staged_ok) cs = 1;
+  if (cs > 1) {
+    per -= per % cs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(combos * per);
+    cfg.blockDim = dim3(kIgemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (max_clusters[cs] == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, twgrad_kernel<AW, BN>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = -1;
+      }
+      max_clusters[cs] = n;
+    }
+    if (max_clusters[cs] < 1) {
+      cs = 1;
+      per = num_sms() / combos < 1 ? 1 : num_sms() / combos;
+      if (per > tiles) per = tiles;
+    } else {
+      // keep the grid within one resident wave of clusters
+      while (per > cs && combos * per > max_clusters[cs] * cs) per -= cs;
+    }
+  }
+  P.cluster = cs;
+  P.ctas_per_combo = per;
+  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kIgemmThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, P));
   return SEG_OK;
 }
 

@@ -110,9 +110,12 @@ class ParamStore(object):
         # launch plan of the Adam kernel: one {segment, first element} pair per block
         ce = N.load().seg_adam_chunk_elems()
         chunks = []
+        self.chunk_first = []           # first Adam chunk of each parameter (+ sentinel)
         for si, p in enumerate(self.params.values()):
+            self.chunk_first.append(len(chunks) // 2)
             for b in range(0, p.numel, ce):
                 chunks += [si, b]
+        self.chunk_first.append(len(chunks) // 2)
         self.nchunks = len(chunks) // 2
         self.chunks = torch.tensor(chunks or [0, 0], dtype=torch.int32, device=dev)
         self.segments = torch.tensor(seg, dtype=torch.int32, device=dev)
@@ -162,12 +165,23 @@ class ParamStore(object):
         self.step += 1
         return lr * math.sqrt(1.0 - beta2 ** self.step) / (1.0 - beta1 ** self.step)
 
+    def chunk_range(self, off_a, off_b):
+        """Adam chunk index range of the parameters whose flat offsets lie in
+        [off_a, off_b) (both must be parameter boundaries)."""
+        offs = [p.offset for p in self.params.values()] + [self.numel]
+        return self.chunk_first[offs.index(off_a)], self.chunk_first[offs.index(off_b)]
+
     def adam_launch(self, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
-                    from_device=False):
-        """from_device=True reads lr_t from self.lr_t_dev (CUDA-graph replay)."""
+                    from_device=False, chunk_range=None):
+        """from_device=True reads lr_t from self.lr_t_dev (CUDA-graph replay).
+        chunk_range=(a, b): update only the parameters covered by chunks [a, b)."""
+        a, b = chunk_range if chunk_range is not None else (0, self.nchunks)
+        if b <= a:
+            return
+        chunks = ctypes.c_void_p(self.chunks.data_ptr() + a * 8)
         N.call('seg_adam_multi', N.ptr(self.master), N.ptr(self.grad), N.ptr(self.m),
                N.ptr(self.v), N.ptr(self.shadow), N.ptr(self.segments),
-               N.ptr(self.shadow_offsets), N.ptr(self.chunks), self.nchunks, lr_t,
+               N.ptr(self.shadow_offsets), chunks, b - a, lr_t,
                N.ptr(self.lr_t_dev) if from_device else None, beta1, beta2,
                eps, grad_scale, N.stream_ptr())
 
@@ -303,10 +317,15 @@ class SideStream(object):
         self.stream = torch.cuda.Stream(device=device)
         self.used = False
 
-    def fork(self):
+    def fork(self, also=None):
+        """`also`: another SideStream whose enqueued work must be waited for as well."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.stream.wait_event(ev)
+        if also is not None and also.used:
+            ev2 = torch.cuda.Event()
+            ev2.record(also.stream)
+            self.stream.wait_event(ev2)
         self.used = True
         return torch.cuda.stream(self.stream)
 

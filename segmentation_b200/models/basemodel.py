@@ -90,8 +90,8 @@ class BaseModel(object):
         self._last_pixels = 1
         self.mc_seed = 0
         self.world_size = 1
-        self._grad_hook = None                    # set by parallel.DataParallel
-        self._bucket_done = None
+        self._allreduce = None                    # set by parallel.DataParallel: f(group index)
+        self.opt_splits = ()                      # layers that start a new optimizer group
         if self.dataset is not None and hasattr(self.dataset, 'set_tf_sess'):
             self.dataset.set_tf_sess(self.sess)
 
@@ -113,7 +113,26 @@ class BaseModel(object):
             if hasattr(layer, 'init_values'):
                 layer.init_values()
         self.store.refresh_shadow()
+        self._init_opt_groups()
         self._init_saver(self.model_name)
+
+    def _init_opt_groups(self):
+        """Optimizer groups = contiguous slices of the flat parameter buffer (in TF variable
+        order) that the backward pass completes one after the other, back to front.  Each
+        group gets its own (data-parallel: all-reduce +) Adam launch as soon as its
+        gradients are complete, beside the rest of the backward pass."""
+        from ..parallel import bucket_boundaries
+        st = self.store
+        splits = [s for s in self.opt_splits if s + '/weights' in st.params]
+        bounds = bucket_boundaries(st, splits)
+        firsts = [None] + [s for s in splits if st.params[s + '/weights'].offset > 0]
+        self.opt_groups = []
+        for a, b, first in zip(bounds[:-1], bounds[1:], firsts):
+            self.opt_groups.append({'first_layer': first, 'slice': (a, b),
+                                    'chunks': st.chunk_range(a, b)})
+        # group 0 starts with the first layer of the model, whatever its name
+        self.group_of_first = {g['first_layer']: i for i, g in enumerate(self.opt_groups)
+                               if g['first_layer'] is not None}
 
     # ----------------------------------------------------------- snapshots
     def _init_saver(self, name='model'):
@@ -267,6 +286,11 @@ class ExecBase(object):
         self._pf = None                # host batch whose copy into the landing buffers is in flight
         self._pf_host = None           # host batch fetched from the dataset but not staged
         self._prepacked = False
+        self.side = E.SideStream(dev)             # weight gradients
+        self.opt = E.SideStream(dev)              # all-reduce + Adam per optimizer group
+        self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
+        self._opt_active = False
+        self._pending = set()
         self.logits = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
         self.probs = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
         self.labelmap = torch.zeros(B, oh, ow, 1, dtype=torch.float32, device=dev)
@@ -301,12 +325,41 @@ class ExecBase(object):
 
     # ---------------------------------------------------------------- steps
     def _step_body(self):
-        self.forward()
-        self.loss(True)
-        self.backward()
-        if self.m._grad_hook is not None:
-            self.m._grad_hook()
-        self.m.store.adam_launch(0.0, grad_scale=1.0 / self.m.world_size, from_device=True)
+        m = self.m
+        self._opt_active = True
+        self._pending = set(range(len(m.opt_groups)))
+        try:
+            self.forward()
+            self.loss(True)
+            self.backward()                       # may call group_ready() as groups complete
+            for i in sorted(self._pending, reverse=True):
+                self.group_ready(i)
+            self.side.join()
+            self.opt.join()
+        finally:
+            self._opt_active = False
+
+    def group_ready(self, i):
+        """Every gradient of optimizer group i has been enqueued (weight gradients on the
+        side stream; the input-gradient kernels that read the group's weights on the current
+        stream).  On the optimizer stream, behind both: data-parallel all-reduce of the
+        group's gradient slice, then Adam on it (which also rewrites the bf16 shadows and
+        zeroes the gradients).  No-op outside a train step."""
+        m = self.m
+        if not self._opt_active or i not in self._pending:
+            return
+        self._pending.discard(i)
+        with self.opt.fork(also=self.side):
+            if m._allreduce is not None:
+                m._allreduce(i)
+            m.store.adam_launch(0.0, grad_scale=1.0 / m.world_size, from_device=True,
+                                chunk_range=m.opt_groups[i]['chunks'])
+
+    def layer_done(self, name):
+        """Backward schedules call this after a layer's backward kernels were enqueued."""
+        gi = self.m.group_of_first.get(name)
+        if gi is not None:
+            self.group_ready(gi)
 
     def pack(self):
         """fp32 [B,H,W,C] landing buffer -> bf16 input tensor with C padded to 16."""

@@ -51,6 +51,8 @@ class UNetModel(BaseModel):
         self.model_name = 'unet'
         self.IN_OUT_CROP = True
         self.n_kernels = n_kernels
+        # encoder conv1..4 | bottleneck conv5_* (61 % of the bytes) | decoder
+        self.opt_splits = ('conv5_1', 'upconv1')
         self._finish_init(seed)
         self.y_hat = None          # logits of the most recent forward (device fp32 tensor)
         self.y_hat_sig = None
@@ -166,8 +168,6 @@ class _UNetExec(ExecBase):
         self._init_io(model, B, H, W, oh, ow, model.n_classes, L['output'].cout_pad, training)
         if training:
             self._alloc_grads()
-        self.side = E.SideStream(dev)
-        self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
 
     # ------------------------------------------------------------- buffers
     def skip_view(self, j):
@@ -229,14 +229,13 @@ class _UNetExec(ExecBase):
     def backward(self):
         L, A, G, impl = self.m.layers, self.act, self.g, self.m.impl
         nc = self.m.n_classes
-        hook = self.m._bucket_done
         side = self.side if self.use_side else None
 
         def bw(name, *args, **kw):
-            # weight gradients go to the side stream; data-parallel: a gradient bucket
-            # may be complete once this layer's are enqueued
-            L[name].backward(*args, impl=impl, side=side,
-                             after=(lambda: hook(name)) if hook is not None else None, **kw)
+            # weight gradients go to the side stream; an optimizer group may be complete
+            # once this layer's kernels are enqueued
+            L[name].backward(*args, impl=impl, side=side, **kw)
+            self.layer_done(name)
 
         # head (no activation): dz = dlogits
         bw('output', A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],

@@ -76,6 +76,7 @@ SIGNATURES = {
     'seg_fill_zero': [_P, _I64, _P],
     'seg_probe_umma': [_I32, _I32, _I32, _I32, _P, _P, _P, _P],
     'seg_probe_mma_rate': [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    'seg_probe_red_rate': [_I32, _I32, _I32, _I32, _I32, _P, _P, _P],
 }
 
 _lib = None
@@ -99,6 +100,10 @@ def load():
     _lib = lib
     if os.environ.get('SEGB200_PDL', '1') == '0':
         lib.seg_set_option(OPT_PDL, 0)
+    if 'SEGB200_WGRAD_MIN_TILES' in os.environ:
+        lib.seg_set_option(OPT_WGRAD_MIN_TILES, int(os.environ['SEGB200_WGRAD_MIN_TILES']))
+    if 'SEGB200_WGRAD_CLUSTER' in os.environ:
+        lib.seg_set_option(OPT_WGRAD_CLUSTER, int(os.environ['SEGB200_WGRAD_CLUSTER']))
     return lib
 
 
@@ -121,6 +126,8 @@ def set_tag(tag):
 OPT_HALO_CONV, OPT_HALO_ROW_ALIGN, OPT_TILE_CONV, OPT_TILE_CONV_MIN_EFF = 1, 2, 3, 4
 OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
 OPT_PDL = 7           # programmatic dependent launch of the hot-path kernels (default on)
+OPT_WGRAD_MIN_TILES = 9  # pixel tiles per CTA below which the weight-gradient grid is narrowed
+OPT_WGRAD_CLUSTER = 8  # CTAs per cluster in the weight-gradient partial-sum reduction (1/2/4/8)
 
 
 def set_option(key, value):

@@ -9,7 +9,8 @@ into the Adam kernel (`grad_scale`).
 
 The flat gradient buffer is laid out in TF variable order (forward order);
 backward completes it from the back, so buckets are contiguous slices that
-become ready one after the other.
+become ready one after the other; each is reduced and then updated by its own
+Adam launch on the executor's optimizer stream while the backward pass goes on.
 """
 import torch
 import torch.distributed as dist
@@ -58,13 +59,15 @@ def bucket_boundaries(store, first_layers):
 
 class DataParallel(object):
     """Wraps a model: identical initial parameters on every rank, world_size for
-    the Adam grad_scale, bucketed gradient all-reduce hooks."""
+    the Adam grad_scale, one gradient bucket per optimizer group of the model
+    (U-Net: encoder | bottleneck conv5_* | decoder).  The executor calls
+    `allreduce_group(i)` on its optimizer stream when group i's gradients are
+    complete; the group's Adam launch follows on the same stream, so reduction and
+    update of the back of the network overlap the backward pass of the front."""
 
-    # U-Net: encoder (conv1..4) | bottleneck conv5_* (61 % of the bytes) | decoder
-    UNET_SPLITS = ('conv5_1', 'upconv1')
-
-    def __init__(self, model, splits=None, group=None):
+    def __init__(self, model, group=None):
         self.model = model
+        self.group = group
         self.world = dist.get_world_size(group)
         model.world_size = self.world
         st = model.store
@@ -72,22 +75,12 @@ class DataParallel(object):
         for t in st.state.values():
             dist.broadcast(t, src=0, group=group)
         st.refresh_shadow()
-        if splits is None:
-            splits = self.UNET_SPLITS if model.model_name == 'unet' else ()
-        self.buckets = GradBuckets(st.grad, bucket_boundaries(st, splits), group)
-        # layer whose backward completes bucket i (buckets are in forward order)
-        self.ready_after = {}
-        names = list(model.layers)
-        first = [0] + [names.index(s) for s in splits if s in names]
-        for i, start in enumerate(first):
-            self.ready_after[names[start]] = i
-        model._bucket_done = self.on_layer_done
-        model._grad_hook = self.buckets.join
+        bounds = [g['slice'][0] for g in model.opt_groups] + [st.numel]
+        self.buckets = GradBuckets(st.grad, bounds, group)
+        model._allreduce = self.allreduce_group
 
-    def on_layer_done(self, layer_name):
-        """Called by the backward schedule after `layer_name`'s wgrad was enqueued:
-        launches the all-reduce of a bucket once its LAST gradient (the first layer
-        of the bucket in forward order) is complete."""
-        i = self.ready_after.get(layer_name)
-        if i is not None:
-            self.buckets.launch(i)
+    def allreduce_group(self, i):
+        """All-reduce (sum) bucket i; the current stream waits for it (no host wait)."""
+        w = dist.all_reduce(self.buckets.slices[i], op=dist.ReduceOp.SUM, group=self.group,
+                            async_op=True)
+        w.wait()

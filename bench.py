@@ -207,7 +207,7 @@ def run_reference(args):
         'e2e': {'value': rate, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def run_ours(args):
@@ -311,9 +311,12 @@ def run_ours(args):
 
     if world > 1:
         dist.barrier()                           # every rank is done with its GPU work
+        torch.cuda.synchronize()
     if rank != 0:
-        dist.destroy_process_group()
-        return
+        # no destroy_process_group(): tearing NCCL down under captured graphs was seen to
+        # hang; the process is done, leave at once
+        sys.stderr.flush()
+        os._exit(0)
     pk = peaks()
     imgs = BATCH * world * K
     value = imgs / (ms_dev * 1e-3)
@@ -347,9 +350,10 @@ def run_ours(args):
         'clocks': clk,
         'loss': loss,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def conv_flops(layer, x_shape, y_shape, which):
@@ -427,8 +431,26 @@ def _watchdog(seconds):
     t.start()
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """The one JSON line: written to the process's original stdout (fd 1 is redirected to
+    stderr for the whole run so that NCCL banners and library prints cannot interleave)."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     _watchdog(int(os.environ.get('SEGB200_BENCH_WATCHDOG', '420')))
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -486,6 +486,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
+      // Whole BN-float row segments go to L2 as one TMA reduce-add each (row-per-thread
+      // red.v4 is 2.7x slower, tools/probe_red.py): the row is staged in the pipeline
+      // shared memory, which is idle once every MMA has completed.
+      constexpr int kPitch = BN + 4;
+      const bool vec_ok = (P.SC & 3) == 0 && (reinterpret_cast<uintptr_t>(P.dw) & 15) == 0;
+      const bool bulk_ok = vec_ok && BN >= 32 && n0 + BN <= P.SC &&
+                           128 * kPitch * 4 <= S * Cfg::kStageBytes;
+      const bool bias_row = P.db != nullptr && dst == P.db;
+      const uint32_t s_row = smem_u32(smem) + (uint32_t)(L * kPitch * 4);
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += (BN >= 32 ? 32 : 16)) {
         constexpr int W = BN >= 32 ? 32 : 16;
@@ -493,8 +502,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + cc;
         if (W == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
-        if (row_ok) {
-          if ((P.SC & 3) == 0 && (reinterpret_cast<uintptr_t>(P.dw) & 15) == 0 && dst != P.db) {
+        if (bulk_ok && !bias_row) {
+#pragma unroll
+          for (int j = 0; j < W; j += 4)
+            sts128(s_row + (uint32_t)(cc + j) * 4, make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+        } else if (row_ok) {
+          if (vec_ok && !bias_row) {
             // 16-byte vector reductions (dW rows are SC floats, SC % 4 == 0 keeps alignment)
 #pragma unroll
             for (int j = 0; j < W; j += 4) {
@@ -511,6 +524,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             }
           }
         }
+      }
+      if (bulk_ok && !bias_row) {
+        fence_proxy_async();
+        if (row_ok) bulk_reduce_add_f32(dst + n0, s_row, BN * 4);
+        bulk_commit_group();
+        bulk_wait_group<0>();
       }
     }
   }

@@ -208,9 +208,24 @@ class _UNetExec(ExecBase):
                               (off + t) * 8 + self.MC_SITES[name])
 
         conv('conv1_1', A['x'])
-        conv('conv1_2', A['conv1_1'])
+        # conv1_2 feeds only the last skip connection (reference models/unet.py:118-120,161):
+        # it runs on the side stream, filling the SMs the small deep layers leave idle
+        fwd_at = int(os.environ.get('SEGB200_FWD_SIDE', '1'))   # 0: off; i: fork before stage i+1
+        fwd_side = self.side if (self.use_side and dropout is None and fwd_at > 0) else None
+
+        def conv1_2():
+            if fwd_side is not None:
+                with fwd_side.fork():
+                    conv('conv1_2', A['conv1_1'])
+            else:
+                conv('conv1_2', A['conv1_1'])
+
+        if fwd_at <= 1:
+            conv1_2()
         E.maxpool_fwd(A['conv1_1'], A['pool1'], self.amax['pool1'])
         for i in range(2, 6):
+            if fwd_at == i:
+                conv1_2()
             conv('conv%d_1' % i, A['pool%d' % (i - 1)])
             conv('conv%d_2' % i, A['conv%d_1' % i])
             if i < 5:
@@ -219,6 +234,8 @@ class _UNetExec(ExecBase):
         for j in range(1, 5):
             up = 'upconv%d' % j
             L[up].forward(below, A[up], impl=impl)
+            if j == 4 and fwd_side is not None:
+                fwd_side.join()                   # conv1_2 is needed from here on
             conv('conv%d_1' % (5 + j), self.skip_view(j), x2=A[up])
             conv('conv%d_2' % (5 + j), A['conv%d_1' % (5 + j)])
             below = A['conv%d_2' % (5 + j)]

@@ -144,6 +144,13 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
 SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
                         const seg_view* add, int32_t add_y0, int32_t add_x0,
                         const seg_view* mask_src, const seg_view* dx, void* stream);
+/* same, given the forward pool output as well: where no `add` gradient arrives the ReLU
+ * mask is taken from pooled_y (x at the argmax is the pooled value; elsewhere the routed
+ * gradient is zero), so mask_src is read only inside the `add` window. */
+SEG_API int32_t seg_maxpool_bwd_y(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                          const seg_view* add, int32_t add_y0, int32_t add_x0,
+                          const seg_view* mask_src, const seg_view* pooled_y, const seg_view* dx,
+                          void* stream);
 /* same with two incoming pool-output gradients (dy + dy2): the pooled tensor has
  * two consumers (FCN pool3/pool4 feed the next conv AND a score conv,
  * models/fcn.py:192-195). */

@@ -82,7 +82,7 @@ __global__ void maxpool_fwd_kernel(seg_view x, int k, int s, seg_view y, uint8_t
 // beyond the last full window (VALID pooling drops them) still get add/mask/zero.
 __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k,
                                          seg_view add, int add_y0, int add_x0, seg_view mask,
-                                         seg_view dx) {
+                                         seg_view pooled, seg_view dx) {
   pdl_trigger();
   pdl_wait();
   const int cv = dx.c / 8;
@@ -113,6 +113,16 @@ __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) { sl[j] = (a.x >> (8 * j)) & 0xffu; sl[4 + j] = (a.y >> (8 * j)) & 0xffu; }
+      if (pooled.ptr) {
+        // the ReLU mask of the routed gradient: x at the argmax IS the pooled value
+        const uint4 pv = *reinterpret_cast<const uint4*>(view_at(pooled, n, p, q) + c0);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(bf16_lo(pw[j]) > 0.f)) gsel[2 * j] = 0.f;
+          if (!(bf16_hi(pw[j]) > 0.f)) gsel[2 * j + 1] = 0.f;
+        }
+      }
     }
     for (int wy = 0; wy < k; ++wy) {
       const int yy = p * k + wy;
@@ -124,6 +134,7 @@ __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_
         float g[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = (in_pool && sl[j] == me) ? gsel[j] : 0.f;
+        bool added = false;
         if (add.ptr) {
           const int ay = yy - add_y0, ax = xx - add_x0;
           if (ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
@@ -131,9 +142,11 @@ __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) { g[2 * j] += bf16_lo(w[j]); g[2 * j + 1] += bf16_hi(w[j]); }
+            added = true;
           }
         }
-        if (mask.ptr) {
+        // with `pooled` the routed part is already masked: x is read only under `add`
+        if (mask.ptr && (added || !pooled.ptr)) {
           const uint4 u = *reinterpret_cast<const uint4*>(view_at(mask, n, yy, xx) + c0);
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -819,27 +832,44 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
   return SEG_OK;
 }
 
-SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
-                        const seg_view* add, int32_t add_y0, int32_t add_x0,
-                        const seg_view* mask_src, const seg_view* dx, void* stream) {
+static int maxpool_bwd_impl(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                            const seg_view* add, int32_t add_y0, int32_t add_x0,
+                            const seg_view* mask_src, const seg_view* pooled, const seg_view* dx,
+                            void* stream) {
   SEG_REQUIRE(dy && argmax && dx, SEG_E_BAD_SHAPE, "maxpool_bwd: null argument");
   SEG_REQUIRE(k == s, SEG_E_UNSUPPORTED, "maxpool_bwd: only non-overlapping windows (k == s)");
   cudaStream_t st = (cudaStream_t)stream;
   const seg_view a = add ? *add : null_view();
   const seg_view mk = mask_src ? *mask_src : null_view();
+  const bool use_y = pooled && pooled->ptr && mask_src && vec8_ok(*pooled) && pooled->h == dy->h &&
+                     pooled->w == dy->w && pooled->c == dy->c && pooled->n == dy->n;
+  const seg_view py = use_y ? *pooled : null_view();
   const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && (reinterpret_cast<uintptr_t>(argmax) % 8) == 0 &&
                   (!add || vec8_ok(a)) && (!mask_src || vec8_ok(mk));
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
   {
     const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, a, add_y0, add_x0, mk, *dx));
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, a, add_y0, add_x0, mk, py, *dx));
   }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
                                                                add_y0, add_x0, mk, *dx);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
+}
+
+SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                        const seg_view* add, int32_t add_y0, int32_t add_x0,
+                        const seg_view* mask_src, const seg_view* dx, void* stream) {
+  return maxpool_bwd_impl(dy, argmax, k, s, add, add_y0, add_x0, mask_src, nullptr, dx, stream);
+}
+
+SEG_API int32_t seg_maxpool_bwd_y(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
+                          const seg_view* add, int32_t add_y0, int32_t add_x0,
+                          const seg_view* mask_src, const seg_view* pooled_y, const seg_view* dx,
+                          void* stream) {
+  return maxpool_bwd_impl(dy, argmax, k, s, add, add_y0, add_x0, mask_src, pooled_y, dx, stream);
 }
 
 SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
@@ -855,7 +885,7 @@ SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const 
   if (v8)
   {
     const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, *dx));
+    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx));
   }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,

@@ -349,7 +349,13 @@ def maxpool_fwd(x, y, argmax, k=2, s=2):
     N.call('seg_maxpool_fwd', N.vref(x), k, s, N.vref(y), N.ptr(argmax), N.stream_ptr())
 
 
-def maxpool_bwd(dy, argmax, dx, k=2, s=2, add=None, add_y0=0, add_x0=0, mask=None):
+def maxpool_bwd(dy, argmax, dx, k=2, s=2, add=None, add_y0=0, add_x0=0, mask=None, pooled=None):
+    """`pooled`: the forward pool output; lets the kernel skip reading `mask` (the pool
+    input) wherever no `add` gradient arrives."""
+    if pooled is not None:
+        N.call('seg_maxpool_bwd_y', N.vref(dy), N.ptr(argmax), k, s, N.vref(add), add_y0, add_x0,
+               N.vref(mask), N.vref(pooled), N.vref(dx), N.stream_ptr())
+        return
     N.call('seg_maxpool_bwd', N.vref(dy), N.ptr(argmax), k, s, N.vref(add), add_y0, add_x0,
            N.vref(mask), N.vref(dx), N.stream_ptr())
 

@@ -277,7 +277,8 @@ class _UNetExec(ExecBase):
                 j = 5 - i
                 y0, x0, _, _ = self.crop[j]
                 E.maxpool_bwd(G['pool%d' % i], self.amax['pool%d' % i], G[c2],
-                              add=G['skip%d' % j], add_y0=y0, add_x0=x0, mask=A[c2])
+                              add=G['skip%d' % j], add_y0=y0, add_x0=x0, mask=A[c2],
+                              pooled=A['pool%d' % i])
                 bw(c2, A[c1], G[c2], dx=G[c1], mask=A[c1])
             bw(c1, A[pool], G[c1], dx=G[pool])
         # conv1_2: output gradient lives only on the skip crop -> run on the crop
@@ -285,7 +286,7 @@ class _UNetExec(ExecBase):
         x_win = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
         bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
         E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['conv1_1'], add=G['conv1_1_part'],
-                      add_y0=y0, add_x0=x0, mask=A['conv1_1'])
+                      add_y0=y0, add_x0=x0, mask=A['conv1_1'], pooled=A['pool1'])
         bw('conv1_1', A['x'], G['conv1_1'], dx=None)
         if side is not None:
             side.join()

@@ -56,6 +56,17 @@ def test_maxpool_fwd_bwd_bit_exact(cuda, shape, k):
     E.maxpool_bwd(dev_bf16(dy), am, dx_d, k, k, add=dev_bf16(add), add_y0=1, add_x0=1, mask=x_d)
     sync()
     assert torch.equal(dx_d.float().cpu(), ref)
+    # same result when the mask of the routed part comes from the pool output (the pool input
+    # is then read only inside the add window); a smaller add window exercises both branches
+    add2 = bfr(torch.randn(Nb, H - 4, W - 4, C, generator=g))
+    addp2 = torch.zeros(shape)
+    addp2[:, 2:H - 2, 2:W - 2] = add2
+    ref2 = bfr((dx_ref + addp2) * (x > 0).float())
+    dx_d.fill_(7.0)
+    E.maxpool_bwd(dev_bf16(dy), am, dx_d, k, k, add=dev_bf16(add2), add_y0=2, add_x0=2, mask=x_d,
+                  pooled=y_d)
+    sync()
+    assert torch.equal(dx_d.float().cpu(), ref2)
 
 
 def test_softmax_xent_and_head(cuda):

@@ -242,6 +242,15 @@ SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, vo
 /* ---- layout helpers */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with channels zero-padded to y.c */
 SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, void* stream);
+/* fp32 NHWC [n,h,w,c] -> bf16 y [n,ho,wo,CP] with the kh x kw x c input patch of every output
+ * pixel packed into the channel axis: y[.., (r*kw+s)*c+ci] = x[.., oy*stride+r-pad_t,
+ * ox*stride+s-pad_l, ci], zero outside the image and for channels >= kh*kw*c.  Turns the
+ * first convolution of a model (3 input channels: `slim.convolution2d(input, ...)`,
+ * models/unet.py:111, models/fcn.py:110) into a 1x1 convolution over CP channels whose
+ * weight matrix is the TF HWIO tensor read as [kh*kw*c][cout]. */
+SEG_API int32_t seg_pack_patches(const float* x, int32_t c, int32_t h, int32_t w, int32_t kh,
+                         int32_t kw, int32_t stride, int32_t pad_t, int32_t pad_l,
+                         const seg_view* y, void* stream);
 SEG_API int32_t seg_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- self-test hooks used by tests/ (tcgen05 descriptor probes) */

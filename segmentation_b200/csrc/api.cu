@@ -173,7 +173,13 @@ SEG_API int32_t seg_deconv2d_fwd(const seg_conv_desc* d, const seg_view* x, cons
   SEG_REQUIRE(desc_ok(d) && x && w_bf16 && y, SEG_E_BAD_SHAPE, "deconv2d_fwd: bad argument");
   SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "deconv2d_fwd: bias missing");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->impl == SEG_IMPL_UMMA) return umma_deconv_fwd(*d, *x, w_bf16, bias, *y, st);
+  if (d->impl == SEG_IMPL_UMMA) {
+    const int rc = umma_deconv_fwd(*d, *x, w_bf16, bias, *y, st);
+    // k > stride runs as stride^2 halo-tile launches; a geometry those cannot stage (padded
+    // row wider than 256 pixels) is handed to the CUDA-core gather kernel below, which
+    // rewrites the whole output
+    if (!(rc == SEG_E_UNSUPPORTED && d->kh > d->stride)) return rc;
+  }
   TransParams P;
   memset(&P, 0, sizeof(P));
   P.src = *x;

@@ -32,6 +32,9 @@ struct HconvParams {
   int a_stage_bytes;
   int chunks1, chunks2;
   int tap_flip, b_rows_per_tap;
+  int use_tap_rows;          // weight-matrix row of tap t (loop order r*kw+s) comes from tap_rows[t]
+  int tap_rows[25];          //   instead of (t or taps-1-t) * b_rows_per_tap: sub-kernels of a
+                             //   strided transposed conv pick every stride-th tap of the k x k bank
   int N_total;
   int SA, SB;
   int b_resident;
@@ -144,14 +147,15 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               if (elect_one()) {
                 uint8_t* sbp = smem_b + sb * kBBytes;
                 mbar_expect_tx(&b_full[sb], kBBytes);
+                const int tap_row = P.use_tap_rows ? P.tap_rows[t] : bt * P.b_rows_per_tap;
                 if (B_MN) {
-                  const int row = bt * P.b_rows_per_tap + j * KC;
+                  const int row = tap_row + j * KC;
 #pragma unroll
                   for (int a = 0; a < BN / kAtomN; ++a)
                     tma_load_2d(&tmB, &b_full[sb], sbp + a * (KC * kAtomN * 2), n0 + a * kAtomN,
                                 row);
                 } else {
-                  tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, bt * P.b_rows_per_tap + n0);
+                  tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, tap_row + n0);
                 }
               }
               __syncwarp();

@@ -752,6 +752,47 @@ __global__ void pack_input16_kernel(const float* __restrict__ x, int C, bf16* __
   }
 }
 
+// fp32 NHWC [n,H,W,C] -> bf16 [n,Ho,Wo,CP]: the kh x kw x C patch of every output pixel is
+// packed into the channel axis, channel (r*kw+s)*C+c of pixel (oy,ox) =
+// x[n, oy*stride+r-pad_t, ox*stride+s-pad_l, c] (zero outside the image and beyond
+// kh*kw*C).  A first conv on few input channels then is a 1x1 conv over CP channels.
+// Thread = (output pixel, 8-channel group); the 9-fold reuse of x is served by L1/L2.
+__global__ void pack_patches_kernel(const float* __restrict__ x, int C, int H, int W, int kh, int kw,
+                                    int stride, int pad_t, int pad_l, seg_view y) {
+  pdl_trigger();
+  pdl_wait();
+  const int groups = y.c / 8;
+  const int real = kh * kw * C;
+  const int64_t total = (int64_t)y.n * y.h * y.w * groups;
+  GRID_STRIDE(idx, total) {
+    const int g = idx % groups;
+    int64_t m = idx / groups;
+    const int ox = m % y.w;
+    m /= y.w;
+    const int oy = m % y.h;
+    const int n = m / y.h;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      v[j] = 0.f;
+      if (ch < real) {
+        const int t = ch / C, c = ch - t * C;
+        const int r = t / kw, sx = t - r * kw;
+        const int yy = oy * stride + r - pad_t, xx = ox * stride + sx - pad_l;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v[j] = __ldg(x + (((int64_t)n * H + yy) * W + xx) * C + c);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(view_at_mut(y, n, oy, ox) + g * 8) = o;
+  }
+}
+
 // per-channel sums with 16-byte loads: thread = (pixel lane, 8-channel group)
 template <int MODE>   // 0: sum + sumsq   2: sum only
 __global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
@@ -1096,6 +1137,20 @@ SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, voi
     pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, *y);
   }
   SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_pack_patches(const float* x, int32_t c, int32_t h, int32_t w, int32_t kh,
+                                 int32_t kw, int32_t stride, int32_t pad_t, int32_t pad_l,
+                                 const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && c >= 1 && kh >= 1 && kw >= 1 && stride >= 1, SEG_E_BAD_SHAPE,
+              "pack_patches: bad argument");
+  SEG_REQUIRE(kh * kw * c <= y->c && vec8_ok(*y), SEG_E_BAD_SHAPE,
+              "pack_patches: %d patch values do not fit %d channels (multiple of 8, 16-byte "
+              "aligned view)", kh * kw * c, y->c);
+  const int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  SEG_CHECK_CUDA(launch_k(pack_patches_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0,
+                          (cudaStream_t)stream, x, c, h, w, kh, kw, stride, pad_t, pad_l, *y));
   return SEG_OK;
 }
 

@@ -407,6 +407,7 @@ struct HconvJob {
   int split_n;
   const float* bias;
   int flags;
+  const int* tap_rows;         // optional: weight-matrix row of tap t = r*kw+s (see HconvParams)
 };
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
@@ -522,6 +523,11 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   P.chunks2 = c2 / KC;
   P.tap_flip = J.tap_flip ? 1 : 0;
   P.b_rows_per_tap = J.b_rows_per_tap;
+  if (J.tap_rows) {
+    if (J.kh * J.kw > 25) return SEG_E_UNSUPPORTED;
+    P.use_tap_rows = 1;
+    for (int t = 0; t < J.kh * J.kw; ++t) P.tap_rows[t] = J.tap_rows[t];
+  }
   P.N_total = J.N_total;
   P.d0 = J.d0; P.d1 = J.d1; P.split_n = J.split_n;
   P.bias = J.bias; P.flags = J.flags;
@@ -1131,16 +1137,71 @@ int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x
   return launch_wgrad(J, st);
 }
 
-// transposed conv with k == stride, VALID: GEMM + pixel shuffle
+// Transposed conv with k > stride, VALID (DeconvModel's 5x5 / stride 2, reference
+// models/deconvolution.py:150-160): output pixel o = stride*j + p receives only the taps
+// k = p + stride*m, so each of the stride^2 output parity classes (py, px) is a stride-1
+// correlation of x with an My x Mx sub-kernel (M_p = ceil((k - p) / stride)) over the fully
+// padded input:  out_p[j] = sum_r x_pad[j + r] * w[p + stride*(M_p - 1 - r)].  Each class
+// runs on the halo-tile kernel with a strided destination view and a tap -> weight-row
+// table.  Returns SEG_E_UNSUPPORTED if a class does not fit that kernel.
+static int deconv_fwd_parity(const seg_conv_desc& d, const seg_view& x, const void* w,
+                             const float* bias, const seg_view& y, cudaStream_t st) {
+  const int s = d.stride, k = d.kh;
+  const size_t esz = (d.flags & SEG_EPI_OUT_F32) ? 4 : 2;
+  for (int py = 0; py < s; ++py) {
+    const int My = (k - py + s - 1) / s;
+    for (int px = 0; px < s; ++px) {
+      const int Mx = (k - px + s - 1) / s;
+      if (My < 1 || Mx < 1) continue;
+      HconvJob H;
+      memset(&H, 0, sizeof(H));
+      H.a1 = x; H.a2 = null_view();
+      H.kh = My; H.kw = Mx;
+      H.pad_t = My - 1; H.pad_l = Mx - 1;
+      H.Hp = x.h + 2 * (My - 1); H.Wp_logical = x.w + 2 * (Mx - 1);
+      H.Ho = x.h + My - 1; H.Wo = x.w + Mx - 1; H.batch = x.n;
+      SEG_REQUIRE(H.Ho == (y.h - py + s - 1) / s && H.Wo == (y.w - px + s - 1) / s,
+                  SEG_E_BAD_SHAPE, "deconv_fwd: output %dx%d is not in*stride + k - stride", y.h,
+                  y.w);
+      seg_view yv = y;
+      yv.ptr = reinterpret_cast<uint8_t*>(y.ptr) + ((int64_t)py * y.sh + (int64_t)px * y.sw) * esz;
+      yv.h = H.Ho; yv.w = H.Wo;
+      yv.sh = y.sh * s; yv.sw = y.sw * s;
+      H.w = w; H.w_rows = k * k * d.cout_pad; H.w_cols = d.cin_pad;
+      H.b_mn = false; H.b_rows_per_tap = d.cout_pad; H.tap_flip = false;
+      H.N_total = d.cout_pad; H.max_bn = d.cout_pad;
+      H.d0 = make_dest(&yv, nullptr);
+      H.bias = bias; H.flags = d.flags;
+      int rows[25];
+      if (My * Mx > 25) return SEG_E_UNSUPPORTED;
+      for (int r = 0; r < My; ++r)
+        for (int c = 0; c < Mx; ++c)
+          rows[r * Mx + c] = ((py + s * (My - 1 - r)) * k + (px + s * (Mx - 1 - c))) * d.cout_pad;
+      H.tap_rows = rows;
+      const int rc = launch_hconv(H, st);
+      if (rc) return rc;
+    }
+  }
+  return SEG_OK;
+}
+
+// transposed conv, VALID: k == stride as GEMM + pixel shuffle, k > stride by output parity
 int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
                     const seg_view& y, cudaStream_t st) {
-  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
-              SEG_E_UNSUPPORTED, "umma deconv_fwd: k == stride, VALID only");
+  SEG_REQUIRE(d.kh == d.kw && d.kh >= d.stride && d.pad_t == 0 && d.pad_l == 0 && d.pad_b == 0 &&
+                  d.pad_r == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_fwd: square k >= stride, VALID only");
+  SEG_REQUIRE(x.c == d.cin_pad, SEG_E_BAD_SHAPE, "deconv_fwd: x.c != cin_pad");
+  if (d.kh > d.stride) {
+    int rc = load_encoders();
+    if (rc) return rc;
+    SEG_REQUIRE(y.c <= d.cout_pad, SEG_E_BAD_SHAPE, "deconv_fwd: y.c > cout_pad");
+    return deconv_fwd_parity(d, x, w, bias, y, st);
+  }
   IgemmJob J;
   memset(&J, 0, sizeof(J));
   J.a1 = x;
   J.a2 = null_view();
-  SEG_REQUIRE(x.c == d.cin_pad, SEG_E_BAD_SHAPE, "deconv_fwd: x.c != cin_pad");
   J.kh = 1; J.kw = 1; J.stride = 1;
   J.Ho = x.h; J.Wo = x.w; J.batch = x.n;
   J.w = w; J.w_rows = d.kh * d.kw * d.cout_pad; J.w_cols = d.cin_pad;
@@ -1154,8 +1215,10 @@ int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, co
 
 int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
                       const seg_view& dx, const seg_view* mask, cudaStream_t st) {
-  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
-              SEG_E_UNSUPPORTED, "umma deconv_dgrad: k == stride, VALID only");
+  // dx[j] = sum_k dz[stride*j + k] * w[k]: a strided correlation over dz, any k >= stride
+  SEG_REQUIRE(d.kh == d.kw && d.kh >= d.stride && d.pad_t == 0 && d.pad_l == 0 && d.pad_b == 0 &&
+                  d.pad_r == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_dgrad: square k >= stride, VALID only");
   SEG_REQUIRE(dz.c == d.cout_pad, SEG_E_BAD_SHAPE, "deconv_dgrad: dz.c != cout_pad");
   IgemmJob J;
   memset(&J, 0, sizeof(J));
@@ -1175,8 +1238,9 @@ int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
 
 int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
                       cudaStream_t st) {
-  SEG_REQUIRE(d.kh == d.stride && d.kw == d.stride && d.pad_t == 0 && d.pad_l == 0,
-              SEG_E_UNSUPPORTED, "umma deconv_wgrad: k == stride, VALID only");
+  SEG_REQUIRE(d.kh == d.kw && d.kh >= d.stride && d.pad_t == 0 && d.pad_l == 0 && d.pad_b == 0 &&
+                  d.pad_r == 0,
+              SEG_E_UNSUPPORTED, "umma deconv_wgrad: square k >= stride, VALID only");
   WgradJob J;
   memset(&J, 0, sizeof(J));
   J.big = dz;

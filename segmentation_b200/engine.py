@@ -42,7 +42,7 @@ def xavier_uniform(shape, gen):
 
 class Param(object):
     __slots__ = ('name', 'shape', 'offset', 'numel', 'shadow_offset', 'shadow_shape',
-                 'trainable', 'store')
+                 'shadow_src', 'trainable', 'store')
 
     def value(self):
         return self.store.master[self.offset:self.offset + self.numel].view(self.shape)
@@ -68,10 +68,13 @@ class ParamStore(object):
         self._ns = 0
         self.finalized = False
 
-    def add(self, name, shape, shadow_shape=None):
+    def add(self, name, shape, shadow_shape=None, shadow_src=None):
+        """shadow_src: the shape the master is read as when it is copied into the padded
+        bf16 shadow (default: `shape`; e.g. an HWIO tensor read as [1,1,H*W*I,O])."""
         assert not self.finalized
         p = Param()
         p.name, p.shape, p.store = name, tuple(shape), self
+        p.shadow_src = tuple(shadow_src) if shadow_src is not None else tuple(shape)
         p.offset, p.numel = self._n, int(np.prod(shape))
         p.trainable = True
         self._n += p.numel
@@ -100,7 +103,7 @@ class ParamStore(object):
         seg, soff = [], []
         for p in self.params.values():
             if p.shadow_shape is not None:
-                inner, mid = p.shape[-1], p.shape[-2]
+                inner, mid = p.shadow_src[-1], p.shadow_src[-2]
                 inner_pad, mid_pad = p.shadow_shape[-1], p.shadow_shape[-2]
             else:
                 inner = inner_pad = p.shape[-1]
@@ -152,8 +155,8 @@ class ParamStore(object):
                 continue
             sh = p.shadow()
             sh.zero_()
-            idx = tuple(slice(0, s) for s in p.shape)
-            sh[idx] = p.value().to(BF16)
+            idx = tuple(slice(0, s) for s in p.shadow_src)
+            sh[idx] = p.value().reshape(p.shadow_src).to(BF16)
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
         """tf.train.AdamOptimizer update over the flat buffer (one launch); also
@@ -305,6 +308,43 @@ class ConvLayer(object):
             d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
             N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(dz),
                    N.ptr(self.w.grad()), st)
+
+
+class PatchConvLayer(ConvLayer):
+    """The first convolution of a model, on the raw few-channel input: seg_pack_patches
+    puts the k x k x cin patch of every output pixel into the channel axis, after which the
+    layer IS a 1x1 convolution over pad16(k*k*cin) channels.  Same TF variables
+    (`<name>/weights` [k,k,cin,cout] HWIO, `<name>/biases`): the HWIO tensor read as
+    [k*k*cin][cout] is the 1x1 weight matrix, and the 1x1 weight gradient lands in the
+    HWIO gradient unchanged.  (3 channels padded to 16 per tap waste 13/16 of every MMA and
+    make 32-byte TMA rows; the packed layer has 9x fewer MMAs and one 64-byte row per pixel.)"""
+
+    def __init__(self, store, name, k, stride, padding, cin, cout, relu=True, gen=None):
+        self.name, self.kind, self.relu = name, 'conv', relu
+        self.patch_k, self.patch_stride, self.patch_padding, self.patch_cin = k, stride, padding, cin
+        self.k, self.stride, self.padding = 1, 1, 'VALID'
+        self.cin, self.cout = k * k * cin, cout
+        self.cin_pad, self.cout_pad = pad16(self.cin), pad16(cout)
+        shape = (k, k, cin, cout)
+        self.w = store.add(name + '/weights', shape, (1, 1, self.cin_pad, self.cout_pad),
+                           shadow_src=(1, 1, self.cin, cout))
+        self.b = store.add(name + '/biases', (cout,))
+        self._init = xavier_uniform(shape, gen) if gen is not None else None
+
+    def patch_out_hw(self, h, w):
+        k, s = self.patch_k, self.patch_stride
+        if self.patch_padding == 'SAME':
+            return -(-h // s), -(-w // s)
+        return (h - k) // s + 1, (w - k) // s + 1
+
+    def pack(self, x_f32, y):
+        """x_f32 [B,H,W,cin] fp32 -> y [B,Ho,Wo,cin_pad] bf16 patch tensor."""
+        k, s = self.patch_k, self.patch_stride
+        h, w = x_f32.shape[1], x_f32.shape[2]
+        pt = same_pad(h, k, s)[0] if self.patch_padding == 'SAME' else 0
+        pl = same_pad(w, k, s)[0] if self.patch_padding == 'SAME' else 0
+        N.call('seg_pack_patches', N.ptr(x_f32), x_f32.shape[3], h, w, k, k, s, pt, pl,
+               N.vref(y), N.stream_ptr())
 
 
 class SideStream(object):

@@ -362,9 +362,14 @@ class ExecBase(object):
             self.group_ready(gi)
 
     def pack(self):
-        """fp32 [B,H,W,C] landing buffer -> bf16 input tensor with C padded to 16."""
+        """fp32 [B,H,W,C] landing buffer -> bf16 input tensor of the first layer."""
         if not self._prepacked:
-            E.pack_input(self.x_f32, self.act['x'])
+            self._pack_now()
+
+    def _pack_now(self):
+        """Default: C zero-padded to 16 channels.  Executors whose first layer is a
+        PatchConvLayer override this with its patch packing."""
+        E.pack_input(self.x_f32, self.act['x'])
 
     def _stage_async(self, x, mask):
         """Copy a batch into the landing buffers: host tensors go over the copy stream
@@ -411,7 +416,7 @@ class ExecBase(object):
         m = self.m
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ev_staged)
-        E.pack_input(self.x_f32, self.act['x'])
+        self._pack_now()
         self.mask.copy_(self.mask_in, non_blocking=True)
         self.ev_consumed.record(cur)
         self._prepacked = True

@@ -16,6 +16,8 @@ This is the only reference model whose MC-dropout placement is reference-defined
 `infer_mc` runs T stochastic passes of one tile as one batch and returns the
 mean / variance maps (BASELINE config 5).
 """
+import os
+
 import torch
 
 from .. import engine as E
@@ -180,10 +182,12 @@ class _DeconvExec(ExecBase):
         L['conv3_0'].forward(A['pool2'], A['conv3_0'], impl=impl); bn('bn3', 'conv3_0')
         E.maxpool_fwd(A['bn3'], A['pool3'], self.amax['pool3'], 3, 3)
         L['conv4_0'].forward(A['pool3'], A['conv4_0'], impl=impl); bn('bn4', 'conv4_0')
-        # 5x5 stride-2 transposed convs: overlapping taps -> CUDA-core gather kernel
-        L['deconv1_0'].forward(A['bn4'], A['deconv1_0'], impl=N.IMPL_SIMT); bn('bn5', 'deconv1_0')
-        L['deconv2_0'].forward(A['bn5'], A['deconv2_0'], impl=N.IMPL_SIMT); bn('bn6', 'deconv2_0')
-        L['deconv2_1'].forward(A['bn6'], A['deconv2_1'], impl=N.IMPL_SIMT); bn('bn7', 'deconv2_1')
+        # 5x5 stride-2 transposed convs: four output-parity classes, each a stride-1
+        # correlation with a 3x3 / 3x2 / 2x3 / 2x2 sub-kernel on the halo-tile tcgen05 kernel
+        dimpl = N.IMPL_SIMT if os.environ.get('SEGB200_DECONV5', 'umma') == 'simt' else impl
+        L['deconv1_0'].forward(A['bn4'], A['deconv1_0'], impl=dimpl); bn('bn5', 'deconv1_0')
+        L['deconv2_0'].forward(A['bn5'], A['deconv2_0'], impl=dimpl); bn('bn6', 'deconv2_0')
+        L['deconv2_1'].forward(A['bn6'], A['deconv2_1'], impl=dimpl); bn('bn7', 'deconv2_1')
         E.resize_bilinear_fwd(A['bn7'], A['resize'])
         nc = m.n_classes
         L['deconv3_0'].forward(A['resize'], A['deconv3_0'][..., :nc], impl=impl)
@@ -203,6 +207,9 @@ class _DeconvExec(ExecBase):
         m, L, A, G, impl = self.m, self.m.layers, self.act, self.g, self.m.impl
         nc = m.n_classes
         S = N.IMPL_SIMT
+        # 5x5 / stride-2 transposed convs: dgrad is a strided correlation over dz and wgrad the
+        # matching strided im2col GEMM - both on the tcgen05 im2col kernels
+        D5 = S if os.environ.get('SEGB200_DECONV5', 'umma') == 'simt' else impl
 
         def bn_bwd(name, src):
             if self._dropout is not None and name in self.SITES:
@@ -215,11 +222,11 @@ class _DeconvExec(ExecBase):
                                 dz_bias=G['deconv3_0'][..., :nc])
         E.resize_bilinear_bwd(G['resize'], G['bn7'])
         bn_bwd('bn7', 'deconv2_1')
-        L['deconv2_1'].backward(A['bn6'], G['deconv2_1'], dx=G['bn6'], impl=S)
+        L['deconv2_1'].backward(A['bn6'], G['deconv2_1'], dx=G['bn6'], impl=D5)
         bn_bwd('bn6', 'deconv2_0')
-        L['deconv2_0'].backward(A['bn5'], G['deconv2_0'], dx=G['bn5'], impl=S)
+        L['deconv2_0'].backward(A['bn5'], G['deconv2_0'], dx=G['bn5'], impl=D5)
         bn_bwd('bn5', 'deconv1_0')
-        L['deconv1_0'].backward(A['bn4'], G['deconv1_0'], dx=G['bn4'], impl=S)
+        L['deconv1_0'].backward(A['bn4'], G['deconv1_0'], dx=G['bn4'], impl=D5)
         bn_bwd('bn4', 'conv4_0')
         L['conv4_0'].backward(A['pool3'], G['conv4_0'], dx=G['pool3'], impl=impl)
         E.maxpool_bwd(G['pool3'], self.amax['pool3'], G['bn3'], 3, 3)

@@ -70,7 +70,16 @@ class UNetModel(BaseModel):
         def up(name, cin, cout):
             L[name] = E.ConvLayer(st, name, 'deconv', 2, 2, 'VALID', cin, cout, True, gen)
 
-        conv('conv1_1', self.input_channel, nk); conv('conv1_2', nk, nk)
+        # first layer.  Optional (SEGB200_PATCH_L1=1): 3x3x3 patch packed into 27 (of 32)
+        # channels + 1x1 conv (engine.PatchConvLayer).  Correct, but measured slower on the
+        # current kernels (1.415 vs 1.248 ms/step): a K=32 GEMM leaves the im2col kernel's
+        # LSU epilogue (~3k cycles per 128x32 tile) and 64-byte TMA rows exposed.
+        if os.environ.get('SEGB200_PATCH_L1', '0') == '1':
+            L['conv1_1'] = E.PatchConvLayer(st, 'conv1_1', 3, 1, 'VALID', self.input_channel, nk,
+                                            True, gen)
+        else:
+            conv('conv1_1', self.input_channel, nk)
+        conv('conv1_2', nk, nk)
         conv('conv2_1', nk, nk * 2); conv('conv2_2', nk * 2, nk * 2)
         conv('conv3_1', nk * 2, nk * 4); conv('conv3_2', nk * 4, nk * 4)
         conv('conv4_1', nk * 4, nk * 8); conv('conv4_2', nk * 8, nk * 8)
@@ -135,7 +144,11 @@ class _UNetExec(ExecBase):
             self.act[name] = torch.zeros(B, h, w, c, dtype=dtype, device=dev)
             return self.act[name]
 
-        buf('x', H, W, L['conv1_1'].cin_pad)
+        self.patch_l1 = isinstance(L['conv1_1'], E.PatchConvLayer)
+        if self.patch_l1:
+            buf('x', H - 2, W - 2, L['conv1_1'].cin_pad)
+        else:
+            buf('x', H, W, L['conv1_1'].cin_pad)
         # ---- encoder geometry
         h, w = H - 2, W - 2
         buf('conv1_1', h, w, nk)
@@ -168,6 +181,12 @@ class _UNetExec(ExecBase):
         self._init_io(model, B, H, W, oh, ow, model.n_classes, L['output'].cout_pad, training)
         if training:
             self._alloc_grads()
+
+    def _pack_now(self):
+        if self.patch_l1:
+            self.m.layers['conv1_1'].pack(self.x_f32, self.act['x'])
+        else:
+            E.pack_input(self.x_f32, self.act['x'])
 
     # ------------------------------------------------------------- buffers
     def skip_view(self, j):

@@ -211,7 +211,10 @@ DECONV_CASES = [
     ('up2_512_256', 1, 8, 8, 512, 256, 2, 2, 'VALID', ('simt', 'umma')),
     ('up2_32_2', 1, 10, 12, 32, 2, 2, 2, 'VALID', ('simt', 'umma')),
     ('up2_odd', 3, 7, 9, 128, 64, 2, 2, 'VALID', ('simt', 'umma')),
-    ('k5s2', 1, 11, 11, 64, 32, 5, 2, 'VALID', ('simt',)),
+    ('k5s2', 1, 11, 11, 64, 32, 5, 2, 'VALID', ('simt', 'umma')),
+    ('k5s2_256_64', 2, 13, 9, 256, 64, 5, 2, 'VALID', ('simt', 'umma')),
+    ('k5s2_32_32', 2, 27, 25, 32, 32, 5, 2, 'VALID', ('umma',)),
+    ('k3s2', 1, 10, 12, 64, 64, 3, 2, 'VALID', ('simt', 'umma')),
     ('k4s2_same', 1, 9, 9, 32, 16, 4, 2, 'SAME', ('simt',)),
 ]
 

@@ -108,7 +108,6 @@ SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const 
               SEG_E_BAD_SHAPE, "conv2d_fwd: output geometry mismatch (%dx%d)", y->h, y->w);
   SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "conv2d_fwd: bias missing");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->impl == SEG_IMPL_UMMA) return umma_conv_fwd(*d, *x, x2, w_bf16, bias, *y, st);
   DirectParams P;
   memset(&P, 0, sizeof(P));
   P.x = *x;
@@ -119,6 +118,9 @@ SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const 
   P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
   P.in_pad = d->cin_pad; P.out_pad = d->cout_pad;
   P.flags = d->flags & (SEG_EPI_BIAS | SEG_EPI_RELU | SEG_EPI_OUT_F32);
+  // class-map heads (<= 4 channels in and out): a streaming kernel for either impl
+  if (simt_tiny_conv_ok(P, d->cin)) return simt_tiny_conv(P, d->cin, st);
+  if (d->impl == SEG_IMPL_UMMA) return umma_conv_fwd(*d, *x, x2, w_bf16, bias, *y, st);
   return simt_direct(P, st);
 }
 

@@ -353,6 +353,50 @@ __global__ void resize_bilinear_fwd_kernel(seg_view x, seg_view y) {
   }
 }
 
+// 8 channels per thread, 16-byte accesses (same arithmetic per element as above)
+__global__ void resize_bilinear_fwd_vec8_kernel(seg_view x, seg_view y) {
+  pdl_trigger();
+  pdl_wait();
+  const float sy = (float)x.h / (float)y.h, sx = (float)x.w / (float)y.w;
+  const int cv = y.c / 8;
+  const int64_t total = (int64_t)y.n * y.h * y.w * cv;
+  GRID_STRIDE(idx, total) {
+    const int c0 = (idx % cv) * 8;
+    int64_t m = idx / cv;
+    const int ox = m % y.w;
+    m /= y.w;
+    const int oy = m % y.h;
+    const int n = m / y.h;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    legacy_src(oy, sy, x.h, y0, y1, ly);
+    legacy_src(ox, sx, x.w, x0, x1, lx);
+    const uint4 a = *reinterpret_cast<const uint4*>(view_at(x, n, y0, x0) + c0);
+    const uint4 b = *reinterpret_cast<const uint4*>(view_at(x, n, y0, x1) + c0);
+    const uint4 c = *reinterpret_cast<const uint4*>(view_at(x, n, y1, x0) + c0);
+    const uint4 d = *reinterpret_cast<const uint4*>(view_at(x, n, y1, x1) + c0);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float tl = e ? bf16_hi(aw[j]) : bf16_lo(aw[j]);
+        const float tr = e ? bf16_hi(bw[j]) : bf16_lo(bw[j]);
+        const float bl = e ? bf16_hi(cw[j]) : bf16_lo(cw[j]);
+        const float br = e ? bf16_hi(dw[j]) : bf16_lo(dw[j]);
+        const float top = tl + (tr - tl) * lx;
+        const float bot = bl + (br - bl) * lx;
+        r[e] = top + (bot - top) * ly;
+      }
+      o[j] = pack_bf16x2(r[0], r[1]);
+    }
+    *reinterpret_cast<uint4*>(view_at_mut(y, n, oy, ox) + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // gather form of ResizeBilinearGrad: each input pixel sums the outputs that read it
 __global__ void resize_bilinear_bwd_kernel(seg_view dy, seg_view dx) {
   const float sy = (float)dx.h / (float)dy.h, sx = (float)dx.w / (float)dy.w;
@@ -473,6 +517,40 @@ __global__ void bn_apply_kernel(seg_view x, const float* mean, const float* rstd
     const float r = is_var ? rsqrtf(rstd_or_var[c] + eps) : rstd_or_var[c];
     const float v = (__bfloat162float(view_at(x, n, yy, xx)[c]) - mean[c]) * r + beta[c];
     view_at_mut(y, n, yy, xx)[c] = __float2bfloat16(v);
+  }
+}
+
+// 8 channels per thread, 16-byte accesses; per-channel scale / shift from L1
+__global__ void bn_apply_vec8_kernel(seg_view x, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd_or_var, float eps, int is_var,
+                                     const float* __restrict__ beta, seg_view y) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = x.c / 8;
+  const int64_t total = (int64_t)x.n * x.h * x.w * cv;
+  GRID_STRIDE(idx, total) {
+    const int c0 = (idx % cv) * 8;
+    int64_t m = idx / cv;
+    const int xx = m % x.w;
+    m /= x.w;
+    const int yy = m % x.h;
+    const int n = m / x.h;
+    const uint4 u = *reinterpret_cast<const uint4*>(view_at(x, n, yy, xx) + c0);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * j + e;
+        const float sc = is_var ? rsqrtf(__ldg(rstd_or_var + c) + eps) : __ldg(rstd_or_var + c);
+        const float v = e ? bf16_hi(w[j]) : bf16_lo(w[j]);
+        r[e] = (v - __ldg(mean + c)) * sc + __ldg(beta + c);
+      }
+      o[j] = pack_bf16x2(r[0], r[1]);
+    }
+    *reinterpret_cast<uint4*>(view_at_mut(y, n, yy, xx) + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -968,7 +1046,11 @@ SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32,
 SEG_API int32_t seg_resize_bilinear_fwd(const seg_view* x, const seg_view* y, void* stream) {
   SEG_REQUIRE(x && y && x->c == y->c && x->n == y->n, SEG_E_BAD_SHAPE, "resize_bilinear_fwd");
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
-  resize_bilinear_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y);
+  if (vec8_ok(*x) && vec8_ok(*y))
+    SEG_CHECK_CUDA(launch_k(resize_bilinear_fwd_vec8_kernel, dim3(grid_for(total / 8, 256)), dim3(256),
+                            (size_t)0, (cudaStream_t)stream, *x, *y));
+  else
+    resize_bilinear_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -1037,8 +1119,12 @@ SEG_API int32_t seg_batchnorm_apply(const seg_view* x, const float* mean, const 
                             const float* beta, const seg_view* y, void* stream) {
   SEG_REQUIRE(x && y && mean && rstd && beta, SEG_E_BAD_SHAPE, "batchnorm_apply");
   const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, mean, rstd, 0.f, 0,
-                                                                          beta, *y);
+  if (vec8_ok(*x) && vec8_ok(*y))
+    SEG_CHECK_CUDA(launch_k(bn_apply_vec8_kernel, dim3(grid_for(total / 8, 256)), dim3(256), (size_t)0,
+                            (cudaStream_t)stream, *x, mean, rstd, 0.f, 0, beta, *y));
+  else
+    bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, mean, rstd, 0.f, 0,
+                                                                            beta, *y);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -1047,8 +1133,12 @@ SEG_API int32_t seg_batchnorm_infer(const seg_view* x, const float* moving_mean,
                             float eps, const float* beta, const seg_view* y, void* stream) {
   SEG_REQUIRE(x && y && moving_mean && moving_var && beta, SEG_E_BAD_SHAPE, "batchnorm_infer");
   const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      *x, moving_mean, moving_var, eps, 1, beta, *y);
+  if (vec8_ok(*x) && vec8_ok(*y))
+    SEG_CHECK_CUDA(launch_k(bn_apply_vec8_kernel, dim3(grid_for(total / 8, 256)), dim3(256), (size_t)0,
+                            (cudaStream_t)stream, *x, moving_mean, moving_var, eps, 1, beta, *y));
+  else
+    bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        *x, moving_mean, moving_var, eps, 1, beta, *y);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

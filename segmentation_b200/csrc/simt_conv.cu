@@ -8,6 +8,12 @@
 
 namespace segb {
 
+static int grid_for(int64_t total, int block) {
+  int64_t g = ceil_div64(total, block);
+  const int64_t cap = (int64_t)num_sms() * 32;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
 // out[n,p,q,oc] = sum_{r,s,ic} in[n,p*st+r-pt,q*st+s-pl,ic] * w[r,s,ic,oc]
 __global__ void direct_conv_kernel(DirectParams P) {
   const int ncg = P.out_pad / 8;
@@ -75,6 +81,74 @@ __global__ void direct_conv_kernel(DirectParams P) {
         reinterpret_cast<bf16*>(P.y.ptr)[off + oc] = __float2bfloat16(v);
     }
   }
+}
+
+// Convolution with <= 4 real input and <= 4 real output channels, stride 1 - a head that maps
+// class scores to class scores (DeconvModel conv_out 2 -> 2 at full resolution, reference
+// models/deconvolution.py:174).  One thread per output pixel, the whole filter bank in
+// shared memory, one 8-byte load per tap.  The tensor-core path would multiply 16 x 16
+// padded channels and is epilogue bound (4.6 ms at 32 x 1024 x 1024); this one streams.
+__global__ void tiny_conv_kernel(DirectParams P, int cin) {
+  __shared__ float sw[25 * 16];
+  __shared__ float sb[4];
+  const int taps = P.kh * P.kw;
+  for (int i = threadIdx.x; i < taps * 16; i += blockDim.x) {
+    const int t = i >> 4, ic = (i >> 2) & 3, oc = i & 3;
+    sw[i] = (ic < cin && oc < P.y.c)
+                ? __bfloat162float(P.w[((int64_t)t * P.in_pad + ic) * P.out_pad + oc]) : 0.f;
+  }
+  if (threadIdx.x < 4)
+    sb[threadIdx.x] = ((P.flags & SEG_EPI_BIAS) && (int)threadIdx.x < P.y.c) ? P.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int64_t total = (int64_t)P.y.n * P.y.h * P.y.w;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < total;
+       m += (int64_t)gridDim.x * blockDim.x) {
+    const int q = m % P.y.w;
+    const int64_t t2 = m / P.y.w;
+    const int p = t2 % P.y.h;
+    const int n = t2 / P.y.h;
+    float acc[4] = {sb[0], sb[1], sb[2], sb[3]};
+    for (int r = 0; r < P.kh; ++r) {
+      const int iy = p + r - P.pad_t;
+      if (iy < 0 || iy >= P.x.h) continue;
+      for (int s = 0; s < P.kw; ++s) {
+        const int ix = q + s - P.pad_l;
+        if (ix < 0 || ix >= P.x.w) continue;
+        const uint2 u = *reinterpret_cast<const uint2*>(view_at(P.x, n, iy, ix));
+        const float xv[4] = {__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                             __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u)};
+        const float* wt = sw + (r * P.kw + s) * 16;
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+          for (int oc = 0; oc < 4; ++oc) acc[oc] += xv[ic] * wt[ic * 4 + oc];
+      }
+    }
+    const int64_t off = n * P.y.sn + p * P.y.sh + q * P.y.sw;
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc) {
+      if (oc >= P.y.c) break;
+      float v = acc[oc];
+      if (P.flags & SEG_EPI_RELU) v = fmaxf(v, 0.f);
+      if (P.flags & SEG_EPI_OUT_F32)
+        reinterpret_cast<float*>(P.y.ptr)[off + oc] = v;
+      else
+        reinterpret_cast<bf16*>(P.y.ptr)[off + oc] = __float2bfloat16(v);
+    }
+  }
+}
+
+bool simt_tiny_conv_ok(const DirectParams& P, int cin) {
+  return cin <= 4 && P.y.c <= 4 && P.stride == 1 && P.x2.ptr == nullptr && P.kh * P.kw <= 25 &&
+         !(P.flags & SEG_EPI_RELU_MASK) && P.x.sw >= 4 && P.x.sw % 4 == 0 && P.x.sh % 4 == 0 &&
+         P.x.sn % 4 == 0 && (reinterpret_cast<uintptr_t>(P.x.ptr) & 7) == 0;
+}
+
+int simt_tiny_conv(const DirectParams& P, int cin, cudaStream_t st) {
+  const int64_t total = (int64_t)P.y.n * P.y.h * P.y.w;
+  tiny_conv_kernel<<<grid_for(total, 256), 256, 0, st>>>(P, cin);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
 }
 
 // out[n,h,w,oc] = sum_{r,s | (h+pt-r)%st==0} sum_ic src[n,(h+pt-r)/st,(w+pl-s)/st,ic]*w[r,s,oc,ic]
@@ -176,11 +250,6 @@ __global__ void corr_wgrad_kernel(WgradParams P) {
   }
 }
 
-static int grid_for(int64_t total, int block) {
-  int64_t g = ceil_div64(total, block);
-  const int64_t cap = (int64_t)num_sms() * 32;
-  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
-}
 
 int simt_direct(const DirectParams& P, cudaStream_t st) {
   const int64_t total = (int64_t)P.y.n * P.y.h * P.y.w * (P.out_pad / 8);

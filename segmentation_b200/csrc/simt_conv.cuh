@@ -34,6 +34,9 @@ struct WgradParams {
 };
 
 int simt_direct(const DirectParams& P, cudaStream_t st);
+// <= 4 real input and output channels, stride 1: streaming one-thread-per-pixel kernel
+bool simt_tiny_conv_ok(const DirectParams& P, int cin);
+int simt_tiny_conv(const DirectParams& P, int cin, cudaStream_t st);
 int simt_transposed(const TransParams& P, cudaStream_t st);
 int simt_wgrad(WgradParams P, cudaStream_t st);
 

@@ -75,7 +75,14 @@ class DeconvModel(BaseModel):
         def bn(name, c):
             L[name] = E.BatchNorm(st, name, c)
 
-        conv('conv1_0', 5, 2, 'SAME', self.input_channel, nk); bn('bn1', nk)
+        # conv1_0: 5x5 / stride 2 / SAME on the raw RGB input.  Optional (SEGB200_PATCH_L1=1):
+        # the 5x5x3 patch packed into 75 (of 80) channels + a 1x1 conv (engine.PatchConvLayer)
+        if os.environ.get('SEGB200_PATCH_L1', '0') == '1':
+            L['conv1_0'] = E.PatchConvLayer(st, 'conv1_0', 5, 2, 'SAME', self.input_channel, nk,
+                                            True, gen)
+        else:
+            conv('conv1_0', 5, 2, 'SAME', self.input_channel, nk)
+        bn('bn1', nk)
         conv('conv2_0', 3, 1, 'VALID', nk, nk * 2); bn('bn2', nk * 2)
         conv('conv3_0', 3, 1, 'VALID', nk * 2, nk * 4); bn('bn3', nk * 4)
         conv('conv4_0', 3, 1, 'VALID', nk * 4, nk * 8); bn('bn4', nk * 8)
@@ -140,8 +147,13 @@ class _DeconvExec(ExecBase):
             self.amax[name] = torch.zeros(B, h, w, t.shape[3], dtype=torch.uint8, device=dev)
             return h, w
 
-        buf('x', H, W, L['conv1_0'].cin_pad)
-        h, w = L['conv1_0'].out_hw(H, W)
+        self.patch_l1 = isinstance(L['conv1_0'], E.PatchConvLayer)
+        if self.patch_l1:
+            h, w = L['conv1_0'].patch_out_hw(H, W)
+            buf('x', h, w, L['conv1_0'].cin_pad)
+        else:
+            buf('x', H, W, L['conv1_0'].cin_pad)
+            h, w = L['conv1_0'].out_hw(H, W)
         pair('conv1_0', 'bn1', h, w, nk)
         h, w = pool('pool1', 'bn1', 2)
         h, w = pair('conv2_0', 'bn2', h - 2, w - 2, nk * 2)
@@ -159,6 +171,12 @@ class _DeconvExec(ExecBase):
             self.g = {name: torch.zeros_like(t) for name, t in self.act.items() if name != 'x'}
             self.g['logits'] = self.dlogits
         self.step_seed = 0
+
+    def _pack_now(self):
+        if self.patch_l1:
+            self.m.layers['conv1_0'].pack(self.x_f32, self.act['x'])
+        else:
+            E.pack_input(self.x_f32, self.act['x'])
 
     def forward(self, bn_training=None, dropout=None, per_image=False):
         m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl

@@ -104,6 +104,8 @@ CONV_CASES = [
     ('s5s2_rgb', 1, 32, 32, 3, 0, 32, 5, 2, 'SAME', True, False),
     ('bigM', 3, 40, 40, 32, 0, 32, 3, 1, 'VALID', True, False),
     ('c512', 1, 10, 10, 256, 0, 512, 3, 1, 'VALID', True, False),
+    ('head3x3_2_2', 2, 21, 19, 2, 0, 2, 3, 1, 'SAME', False, True),      # streaming class-map head
+    ('tiny_4_3', 1, 16, 18, 4, 0, 3, 3, 1, 'SAME', True, False),
 ]
 
 

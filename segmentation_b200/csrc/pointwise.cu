@@ -257,41 +257,76 @@ __device__ __forceinline__ double bil_w(int a, int k) {
   return 1.0 - fabs((double)a - center) / (double)F;
 }
 
-__global__ void bilinear_up_fwd_kernel(seg_view x, int f, seg_view add, seg_view y, int y_f32) {
+// The k tap weights are tabulated once per block (in double, as the reference's numpy code
+// computes them, utils/upsampling.py:13-24): evaluating bil_w per tap costs two double
+// divisions and made these kernels 10-30x slower than their memory traffic.
+constexpr int kBilMaxK = 64;
+
+// One thread = one output pixel x G consecutive channels (G <= 8 divides C): the tap
+// geometry and weights are shared by the G channels; 32-bit index arithmetic.
+__global__ void bilinear_up_fwd_kernel(seg_view x, int f, seg_view add, seg_view y, int y_f32,
+                                       int G) {
+  pdl_trigger();
   const int k = 2 * f - (f & 1);
   const int before = (k - f) / 2;
-  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
-  GRID_STRIDE(idx, total) {
-    const int c = idx % y.c;
-    int64_t m = idx / y.c;
+  __shared__ double swt[kBilMaxK];
+  for (int a = threadIdx.x; a < k; a += blockDim.x) swt[a] = bil_w(a, k);
+  __syncthreads();
+  pdl_wait();
+  const uint32_t cg = (uint32_t)(y.c / G);
+  const uint32_t total = (uint32_t)y.n * y.h * y.w * cg;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % cg) * G;
+    uint32_t m = idx / cg;
     const int ox = m % y.w;
     m /= y.w;
     const int oy = m % y.h;
     const int n = m / y.h;
     const int ty = oy + before, tx = ox + before;
-    float acc = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc[g] = 0.f;
     // contributing inputs i: 0 <= ty - i*f < k
     for (int i = ty / f; i >= 0 && ty - i * f < k; --i) {
       if (i >= x.h) continue;
-      const double wy = bil_w(ty - i * f, k);
+      const double wy = swt[ty - i * f];
       for (int j = tx / f; j >= 0 && tx - j * f < k; --j) {
         if (j >= x.w) continue;
-        const float wgt = (float)(wy * bil_w(tx - j * f, k));
-        acc += __bfloat162float(view_at(x, n, i, j)[c]) * wgt;
+        const float wgt = (float)(wy * swt[tx - j * f]);
+        const bf16* xp = view_at(x, n, i, j) + c0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (g < G) acc[g] += __bfloat162float(xp[g]) * wgt;
       }
     }
-    if (add.ptr) acc += __bfloat162float(view_at(add, n, oy, ox)[c]);
-    const int64_t off = n * y.sn + oy * y.sh + ox * y.sw + c;
-    if (y_f32)
-      reinterpret_cast<float*>(y.ptr)[off] = acc;
-    else
-      reinterpret_cast<bf16*>(y.ptr)[off] = __float2bfloat16(acc);
+    if (add.ptr) {
+      const bf16* ap = view_at(add, n, oy, ox) + c0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g < G) acc[g] += __bfloat162float(ap[g]);
+    }
+    const int64_t off = n * y.sn + oy * y.sh + ox * y.sw + c0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g < G) {
+        if (y_f32)
+          reinterpret_cast<float*>(y.ptr)[off + g] = acc[g];
+        else
+          reinterpret_cast<bf16*>(y.ptr)[off + g] = __float2bfloat16(acc[g]);
+      }
+    }
   }
 }
 
 __global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view mask, seg_view dx) {
+  pdl_trigger();
   const int k = 2 * f - (f & 1);
   const int before = (k - f) / 2;
+  __shared__ double swt[kBilMaxK];
+  for (int a = threadIdx.x; a < k; a += blockDim.x) swt[a] = bil_w(a, k);
+  __syncthreads();
+  pdl_wait();
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * dx.c;
   GRID_STRIDE(idx, total) {
     const int c = idx % dx.c;
@@ -304,12 +339,13 @@ __global__ void bilinear_up_bwd_kernel(seg_view dy, int dy_f32, int f, seg_view 
     for (int a = 0; a < k; ++a) {
       const int oy = i * f + a - before;
       if (oy < 0 || oy >= dy.h) continue;
-      const double wy = bil_w(a, k);
+      const double wy = swt[a];
+      const int64_t row = n * dy.sn + oy * dy.sh + c;
       for (int b = 0; b < k; ++b) {
         const int ox = j * f + b - before;
         if (ox < 0 || ox >= dy.w) continue;
-        const float wgt = (float)(wy * bil_w(b, k));
-        const int64_t off = n * dy.sn + oy * dy.sh + ox * dy.sw + c;
+        const float wgt = (float)(wy * swt[b]);
+        const int64_t off = row + ox * dy.sw;
         const float g = dy_f32 ? reinterpret_cast<const float*>(dy.ptr)[off]
                                : __bfloat162float(reinterpret_cast<const bf16*>(dy.ptr)[off]);
         acc += g * wgt;
@@ -618,6 +654,12 @@ __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* los
   pdl_wait();
   const int C = logits.c;
   const int64_t pixels = (int64_t)logits.n * logits.h * logits.w;
+  // fast path: the pixel's logits live in registers (one read), exp evaluated once, the
+  // bf16 gradient row leaves as 16-byte stores
+  const bool reg_path = C <= 32 && (!dlogits.ptr || (dlogits.c <= 32 && dlogits.c % 8 == 0 &&
+                                                     dlogits.sw % 8 == 0 && dlogits.sh % 8 == 0 &&
+                                                     dlogits.sn % 8 == 0 &&
+                                                     (reinterpret_cast<uintptr_t>(dlogits.ptr) & 15) == 0));
   float local = 0.f;
   GRID_STRIDE(m, pixels) {
     const int xx = m % logits.w;
@@ -628,6 +670,42 @@ __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* los
         reinterpret_cast<const float*>(logits.ptr) + n * logits.sn + yy * logits.sh + xx * logits.sw;
     const int lab = reinterpret_cast<const uint8_t*>(labels.ptr)[n * labels.sn + yy * labels.sh +
                                                                  xx * labels.sw];
+    if (reg_path) {
+      float v[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        v[c] = c < C ? lp[c] : -INFINITY;
+        mx = fmaxf(mx, v[c]);
+      }
+      float se = 0.f, picked = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c == lab) picked = v[c];
+        v[c] = c < C ? expf(v[c] - mx) : 0.f;
+        se += v[c];
+      }
+      local += mx + logf(se) - (lab < C ? picked : 0.f);
+      if (dlogits.ptr) {
+        bf16* dp = view_at_mut(dlogits, n, yy, xx);
+        const float inv_se = 1.f / se;
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          if (c8 < dlogits.c) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = c8 + 2 * j;
+              const float g0 = c < C ? (v[c] * inv_se - (c == lab ? 1.f : 0.f)) * inv_pixels : 0.f;
+              const float g1 = c + 1 < C ? (v[c + 1] * inv_se - (c + 1 == lab ? 1.f : 0.f)) * inv_pixels : 0.f;
+              o[j] = pack_bf16x2(g0, g1);
+            }
+            *reinterpret_cast<uint4*>(dp + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      continue;
+    }
     float mx = -INFINITY;
     for (int c = 0; c < C; ++c) mx = fmaxf(mx, lp[c]);
     float se = 0.f;
@@ -1023,19 +1101,25 @@ SEG_API int32_t seg_relu_grad(const seg_view* dy, const seg_view* y, const seg_v
 
 SEG_API int32_t seg_bilinear_upsample_fwd(const seg_view* x, int32_t factor, const seg_view* add,
                                   const seg_view* y, int32_t y_is_f32, void* stream) {
-  SEG_REQUIRE(x && y && factor >= 1, SEG_E_BAD_SHAPE, "bilinear_upsample_fwd: bad argument");
+  SEG_REQUIRE(x && y && factor >= 1 && factor <= 32, SEG_E_BAD_SHAPE,
+              "bilinear_upsample_fwd: bad argument");
   SEG_REQUIRE(y->h == x->h * factor && y->w == x->w * factor && y->c == x->c, SEG_E_BAD_SHAPE,
               "bilinear_upsample_fwd: y must be x scaled by factor");
-  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  int G = 1;
+  for (int g = 8; g >= 2; --g)
+    if (y->c % g == 0) { G = g; break; }
+  const int64_t total = (int64_t)y->n * y->h * y->w * (y->c / G);
+  SEG_REQUIRE(total < (int64_t)1 << 31, SEG_E_UNSUPPORTED, "bilinear_upsample_fwd: tensor too large");
   bilinear_up_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      *x, factor, add ? *add : null_view(), *y, y_is_f32);
+      *x, factor, add ? *add : null_view(), *y, y_is_f32, G);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
 
 SEG_API int32_t seg_bilinear_upsample_bwd(const seg_view* dy, int32_t dy_is_f32, int32_t factor,
                                   const seg_view* mask_src, const seg_view* dx, void* stream) {
-  SEG_REQUIRE(dy && dx && factor >= 1, SEG_E_BAD_SHAPE, "bilinear_upsample_bwd: bad argument");
+  SEG_REQUIRE(dy && dx && factor >= 1 && factor <= 32, SEG_E_BAD_SHAPE,
+              "bilinear_upsample_bwd: bad argument");
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * dx->c;
   bilinear_up_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       *dy, dy_is_f32, factor, mask_src ? *mask_src : null_view(), *dx);

@@ -38,7 +38,7 @@ def timed(fn, n):
 
 
 out = []
-which = sys.argv[1:] or ['2', '4', '5u', '5d']
+which = (sys.argv[1:] if __name__ == "__main__" else ["none"]) or ['2', '4', '5u', '5d']
 if '2' in which:
     ds = DS(16, 512, 21)
     m = FCNModel(None, dataset=ds, n_classes=21, fcn_type='8s', input_dims=512, n_kernels=32,

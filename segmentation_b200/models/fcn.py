@@ -163,6 +163,13 @@ class _FCNExec(ExecBase):
 
     def backward(self):
         m, L, A, G, impl, v = self.m, self.m.layers, self.act, self.g, self.m.impl, self.v
+        side = self.side if self.use_side else None
+
+        def bw(name, *args, **kw):
+            # weight gradients on the side stream (they only feed the optimizer)
+            L[name].backward(*args, impl=impl, side=side, **kw)
+            self.layer_done(name)
+
         t = m.fcn_type
         dl = v(G['logits'])
         if t == '32s':
@@ -171,30 +178,28 @@ class _FCNExec(ExecBase):
             E.bilinear_upsample_bwd(dl, 16, v(G['fuse4']))
             E.relu_grad(v(G['fuse4']), v(A['pool4_score']), v(G['pool4_score']))
             E.bilinear_upsample_bwd(v(G['fuse4']), 2, v(G['conv_fr']), mask=v(A['conv_fr']))
-            L['fcn16s/pool4_score'].backward(A['pool4'], G['pool4_score'], dx=G['pool4_b'],
-                                             impl=impl)
+            bw('fcn16s/pool4_score', A['pool4'], G['pool4_score'], dx=G['pool4_b'])
         else:
             E.bilinear_upsample_bwd(dl, 8, v(G['fuse3']))
             E.relu_grad(v(G['fuse3']), v(A['pool3_score']), v(G['pool3_score']))
             E.bilinear_upsample_bwd(v(G['fuse3']), 2, v(G['fuse4']))
             E.relu_grad(v(G['fuse4']), v(A['pool4_score']), v(G['pool4_score']))
             E.bilinear_upsample_bwd(v(G['fuse4']), 2, v(G['conv_fr']), mask=v(A['conv_fr']))
-            L['fcn8s/pool3_score'].backward(A['pool3'], G['pool3_score'], dx=G['pool3_b'],
-                                            impl=impl)
-            L['fcn8s/pool4_score'].backward(A['pool4'], G['pool4_score'], dx=G['pool4_b'],
-                                            impl=impl)
-        L['conv_fr'].backward(A['conv7'], G['conv_fr'], dx=G['conv7'], mask=A['conv7'], impl=impl)
-        L['conv7'].backward(A['conv6'], G['conv7'], dx=G['conv6'], mask=A['conv6'], impl=impl)
-        L['conv6'].backward(A['pool5'], G['conv6'], dx=G['pool5'], impl=impl)
+            bw('fcn8s/pool3_score', A['pool3'], G['pool3_score'], dx=G['pool3_b'])
+            bw('fcn8s/pool4_score', A['pool4'], G['pool4_score'], dx=G['pool4_b'])
+        bw('conv_fr', A['conv7'], G['conv_fr'], dx=G['conv7'], mask=A['conv7'])
+        bw('conv7', A['conv6'], G['conv7'], dx=G['conv6'], mask=A['conv6'])
+        bw('conv6', A['pool5'], G['conv6'], dx=G['pool5'])
         for i in range(5, 0, -1):
             conv, pool = 'conv%d' % i, 'pool%d' % i
             second = G.get(pool + '_b')
             if second is not None:
                 E.maxpool_bwd2(G[pool], second, self.amax[pool], G[conv], mask=A[conv])
             else:
-                E.maxpool_bwd(G[pool], self.amax[pool], G[conv], mask=A[conv])
+                E.maxpool_bwd(G[pool], self.amax[pool], G[conv], mask=A[conv], pooled=A[pool])
             if i > 1:
-                L[conv].backward(A['pool%d' % (i - 1)], G[conv], dx=G['pool%d' % (i - 1)],
-                                 impl=impl)
+                bw(conv, A['pool%d' % (i - 1)], G[conv], dx=G['pool%d' % (i - 1)])
             else:
-                L[conv].backward(A['x'], G[conv], dx=None, impl=impl)
+                bw(conv, A['x'], G[conv], dx=None)
+        if side is not None:
+            side.join()

@@ -43,6 +43,34 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'src': 'fallback'}
 
 
+_ALL_CORES = os.sched_getaffinity(0)
+
+
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process to the CPU cores of the GPU's NUMA node before any pinned host memory
+    is allocated (first-touch places the pages there), so H2D DMA does not cross sockets.
+    Returns a short description for the bench line; silently does nothing where sysfs does
+    not expose the topology (single node, containers without /sys access)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(gpu_index)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read().strip())
+        if node < 0:
+            return 'numa_node=-1 (no binding)'
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 'numa_node=%d (no usable cores)' % node
+        os.sched_setaffinity(0, cpus)
+        return 'numa_node=%d, %d cores' % (node, len(cpus))
+    except Exception as e:                       # noqa: BLE001 - best effort
+        return 'unavailable (%s)' % type(e).__name__
+
+
 class SyntheticDataSet(object):
     """images fp32 [B,256,256,3] ~ U[0,1), masks uint8 [B,256,256,1] ~ Bernoulli(.5)
     (reference utils/datasets.py:174-190 tensor contract); a small pool of pinned
@@ -223,6 +251,7 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
@@ -331,6 +360,7 @@ def run_ours(args):
     if args.skip_cpu:
         cpu_rate, cores, sample = None, 0, 'skipped (--skip-cpu)'
     else:
+        os.sched_setaffinity(0, _ALL_CORES)      # the CPU baseline gets every host core
         cpu_rate, cores, sample, _ = cpu_oracle_rate(2, 1)
     line = {
         'metric': 'U-Net train img/s (256x256, bs16/GPU)', 'value': value, 'unit': 'img/s',
@@ -342,7 +372,8 @@ def run_ours(args):
                    'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
                    'l2': 'per-step working set (>1 GB activations+gradients) exceeds the 126 MB L2; '
                          '4 distinct input batches cycled',
-                   'impl': 'umma' if model.impl == 0 else 'simt', 'cuda_graph': True},
+                   'impl': 'umma' if model.impl == 0 else 'simt', 'cuda_graph': True,
+                   'cpu_affinity': affinity},
         'e2e': {'value': e2e, 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K},
         'gpu_launches': launches_per_step * K,

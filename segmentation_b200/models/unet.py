@@ -51,8 +51,9 @@ class UNetModel(BaseModel):
         self.model_name = 'unet'
         self.IN_OUT_CROP = True
         self.n_kernels = n_kernels
-        # encoder conv1..4 | bottleneck conv5_* (61 % of the bytes) | decoder
-        self.opt_splits = ('conv5_1', 'upconv1')
+        # conv1-2 | conv3-4 | bottleneck conv5_* (61 % of the bytes) | decoder: the group that
+        # completes last (and whose all-reduce + Adam is exposed at the end of the step) is small
+        self.opt_splits = tuple(os.environ.get('SEGB200_OPT_SPLITS', 'conv3_1,conv5_1,upconv1').split(','))
         self._finish_init(seed)
         self.y_hat = None          # logits of the most recent forward (device fp32 tensor)
         self.y_hat_sig = None

@@ -44,3 +44,26 @@ print('stage only: %.3f ms' % timed(lambda: ex.stage(x, y)))
 print('train_step(batch) no readback: %.3f ms' % timed(lambda: model.train_step(ds.next_batch())))
 print('train_step(batch) + loss: %.3f ms' % timed(lambda: (model.train_step(ds.next_batch()), model.seg_loss_op)))
 print('train_step() + loss: %.3f ms' % timed(lambda: (model.train_step(), model.seg_loss_op)))
+
+# distribution of the end-to-end step time: 6 x 30 steps, per-step host wall times
+import statistics
+for rep in range(6):
+    ts = []
+    torch.cuda.synchronize()
+    for i in range(30):
+        t0 = time.perf_counter()
+        model.train_step(); _ = model.seg_loss_op
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print('rep %d: mean %.3f median %.3f max %.3f ms  slow steps(>2ms): %d' %
+          (rep, statistics.mean(ts), statistics.median(ts), max(ts), sum(t > 2 for t in ts)))
+# same with the NVML sampler thread of bench.py running
+cs = bench.ClockSampler(0)
+for rep in range(3):
+    ts = []
+    for i in range(30):
+        t0 = time.perf_counter()
+        model.train_step(); _ = model.seg_loss_op
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print('with sampler rep %d: mean %.3f median %.3f max %.3f ms  slow steps(>2ms): %d' %
+          (rep, statistics.mean(ts), statistics.median(ts), max(ts), sum(t > 2 for t in ts)))
+print(cs.stop())

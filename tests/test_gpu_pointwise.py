@@ -233,3 +233,33 @@ def test_mc_mean_var_and_pack(cuda):
     assert torch.allclose(var.cpu(), probs.var(0, unbiased=False), atol=1e-6)
     assert torch.equal(y.float().cpu()[..., :3], bfr(x))
     assert float(y.float().cpu()[..., 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('k,stride,padding', [(3, 1, 'VALID'), (3, 1, 'SAME'), (5, 2, 'SAME')])
+def test_pack_patches_bit_exact(cuda, k, stride, padding):
+    """seg_pack_patches: channel (r*k+s)*C+c of output pixel (oy,ox) is the bf16 rounding of
+    x[oy*stride+r-pad_t, ox*stride+s-pad_l, c] (TF SAME padding: extra pixel bottom/right),
+    zero outside the image and in the padding channels."""
+    g = _gen(21)
+    Nb, H, W, C = 2, 13, 18, 3
+    x = torch.rand(Nb, H, W, C, generator=g)
+    st = E.ParamStore(torch.device('cuda'))
+    lay = E.PatchConvLayer(st, 'c', k, stride, padding, C, 32)
+    Ho, Wo = lay.patch_out_hw(H, W)
+    y = torch.full((Nb, Ho, Wo, lay.cin_pad), float('nan'), dtype=BF16, device='cuda')
+    lay.pack(x.cuda(), y)
+    sync()
+    pt = E.same_pad(H, k, stride)[0] if padding == 'SAME' else 0
+    pl = E.same_pad(W, k, stride)[0] if padding == 'SAME' else 0
+    ref = torch.zeros(Nb, Ho, Wo, lay.cin_pad)
+    for r in range(k):
+        for s in range(k):
+            for oy in range(Ho):
+                yy = oy * stride + r - pt
+                if not 0 <= yy < H:
+                    continue
+                for ox in range(Wo):
+                    xx = ox * stride + s - pl
+                    if 0 <= xx < W:
+                        ref[:, oy, ox, (r * k + s) * C:(r * k + s + 1) * C] = x[:, yy, xx]
+    assert torch.equal(y.float().cpu(), bfr(ref))

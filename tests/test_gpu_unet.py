@@ -218,3 +218,31 @@ def test_unet_config1_full_size_parity(cuda):
     report('unet_config1', rec)
     assert abs(loss - float(loss_ref)) < 2e-3 and rec['logits'] < 1e-2, rec
     assert not bad, bad
+
+
+def test_train_step_prefetch_pipeline_matches_explicit_batches(cuda):
+    """train_step() (batch pulled from the dataset, next batch's H2D issued on the copy
+    stream behind the step) and train_step(batch) walk through identical losses; an
+    explicit batch in between neither drops nor reorders the dataset's batches."""
+    model_a, ds_a, _ = _make('umma', lr=1e-4)
+    model_b, ds_b, _ = _make('umma', lr=1e-4)
+    feed = FeedDataSet(2, 188, 188)
+    batches = [feed.next_batch() for _ in range(5)]
+    la, lb = [], []
+    for it in range(5):
+        model_a.train_step()                       # pulls batches[it] from ds_a, prefetches it+1
+        la.append(model_a.seg_loss_op)
+        model_b.train_step(batches[it])
+        lb.append(model_b.seg_loss_op)
+    report('unet_prefetch', {'pipelined': la, 'explicit': lb})
+    # same kernels on the same batches; the fp32 reductions of the weight gradients are
+    # unordered, so the trajectories agree to rounding, not bit for bit
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-4, (la, lb)
+    # an explicit batch while a prefetched one is pending keeps the pending one for later
+    b5 = feed.next_batch()                         # the dataset's batch number 5
+    model_a.train_step(batches[0])
+    model_b.train_step(batches[0])
+    model_a.train_step()                           # must consume batch number 5 (a wrong batch
+                                                   # shows as a ~1e-2 difference)
+    model_b.train_step(b5)
+    assert abs(model_a.seg_loss_op - model_b.seg_loss_op) < 5e-4, (model_a.seg_loss_op, model_b.seg_loss_op)

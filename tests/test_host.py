@@ -61,3 +61,49 @@ def test_adam_lr_t_schedule():
     assert abs(l1 - 1e-4 * np.sqrt(1 - 0.999) / (1 - 0.9)) < 1e-12 and st.step == 1
     l2 = st.next_lr_t(1e-4)
     assert abs(l2 - 1e-4 * np.sqrt(1 - 0.999 ** 2) / (1 - 0.9 ** 2)) < 1e-12
+
+
+def test_optimizer_groups_partition_the_parameters():
+    """Optimizer groups (engine.ParamStore.chunk_range + BaseModel._init_opt_groups logic):
+    contiguous parameter slices in TF variable order whose Adam chunk ranges partition the
+    chunk table; boundaries coincide with the data-parallel bucket boundaries."""
+    from segmentation_b200 import parallel as P
+    st = E.ParamStore(torch.device('cpu'))
+    gen = np.random.default_rng(0)
+    names = ['conv1_1', 'conv3_1', 'conv5_1', 'conv5_2', 'upconv1', 'conv6_1', 'output']
+    for n in names:
+        E.ConvLayer(st, n, 'deconv' if n.startswith('up') else 'conv', 2 if n.startswith('up') else 3,
+                    1, 'VALID', 48, 80, True, gen)
+    st.finalize()
+    bounds = P.bucket_boundaries(st, ('conv3_1', 'conv5_1', 'upconv1'))
+    assert bounds[0] == 0 and bounds[-1] == st.numel and len(bounds) == 5
+    ranges = [st.chunk_range(a, b) for a, b in zip(bounds[:-1], bounds[1:])]
+    assert ranges[0][0] == 0 and ranges[-1][1] == st.nchunks
+    for (a0, a1), (b0, b1) in zip(ranges[:-1], ranges[1:]):
+        assert a1 == b0 and a0 < a1
+    # every chunk of a group addresses a parameter inside the group's slice
+    ch = st.chunks.view(-1, 2).tolist()
+    seg = st.segments.view(-1, 6).tolist()
+    for (c0, c1), (lo, hi) in zip(ranges, zip(bounds[:-1], bounds[1:])):
+        for si, first in ch[c0:c1]:
+            assert lo <= seg[si][0] + first < hi
+
+
+def test_patch_conv_layer_shadow_is_the_hwio_tensor_read_as_a_matrix():
+    """PatchConvLayer: same TF variable [k,k,cin,cout]; the bf16 shadow is that tensor read as
+    [k*k*cin][cout] with rows padded to a multiple of 16 (a 1x1 conv over packed patches)."""
+    st = E.ParamStore(torch.device('cpu'))
+    gen = np.random.default_rng(1)
+    lay = E.PatchConvLayer(st, 'conv1_1', 3, 1, 'VALID', 3, 32, True, gen)
+    st.finalize()
+    lay.init_values()
+    st.refresh_shadow()
+    assert lay.w.value().shape == (3, 3, 3, 32) and lay.w.shadow().shape == (1, 1, 32, 32)
+    assert (lay.k, lay.cin, lay.cin_pad, lay.cout_pad) == (1, 27, 32, 32)
+    assert lay.patch_out_hw(256, 256) == (254, 254)
+    sh = lay.w.shadow().float()[0, 0]
+    assert torch.equal(sh[:27], lay.w.value().reshape(27, 32).to(torch.bfloat16).float())
+    assert float(sh[27:].abs().max()) == 0.0
+    assert st.segments.view(-1, 6)[0].tolist() == [0, 864, 32, 32, 27, 32]
+    big = E.PatchConvLayer(E.ParamStore(torch.device('cpu')), 'conv1_0', 5, 2, 'SAME', 3, 32)
+    assert (big.cin, big.cin_pad) == (75, 80) and big.patch_out_hw(1024, 1024) == (512, 512)

@@ -54,7 +54,7 @@ __device__ __forceinline__ void prof_mark(long long* prof, int role, int tile_i,
 constexpr int kHconvMaxSB = 40;
 
 template <int KC, int BN, bool B_MN>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const HconvParams P) {
   constexpr int SWZ = KC * 2;
@@ -91,7 +91,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -241,6 +241,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   } else {
     // ============================= epilogue =============================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;              // two epilogue warps per TMEM lane quadrant
     int as = 0;
     uint32_t aphase = 0;
     const int img_stride = P.Hp * P.Wp;
@@ -265,7 +266,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tc_fence_after();
       prof_mark(eprof, 2, ti, 1);
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += (BN >= 32 ? 32 : 16)) {
+      for (int cc = half * (BN >= 32 ? 32 : 16); cc < BN; cc += 2 * (BN >= 32 ? 32 : 16)) {
         constexpr int W = BN >= 32 ? 32 : 16;
         uint32_t r[W];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + cc;

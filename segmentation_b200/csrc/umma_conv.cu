@@ -245,7 +245,7 @@ static int launch_igemm_t(const IgemmJob& J, cudaStream_t st) {
   const int m_tiles = (P.M_total + kBlockM - 1) / kBlockM;
   const int tiles = m_tiles * (J.N_total / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  SEG_CHECK_CUDA(launch_k(igemm_kernel<KC, BN, B_MN>, dim3(grid), dim3(kIgemmThreads), (size_t)(Cfg::kSmemBytes), st, tmA1, tmA2, tmB, P));
+  SEG_CHECK_CUDA(launch_k(igemm_kernel<KC, BN, B_MN>, dim3(grid), dim3(kConvThreads), (size_t)(Cfg::kSmemBytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -461,7 +461,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
     grid -= grid % n_tiles;           // every CTA must keep one N-slice for its lifetime
     if (grid < n_tiles) P.b_resident = 0, grid = tiles < num_sms() ? tiles : num_sms();
   }
-  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN>, dim3(grid), dim3(kIgemmThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
+  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN>, dim3(grid), dim3(kConvThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

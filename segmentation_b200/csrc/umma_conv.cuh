@@ -21,7 +21,12 @@
 namespace segb {
 
 constexpr int kBlockM = 128;
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 192;   // producer + MMA issuer + 4 epilogue warps (weight-gradient kernels)
+// conv kernels with the register/LSU epilogue: 8 epilogue warps, two per TMEM lane quadrant,
+// taking the 32-column chunks of a tile alternately.  One warp per scheduler issues only one
+// instruction per ~5 cycles in this dependent code (3.1k cycles per chunk measured with 4
+// warps), and for the small layers the epilogue of the last tile is not hidden by anything.
+constexpr int kConvThreads = 320;
 
 struct EpiDest {
   void* ptr;          // bf16 or fp32
@@ -71,7 +76,7 @@ struct IgemmCfg {
 };
 
 template <int KC, int BN, bool B_MN>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const IgemmParams P) {
   using Cfg = IgemmCfg<KC, BN>;
@@ -106,7 +111,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -208,6 +213,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   } else {
     // ============================= epilogue =============================
     const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;     // which warp of the quadrant's pair
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -238,7 +244,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += (BN >= 32 ? 32 : 16)) {
+      for (int cc = half * (BN >= 32 ? 32 : 16); cc < BN; cc += 2 * (BN >= 32 ? 32 : 16)) {
         constexpr int W = BN >= 32 ? 32 : 16;
         uint32_t r[W];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + cc;

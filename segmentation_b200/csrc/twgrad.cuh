@@ -52,7 +52,7 @@ constexpr int kTwTH = 8, kTwTW = 16, kTwPW = kTwTW + 2, kTwPH = kTwTH + 2;
 constexpr int kTwMaxStages = 8;
 
 template <int AW, int BN>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
               const __grid_constant__ CUtensorMap tmZ, const TwgradParams P) {
   constexpr int rowA = AW * 2;                          // bytes per staged X pixel
@@ -178,10 +178,13 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       }
     } else {
       // ====================== bias gradient + epilogue ======================
+      // 8 warps, two per TMEM lane quadrant; the first four also sum the bias gradient
+      // during the main loop, all eight share the accumulator drain (alternate MMAs)
       const int quad = warp & 3;
-      const int et = quad * 32 + lane;                 // 0..127 among the epilogue threads
-      if (clustered && et < BN) s_db[et] = 0.f;
-      if (do_db) {
+      const int half = (warp - 2) >> 2;
+      const int et = quad * 32 + lane;                 // 0..127 within each group of four warps
+      if (clustered && half == 0 && et < BN) s_db[et] = 0.f;
+      if (do_db && half == 0) {
         // thread -> one 16-byte chunk (8 channels) of the dZ rows r with r % kRG == rg
         constexpr int kChunks = BN / 8;                // 16-byte chunks per pixel (all atoms)
         constexpr int kRG = 128 / kChunks;             // row groups
@@ -232,9 +235,9 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       tc_fence_after();
       // every MMA has completed, so all stages were consumed; the other epilogue warps may
       // still be summing the last dZ tiles out of them
-      if (clustered || bulk_ok) named_bar_sync(2, 128);
+      if (clustered || bulk_ok) named_bar_sync(2, 256);
 #pragma unroll 1
-      for (int m = 0; m < kNMma; ++m) {
+      for (int m = half; m < kNMma; m += 2) {
         const int tap = AW == 64 ? 2 * m + a : (a < 3 ? 3 * m + a : 9);
         const bool row_ok = tap < 9 && ci < P.BC;
         float* dst = P.dw + ((int64_t)tap * P.BC + ci) * P.SC;
@@ -285,7 +288,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
 
   if (clustered) {
     // ---- cluster reduction: rank r owns accumulator columns [r*W, (r+1)*W) ----
-    if (my_tiles <= 0 && warp >= 2) {                  // (the launch gives every CTA a tile)
+    if (my_tiles <= 0 && warp >= 2 && warp < 6) {      // (the launch gives every CTA a tile)
       const int L = (warp & 3) * 32 + lane;
       for (int c = 0; c < kCols; c += 4)
         sts128(smem_u32(smem) + (uint32_t)((L * kPitch + c) * 4), make_uint4(0u, 0u, 0u, 0u));
@@ -293,7 +296,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     }
     __syncwarp();
     cluster_sync_all();                                // every member's S (and s_db) is complete
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int L = (warp & 3) * 32 + lane;
       const int a = L / AW, cl = L % AW;
       const int ci = chunk * AW + cl;

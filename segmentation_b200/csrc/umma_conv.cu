@@ -928,7 +928,7 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(combos * per);
-    cfg.blockDim = dim3(kIgemmThreads);
+    cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -954,7 +954,7 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   }
   P.cluster = cs;
   P.ctas_per_combo = per;
-  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kIgemmThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, P));
+  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kConvThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, P));
   return SEG_OK;
 }
 

@@ -309,9 +309,12 @@ def run_ours(args):
     barrier()
     e0.record()
     loss = 0.0
+    step_ms = []
     for i in range(K):
+        t0 = time.perf_counter()
         model.train_step()
         loss = model.seg_loss_op                 # D2H read of the step's loss
+        step_ms.append((time.perf_counter() - t0) * 1e3)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -380,7 +383,12 @@ def run_ours(args):
                    'impl': 'umma' if model.impl == 0 else 'simt', 'cuda_graph': True,
                    'cpu_affinity': affinity},
         'e2e': {'value': e2e, 'unit': 'img/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K},
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K,
+                # host wall time of the individual steps (rank 0): a slow host<->device link
+                # or a descheduled host thread shows here, not in the device-timed `value`
+                'host_step_ms': {'median': sorted(step_ms)[len(step_ms) // 2],
+                                 'p90': sorted(step_ms)[int(len(step_ms) * 0.9)],
+                                 'max': max(step_ms)}},
         'gpu_launches': launches_per_step * K,
         'launches_per_step': launches_per_step,
         'conv_tensor_frac': {'of_burst': value / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk['tf_burst'],

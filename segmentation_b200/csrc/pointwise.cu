@@ -949,6 +949,47 @@ __global__ void pack_patches_kernel(const float* __restrict__ x, int C, int H, i
   }
 }
 
+// Compile-time geometry: one thread builds the whole packed pixel in registers (KH*KW*C
+// values, fully unrolled, no index arithmetic per channel) and writes it as CP/8 16-byte
+// stores; neighbouring threads read overlapping input rows out of L1.
+template <int KH, int KW, int C>
+__global__ void pack_patches_fixed_kernel(const float* __restrict__ x, int H, int W, int stride,
+                                          int pad_t, int pad_l, seg_view y) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int R = KH * KW * C;
+  constexpr int CP = (R + 15) / 16 * 16;
+  const int64_t total = (int64_t)y.n * y.h * y.w;
+  GRID_STRIDE(m, total) {
+    const int ox = m % y.w;
+    const int64_t t = m / y.w;
+    const int oy = t % y.h;
+    const int n = t / y.h;
+    float v[CP];
+#pragma unroll
+    for (int i = R; i < CP; ++i) v[i] = 0.f;
+    const int y0 = oy * stride - pad_t, x0 = ox * stride - pad_l;
+#pragma unroll
+    for (int r = 0; r < KH; ++r) {
+      const int yy = y0 + r;
+      const bool row_in = yy >= 0 && yy < H;
+      const float* xr = x + (((int64_t)n * H + (row_in ? yy : 0)) * W) * C;
+#pragma unroll
+      for (int sx = 0; sx < KW; ++sx) {
+        const int xx = x0 + sx;
+        const bool in = row_in && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[(r * KW + sx) * C + c] = in ? __ldg(xr + (int64_t)xx * C + c) : 0.f;
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(view_at_mut(y, n, oy, ox));
+#pragma unroll
+    for (int g = 0; g < CP / 8; ++g)
+      dst[g] = make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                          pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+  }
+}
+
 // per-channel sums with 16-byte loads: thread = (pixel lane, 8-channel group)
 template <int MODE>   // 0: sum + sumsq   2: sum only
 __global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
@@ -1322,7 +1363,19 @@ SEG_API int32_t seg_pack_patches(const float* x, int32_t c, int32_t h, int32_t w
   SEG_REQUIRE(kh * kw * c <= y->c && vec8_ok(*y), SEG_E_BAD_SHAPE,
               "pack_patches: %d patch values do not fit %d channels (multiple of 8, 16-byte "
               "aligned view)", kh * kw * c, y->c);
-  const int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  const int64_t pixels = (int64_t)y->n * y->h * y->w;
+  const int cp = (kh * kw * c + 15) / 16 * 16;
+  if (c == 3 && kh == 3 && kw == 3 && y->c == cp) {
+    SEG_CHECK_CUDA(launch_k(pack_patches_fixed_kernel<3, 3, 3>, dim3(grid_for(pixels, 128)), dim3(128),
+                            (size_t)0, (cudaStream_t)stream, x, h, w, stride, pad_t, pad_l, *y));
+    return SEG_OK;
+  }
+  if (c == 3 && kh == 5 && kw == 5 && y->c == cp) {
+    SEG_CHECK_CUDA(launch_k(pack_patches_fixed_kernel<5, 5, 3>, dim3(grid_for(pixels, 128)), dim3(128),
+                            (size_t)0, (cudaStream_t)stream, x, h, w, stride, pad_t, pad_l, *y));
+    return SEG_OK;
+  }
+  const int64_t total = pixels * (y->c / 8);
   SEG_CHECK_CUDA(launch_k(pack_patches_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0,
                           (cudaStream_t)stream, x, c, h, w, kh, kw, stride, pad_t, pad_l, *y));
   return SEG_OK;

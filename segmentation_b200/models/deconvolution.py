@@ -75,9 +75,10 @@ class DeconvModel(BaseModel):
         def bn(name, c):
             L[name] = E.BatchNorm(st, name, c)
 
-        # conv1_0: 5x5 / stride 2 / SAME on the raw RGB input.  Optional (SEGB200_PATCH_L1=1):
-        # the 5x5x3 patch packed into 75 (of 80) channels + a 1x1 conv (engine.PatchConvLayer)
-        if os.environ.get('SEGB200_PATCH_L1', '0') == '1':
+        # conv1_0: 5x5 / stride 2 / SAME on the raw RGB input: the 5x5x3 patch is packed into 75
+        # (of 80) channels and the layer runs as a 1x1 conv (engine.PatchConvLayer): 25 taps of
+        # 16 zero-padded channels through TMA-im2col cost 2.96 ms at 32 x 1024^2, this ~1 ms
+        if os.environ.get('SEGB200_PATCH_DECONV', '1') == '1':
             L['conv1_0'] = E.PatchConvLayer(st, 'conv1_0', 5, 2, 'SAME', self.input_channel, nk,
                                             True, gen)
         else:

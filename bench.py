@@ -108,7 +108,7 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index, period=0.02):
+    def __init__(self, gpu_index, period=0.005):
         import threading
         self.sm, self.reasons, self.sm_max = [], set(), None
         self.p = self.f = self.thread = None
@@ -276,11 +276,6 @@ def run_ours(args):
         return float(t.item())
 
     W, K = max(3, args.warmup), args.steps
-    if world > 1:
-        # the first replays of a graph that contains NCCL collectives are slow (lazy channel
-        # setup): 1.60 ms/step over steps 6-25 vs 1.45 ms in steady state at 2 GPUs.  The
-        # line reports the warm-up actually done.
-        W = max(W, 10)
     dev_batches = [(x.to(dev), y.to(dev)) for x, y in ds.pool]
 
     # ---- launches per step (eager first step), then graph capture in warm-up
@@ -291,8 +286,10 @@ def run_ours(args):
         model.train_step(dev_batches[i % len(dev_batches)])
 
     # ---- value: inputs resident in HBM
-    barrier()
+    # (the sampler starts BEFORE the barrier: NVML initialisation takes tens of milliseconds
+    # on rank 0 only, and the other ranks would wait for it inside the first all-reduce)
     clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):

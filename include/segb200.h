@@ -211,6 +211,17 @@ SEG_API int32_t seg_dropout(const seg_view* x, uint64_t seed, uint32_t stream_id
 SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view* labels,
                                  float* loss_sum, const seg_view* dlogits, void* stream);
 
+/* Fused classification head for training: a 1x1 convolution to n_classes <= 4 (x bf16
+ * [n,h,w,cin], cin 16 or 32; w_bf16 = its [cin_pad][cout_pad] shadow; models/unet.py:166-167)
+ * + the loss above + the whole backward of that layer in one pass over x:
+ * logits (nullable, fp32 [n,h,w,n_classes]) = x.W + b; loss_sum += sum xent;
+ * dx = relu_mask_x(dlogits.W^T) (bf16, same geometry as x); dw [cin][n_classes] and
+ * db [n_classes] (fp32) are accumulated (+=).  dlogits is rounded to bf16 before it is
+ * used, as in the unfused path. */
+SEG_API int32_t seg_head1x1_xent(const seg_view* x, const void* w_bf16, int32_t cout_pad,
+                         const float* bias, const seg_view* labels, int32_t n_classes,
+                         const seg_view* logits, float* loss_sum, const seg_view* dx, float* dw,
+                         float* db, void* stream);
 /* ---- inference head (models/unet.py:76-79): probs = sigmoid(logits) (fp32),
  * labelmap = float32(argmax(sigmoid(logits), 3)), first index on ties. */
 SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* labelmap,

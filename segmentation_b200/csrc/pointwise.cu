@@ -1044,6 +1044,164 @@ __global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
   }
 }
 
+// ---------------------------------------------------- fused 1x1 head + loss + backward
+// The classification head of U-Net is a 1x1 convolution to <= 4 classes (reference
+// models/unet.py:166-167): per pixel, logits = x . W + b, softmax cross-entropy against the
+// label, dlogits, the head's weight / bias gradient and the input gradient
+// dx = relu_mask(dlogits . W^T) are all functions of that pixel's CIN channels.  One pass
+// over x (bf16) replaces five launches (conv fwd, loss, wgrad, dgrad, memset) at the
+// forward/backward turning point where nothing else can overlap.  Arithmetic matches the
+// unfused path: bf16 operands, fp32 accumulation, dlogits rounded to bf16 before use.
+template <int CIN, int CO>
+__global__ void __launch_bounds__(256)
+head1x1_xent_kernel(seg_view x, const bf16* __restrict__ w, int cout_pad,
+                    const float* __restrict__ bias, seg_view labels, seg_view logits,
+                    float* loss_sum, seg_view dx, float* dw, float* db, float inv_pixels) {
+  // two threads (a lane pair) per pixel, CIN/2 channels each: halves the per-thread
+  // weight-gradient accumulators so two blocks fit an SM
+  constexpr int HC = CIN / 2;
+  pdl_trigger();
+  __shared__ float sw[CIN * CO];
+  __shared__ float sb[CO];
+  __shared__ float red[8][CIN * CO + CO + 1];
+  pdl_wait();
+  for (int i = threadIdx.x; i < CIN * CO; i += blockDim.x)
+    sw[i] = __bfloat162float(w[(int64_t)(i / CO) * cout_pad + (i % CO)]);
+  if (threadIdx.x < CO) sb[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int h = threadIdx.x & 1;                  // which half of the channels
+  const float* swh = sw + h * HC * CO;
+  float gw[HC * CO];
+  float gb[CO];
+#pragma unroll
+  for (int i = 0; i < HC * CO; ++i) gw[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) gb[c] = 0.f;
+  float local = 0.f;
+  const int64_t pixels = (int64_t)x.n * x.h * x.w;
+  // every lane runs the same number of iterations (the pair shuffle below is full-warp);
+  // lanes past the end recompute the last pixel with a zero gradient and no stores
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 1;
+  const int64_t first = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 1;
+  const int64_t iters = (pixels + stride - 1) / stride;
+  for (int64_t it = 0; it < iters; ++it) {
+    int64_t m = first + it * stride;
+    const bool live = m < pixels;
+    if (!live) m = pixels - 1;
+    const int xx = m % x.w;
+    const int64_t t = m / x.w;
+    const int yy = t % x.h;
+    const int n = t / x.h;
+    float xv[HC];
+    const uint4* xp = reinterpret_cast<const uint4*>(view_at(x, n, yy, xx) + h * HC);
+#pragma unroll
+    for (int q = 0; q < HC / 8; ++q) {
+      const uint4 u = xp[q];
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { xv[8 * q + 2 * e] = bf16_lo(w4[e]); xv[8 * q + 2 * e + 1] = bf16_hi(w4[e]); }
+    }
+    float lg[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) lg[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < HC; ++k)
+#pragma unroll
+      for (int c = 0; c < CO; ++c) lg[c] += xv[k] * swh[k * CO + c];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      // the pair's partial sums in a fixed order (even-lane half first) on both lanes
+      const float other = __shfl_xor_sync(0xffffffffu, lg[c], 1);
+      lg[c] = (h == 0 ? lg[c] + other : other + lg[c]) + sb[c];
+      mx = fmaxf(mx, lg[c]);
+    }
+    if (logits.ptr && h == 0 && live) {
+      float* lp = reinterpret_cast<float*>(logits.ptr) + n * logits.sn + yy * logits.sh + xx * logits.sw;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) lp[c] = lg[c];
+    }
+    const int lab = reinterpret_cast<const uint8_t*>(labels.ptr)[n * labels.sn + yy * labels.sh +
+                                                                 xx * labels.sw];
+    float e[CO], se = 0.f, picked = 0.f;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      e[c] = expf(lg[c] - mx);
+      se += e[c];
+      if (c == lab) picked = lg[c];
+    }
+    if (h == 0 && live) local += mx + logf(se) - picked;
+    const float inv_se = 1.f / se;
+    float dl[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      dl[c] = live ? __bfloat162float(__float2bfloat16((e[c] * inv_se - (c == lab ? 1.f : 0.f)) * inv_pixels))
+                   : 0.f;
+      if (h == 0) gb[c] += dl[c];
+    }
+    uint32_t o[HC / 2];
+#pragma unroll
+    for (int k = 0; k < HC; k += 2) {
+      float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        g0 += dl[c] * swh[k * CO + c];
+        g1 += dl[c] * swh[(k + 1) * CO + c];
+        gw[k * CO + c] += xv[k] * dl[c];
+        gw[(k + 1) * CO + c] += xv[k + 1] * dl[c];
+      }
+      o[k / 2] = pack_bf16x2(xv[k] > 0.f ? g0 : 0.f, xv[k + 1] > 0.f ? g1 : 0.f);
+    }
+    if (live) {
+      uint4* dp = reinterpret_cast<uint4*>(view_at_mut(dx, n, yy, xx) + h * HC);
+#pragma unroll
+      for (int q = 0; q < HC / 8; ++q) dp[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+  }
+  // block reduction of dW, db and the loss: lanes of equal parity hold the same channel half
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < HC * CO; ++i) {
+    float v = gw[i];
+#pragma unroll
+    for (int o2 = 16; o2 >= 2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+    if (lane < 2) red[warp][lane * HC * CO + i] = v;
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const float v = warp_sum(gb[c]);
+    if (lane == 0) red[warp][CIN * CO + c] = v;
+  }
+  local = warp_sum(local);
+  if (lane == 0) red[warp][CIN * CO + CO] = local;
+  __syncthreads();
+  for (int i = threadIdx.x; i < CIN * CO + CO + 1; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += red[wq][i];
+    if (i < CIN * CO) atomicAdd(dw + i, v);
+    else if (i < CIN * CO + CO) atomicAdd(db + (i - CIN * CO), v);
+    else atomicAdd(loss_sum, v);
+  }
+}
+
+template <int CIN>
+static int launch_head1x1(int co, const seg_view& x, const bf16* w, int cout_pad, const float* bias,
+                          const seg_view& labels, const seg_view& logits, float* loss_sum,
+                          const seg_view& dx, float* dw, float* db, cudaStream_t st) {
+  const int64_t pixels = (int64_t)x.n * x.h * x.w;
+  int grid = num_sms() * 2;                                                  // one resident wave
+  if ((int64_t)grid * 128 > pixels) grid = (int)ceil_div64(pixels, 128);     // 2 threads per pixel
+  const float inv = 1.f / (float)pixels;
+  switch (co) {
+    case 2: SEG_CHECK_CUDA(launch_k(head1x1_xent_kernel<CIN, 2>, dim3(grid), dim3(256), (size_t)0, st, x, w, cout_pad, bias, labels, logits, loss_sum, dx, dw, db, inv)); return SEG_OK;
+    case 3: SEG_CHECK_CUDA(launch_k(head1x1_xent_kernel<CIN, 3>, dim3(grid), dim3(256), (size_t)0, st, x, w, cout_pad, bias, labels, logits, loss_sum, dx, dw, db, inv)); return SEG_OK;
+    case 4: SEG_CHECK_CUDA(launch_k(head1x1_xent_kernel<CIN, 4>, dim3(grid), dim3(256), (size_t)0, st, x, w, cout_pad, bias, labels, logits, loss_sum, dx, dw, db, inv)); return SEG_OK;
+  }
+  set_error("head1x1_xent: 2..4 classes supported, got %d", co);
+  return SEG_E_UNSUPPORTED;
+}
+
 }  // namespace segb
 
 using namespace segb;
@@ -1308,6 +1466,27 @@ SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view*
   SEG_CHECK_CUDA(launch_k(softmax_xent_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *logits, *labels, loss_sum, dlogits ? *dlogits : null_view(), 1.f / (float)pixels));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
+}
+
+SEG_API int32_t seg_head1x1_xent(const seg_view* x, const void* w_bf16, int32_t cout_pad,
+                                 const float* bias, const seg_view* labels, int32_t n_classes,
+                                 const seg_view* logits, float* loss_sum, const seg_view* dx,
+                                 float* dw, float* db, void* stream) {
+  SEG_REQUIRE(x && w_bf16 && labels && loss_sum && dx && dw && db, SEG_E_BAD_SHAPE,
+              "head1x1_xent: null argument");
+  SEG_REQUIRE(labels->h == x->h && labels->w == x->w && labels->n == x->n && dx->h == x->h &&
+                  dx->w == x->w && dx->n == x->n && dx->c == x->c,
+              SEG_E_BAD_SHAPE, "head1x1_xent: geometry mismatch");
+  SEG_REQUIRE(vec8_ok(*x) && vec8_ok(*dx), SEG_E_ALIGN, "head1x1_xent: x / dx must allow 16-byte rows");
+  const seg_view lg = logits ? *logits : null_view();
+  const bf16* w = reinterpret_cast<const bf16*>(w_bf16);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x->c) {
+    case 16: return launch_head1x1<16>(n_classes, *x, w, cout_pad, bias, *labels, lg, loss_sum, *dx, dw, db, st);
+    case 32: return launch_head1x1<32>(n_classes, *x, w, cout_pad, bias, *labels, lg, loss_sum, *dx, dw, db, st);
+  }
+  set_error("head1x1_xent: 16 or 32 input channels supported, got %d", x->c);
+  return SEG_E_UNSUPPORTED;
 }
 
 SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* labelmap, void* stream) {

@@ -405,6 +405,15 @@ def softmax_xent(logits, labels, loss_sum, dlogits=None):
            N.vref(dlogits), N.stream_ptr())
 
 
+def head1x1_xent(x, layer, labels, logits, loss_sum, dx):
+    """Fused training head: 1x1 conv `layer` (<= 4 classes) + softmax x-entropy + the
+    layer's weight / bias gradient + the input gradient dx, one pass over x."""
+    N.set_tag(layer.name)
+    N.call('seg_head1x1_xent', N.vref(x), N.ptr(layer.w.shadow()), layer.cout_pad,
+           N.ptr(layer.b.value()), N.vref(labels), layer.cout, N.vref(logits), N.ptr(loss_sum),
+           N.vref(dx), N.ptr(layer.w.grad()), N.ptr(layer.b.grad()), N.stream_ptr())
+
+
 def sigmoid_argmax(logits, probs, labelmap):
     N.call('seg_sigmoid_argmax', N.vref(logits), N.ptr(probs), N.ptr(labelmap), N.stream_ptr())
 

@@ -182,6 +182,10 @@ class _UNetExec(ExecBase):
         self._init_io(model, B, H, W, oh, ow, model.n_classes, L['output'].cout_pad, training)
         if training:
             self._alloc_grads()
+        # training: the 1x1 head, the loss and the head's backward are one kernel
+        self.fused_head = (training and model.n_classes <= 4 and nk in (16, 32) and
+                           model.impl == N.IMPL_UMMA and
+                           os.environ.get('SEGB200_FUSED_HEAD', '1') != '0')
 
     def _pack_now(self):
         if self.patch_l1:
@@ -259,8 +263,19 @@ class _UNetExec(ExecBase):
             conv('conv%d_1' % (5 + j), self.skip_view(j), x2=A[up])
             conv('conv%d_2' % (5 + j), A['conv%d_1' % (5 + j)])
             below = A['conv%d_2' % (5 + j)]
-        L['output'].forward(below, self.logits, impl=impl, out_f32=True)
+        if not self.fused_head:                   # else loss() runs the head as well
+            L['output'].forward(below, self.logits, impl=impl, out_f32=True)
         m.y_hat = self.logits
+
+    def loss(self, with_grad):
+        if not (self.fused_head and with_grad):
+            if self.fused_head:                   # loss only, on a training executor
+                self.m.layers['output'].forward(self.act['conv9_2'], self.logits, impl=self.m.impl,
+                                                out_f32=True)
+            return super(_UNetExec, self).loss(with_grad)
+        E.fill_zero(self.loss_sum)
+        E.head1x1_xent(self.act['conv9_2'], self.m.layers['output'], self.mask_view(), self.logits,
+                       self.loss_sum, self.g['conv9_2'])
 
     # ------------------------------------------------------------ backward
     def backward(self):
@@ -274,9 +289,10 @@ class _UNetExec(ExecBase):
             L[name].backward(*args, impl=impl, side=side, **kw)
             self.layer_done(name)
 
-        # head (no activation): dz = dlogits
-        bw('output', A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],
-           dz_bias=G['logits'][..., :nc])
+        # head (no activation): dz = dlogits; already done by loss() when the head is fused
+        if not self.fused_head:
+            bw('output', A['conv9_2'], G['logits'], dx=G['conv9_2'], mask=A['conv9_2'],
+               dz_bias=G['logits'][..., :nc])
         for j in range(4, 0, -1):
             c1, c2, up = 'conv%d_1' % (5 + j), 'conv%d_2' % (5 + j), 'upconv%d' % j
             below = 'conv%d_2' % (4 + j) if j > 1 else 'conv5_2'

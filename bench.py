@@ -108,7 +108,7 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index, period=0.005):
+    def __init__(self, gpu_index, period=0.02):
         import threading
         self.sm, self.reasons, self.sm_max = [], set(), None
         self.p = self.f = self.thread = None
@@ -289,6 +289,11 @@ def run_ours(args):
     # (the sampler starts BEFORE the barrier: NVML initialisation takes tens of milliseconds
     # on rank 0 only, and the other ranks would wait for it inside the first all-reduce)
     clocks = ClockSampler(local) if rank == 0 else None
+    # no cyclic-GC pauses inside the timed regions (the e2e loop is host-synchronous: a
+    # collection of the model's object graph shows up as one multi-millisecond step)
+    import gc
+    gc.collect()
+    gc.disable()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -315,6 +320,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    gc.enable()
     clk = clocks.stop() if clocks is not None else None
 
     # ---- per-launch timeline (un-captured pass) -> dominant kernel roofline
@@ -385,7 +391,8 @@ def run_ours(args):
                 # or a descheduled host thread shows here, not in the device-timed `value`
                 'host_step_ms': {'median': sorted(step_ms)[len(step_ms) // 2],
                                  'p90': sorted(step_ms)[int(len(step_ms) * 0.9)],
-                                 'max': max(step_ms)}},
+                                 'max': max(step_ms),
+                                 'argmax': step_ms.index(max(step_ms))}},
         'gpu_launches': launches_per_step * K,
         'launches_per_step': launches_per_step,
         'conv_tensor_frac': {'of_burst': value / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk['tf_burst'],

@@ -412,6 +412,7 @@ struct HconvJob {
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
 void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
+static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
 template <int KC, int BN, bool B_MN>
@@ -563,6 +564,21 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   while (BN > 64 && m_tiles * (J.N_total / BN) < num_sms()) {
     BN >>= 1;
     plan(BN, &SA, &SB, &res);
+  }
+  // wave quantisation: these layers are bound by what a CTA ingests per tile (A once per
+  // chunk, B once per chunk and tap), so compare waves x bytes for BN and BN/2 - e.g. 196
+  // tiles of BN=128 on 148 SMs cost two full tile times, 392 of BN=64 three half ones
+  if (BN > 64 && g_hconv_waveq) {
+    auto cost = [&](int bn) {
+      const int64_t tiles = m_tiles * (J.N_total / bn);
+      const int64_t waves = (tiles + num_sms() - 1) / num_sms();
+      return (double)waves * chunks * ((double)P.a_stage_bytes + (double)taps * bn * KC * 2);
+    };
+    int sa2, sb2, res2;
+    if (cost(BN / 2) < 0.95 * cost(BN) && plan(BN / 2, &sa2, &sb2, &res2) && sa2 >= 2) {
+      BN >>= 1;
+      SA = sa2; SB = sb2; res = res2;
+    }
   }
   P.SA = SA; P.SB = SB; P.b_resident = res;
   const int smem = SA * P.a_stage_bytes + SB * BN * KC * 2 + 2048;
@@ -994,6 +1010,7 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
 }
 
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
+void hconv_set_waveq(int on) { g_hconv_waveq = on != 0; }
 
 static bool g_use_hconv = true;
 void hconv_enable(int on) { g_use_hconv = on != 0; }

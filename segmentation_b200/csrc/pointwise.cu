@@ -166,6 +166,213 @@ __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_
   }
 }
 
+// Row-mapped forms of the two pool kernels (8 channels per thread, k == s).  blockIdx.y is
+// one (image, pool row); the threads of a block walk that row with 32-bit indices, so the
+// only divisions left are by the channel-vector count and k (compile-time for k = 2, 3).
+// Backward: a thread owns ONE input column and the k input rows of the window row, so a
+// warp's 16-byte stores are contiguous (512 bytes per row); the k threads of a window read
+// the same dy / argmax / pooled vectors (L1 hits).
+static int g_pool_rows = 1;     // seg_set_option key 11
+void pool_set_rows(int on) { g_pool_rows = on != 0; }
+
+// per-halfword mask (0xffff / 0): bf16 pair a > b (ordered compare, false on NaN)
+__device__ __forceinline__ uint32_t bf16x2_gt_mask(uint32_t a, uint32_t b) {
+  __nv_bfloat162 va, vb;
+  memcpy(&va, &a, 4);
+  memcpy(&vb, &b, 4);
+  return __hgt2_mask(va, vb);                                   // one HSET2.BF16
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_row8_kernel(seg_view x, int k_rt, seg_view y, uint8_t* argmax) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = K ? K : k_rt;
+  const int cv = y.c >> 3;
+  const int rowlen = y.w * cv;
+  const int n = blockIdx.y / y.h, p = blockIdx.y - n * y.h;
+  const bf16* xrow = view_at(x, n, p * k, 0);
+  bf16* yrow = view_at_mut(y, n, p, 0);
+  uint8_t* arow = argmax + ((int64_t)n * y.h + p) * y.w * y.c;
+  const int x_sw = (int)x.sw, y_sw = (int)y.sw, yc = y.c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
+    const int q = i / cv;
+    const int c0 = (i - q * cv) * 8;
+    // running max and its window slot per bf16 pair, selected with halfword masks
+    uint32_t best[4] = {0u, 0u, 0u, 0u}, slot[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int dy = 0; dy < (K ? K : 8); ++dy) {
+      if (dy >= k) break;
+#pragma unroll
+      for (int dx = 0; dx < (K ? K : 8); ++dx) {
+        if (dx >= k) break;
+        const uint4 u = *reinterpret_cast<const uint4*>(xrow + dy * x.sh + (q * k + dx) * x_sw + c0);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        if (dy == 0 && dx == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = w[j];
+        } else {
+          const uint32_t sc = (uint32_t)(dy * k + dx) * 0x00010001u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = bf16x2_gt_mask(w[j], best[j]);     // strict >: first max wins
+            best[j] = (w[j] & m) | (best[j] & ~m);
+            slot[j] = (sc & m) | (slot[j] & ~m);
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(yrow + q * y_sw + c0) = make_uint4(best[0], best[1], best[2], best[3]);
+    uint2 a;
+    a.x = __byte_perm(slot[0], slot[1], 0x6420);
+    a.y = __byte_perm(slot[2], slot[3], 0x6420);
+    *reinterpret_cast<uint2*>(arow + q * yc + c0) = a;
+  }
+}
+
+// per-halfword mask (0xffff / 0) of the bf16 pairs in `w` that are > 0 (NaN: not > 0)
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
+  __nv_bfloat162 v;
+  memcpy(&v, &w, 4);
+  return __hgt2_mask(v, __floats2bfloat162_rn(0.f, 0.f));       // one HSET2.BF16
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_row8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k_rt, seg_view add,
+                        int add_y0, int add_x0, seg_view mask, seg_view pooled, seg_view dx) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = K ? K : k_rt;
+  const int cv = dx.c >> 3;
+  const int ch = (dx.h + k - 1) / k;
+  const int rowlen = dx.w * cv;
+  const int n = blockIdx.y / ch, p = blockIdx.y - n * ch;
+  const bool p_ok = p < dy.h;
+  // row bases (64-bit once per block); inside the row everything is 32-bit
+  const bf16* dy_row = p_ok ? view_at(dy, n, p, 0) : nullptr;
+  const bf16* dy2_row = (p_ok && dy2.ptr) ? view_at(dy2, n, p, 0) : nullptr;
+  const bf16* po_row = (p_ok && pooled.ptr) ? view_at(pooled, n, p, 0) : nullptr;
+  const uint8_t* am_row = p_ok ? argmax + ((int64_t)n * dy.h + p) * dy.w * dy.c : nullptr;
+  bf16* dx_row = view_at_mut(dx, n, p * k, 0);
+  const bf16* mk_row = mask.ptr ? view_at(mask, n, p * k, 0) : nullptr;
+  const int dy_sw = (int)dy.sw, dy2_sw = (int)dy2.sw, po_sw = (int)pooled.sw, dyc = dy.c;
+  const int dx_sw = (int)dx.sw, mk_sw = (int)mask.sw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
+    const int xx = i / cv;
+    const int c0 = (i - xx * cv) * 8;
+    const int q = xx / k;
+    const uint32_t wx = (uint32_t)(xx - q * k);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};      // routed gradient of the window, bf16 pairs
+    uint2 a = make_uint2(0u, 0u);          // outside the pool grid w == 0, any slot will do
+    float gsel[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gsel[j] = 0.f;
+    const bool in_pool = p_ok && q < dy.w;
+    const bool two = dy2_row != nullptr;
+    if (in_pool) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dy_row + q * dy_sw + c0);
+      a = *reinterpret_cast<const uint2*>(am_row + q * dyc + c0);
+      w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+      if (two) {
+        const uint4 u2 = *reinterpret_cast<const uint4*>(dy2_row + q * dy2_sw + c0);
+        const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gsel[2 * j] = bf16_lo(w[j]) + bf16_lo(w2[j]);
+          gsel[2 * j + 1] = bf16_hi(w[j]) + bf16_hi(w2[j]);
+        }
+      }
+      if (po_row) {
+        // the ReLU mask of the routed gradient: x at the argmax IS the pooled value
+        const uint4 pv = *reinterpret_cast<const uint4*>(po_row + q * po_sw + c0);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = bf16x2_gt0_mask(pw[j]);
+          w[j] &= m;
+          if (two) {
+            if (!(m & 0xffffu)) gsel[2 * j] = 0.f;
+            if (!(m >> 16)) gsel[2 * j + 1] = 0.f;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int wy = 0; wy < (K ? K : 8); ++wy) {
+      const int yy = p * k + wy;
+      if (wy >= k || yy >= dx.h) break;
+      const uint32_t me = (uint32_t)(wy * k) + wx;
+      // sel[j]: 0xffff per channel of pair j whose argmax slot is this pixel
+      uint32_t sel[4];
+      if (K == 2) {
+        // slots 0..3 used as PRMT byte selectors into a word whose byte `me` is 0xff;
+        // slot * 0x11 doubles each selector nibble (one mask byte per bf16 half)
+        const uint32_t cm = 0xffu << (8 * me);
+        const uint32_t t0 = a.x * 0x11u, t1 = a.y * 0x11u;
+        sel[0] = __byte_perm(cm, 0u, t0);
+        sel[1] = __byte_perm(cm, 0u, t0 >> 16);
+        sel[2] = __byte_perm(cm, 0u, t1);
+        sel[3] = __byte_perm(cm, 0u, t1 >> 16);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t word = j < 2 ? a.x : a.y;
+          const uint32_t s0 = (word >> (16 * (j & 1))) & 0xffu, s1 = (word >> (16 * (j & 1) + 8)) & 0xffu;
+          sel[j] = (s0 == me ? 0xffffu : 0u) | (s1 == me ? 0xffff0000u : 0u);
+        }
+      }
+      bool added = false;
+      const int ay = yy - add_y0, ax = xx - add_x0;
+      if (add.ptr && ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) added = true;
+      uint4 o;
+      if (!added && !two) {
+        // integer path: select, then (without `pooled`) the ReLU mask of the pool input
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = w[j] & sel[j];
+        if (mk_row && !po_row) {
+          const uint4 u = *reinterpret_cast<const uint4*>(mk_row + wy * mask.sh + xx * mk_sw + c0);
+          r[0] &= bf16x2_gt0_mask(u.x); r[1] &= bf16x2_gt0_mask(u.y);
+          r[2] &= bf16x2_gt0_mask(u.z); r[3] &= bf16x2_gt0_mask(u.w);
+        }
+        o = make_uint4(r[0], r[1], r[2], r[3]);
+      } else {
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = two ? gsel[2 * j] : bf16_lo(w[j]);
+          const float hi = two ? gsel[2 * j + 1] : bf16_hi(w[j]);
+          g[2 * j] = (sel[j] & 0xffffu) ? lo : 0.f;
+          g[2 * j + 1] = (sel[j] >> 16) ? hi : 0.f;
+        }
+        if (added) {
+          const uint4 u = *reinterpret_cast<const uint4*>(view_at(add, n, ay, ax) + c0);
+          const uint32_t wa[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g[2 * j] += bf16_lo(wa[j]); g[2 * j + 1] += bf16_hi(wa[j]); }
+        }
+        // with `pooled` the routed part is already masked: x is read only under `add`
+        if (mk_row && (added || !po_row)) {
+          const uint4 u = *reinterpret_cast<const uint4*>(mk_row + wy * mask.sh + xx * mk_sw + c0);
+          const uint32_t wm[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(bf16_lo(wm[j]) > 0.f)) g[2 * j] = 0.f;
+            if (!(bf16_hi(wm[j]) > 0.f)) g[2 * j + 1] = 0.f;
+          }
+        }
+        o.x = pack_bf16x2(g[0], g[1]);
+        o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]);
+        o.w = pack_bf16x2(g[6], g[7]);
+      }
+      *reinterpret_cast<uint4*>(dx_row + wy * dx.sh + xx * dx_sw + c0) = o;
+    }
+  }
+}
+
 // dx = relu_mask(route(dy, argmax) + add).  Non-overlapping windows (k == s).
 template <int VEC>
 __global__ void maxpool_bwd_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k, int s,
@@ -1211,6 +1418,18 @@ using namespace segb;
 // =========================================================================
 extern "C" {
 
+// Launch geometry of the row-mapped pool kernels: `rows` block rows of `rowlen` 16-byte
+// items.  A thread's setup (row base pointers) is amortised over up to 8 items of its row
+// as long as the grid still fills the machine with ~2048 threads per SM.
+static inline void pool_row_geometry(int64_t rows, int rowlen, dim3* grid, dim3* block) {
+  int64_t ipt = rows * rowlen / ((int64_t)num_sms() * 2048);
+  ipt = ipt < 1 ? 1 : (ipt > 8 ? 8 : ipt);
+  int bt = (int)(((rowlen + ipt - 1) / ipt + 31) / 32 * 32);
+  bt = bt > 256 ? 256 : bt;
+  *block = dim3(bt);
+  *grid = dim3((unsigned)((rowlen + bt * ipt - 1) / (bt * ipt)), (unsigned)rows);
+}
+
 SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const seg_view* y,
                         uint8_t* argmax, void* stream) {
   SEG_REQUIRE(x && y && argmax, SEG_E_BAD_SHAPE, "maxpool_fwd: null argument");
@@ -1220,12 +1439,42 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
   cudaStream_t st = (cudaStream_t)stream;
   const bool v8 = vec8_ok(*x) && vec8_ok(*y) && (reinterpret_cast<uintptr_t>(argmax) % 8) == 0;
   const int64_t total = (int64_t)y->n * y->h * y->w * (v8 ? y->c / 8 : y->c);
-  if (v8)
+  const int64_t f_rows = (int64_t)y->n * y->h;
+  if (v8 && g_pool_rows && k == s && k <= 8 && f_rows <= 65535 && f_rows > 0) {
+    const int rowlen = y->w * (y->c / 8);
+    dim3 grid, block;
+    pool_row_geometry(f_rows, rowlen, &grid, &block);
+    if (k == 2)
+      SEG_CHECK_CUDA(launch_k(maxpool_fwd_row8_kernel<2>, grid, block, (size_t)(0), st, *x, k, *y, argmax));
+    else if (k == 3)
+      SEG_CHECK_CUDA(launch_k(maxpool_fwd_row8_kernel<3>, grid, block, (size_t)(0), st, *x, k, *y, argmax));
+    else
+      SEG_CHECK_CUDA(launch_k(maxpool_fwd_row8_kernel<0>, grid, block, (size_t)(0), st, *x, k, *y, argmax));
+  } else if (v8)
     SEG_CHECK_CUDA(launch_k(maxpool_fwd_kernel<8>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, *x, k, s, *y, argmax));
   else
     maxpool_fwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*x, k, s, *y, argmax);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
+}
+
+// row-mapped backward launch; false: geometry outside its limits (caller uses the cell form)
+static bool launch_pool_bwd_rows(const seg_view& dy, const seg_view& dy2, const uint8_t* argmax,
+                                 int k, const seg_view& add, int add_y0, int add_x0,
+                                 const seg_view& mask, const seg_view& pooled, const seg_view& dx,
+                                 cudaStream_t st, cudaError_t* err) {
+  const int64_t rows = (int64_t)dx.n * ((dx.h + k - 1) / k);
+  if (!g_pool_rows || k > 8 || rows > 65535 || rows <= 0) return false;
+  const int rowlen = dx.w * (dx.c / 8);
+  dim3 grid, block;
+  pool_row_geometry(rows, rowlen, &grid, &block);
+  if (k == 2)
+    *err = launch_k(maxpool_bwd_row8_kernel<2>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
+  else if (k == 3)
+    *err = launch_k(maxpool_bwd_row8_kernel<3>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
+  else
+    *err = launch_k(maxpool_bwd_row8_kernel<0>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
+  return true;
 }
 
 static int maxpool_bwd_impl(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
@@ -1245,8 +1494,13 @@ static int maxpool_bwd_impl(const seg_view* dy, const uint8_t* argmax, int32_t k
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
   {
-    const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, a, add_y0, add_x0, mk, py, *dx));
+    cudaError_t e = cudaSuccess;
+    if (launch_pool_bwd_rows(*dy, null_view(), argmax, k, a, add_y0, add_x0, mk, py, *dx, st, &e)) {
+      SEG_CHECK_CUDA(e);
+    } else {
+      const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
+      SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, null_view(), argmax, k, a, add_y0, add_x0, mk, py, *dx));
+    }
   }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, null_view(), argmax, k, s, a,
@@ -1280,8 +1534,13 @@ SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const 
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
   {
-    const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
-    SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx));
+    cudaError_t e = cudaSuccess;
+    if (launch_pool_bwd_rows(*dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx, st, &e)) {
+      SEG_CHECK_CUDA(e);
+    } else {
+      const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
+      SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx));
+    }
   }
   else
     maxpool_bwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(*dy, *dy2, argmax, k, s,

@@ -353,29 +353,43 @@ class SideStream(object):
     enqueued so far on the current stream; join(): the current stream waits for the side
     stream.  Works inside CUDA-graph capture (fork/join become graph edges)."""
 
-    def __init__(self, device):
-        self.stream = torch.cuda.Stream(device=device)
-        self.used = False
+    def __init__(self, device, lanes=1):
+        """`lanes` > 1: successive fork()s rotate over that many streams, so that narrow
+        kernels of different layers (weight-gradient grids of 30-128 CTAs) can overlap each
+        other as well as the current stream."""
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, lanes))]
+        self.stream = self.streams[0]
+        self._used = [False] * len(self.streams)
+        self._next = 0
+
+    @property
+    def used(self):
+        return any(self._used)
+
+    def wait_into(self, stream):
+        """`stream` waits for everything enqueued on this side stream's lanes."""
+        for s, u in zip(self.streams, self._used):
+            if u:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                stream.wait_event(ev)
 
     def fork(self, also=None):
         """`also`: another SideStream whose enqueued work must be waited for as well."""
+        i = self._next
+        self._next = (i + 1) % len(self.streams)
+        self.stream = self.streams[i]
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.stream.wait_event(ev)
-        if also is not None and also.used:
-            ev2 = torch.cuda.Event()
-            ev2.record(also.stream)
-            self.stream.wait_event(ev2)
-        self.used = True
+        if also is not None:
+            also.wait_into(self.stream)
+        self._used[i] = True
         return torch.cuda.stream(self.stream)
 
     def join(self):
-        if not self.used:
-            return
-        ev = torch.cuda.Event()
-        ev.record(self.stream)
-        torch.cuda.current_stream().wait_event(ev)
-        self.used = False
+        self.wait_into(torch.cuda.current_stream())
+        self._used = [False] * len(self.streams)
 
 
 # ---------------------------------------------------------------------------

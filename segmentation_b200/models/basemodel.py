@@ -235,7 +235,17 @@ class BaseModel(object):
         ex = self._exec.get((self.batch_size, True))
         if ex is None:
             return float('nan')
-        return float(ex.loss_sum.item()) / ex.loss_pixels
+        return ex.loss_value(0)
+
+    @property
+    def seg_loss_lagged(self):
+        """Mean cross-entropy of the step BEFORE the most recent train_step: a training
+        loop that logs this keeps one step in flight on the GPU instead of draining the
+        stream after every step (every step's loss is still copied to the host)."""
+        ex = self._exec.get((self.batch_size, True))
+        if ex is None:
+            return float('nan')
+        return ex.loss_value(1)
 
     # ---------------------------------------------------------------- infer
     def infer(self, imgs):
@@ -286,7 +296,7 @@ class ExecBase(object):
         self._pf = None                # host batch whose copy into the landing buffers is in flight
         self._pf_host = None           # host batch fetched from the dataset but not staged
         self._prepacked = False
-        self.side = E.SideStream(dev)             # weight gradients
+        self.side = E.SideStream(dev, lanes=int(os.environ.get('SEGB200_WGRAD_LANES', '1')))   # weight gradients
         self.opt = E.SideStream(dev)              # all-reduce + Adam per optimizer group
         self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
         self._opt_active = False
@@ -295,6 +305,8 @@ class ExecBase(object):
         self.probs = torch.zeros(B, oh, ow, n_out, dtype=torch.float32, device=dev)
         self.labelmap = torch.zeros(B, oh, ow, 1, dtype=torch.float32, device=dev)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         self.loss_pixels = B * oh * ow
         # mask centre crop when the logits are smaller than the input (unet.py:71-72)
         self.my0, self.mx0 = (H - oh) // 2, (W - ow) // 2
@@ -444,7 +456,21 @@ class ExecBase(object):
             self.graph.replay()
         else:
             self._step_body()
+        # the step's loss goes to pinned host memory behind the step (4 bytes, asynchronous):
+        # the host can read step i's loss while step i+1 runs (BaseModel.seg_loss_lagged)
+        slot = self.calls & 1
+        self._loss_host[slot].copy_(self.loss_sum[0], non_blocking=True)
+        self._loss_ev[slot].record(torch.cuda.current_stream())
         self.calls += 1
+
+    def loss_value(self, lag=0):
+        """Mean loss of the most recent step (lag=0) or of the one before it (lag=1), read
+        from the pinned copy once that step's event has completed."""
+        if self.calls == 0:
+            return float('nan')
+        n = self.calls - 1 - (lag if self.calls > lag else 0)
+        self._loss_ev[n & 1].synchronize()
+        return float(self._loss_host[n & 1]) / self.loss_pixels
 
     def infer(self, x):
         self.stage(x, None)

@@ -246,3 +246,19 @@ def test_train_step_prefetch_pipeline_matches_explicit_batches(cuda):
                                                    # shows as a ~1e-2 difference)
     model_b.train_step(b5)
     assert abs(model_a.seg_loss_op - model_b.seg_loss_op) < 5e-4, (model_a.seg_loss_op, model_b.seg_loss_op)
+
+
+def test_lagged_loss_read_is_the_previous_steps_loss(cuda):
+    """seg_loss_lagged (the pipelined host read bench.py's e2e loop uses) returns, after
+    step i, exactly what seg_loss_op returned after step i-1; after the first step it
+    falls back to that step's own loss."""
+    model, ds, _ = _make('umma', lr=1e-4)
+    model.train_step()
+    first = model.seg_loss_op
+    assert model.seg_loss_lagged == first
+    prev = first
+    for it in range(4):                            # crosses the eager -> graph-replay switch
+        model.train_step()
+        assert model.seg_loss_lagged == prev
+        prev = model.seg_loss_op
+        assert prev == prev and prev > 0.0

@@ -97,7 +97,9 @@ SEG_API const char* seg_last_error_string(void);
  * CTAs (fewer partial sums to reduce, SMs left to the concurrent input-gradient stream).
  * key 10: let the halo kernel halve its N tile when that lowers waves x bytes ingested per
  * CTA (wave quantisation on 148 SMs; default 0 - measured slower on the U-Net step).  key 11: row-mapped max-pool kernels
- * (one block row per pool row, contiguous 16-byte stores; default 1). */
+ * (one block row per pool row, contiguous 16-byte stores; default 1).  key 12: the halo
+ * kernel may give a tile two 128-position accumulators that share one weight stream when a
+ * TMA-ingest / MMA-issue cost model favours it (default 0). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */
@@ -114,6 +116,12 @@ SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const 
 SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,
                          const seg_view* dx, const seg_view* dx2, const seg_view* mask_src,
                          const seg_view* mask_src2, void* stream);
+/* The same gradient for the input-channel slice [cin_lo, cin_lo + dx->c) only (cin_lo a
+ * multiple of 16): a convolution over a virtual concat (models/unet.py:141-142) can send the
+ * skip-connection half and the decoder half of its input gradient to different streams. */
+SEG_API int32_t seg_conv2d_dgrad_slice(const seg_conv_desc* d, const seg_view* dz,
+                                       const void* w_bf16, int32_t cin_lo, const seg_view* dx,
+                                       const seg_view* mask_src, void* stream);
 /* dw (fp32, master layout [kh][kw][cin][cout]) += x^T * dz;  caller zeroes dw.
  * db (nullable, fp32 [cout]) += sum over pixels of dz (BiasAddGrad), fused: on the
  * tcgen05 path it is one extra all-ones A-atom of the same GEMM. */

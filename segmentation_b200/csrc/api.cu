@@ -21,7 +21,7 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                   const float* bias, const seg_view& y, cudaStream_t st);
 int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, const seg_view& dx,
                     const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
-                    cudaStream_t st);
+                    cudaStream_t st, int cin_lo);
 int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                     const seg_view& dz, float* dw, float* db, cudaStream_t st);
 int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
@@ -43,6 +43,7 @@ int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, in
 void hconv_set_row_align(int a);
 void hconv_set_waveq(int on);
 void pool_set_rows(int on);
+void hconv_set_mt(int on);
 void hconv_set_prof(void* p);
 void hconv_enable(int on);
 void tconv_enable(int on);
@@ -88,6 +89,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 9: twgrad_set_min_tiles(value); return SEG_OK;
     case 10: hconv_set_waveq(value); return SEG_OK;
     case 11: pool_set_rows(value); return SEG_OK;
+    case 12: hconv_set_mt(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;
@@ -135,8 +137,11 @@ SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, con
   cudaStream_t st = (cudaStream_t)stream;
   seg_conv_desc dd = *d;
   dd.flags = (mask_src || mask_src2) ? SEG_EPI_RELU_MASK : 0;
-  if (d->impl == SEG_IMPL_UMMA)
-    return umma_conv_dgrad(dd, *dz, w_bf16, *dx, dx2, mask_src, mask_src2, st);
+  if (d->impl == SEG_IMPL_UMMA) {
+    SEG_REQUIRE(dx->c + ((dx2 && dx2->ptr) ? dx2->c : 0) == d->cin_pad, SEG_E_BAD_SHAPE,
+                "conv2d_dgrad: dx channels mismatch");
+    return umma_conv_dgrad(dd, *dz, w_bf16, *dx, dx2, mask_src, mask_src2, st, 0);
+  }
   TransParams P;
   memset(&P, 0, sizeof(P));
   P.src = *dz;
@@ -150,6 +155,17 @@ SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, con
   P.oc_pad = d->cin_pad; P.ic_pad = d->cout_pad;
   P.flags = dd.flags;
   return simt_transposed(P, st);
+}
+
+SEG_API int32_t seg_conv2d_dgrad_slice(const seg_conv_desc* d, const seg_view* dz,
+                                       const void* w_bf16, int32_t cin_lo, const seg_view* dx,
+                                       const seg_view* mask_src, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && dz && w_bf16 && dx, SEG_E_BAD_SHAPE, "conv2d_dgrad_slice: bad argument");
+  SEG_REQUIRE(d->impl == SEG_IMPL_UMMA, SEG_E_UNSUPPORTED, "conv2d_dgrad_slice: tcgen05 path only");
+  seg_conv_desc dd = *d;
+  dd.flags = mask_src ? SEG_EPI_RELU_MASK : 0;
+  return umma_conv_dgrad(dd, *dz, w_bf16, *dx, nullptr, mask_src, nullptr, (cudaStream_t)stream,
+                         cin_lo);
 }
 
 SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,

@@ -1,5 +1,7 @@
 // Host side of the tcgen05 implicit-GEMM kernels: tensor-map construction (tiled
 // and im2col), tile-shape selection and launches.
+#include <cstdio>
+#include <cstdlib>
 #include "umma_conv.cuh"
 #include "hconv.cuh"
 #include "tconv.cuh"
@@ -412,6 +414,7 @@ struct HconvJob {
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
 void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
+static int g_hconv_mt = 0;          // seg_set_option key 12: two accumulators per tile where the model says so
 static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
@@ -454,7 +457,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
   else
     rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN, KC * 2);
   if (rc) return rc;
-  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
+  const int m_tiles = (P.P_total + kBlockM * P.mt - 1) / (kBlockM * P.mt);
   const int n_tiles = J.N_total / BN;
   const int tiles = m_tiles * n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -500,22 +503,36 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   const bool nopad = J.pad_t == 0 && J.pad_l == 0 && J.Hp == J.a1.h && J.Wp_logical == J.a1.w;
   P.flat = (dense && nopad) ? 1 : 0;
   P.row_px = J.Wp_logical;
-  if (P.flat) {
-    P.Wp = J.Wp_logical;
-    const int need = kBlockM + (J.kh - 1) * P.Wp + J.kw - 1;
-    P.box_rows = need <= 256 ? ((need + 7) / 8) * 8 : 128;
-    P.nboxes = (need + P.box_rows - 1) / P.box_rows;
-    P.a_stage_bytes = P.nboxes * P.box_rows * SWZ;
-  } else {
+  if (!P.flat) {
     if (J.Wp_logical > 256) return SEG_E_UNSUPPORTED;
     int align = 128 / SWZ;                       // TMA smem destinations: 128-byte aligned
     if (g_hconv_row_align > align) align = g_hconv_row_align;
     P.Wp = ((J.Wp_logical + align - 1) / align) * align;
-    const int nrows = (P.Wp - 1 + kBlockM - 1 + (J.kh - 1) * P.Wp + J.kw - 1) / P.Wp + 1;
-    P.a_stage_bytes = nrows * P.Wp * SWZ;
+  } else {
+    P.Wp = J.Wp_logical;
   }
-  P.a_stage_bytes = ((P.a_stage_bytes + 1023) / 1024) * 1024;
-  if (P.a_stage_bytes > 72 * 1024) return SEG_E_UNSUPPORTED;
+  // staging geometry of one tile of mt x 128 positions (+ halo); false: does not fit
+  auto geom = [&](int mt, int* box_rows, int* nboxes, int* stage_bytes, int* live_bytes) {
+    const int tile_m = kBlockM * mt;
+    int bytes;
+    if (P.flat) {
+      const int need = tile_m + (J.kh - 1) * P.Wp + J.kw - 1;
+      *box_rows = need <= 256 ? ((need + 7) / 8) * 8 : 128;
+      *nboxes = (need + *box_rows - 1) / *box_rows;
+      bytes = *nboxes * *box_rows * SWZ;
+      *live_bytes = bytes;
+    } else {
+      *box_rows = 0; *nboxes = 0;
+      const int nrows = (P.Wp - 1 + tile_m - 1 + (J.kh - 1) * P.Wp + J.kw - 1) / P.Wp + 1;
+      bytes = nrows * P.Wp * SWZ;
+      *live_bytes = nrows * J.Wp_logical * SWZ;
+    }
+    *stage_bytes = ((bytes + 1023) / 1024) * 1024;
+    return *stage_bytes <= (mt == 1 ? 72 : 100) * 1024;
+  };
+  int live1 = 0;
+  if (!geom(1, &P.box_rows, &P.nboxes, &P.a_stage_bytes, &live1)) return SEG_E_UNSUPPORTED;
+  P.mt = 1;
   P.Hp = J.Hp; P.batch = J.batch; P.Ho = J.Ho; P.Wo = J.Wo;
   P.P_total = J.batch * J.Hp * P.Wp;
   P.kh = J.kh; P.kw = J.kw;
@@ -580,8 +597,55 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
       SA = sa2; SB = sb2; res = res2;
     }
   }
+  // Two accumulators per tile (seg_set_option key 12).  These layers are bound by what a
+  // CTA ingests through TMA (~25 B/clk: A once per chunk, B once per chunk and tap) or by
+  // the MMA issue rate at small N: model both for every (mt, BN) and take the cheapest -
+  // a tile of 2 x 128 positions shares one B stream, which also lets BN halve at the same
+  // A traffic.  The single-accumulator plan above stays unless the model gains > 10 %.
+  if (g_hconv_mt && !res) {
+    auto mma_clk = [&](int bn) {              // tools/probe_rate.py, cycles per 128 x bn x 16
+      const double fixed = KC == 64 ? 32.0 : (KC == 32 ? 42.0 : 53.0);
+      const double c = fixed + bn / 4.0;
+      return c > bn / 2.0 ? c : bn / 2.0;
+    };
+    auto cost = [&](int mt, int bn, int live) {
+      const int64_t tiles = ceil_div64(P.P_total, (int64_t)kBlockM * mt) * (J.N_total / bn);
+      const int64_t waves = (tiles + num_sms() - 1) / num_sms();
+      const double ingest = chunks * ((double)live + (double)taps * bn * KC * 2) / 25.0;
+      const double mma = (double)mt * chunks * taps * (KC / 16) * mma_clk(bn);
+      return (double)waves * (ingest > mma ? ingest : mma) + 4000.0;
+    };
+    double best = cost(1, BN, live1);
+    int best_bn = 0, b_rows = 0, b_nb = 0, b_stage = 0, b_sa = 0, b_sb = 0;
+    for (int bn = BN > 128 ? 128 : BN; bn >= g_hconv_mt; bn >>= 1) {
+      if (J.N_total % bn) continue;
+      int br, nb, stage, live;
+      if (!geom(2, &br, &nb, &stage, &live)) break;
+      const int bbytes = bn * KC * 2;
+      int sb = (64 * 1024) / bbytes;
+      sb = sb < 2 ? 2 : (sb > 12 ? 12 : sb);
+      int sa = (budget - sb * bbytes) / stage;
+      if (sa > kHconvMaxSA) sa = kHconvMaxSA;
+      if (sa < 2) continue;
+      const double c = cost(2, bn, live);
+      if (c < 0.9 * best) {
+        best = c / 0.9;                        // later candidates must beat this one outright
+        best_bn = bn; b_rows = br; b_nb = nb; b_stage = stage; b_sa = sa; b_sb = sb;
+      }
+    }
+    if (best_bn) {
+      BN = best_bn; SA = b_sa; SB = b_sb; res = 0;
+      P.mt = 2; P.box_rows = b_rows; P.nboxes = b_nb; P.a_stage_bytes = b_stage;
+    }
+  }
   P.SA = SA; P.SB = SB; P.b_resident = res;
   const int smem = SA * P.a_stage_bytes + SB * BN * KC * 2 + 2048;
+  static const bool dbg = getenv("SEGB200_DEBUG_PLAN") != nullptr;
+  if (dbg)
+    fprintf(stderr, "hconv plan: P=%d N=%d k=%dx%d chunks=%d KC=%d flat=%d Wp=%d -> mt=%d BN=%d SA=%d "
+            "SB=%d res=%d stage=%d tiles=%lld\n", P.P_total, J.N_total, J.kh, J.kw, chunks, KC, P.flat,
+            P.Wp, P.mt, BN, SA, SB, res, P.a_stage_bytes,
+            (long long)(ceil_div64(P.P_total, (int64_t)kBlockM * P.mt) * (J.N_total / BN)));
   if (J.b_mn) {
     switch (KC) {
       case 64: return launch_hconv_bn<64, true>(J, P, BN, smem, st);
@@ -1011,6 +1075,7 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
 
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
 void hconv_set_waveq(int on) { g_hconv_waveq = on != 0; }
+void hconv_set_mt(int v) { g_hconv_mt = v <= 0 ? 0 : (v < 32 ? 32 : v); }   // value = smallest BN allowed with two accumulators
 
 static bool g_use_hconv = true;
 void hconv_enable(int on) { g_use_hconv = on != 0; }
@@ -1066,12 +1131,18 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
   return launch_igemm(J, st);
 }
 
+// cin_lo: first input channel of the slice [cin_lo, cin_lo + dx.c (+ dx2.c)) this call
+// computes (0 and all of cin_pad for the whole gradient): the weight rows of tap t start at
+// t * cin_pad + cin_lo, i.e. the same matrix seen from a row offset.
 int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, const seg_view& dx,
                     const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
-                    cudaStream_t st) {
+                    cudaStream_t st, int cin_lo) {
   SEG_REQUIRE(d.stride == 1, SEG_E_UNSUPPORTED, "umma conv_dgrad: stride 1 only");
   SEG_REQUIRE(dz.c == d.cout_pad, SEG_E_BAD_SHAPE, "conv_dgrad: dz.c %d != cout_pad %d", dz.c,
               d.cout_pad);
+  const int n_slice = dx.c + ((dx2 && dx2->ptr) ? dx2->c : 0);
+  SEG_REQUIRE(cin_lo >= 0 && cin_lo % 16 == 0 && cin_lo + n_slice <= d.cin_pad, SEG_E_BAD_SHAPE, "conv_dgrad: channel slice [%d, %d) outside cin_pad %d", cin_lo,
+              cin_lo + n_slice, d.cin_pad);
   IgemmJob J;
   memset(&J, 0, sizeof(J));
   J.a1 = dz;
@@ -1080,9 +1151,10 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
   J.low_h = -(d.kh - 1 - d.pad_t); J.low_w = -(d.kw - 1 - d.pad_l);
   J.up_h = dx.h - dz.h + J.low_h; J.up_w = dx.w - dz.w + J.low_w;
   J.Ho = dx.h; J.Wo = dx.w; J.batch = dx.n;
-  J.w = w; J.w_rows = d.kh * d.kw * d.cin_pad; J.w_cols = d.cout_pad;
+  J.w = reinterpret_cast<const uint8_t*>(w) + (size_t)cin_lo * d.cout_pad * 2;
+  J.w_rows = d.kh * d.kw * d.cin_pad - cin_lo; J.w_cols = d.cout_pad;
   J.b_mn = false; J.b_rows_per_tap = d.cin_pad; J.tap_flip = true;
-  J.N_total = d.cin_pad;
+  J.N_total = n_slice;
   J.d0 = make_dest(&dx, mask);
   if (dx2 && dx2->ptr) {
     J.d1 = make_dest(dx2, mask2);
@@ -1090,10 +1162,10 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
     J.max_bn = dx.c;
     for (int c = 256; c >= 16; c >>= 1)
       if (dx.c % c == 0 && dx2->c % c == 0) { J.max_bn = c; break; }
-    SEG_REQUIRE(dx.c + dx2->c == d.cin_pad, SEG_E_BAD_SHAPE, "conv_dgrad: dx channels mismatch");
   } else {
-    J.max_bn = d.cin_pad;
+    J.max_bn = n_slice;
   }
+
   J.flags = d.flags & (SEG_EPI_RELU_MASK);
   if (g_use_tconv && d.kh == 3 && d.kw == 3) {
     TconvJob T;

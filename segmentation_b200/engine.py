@@ -294,6 +294,16 @@ class ConvLayer(object):
             N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz),
                    N.ptr(self.w.shadow()), N.vref(dx), N.vref(mask), st)
 
+    def dgrad_slice(self, dz, cin_lo, dx, mask=None, impl=N.IMPL_UMMA):
+        """Input gradient of the channel slice [cin_lo, cin_lo + dx.c) only (tcgen05 path):
+        the two halves of a virtual concat can be computed by separate launches, the skip
+        half off the critical path (seg_conv2d_dgrad_slice)."""
+        assert self.kind == 'conv'
+        N.set_tag(self.name)
+        d = self.desc(dx.shape[1], dx.shape[2], 0, impl)
+        N.call('seg_conv2d_dgrad_slice', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
+               int(cin_lo), N.vref(dx), N.vref(mask), N.stream_ptr())
+
     def _wgrad(self, x, dz, x2, impl, dz_bias):
         st = N.stream_ptr()
         if self.kind == 'conv':
@@ -383,7 +393,8 @@ class SideStream(object):
         ev.record(torch.cuda.current_stream())
         self.stream.wait_event(ev)
         if also is not None:
-            also.wait_into(self.stream)
+            for o in (also if isinstance(also, (tuple, list)) else (also,)):
+                o.wait_into(self.stream)
         self._used[i] = True
         return torch.cuda.stream(self.stream)
 

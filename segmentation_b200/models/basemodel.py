@@ -298,6 +298,7 @@ class ExecBase(object):
         self._prepacked = False
         self.side = E.SideStream(dev, lanes=int(os.environ.get('SEGB200_WGRAD_LANES', '1')))   # weight gradients
         self.opt = E.SideStream(dev)              # all-reduce + Adam per optimizer group
+        self.skipside = E.SideStream(dev)         # skip-connection halves of the concat input gradients
         self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
         self._opt_active = False
         self._pending = set()
@@ -347,6 +348,7 @@ class ExecBase(object):
             for i in sorted(self._pending, reverse=True):
                 self.group_ready(i)
             self.side.join()
+            self.skipside.join()
             self.opt.join()
         finally:
             self._opt_active = False
@@ -361,7 +363,7 @@ class ExecBase(object):
         if not self._opt_active or i not in self._pending:
             return
         self._pending.discard(i)
-        with self.opt.fork(also=self.side):
+        with self.opt.fork(also=(self.side, self.skipside)):
             if m._allreduce is not None:
                 m._allreduce(i)
             m.store.adam_launch(0.0, grad_scale=1.0 / m.world_size, from_device=True,

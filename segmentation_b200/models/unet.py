@@ -183,6 +183,14 @@ class _UNetExec(ExecBase):
         if training:
             self._alloc_grads()
         # training: the 1x1 head, the loss and the head's backward are one kernel
+        # optional backward schedules (both measured neutral-to-slower, 1.175 -> 1.18-1.19
+        # ms/step: the step is bound by total SM time, not by the main stream's chain):
+        # decoder stages whose concat input gradient is split into a decoder half (main
+        # stream) and a skip half (skip stream); conv1_2's backward pass right behind
+        # conv9_1's instead of at the end
+        self.skip_split = set(int(v) for v in
+                              os.environ.get('SEGB200_SKIP_SPLIT', '').split(',') if v.strip())
+        self.early_conv1_2 = os.environ.get('SEGB200_EARLY_C12', '0') != '0'
         self.fused_head = (training and model.n_classes <= 4 and nk in (16, 32) and
                            model.impl == N.IMPL_UMMA and
                            os.environ.get('SEGB200_FUSED_HEAD', '1') != '0')
@@ -282,6 +290,10 @@ class _UNetExec(ExecBase):
         L, A, G, impl = self.m.layers, self.act, self.g, self.m.impl
         nc = self.m.n_classes
         side = self.side if self.use_side else None
+        skipside = self.skipside if (self.use_side and impl == N.IMPL_UMMA) else None
+        # conv1_2: output gradient lives only on the skip crop -> run on the crop
+        y0, x0, h, w = self.crop[4]
+        x_win = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
 
         def bw(name, *args, **kw):
             # weight gradients go to the side stream; an optimizer group may be complete
@@ -301,8 +313,23 @@ class _UNetExec(ExecBase):
             # The skip gradient is ReLU-masked later by the pool backward that merges
             # it (j<4); for j==4 conv1_2 has no other consumer, so mask it here.
             sk = self.skip_view(j)
-            bw(c1, sk, G[c1], dx=G['skip%d' % j], x2=A[up], dx2=G[up],
-               mask=sk if j == 4 else None, mask2=A[up])
+            if skipside is not None and j in self.skip_split:
+                # the skip half of the input gradient is not needed before the encoder's
+                # backward pass: only the decoder half stays on the critical path
+                L[c1].backward(sk, G[c1], dx=None, x2=A[up], impl=impl, side=side)   # dW only
+                with skipside.fork():
+                    L[c1].dgrad_slice(G[c1], 0, G['skip%d' % j], mask=sk if j == 4 else None,
+                                      impl=impl)
+                L[c1].dgrad_slice(G[c1], sk.shape[3], G[up], mask=A[up], impl=impl)
+                self.layer_done(c1)               # after every kernel that reads its weights
+            else:
+                bw(c1, sk, G[c1], dx=G['skip%d' % j], x2=A[up], dx2=G[up],
+                   mask=sk if j == 4 else None, mask2=A[up])
+            if j == 4 and skipside is not None and self.early_conv1_2:
+                # conv1_2 feeds only this skip connection (models/unet.py:118-120,161): its
+                # whole backward pass can run here, beside the rest of the decoder
+                with skipside.fork():
+                    L['conv1_2'].backward(x_win, G['skip4'], dx=G['conv1_1_part'], impl=impl)
             bw(up, A[below], G[up], dx=G[below], mask=A[below])
         # encoder
         bw('conv5_2', A['conv5_1'], G['conv5_2'], dx=G['conv5_1'], mask=A['conv5_1'])
@@ -312,15 +339,20 @@ class _UNetExec(ExecBase):
                 # dZ(conv i_2) = relu_mask(pool_i backward + skip gradient at the crop)
                 j = 5 - i
                 y0, x0, _, _ = self.crop[j]
+                if skipside is not None:
+                    skipside.join()               # G[skip j] may come from the skip stream
                 E.maxpool_bwd(G['pool%d' % i], self.amax['pool%d' % i], G[c2],
                               add=G['skip%d' % j], add_y0=y0, add_x0=x0, mask=A[c2],
                               pooled=A['pool%d' % i])
                 bw(c2, A[c1], G[c2], dx=G[c1], mask=A[c1])
             bw(c1, A[pool], G[c1], dx=G[pool])
-        # conv1_2: output gradient lives only on the skip crop -> run on the crop
         y0, x0, h, w = self.crop[4]
-        x_win = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
-        bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
+        if skipside is not None:
+            skipside.join()
+        if not (skipside is not None and self.early_conv1_2):
+            bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
+        else:
+            self.layer_done('conv1_2')
         E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['conv1_1'], add=G['conv1_1_part'],
                       add_y0=y0, add_x0=x0, mask=A['conv1_1'], pooled=A['pool1'])
         bw('conv1_1', A['x'], G['conv1_1'], dx=None)

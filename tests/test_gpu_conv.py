@@ -202,6 +202,21 @@ def test_conv_bwd(cuda, case, impl_name, impl):
         ok = ok and e_x < TOL_BF16
     report('conv_bwd', rec)
     assert ok, rec
+    if do_dgrad and C2 and impl == N.IMPL_UMMA and s == 1:
+        # the two halves of the virtual concat as separate channel-slice launches
+        # (seg_conv2d_dgrad_slice) are the same numbers as the two-destination launch
+        s1 = torch.full_like(dx1, float('nan'))
+        s2 = torch.full_like(dx2, float('nan'))
+        N.call('seg_conv2d_dgrad_slice', ctypes.byref(d), N.vref(dz_d), N.ptr(w_d), 0,
+               N.vref(s1), N.vref(x1_d), st)
+        N.call('seg_conv2d_dgrad_slice', ctypes.byref(d), N.vref(dz_d), N.ptr(w_d), C1,
+               N.vref(s2), N.vref(x2_d), st)
+        sync()
+        # (same K order per output channel; a different tile plan may round a few values
+        # differently in bf16, hence a tolerance well below TOL_BF16 instead of equality)
+        e1 = rel_l2(s1.float().cpu(), dx1.float().cpu())
+        e2 = rel_l2(s2.float().cpu(), dx2.float().cpu())
+        assert e1 < 1e-3 and e2 < 1e-3, (name, e1, e2)
 
 
 # ---------------------------------------------------------------------------

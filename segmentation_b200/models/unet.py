@@ -188,6 +188,7 @@ class _UNetExec(ExecBase):
         # decoder stages whose concat input gradient is split into a decoder half (main
         # stream) and a skip half (skip stream); conv1_2's backward pass right behind
         # conv9_1's instead of at the end
+        self.c12_crop = os.environ.get('SEGB200_C12_CROP', '1') != '0'
         self.skip_split = set(int(v) for v in
                               os.environ.get('SEGB200_SKIP_SPLIT', '').split(',') if v.strip())
         self.early_conv1_2 = os.environ.get('SEGB200_EARLY_C12', '0') != '0'
@@ -246,11 +247,21 @@ class _UNetExec(ExecBase):
         fwd_side = self.side if (self.use_side and dropout is None and fwd_at > 0) else None
 
         def conv1_2():
+            if self.c12_crop:
+                # only the centre crop of conv1_2's output has a consumer (concat4; pool1
+                # takes conv1_1, reference models/unet.py:118-120,159-161): evaluate the
+                # layer on that window - identical skip tensor, 1/12 of the work
+                y0, x0, h, w = self.crop[4]
+                src = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :]
+                dst = A['conv1_2'][:, y0:y0 + h, x0:x0 + w, :]
+                run = lambda: L['conv1_2'].forward(src, dst, impl=impl)
+            else:
+                run = lambda: conv('conv1_2', A['conv1_1'])
             if fwd_side is not None:
                 with fwd_side.fork():
-                    conv('conv1_2', A['conv1_1'])
+                    run()
             else:
-                conv('conv1_2', A['conv1_1'])
+                run()
 
         if fwd_at <= 1:
             conv1_2()

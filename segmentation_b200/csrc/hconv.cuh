@@ -38,7 +38,6 @@ struct HconvParams {
   int N_total;
   int SA, SB;
   int b_resident;
-  int mt;                    // 128-position accumulators per tile (1 or 2) sharing one B stream
   EpiDest d0, d1;
   int split_n;
   const float* bias;
@@ -61,9 +60,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   constexpr int SWZ = KC * 2;
   constexpr int kBBytes = BN * KC * 2;
   constexpr int kAtomN = BN < 64 ? BN : 64;
-  // two accumulator stages of up to two 128-row accumulators each (BN = 256: one)
-  constexpr int kTmemCols = 4 * BN <= 32 ? 32 : 4 * BN <= 64 ? 64 : 4 * BN <= 128 ? 128
-                            : 4 * BN <= 256 ? 256 : 512;
+  constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                            : 2 * BN <= 256 ? 256 : 512;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -82,8 +80,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int lane = threadIdx.x & 31;
   const int taps = P.kh * P.kw;
   const int chunks = P.chunks1 + P.chunks2;
-  const int tile_m = kBlockM * P.mt;              // positions per tile
-  const int m_tiles = (P.P_total + tile_m - 1) / tile_m;
+  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
   const int n_tiles = P.N_total / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int halo = (P.kh - 1) * P.Wp + P.kw - 1;
@@ -113,11 +110,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       bool first_tile = true;
       int ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int m0 = (tile / n_tiles) * tile_m;
+        const int m0 = (tile / n_tiles) * kBlockM;
         const int n0 = (tile % n_tiles) * BN;
         if (lane == 0) prof_mark(P.prof, 0, ti, 0);
         const int g0 = m0 / P.Wp;                          // first padded row (global)
-        const int g1 = (m0 + tile_m - 1 + halo) / P.Wp;    // last padded row needed
+        const int g1 = (m0 + kBlockM - 1 + halo) / P.Wp;   // last padded row needed
         for (int j = 0; j < chunks; ++j) {
           const bool second = j >= P.chunks1;
           const CUtensorMap* tm = second ? &tmA2 : &tmA1;
@@ -189,13 +186,13 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       bool first_tile = true;
       int ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int m0 = (tile / n_tiles) * tile_m;
+        const int m0 = (tile / n_tiles) * kBlockM;
         const int a_off = P.flat ? 0 : m0 - (m0 / P.Wp) * P.Wp;
         if (lane == 0) prof_mark(P.prof, 1, ti, 0);
         mbar_wait(&tempty[as], aphase ^ 1u);
         tc_fence_after();
         if (lane == 0) prof_mark(P.prof, 1, ti, 1);
-        const uint32_t tmem_d = tmem_base + as * (P.mt * BN);
+        const uint32_t tmem_d = tmem_base + as * BN;
         if (P.b_resident) sb = 0;
         uint32_t acc = 0;
         for (int j = 0; j < chunks; ++j) {
@@ -214,16 +211,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               }
               const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b + sb * kBBytes), lboB);
               if (elect_one()) {
-                // every 128-row accumulator of the tile consumes the same staged B tile
-                for (int sub = 0; sub < P.mt; ++sub) {
-                  const uint32_t a_sub = a_tap + (uint32_t)(sub * kBlockM) * row16;
-                  uint32_t acc_k = acc;
 #pragma unroll
-                  for (int kk = 0; kk < KC / 16; ++kk) {
-                    umma_f16(tmem_d + sub * BN, umma_desc_pack(hiA, a_sub + kk * 2),
-                             umma_desc_pack(hiB, b_lo0 + kk * kstepB), idesc, acc_k);
-                    acc_k = 1;
-                  }
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  umma_f16(tmem_d, umma_desc_pack(hiA, a_tap + kk * 2),
+                           umma_desc_pack(hiB, b_lo0 + kk * kstepB), idesc, acc);
+                  acc = 1;
                 }
                 if (!P.b_resident) umma_commit(&b_empty[sb]);
                 // per-tap issue timestamps of tiles 2 and 3 (role 3 of the timeline hook)
@@ -256,31 +248,28 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int ti = 0;
     long long* eprof = (warp == 2 && lane == 0) ? P.prof : nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile / n_tiles) * tile_m;
+      const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
-      const bool second = P.d1.ptr != nullptr && n0 >= P.split_n;
-      const EpiDest& D = second ? P.d1 : P.d0;
-      const int nl0 = second ? n0 - P.split_n : n0;
-      prof_mark(eprof, 2, ti, 0);
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      prof_mark(eprof, 2, ti, 1);
-#pragma unroll 1
-      for (int sub = 0; sub < P.mt; ++sub) {
-      const int m = m0 + sub * kBlockM + quad * 32 + lane;
+      const int m = m0 + quad * 32 + lane;
       const int img = m / img_stride;
       const int rem = m - img * img_stride;
       const int yp = rem / P.Wp;
       const int xp = rem - yp * P.Wp;
       const bool row_ok = img < P.batch && yp < P.Ho && xp < P.Wo;
+      const bool second = P.d1.ptr != nullptr && n0 >= P.split_n;
+      const EpiDest& D = second ? P.d1 : P.d0;
+      const int nl0 = second ? n0 - P.split_n : n0;
       const int64_t off = row_ok ? img * D.sn + yp * D.sh + xp * D.sw : 0;
       const int64_t moff = row_ok ? img * D.msn + yp * D.msh + xp * D.msw : 0;
+      prof_mark(eprof, 2, ti, 0);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      prof_mark(eprof, 2, ti, 1);
 #pragma unroll 1
       for (int cc = half * (BN >= 32 ? 32 : 16); cc < BN; cc += 2 * (BN >= 32 ? 32 : 16)) {
         constexpr int W = BN >= 32 ? 32 : 16;
         uint32_t r[W];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (P.mt * BN) +
-                               sub * BN + cc;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + cc;
         if (W == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
         if (row_ok) {
@@ -330,7 +319,6 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             }
           }
         }
-      }
       }
       prof_mark(eprof, 2, ti, 2);
       tc_fence_before();

@@ -414,7 +414,6 @@ struct HconvJob {
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
 void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
-static int g_hconv_mt = 0;          // seg_set_option key 12: two accumulators per tile where the model says so
 static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
@@ -457,7 +456,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
   else
     rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN, KC * 2);
   if (rc) return rc;
-  const int m_tiles = (P.P_total + kBlockM * P.mt - 1) / (kBlockM * P.mt);
+  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
   const int n_tiles = J.N_total / BN;
   const int tiles = m_tiles * n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -512,6 +511,8 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
     P.Wp = J.Wp_logical;
   }
   // staging geometry of one tile of mt x 128 positions (+ halo); false: does not fit
+  // (the kernel runs mt = 1: a two-accumulator variant sharing one B stream was built and
+  // measured neutral at best, and its loop overhead cost every halo launch ~10 %)
   auto geom = [&](int mt, int* box_rows, int* nboxes, int* stage_bytes, int* live_bytes) {
     const int tile_m = kBlockM * mt;
     int bytes;
@@ -528,11 +529,10 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
       *live_bytes = nrows * J.Wp_logical * SWZ;
     }
     *stage_bytes = ((bytes + 1023) / 1024) * 1024;
-    return *stage_bytes <= (mt == 1 ? 72 : 100) * 1024;
+    return *stage_bytes <= 72 * 1024;
   };
   int live1 = 0;
   if (!geom(1, &P.box_rows, &P.nboxes, &P.a_stage_bytes, &live1)) return SEG_E_UNSUPPORTED;
-  P.mt = 1;
   P.Hp = J.Hp; P.batch = J.batch; P.Ho = J.Ho; P.Wo = J.Wo;
   P.P_total = J.batch * J.Hp * P.Wp;
   P.kh = J.kh; P.kw = J.kw;
@@ -597,55 +597,14 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
       SA = sa2; SB = sb2; res = res2;
     }
   }
-  // Two accumulators per tile (seg_set_option key 12).  These layers are bound by what a
-  // CTA ingests through TMA (~25 B/clk: A once per chunk, B once per chunk and tap) or by
-  // the MMA issue rate at small N: model both for every (mt, BN) and take the cheapest -
-  // a tile of 2 x 128 positions shares one B stream, which also lets BN halve at the same
-  // A traffic.  The single-accumulator plan above stays unless the model gains > 10 %.
-  if (g_hconv_mt && !res) {
-    auto mma_clk = [&](int bn) {              // tools/probe_rate.py, cycles per 128 x bn x 16
-      const double fixed = KC == 64 ? 32.0 : (KC == 32 ? 42.0 : 53.0);
-      const double c = fixed + bn / 4.0;
-      return c > bn / 2.0 ? c : bn / 2.0;
-    };
-    auto cost = [&](int mt, int bn, int live) {
-      const int64_t tiles = ceil_div64(P.P_total, (int64_t)kBlockM * mt) * (J.N_total / bn);
-      const int64_t waves = (tiles + num_sms() - 1) / num_sms();
-      const double ingest = chunks * ((double)live + (double)taps * bn * KC * 2) / 25.0;
-      const double mma = (double)mt * chunks * taps * (KC / 16) * mma_clk(bn);
-      return (double)waves * (ingest > mma ? ingest : mma) + 4000.0;
-    };
-    double best = cost(1, BN, live1);
-    int best_bn = 0, b_rows = 0, b_nb = 0, b_stage = 0, b_sa = 0, b_sb = 0;
-    for (int bn = BN > 128 ? 128 : BN; bn >= g_hconv_mt; bn >>= 1) {
-      if (J.N_total % bn) continue;
-      int br, nb, stage, live;
-      if (!geom(2, &br, &nb, &stage, &live)) break;
-      const int bbytes = bn * KC * 2;
-      int sb = (64 * 1024) / bbytes;
-      sb = sb < 2 ? 2 : (sb > 12 ? 12 : sb);
-      int sa = (budget - sb * bbytes) / stage;
-      if (sa > kHconvMaxSA) sa = kHconvMaxSA;
-      if (sa < 2) continue;
-      const double c = cost(2, bn, live);
-      if (c < 0.9 * best) {
-        best = c / 0.9;                        // later candidates must beat this one outright
-        best_bn = bn; b_rows = br; b_nb = nb; b_stage = stage; b_sa = sa; b_sb = sb;
-      }
-    }
-    if (best_bn) {
-      BN = best_bn; SA = b_sa; SB = b_sb; res = 0;
-      P.mt = 2; P.box_rows = b_rows; P.nboxes = b_nb; P.a_stage_bytes = b_stage;
-    }
-  }
   P.SA = SA; P.SB = SB; P.b_resident = res;
   const int smem = SA * P.a_stage_bytes + SB * BN * KC * 2 + 2048;
   static const bool dbg = getenv("SEGB200_DEBUG_PLAN") != nullptr;
   if (dbg)
-    fprintf(stderr, "hconv plan: P=%d N=%d k=%dx%d chunks=%d KC=%d flat=%d Wp=%d -> mt=%d BN=%d SA=%d "
+    fprintf(stderr, "hconv plan: P=%d N=%d k=%dx%d chunks=%d KC=%d flat=%d Wp=%d -> BN=%d SA=%d "
             "SB=%d res=%d stage=%d tiles=%lld\n", P.P_total, J.N_total, J.kh, J.kw, chunks, KC, P.flat,
-            P.Wp, P.mt, BN, SA, SB, res, P.a_stage_bytes,
-            (long long)(ceil_div64(P.P_total, (int64_t)kBlockM * P.mt) * (J.N_total / BN)));
+            P.Wp, BN, SA, SB, res, P.a_stage_bytes,
+            (long long)(ceil_div64(P.P_total, (int64_t)kBlockM) * (J.N_total / BN)));
   if (J.b_mn) {
     switch (KC) {
       case 64: return launch_hconv_bn<64, true>(J, P, BN, smem, st);
@@ -1075,7 +1034,6 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
 
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
 void hconv_set_waveq(int on) { g_hconv_waveq = on != 0; }
-void hconv_set_mt(int v) { g_hconv_mt = v <= 0 ? 0 : (v < 32 ? 32 : v); }   // value = smallest BN allowed with two accumulators
 
 static bool g_use_hconv = true;
 void hconv_enable(int on) { g_use_hconv = on != 0; }

@@ -189,6 +189,7 @@ class _UNetExec(ExecBase):
         # stream) and a skip half (skip stream); conv1_2's backward pass right behind
         # conv9_1's instead of at the end
         self.c12_crop = os.environ.get('SEGB200_C12_CROP', '1') != '0'
+        self.tail_split = max(1, int(os.environ.get('SEGB200_TAIL_SPLIT', '1')))
         self.skip_split = set(int(v) for v in
                               os.environ.get('SEGB200_SKIP_SPLIT', '').split(',') if v.strip())
         self.early_conv1_2 = os.environ.get('SEGB200_EARLY_C12', '0') != '0'
@@ -364,8 +365,20 @@ class _UNetExec(ExecBase):
             bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
         else:
             self.layer_done('conv1_2')
-        E.maxpool_bwd(G['pool1'], self.amax['pool1'], G['conv1_1'], add=G['conv1_1_part'],
-                      add_y0=y0, add_x0=x0, mask=A['conv1_1'], pooled=A['pool1'])
-        bw('conv1_1', A['x'], G['conv1_1'], dx=None)
+        # The step ends with pool1's backward -> conv1_1's weight gradient -> Adam of the
+        # first group, a chain nothing else is left to overlap.  Optionally (tail_split
+        # batch slices) the weight gradient of slice k runs on the side stream while the
+        # pool backward of slice k+1 runs here; partial sums meet in the fp32 reductions.
+        ts = self.tail_split if (side is not None and self.B % max(self.tail_split, 1) == 0) else 1
+        nb = self.B // ts
+        for k in range(ts):
+            sl = slice(k * nb, (k + 1) * nb)
+            E.maxpool_bwd(G['pool1'][sl], self.amax['pool1'][sl], G['conv1_1'][sl],
+                          add=G['conv1_1_part'][sl], add_y0=y0, add_x0=x0, mask=A['conv1_1'][sl],
+                          pooled=A['pool1'][sl])
+            if k < ts - 1:
+                L['conv1_1'].backward(A['x'][sl], G['conv1_1'][sl], dx=None, impl=impl, side=side)
+            else:
+                bw('conv1_1', A['x'][sl], G['conv1_1'][sl], dx=None)
         if side is not None:
             side.join()

@@ -107,8 +107,7 @@ def load():
     for env, key in (('SEGB200_TCONV_MIN_EFF', OPT_TILE_CONV_MIN_EFF),
                      ('SEGB200_TWGRAD_MIN_EFF', OPT_TILE_WGRAD_MIN_EFF),
                      ('SEGB200_HCONV_WAVEQ', OPT_HALO_WAVEQ),
-                     ('SEGB200_POOL_ROWS', OPT_POOL_ROWS),
-                     ('SEGB200_HCONV_MT', OPT_HALO_MT)):
+                     ('SEGB200_POOL_ROWS', OPT_POOL_ROWS)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
     if 'SEGB200_WGRAD_MIN_TILES' in os.environ:
@@ -139,7 +138,6 @@ OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
 OPT_PDL = 7           # programmatic dependent launch of the hot-path kernels (default on)
 OPT_WGRAD_MIN_TILES = 9  # pixel tiles per CTA below which the weight-gradient grid is narrowed
 OPT_HALO_WAVEQ = 10    # halo kernel: halve the N tile when waves x bytes per CTA drops
-OPT_HALO_MT = 12       # halo kernel: two accumulators per tile where the cost model says so
 OPT_POOL_ROWS = 11     # row-mapped max-pool kernels (default on)
 OPT_WGRAD_CLUSTER = 8  # CTAs per cluster in the weight-gradient partial-sum reduction (1/2/4/8)
 

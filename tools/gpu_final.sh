@@ -12,5 +12,6 @@ SEGB200_WGRAD_STREAM=0 ncu --metrics gpu__time_duration.sum --clock-control none
   --log-file gpurun_out/launches.csv $CMD > gpurun_out/prof_ncu1.log 2>&1
 python tools/launch_list.py gpurun_out/launches.csv -v > gpurun_out/launch_summary.txt; head -2 gpurun_out/launch_summary.txt
 bash tools/ncu_bench.sh r01_twgrad16_conv1_1 "twgrad_kernel<.int.16, .int.32>" 0
-bash tools/ncu_bench.sh r01_tconv_conv1_2_fwd "tconv_kernel<.int.32, .int.32, .bool.1, .int.2>" 0
-bash tools/ncu_bench.sh r01_twgrad64_conv2_2 "twgrad_kernel<.int.64, .int.64>" 11
+bash tools/ncu_bench.sh r01_tconv_conv2_2_fwd "tconv_kernel<.int.64, .int.64, .bool.1, .int.2>" 0
+bash tools/ncu_bench.sh r01_pool1_bwd "maxpool_bwd_row8_kernel" 3
+bash tools/ncu_bench.sh r01_pool1_fwd "maxpool_fwd_row8_kernel" 0

@@ -19,6 +19,8 @@ SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu', 'probe.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
+if os.environ.get('SEGB200_KERNEL_PROF') == '1':      # in-kernel timeline marks (tools/layer_prof.py)
+    NVCC_FLAGS.append('-DSEGB200_KERNEL_PROF=1')
 
 
 def _nvcc():

@@ -47,9 +47,17 @@ struct HconvParams {
 
 constexpr int kHconvMaxSA = 8;
 constexpr int kProfTiles = 16;     // tiles recorded per role; 4 events each
+// The timeline hook is compiled in only with -DSEGB200_KERNEL_PROF=1 (tools/layer_prof.py):
+// its checks sit inside the single-thread MMA issue loop, which is on the critical path of
+// the small deep layers.
+#ifndef SEGB200_KERNEL_PROF
+#define SEGB200_KERNEL_PROF 0
+#endif
 __device__ __forceinline__ void prof_mark(long long* prof, int role, int tile_i, int ev) {
+#if SEGB200_KERNEL_PROF
   if (prof != nullptr && blockIdx.x == 0 && tile_i < kProfTiles)
     prof[(role * kProfTiles + tile_i) * 4 + ev] = clock64();
+#endif
 }
 constexpr int kHconvMaxSB = 40;
 
@@ -218,9 +226,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                   acc = 1;
                 }
                 if (!P.b_resident) umma_commit(&b_empty[sb]);
+#if SEGB200_KERNEL_PROF
                 // per-tap issue timestamps of tiles 2 and 3 (role 3 of the timeline hook)
                 if (P.prof != nullptr && blockIdx.x == 0 && (ti == 2 || ti == 3) && j == 0)
                   P.prof[3 * kProfTiles * 4 + (ti - 2) * 16 + r * P.kw + s] = clock64();
+#endif
               }
               __syncwarp();
               acc = 1;

@@ -1,5 +1,6 @@
 """Per-layer micro-benchmark of the U-Net conv launches (bs16, 256x256) + in-kernel
-timeline of CTA 0 of the halo conv kernel.  python tools/layer_prof.py [layer ...]"""
+timeline of CTA 0 of the halo conv kernel.  python tools/layer_prof.py [layer ...]
+(the in-kernel marks need a library built with -DSEGB200_KERNEL_PROF=1: SEGB200_KERNEL_PROF=1 python -m segmentation_b200.build)"""
 import ctypes, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -43,6 +43,7 @@ int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, in
 void hconv_set_row_align(int a);
 void hconv_set_waveq(int on);
 void pool_set_rows(int on);
+void conv_set_deep_b_ring(int on);
 void hconv_set_prof(void* p);
 void hconv_enable(int on);
 void tconv_enable(int on);
@@ -88,6 +89,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 9: twgrad_set_min_tiles(value); return SEG_OK;
     case 10: hconv_set_waveq(value); return SEG_OK;
     case 11: pool_set_rows(value); return SEG_OK;
+    case 12: conv_set_deep_b_ring(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

@@ -414,6 +414,8 @@ struct HconvJob {
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
 void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
+static int g_deep_b_ring = 1;       // seg_set_option key 12: streamed-B rings as deep as smem allows
+void conv_set_deep_b_ring(int on) { g_deep_b_ring = on != 0; }
 static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
@@ -566,6 +568,17 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
       *resident = 0;
       int s = (64 * 1024) / bbytes;
       *sb = s < 2 ? 2 : (s > 12 ? 12 : s);
+      if (g_deep_b_ring) {
+        // B is the bulk of what a tile ingests (taps x more than A) and every B stage is
+        // re-armed only after the MMA that read it retires: the ring depth, not bandwidth,
+        // sets the ingest rate (measured ~25 B/clk at 64 KB in flight).  Give A what one
+        // tile keeps busy (<= 3 stages) and B the rest.
+        const int a_keep = chunks < 3 ? (chunks < 2 ? 2 : chunks) : 3;
+        int deep = (budget - a_keep * P.a_stage_bytes) / bbytes;
+        if (deep > kHconvMaxSB) deep = kHconvMaxSB;
+        if (deep > taps * chunks) deep = taps * chunks;
+        if (deep > *sb) *sb = deep;
+      }
     }
     int a = (budget - *sb * bbytes) / P.a_stage_bytes;
     *sa = a > kHconvMaxSA ? kHconvMaxSA : a;
@@ -763,6 +776,12 @@ static bool tconv_plan(const TconvJob& J, int KC, int BN, int MT, int chunks, Tc
     resident = 0;
     SB = (48 * 1024) / bbytes;
     SB = SB < 3 ? 3 : (SB > 9 ? 9 : SB);
+    if (g_deep_b_ring) {                                  // see launch_hconv's plan()
+      int deep = (budget - fixed - 3 * a_stage) / bbytes;
+      if (deep > kTconvMaxSB) deep = kTconvMaxSB;
+      if (deep > 9 * chunks) deep = 9 * chunks;
+      if (deep > SB) SB = deep;
+    }
   }
   int SA = (budget - fixed - SB * bbytes) / a_stage;
   if (SA > kTconvMaxSA) SA = kTconvMaxSA;

@@ -107,7 +107,8 @@ def load():
     for env, key in (('SEGB200_TCONV_MIN_EFF', OPT_TILE_CONV_MIN_EFF),
                      ('SEGB200_TWGRAD_MIN_EFF', OPT_TILE_WGRAD_MIN_EFF),
                      ('SEGB200_HCONV_WAVEQ', OPT_HALO_WAVEQ),
-                     ('SEGB200_POOL_ROWS', OPT_POOL_ROWS)):
+                     ('SEGB200_POOL_ROWS', OPT_POOL_ROWS),
+                     ('SEGB200_DEEP_B', OPT_DEEP_B_RING)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
     if 'SEGB200_WGRAD_MIN_TILES' in os.environ:
@@ -138,6 +139,7 @@ OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
 OPT_PDL = 7           # programmatic dependent launch of the hot-path kernels (default on)
 OPT_WGRAD_MIN_TILES = 9  # pixel tiles per CTA below which the weight-gradient grid is narrowed
 OPT_HALO_WAVEQ = 10    # halo kernel: halve the N tile when waves x bytes per CTA drops
+OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep as shared memory allows
 OPT_POOL_ROWS = 11     # row-mapped max-pool kernels (default on)
 OPT_WGRAD_CLUSTER = 8  # CTAs per cluster in the weight-gradient partial-sum reduction (1/2/4/8)
 

@@ -108,7 +108,7 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index, period=0.02):
+    def __init__(self, gpu_index, period=0.01):
         import threading
         self.sm, self.reasons, self.sm_max = [], set(), None
         self.p = self.f = self.thread = None

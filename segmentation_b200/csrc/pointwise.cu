@@ -196,9 +196,15 @@ maxpool_fwd_row8_kernel(seg_view x, int k_rt, seg_view y, uint8_t* argmax) {
   bf16* yrow = view_at_mut(y, n, p, 0);
   uint8_t* arow = argmax + ((int64_t)n * y.h + p) * y.w * y.c;
   const int x_sw = (int)x.sw, y_sw = (int)y.sw, yc = y.c;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
-    const int q = i / cv;
-    const int c0 = (i - q * cv) * 8;
+  // (column, channel-vector) of the thread's items advance by a fixed step: one division
+  // per thread instead of one per item
+  const int step = gridDim.x * blockDim.x;
+  const int step_q = step / cv, step_c = step - step_q * cv;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int q = i / cv, c8 = i - q * cv;
+  for (; i < rowlen; i += step, q += step_q, c8 += step_c) {
+    if (c8 >= cv) { c8 -= cv; ++q; }
+    const int c0 = c8 * 8;
     // running max and its window slot per bf16 pair, selected with halfword masks
     uint32_t best[4] = {0u, 0u, 0u, 0u}, slot[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -238,7 +244,7 @@ __device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
   return __hgt2_mask(v, __floats2bfloat162_rn(0.f, 0.f));       // one HSET2.BF16
 }
 
-template <int K>
+template <int K, bool TWO>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_row8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k_rt, seg_view add,
                         int add_y0, int add_x0, seg_view mask, seg_view pooled, seg_view dx) {
@@ -259,9 +265,13 @@ maxpool_bwd_row8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k_
   const bf16* mk_row = mask.ptr ? view_at(mask, n, p * k, 0) : nullptr;
   const int dy_sw = (int)dy.sw, dy2_sw = (int)dy2.sw, po_sw = (int)pooled.sw, dyc = dy.c;
   const int dx_sw = (int)dx.sw, mk_sw = (int)mask.sw;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
-    const int xx = i / cv;
-    const int c0 = (i - xx * cv) * 8;
+  const int step = gridDim.x * blockDim.x;
+  const int step_x = step / cv, step_c = step - step_x * cv;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int xx = i / cv, c8 = i - xx * cv;
+  for (; i < rowlen; i += step, xx += step_x, c8 += step_c) {
+    if (c8 >= cv) { c8 -= cv; ++xx; }
+    const int c0 = c8 * 8;
     const int q = xx / k;
     const uint32_t wx = (uint32_t)(xx - q * k);
     uint32_t w[4] = {0u, 0u, 0u, 0u};      // routed gradient of the window, bf16 pairs
@@ -270,7 +280,7 @@ maxpool_bwd_row8_kernel(seg_view dy, seg_view dy2, const uint8_t* argmax, int k_
 #pragma unroll
     for (int j = 0; j < 8; ++j) gsel[j] = 0.f;
     const bool in_pool = p_ok && q < dy.w;
-    const bool two = dy2_row != nullptr;
+    constexpr bool two = TWO;               // a second gradient (dy2) is summed in fp32
     if (in_pool) {
       const uint4 u = *reinterpret_cast<const uint4*>(dy_row + q * dy_sw + c0);
       a = *reinterpret_cast<const uint2*>(am_row + q * dyc + c0);
@@ -1468,12 +1478,14 @@ static bool launch_pool_bwd_rows(const seg_view& dy, const seg_view& dy2, const 
   const int rowlen = dx.w * (dx.c / 8);
   dim3 grid, block;
   pool_row_geometry(rows, rowlen, &grid, &block);
-  if (k == 2)
-    *err = launch_k(maxpool_bwd_row8_kernel<2>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
-  else if (k == 3)
-    *err = launch_k(maxpool_bwd_row8_kernel<3>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
-  else
-    *err = launch_k(maxpool_bwd_row8_kernel<0>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, add, add_y0, add_x0, mask, pooled, dx);
+  const bool two = dy2.ptr != nullptr;
+#define SEG_POOL_BWD(KK, TT) \
+  *err = launch_k(maxpool_bwd_row8_kernel<KK, TT>, grid, block, (size_t)(0), st, dy, dy2, argmax, k, \
+                  add, add_y0, add_x0, mask, pooled, dx)
+  if (k == 2) { if (two) SEG_POOL_BWD(2, true); else SEG_POOL_BWD(2, false); }
+  else if (k == 3) { if (two) SEG_POOL_BWD(3, true); else SEG_POOL_BWD(3, false); }
+  else { if (two) SEG_POOL_BWD(0, true); else SEG_POOL_BWD(0, false); }
+#undef SEG_POOL_BWD
   return true;
 }
 

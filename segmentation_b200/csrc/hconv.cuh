@@ -61,7 +61,13 @@ __device__ __forceinline__ void prof_mark(long long* prof, int role, int tile_i,
 }
 constexpr int kHconvMaxSB = 40;
 
-template <int KC, int BN, bool B_MN>
+// CL: clusters of two CTAs that work on two adjacent M tiles of the same N slice.  Each
+// CTA fetches HALF of every streamed weight tile and multicasts it to both, so a CTA's TMA
+// unit issues half the weight rows (the producers of the small deep layers are bound by the
+// ~5 cycles the unit spends per 128-byte row, profiles/r01_ncu_kernels.md §5).  A weight
+// stage is re-armed once BOTH CTAs' MMAs have read it (multicast tcgen05.commit, barrier
+// count 2).  Streamed weights only (the launcher never combines CL with resident B).
+template <int KC, int BN, bool B_MN, bool CL = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const HconvParams P) {
@@ -90,15 +96,22 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int chunks = P.chunks1 + P.chunks2;
   const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
   const int n_tiles = P.N_total / BN;
-  const int total_tiles = m_tiles * n_tiles;
   const int halo = (P.kh - 1) * P.Wp + P.kw - 1;
+  // schedule units: one tile, or (CL) one pair of adjacent M tiles per cluster
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  const int total_tiles = CL ? ((m_tiles + 1) >> 1) * n_tiles : m_tiles * n_tiles;
+  const int first_unit = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int unit) {
+    return (CL ? (unit / n_tiles) * 2 + (int)crank : unit / n_tiles) * kBlockM;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_mbar_init();
   }
@@ -106,6 +119,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL) cluster_sync_all();   // the peer's barriers are initialised before anything lands
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // everything above overlaps the previous kernel's tail
 
@@ -117,8 +131,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       uint32_t pa = 0, pb = 0;
       bool first_tile = true;
       int ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int m0 = (tile / n_tiles) * kBlockM;
+      for (int tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
+        const int m0 = tile_m0(tile);
         const int n0 = (tile % n_tiles) * BN;
         if (lane == 0) prof_mark(P.prof, 0, ti, 0);
         const int g0 = m0 / P.Wp;                          // first padded row (global)
@@ -156,7 +170,20 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 uint8_t* sbp = smem_b + sb * kBBytes;
                 mbar_expect_tx(&b_full[sb], kBBytes);
                 const int tap_row = P.use_tap_rows ? P.tap_rows[t] : bt * P.b_rows_per_tap;
-                if (B_MN) {
+                if (CL) {
+                  // this CTA's half of the tile (tmB boxes are half tiles), to both CTAs
+                  if (B_MN) {
+                    const int row = tap_row + j * KC + (int)crank * (KC / 2);
+#pragma unroll
+                    for (int a = 0; a < BN / kAtomN; ++a)
+                      tma_load_2d_mc(&tmB, &b_full[sb],
+                                     sbp + a * (KC * kAtomN * 2) + crank * ((KC / 2) * kAtomN * 2),
+                                     n0 + a * kAtomN, row, (uint16_t)3);
+                  } else {
+                    tma_load_2d_mc(&tmB, &b_full[sb], sbp + crank * ((BN / 2) * SWZ), j * KC,
+                                   tap_row + n0 + (int)crank * (BN / 2), (uint16_t)3);
+                  }
+                } else if (B_MN) {
                   const int row = tap_row + j * KC;
 #pragma unroll
                   for (int a = 0; a < BN / kAtomN; ++a)
@@ -193,8 +220,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       uint32_t pa = 0, pb = 0, aphase = 0;
       bool first_tile = true;
       int ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int m0 = (tile / n_tiles) * kBlockM;
+      for (int tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
+        const int m0 = tile_m0(tile);
         const int a_off = P.flat ? 0 : m0 - (m0 / P.Wp) * P.Wp;
         if (lane == 0) prof_mark(P.prof, 1, ti, 0);
         mbar_wait(&tempty[as], aphase ^ 1u);
@@ -225,7 +252,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                            umma_desc_pack(hiB, b_lo0 + kk * kstepB), idesc, acc);
                   acc = 1;
                 }
-                if (!P.b_resident) umma_commit(&b_empty[sb]);
+                if (CL) umma_commit_mc(&b_empty[sb], (uint16_t)3);
+                else if (!P.b_resident) umma_commit(&b_empty[sb]);
 #if SEGB200_KERNEL_PROF
                 // per-tap issue timestamps of tiles 2 and 3 (role 3 of the timeline hook)
                 if (P.prof != nullptr && blockIdx.x == 0 && (ti == 2 || ti == 3) && j == 0)
@@ -257,8 +285,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     const int img_stride = P.Hp * P.Wp;
     int ti = 0;
     long long* eprof = (warp == 2 && lane == 0) ? P.prof : nullptr;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile / n_tiles) * kBlockM;
+    for (int tile = first_unit; tile < total_tiles; tile += unit_step, ++ti) {
+      const int m0 = tile_m0(tile);
       const int n0 = (tile % n_tiles) * BN;
       const int m = m0 + quad * 32 + lane;
       const int img = m / img_stride;
@@ -341,6 +369,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

@@ -96,6 +96,18 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// The same load delivered to the same shared-memory offset (data and mbarrier) of every
+// CTA of the cluster whose bit is set in cta_mask.
+__device__ __forceinline__ void tma_load_2d_mc(const void* tmap, uint64_t* bar, void* dst, int c0,
+                                               int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0),
+      "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, void* dst, int c0,
                                             int c1, int c2, int c3) {
   asm volatile(
@@ -180,6 +192,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           smem_u32(bar))
+      : "memory");
+}
+// ... on the barrier at the same offset in every CTA of the cluster selected by cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread

@@ -471,6 +471,94 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
   return SEG_OK;
 }
 
+// Cluster-of-two variant (hconv.cuh, CL): streamed weights, KC = 64.  Returns
+// SEG_E_UNSUPPORTED (nothing launched) if no cluster can be resident.
+static int g_hconv_cluster = 0;        // seg_set_option key 13
+void hconv_set_cluster(int on) { g_hconv_cluster = on != 0; }
+
+template <int BN, bool B_MN>
+static int launch_hconv_cl_t(const HconvJob& J, const HconvParams& P0, int smem_bytes,
+                             cudaStream_t st) {
+  constexpr int KC = 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  constexpr int kAtomN = BN < 64 ? BN : 64;
+  HconvParams P = P0;
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc;
+  if (P.flat) {
+    rc = make_tmap_2d(&tmA1, J.a1.ptr, J.a1.c, (int64_t)J.batch * P.Hp * P.Wp, J.a1.sw, KC,
+                      P.box_rows, KC * 2);
+    if (rc) return rc;
+    if (J.a2.ptr) {
+      rc = make_tmap_2d(&tmA2, J.a2.ptr, J.a2.c, (int64_t)J.batch * P.Hp * P.Wp, J.a2.sw, KC,
+                        P.box_rows, KC * 2);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA1;
+    }
+  } else {
+    rc = make_tmap_rows(&tmA1, J.a1, KC, P.row_px, KC * 2);
+    if (rc) return rc;
+    if (J.a2.ptr) {
+      rc = make_tmap_rows(&tmA2, J.a2, KC, P.row_px, KC * 2);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA1;
+    }
+  }
+  // half-tile boxes: each CTA of the pair fetches one half and multicasts it
+  if (B_MN)
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, kAtomN, KC / 2, kAtomN * 2);
+  else
+    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN / 2, KC * 2);
+  if (rc) return rc;
+  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
+  const int units = ((m_tiles + 1) / 2) * (J.N_total / BN);
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(num_sms() & ~1);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = 227 * 1024 - 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, hconv_kernel<KC, BN, B_MN, true>, &cfg) != cudaSuccess ||
+        n < 1) {
+      cudaGetLastError();
+      n = -1;
+    }
+    max_clusters = n;
+  }
+  if (max_clusters < 1) return SEG_E_UNSUPPORTED;
+  int clusters = units < max_clusters ? units : max_clusters;
+  if (clusters > num_sms() / 2) clusters = num_sms() / 2;
+  P.b_resident = 0;
+  SEG_CHECK_CUDA(launch_kc(hconv_kernel<KC, BN, B_MN, true>, dim3(2 * clusters), dim3(kConvThreads),
+                           (size_t)(smem_bytes), st, 2, tmA1, tmA2, tmB, P));
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+template <bool B_MN>
+static int launch_hconv_cl_bn(const HconvJob& J, const HconvParams& P, int BN, int smem,
+                              cudaStream_t st) {
+  switch (BN) {
+    case 128: return launch_hconv_cl_t<128, B_MN>(J, P, smem, st);
+    case 64: return launch_hconv_cl_t<64, B_MN>(J, P, smem, st);
+    case 32: return launch_hconv_cl_t<32, B_MN>(J, P, smem, st);
+  }
+  return SEG_E_UNSUPPORTED;
+}
+
 template <int KC, bool B_MN>
 static int launch_hconv_bn(const HconvJob& J, const HconvParams& P, int BN, int smem,
                            cudaStream_t st) {
@@ -618,6 +706,12 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
             "SB=%d res=%d stage=%d tiles=%lld\n", P.P_total, J.N_total, J.kh, J.kw, chunks, KC, P.flat,
             P.Wp, BN, SA, SB, res, P.a_stage_bytes,
             (long long)(ceil_div64(P.P_total, (int64_t)kBlockM) * (J.N_total / BN)));
+  if (g_hconv_cluster && !res && KC == 64 && BN >= 32 && BN <= 128 &&
+      ceil_div64(P.P_total, kBlockM) >= 2) {
+    const int rc2 = J.b_mn ? launch_hconv_cl_bn<true>(J, P, BN, smem, st)
+                           : launch_hconv_cl_bn<false>(J, P, BN, smem, st);
+    if (rc2 != SEG_E_UNSUPPORTED) return rc2;
+  }
   if (J.b_mn) {
     switch (KC) {
       case 64: return launch_hconv_bn<64, true>(J, P, BN, smem, st);

@@ -146,6 +146,42 @@ def test_conv_fwd(cuda, case, impl_name, impl):
     assert err < (TOL_F32 if f32 else TOL_BF16), (name, impl_name, err)
 
 
+CLUSTER_CASES = [c for c in CONV_CASES if c[0] in ('c512', 'v3_128_256', 'concat')]
+
+
+@pytest.mark.parametrize('case', CLUSTER_CASES, ids=[c[0] for c in CLUSTER_CASES])
+def test_conv_fwd_cluster_multicast_option(cuda, case):
+    """seg_set_option key 13 (halo kernel in clusters of two CTAs, each fetching half of every
+    streamed weight tile and multicasting it): same numbers as the default plan.  Layers whose
+    weights stay resident in shared memory ignore the option."""
+    name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
+    x, w, b = _conv_inputs(case)
+    cin, cin_pad, cout_pad = C1 + C2, pad16(C1 + C2), pad16(Co)
+    if C2:
+        x1_d, x2_d = dev_bf16(x[..., :C1]), dev_bf16(x[..., C1:])
+    else:
+        x1_d, x2_d = dev_bf16(x, cin_pad), None
+    w_d = shadow_conv(w, cin_pad, cout_pad)
+    b_d = b.cuda()
+    Ho, Wo = (H - k + 1, W - k + 1) if padding == 'VALID' else (H, W)
+    flags = N.EPI_BIAS | (N.EPI_RELU if relu else 0)
+    d = desc(k, s, conv_pads(H, W, k, s, padding), cin, Co, cin_pad, cout_pad, flags, N.IMPL_UMMA)
+    outs = []
+    try:
+        for on in (0, 1):
+            N.set_option(N.OPT_HALO_CLUSTER, on)
+            y_d = torch.full((Nb, Ho, Wo, Co), float('nan'), dtype=torch.bfloat16, device='cuda')
+            N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x1_d), N.vref(x2_d), N.ptr(w_d),
+                   N.ptr(b_d), N.vref(y_d), N.stream_ptr())
+            sync()
+            outs.append(y_d.float().cpu())
+    finally:
+        N.set_option(N.OPT_HALO_CLUSTER, 0)
+    ref = torch.relu(T.conv2d(x, w, b, s, padding)) if relu else T.conv2d(x, w, b, s, padding)
+    assert rel_l2(outs[1], ref) < TOL_BF16, name
+    assert torch.equal(outs[0], outs[1]), name     # same K order, same rounding
+
+
 # ---------------------------------------------------------------------------
 # conv dgrad / wgrad / bias grad
 # ---------------------------------------------------------------------------

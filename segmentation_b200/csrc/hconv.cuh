@@ -67,12 +67,18 @@ constexpr int kHconvMaxSB = 40;
 // ~5 cycles the unit spends per 128-byte row, profiles/r01_ncu_kernels.md §5).  A weight
 // stage is re-armed once BOTH CTAs' MMAs have read it (multicast tcgen05.commit, barrier
 // count 2).  Streamed weights only (the launcher never combines CL with resident B).
-template <int KC, int BN, bool B_MN, bool CL = false>
+// TPS: filter taps per weight stage (1, or 3 = one filter row of a k x 3 kernel per stage:
+// a third of the full/empty barrier waits, commits and elections in the single-thread issue
+// loop, whose ~80 instructions per tap - not the tensor pipe - set the pace of the small
+// deep layers, profiles/r01_ncu_kernels.md §5).  Streamed weights only.
+template <int KC, int BN, bool B_MN, bool CL = false, int TPS = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const HconvParams P) {
   constexpr int SWZ = KC * 2;
   constexpr int kBBytes = BN * KC * 2;
+  constexpr int kStageB = TPS * kBBytes;          // one weight stage
+  static_assert(TPS == 1 || (TPS == 3 && !CL), "weight stages hold one tap or one filter row");
   constexpr int kAtomN = BN < 64 ? BN : 64;
   constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                             : 2 * BN <= 256 ? 256 : 512;
@@ -81,7 +87,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_b = smem + P.SA * P.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P.SB * kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P.SB * kStageB);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kHconvMaxSA;
   uint64_t* b_full = bars + 2 * kHconvMaxSA;
@@ -164,12 +170,15 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           if (++sa == P.SA) { sa = 0; pa ^= 1u; }
           if (!P.b_resident || first_tile) {
             int bt = P.tap_flip ? taps - 1 : 0;
-            for (int t = 0; t < taps; ++t) {
+            for (int t = 0; t < taps; t += TPS) {
               mbar_wait(&b_empty[sb], pb ^ 1u);
               if (elect_one()) {
-                uint8_t* sbp = smem_b + sb * kBBytes;
-                mbar_expect_tx(&b_full[sb], kBBytes);
-                const int tap_row = P.use_tap_rows ? P.tap_rows[t] : bt * P.b_rows_per_tap;
+                mbar_expect_tx(&b_full[sb], kStageB);
+#pragma unroll
+                for (int u = 0; u < TPS; ++u) {
+                uint8_t* sbp = smem_b + sb * kStageB + u * kBBytes;
+                const int bt_u = bt + (P.tap_flip ? -u : u);
+                const int tap_row = P.use_tap_rows ? P.tap_rows[t + u] : bt_u * P.b_rows_per_tap;
                 if (CL) {
                   // this CTA's half of the tile (tmB boxes are half tiles), to both CTAs
                   if (B_MN) {
@@ -192,9 +201,10 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 } else {
                   tma_load_2d(&tmB, &b_full[sb], sbp, j * KC, tap_row + n0);
                 }
+                }
               }
               __syncwarp();
-              bt += P.tap_flip ? -1 : 1;
+              bt += P.tap_flip ? -TPS : TPS;
               if (++sb == P.SB) { sb = 0; pb ^= 1u; }
             }
           }
@@ -237,6 +247,30 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           const uint32_t a_lo0 =
               umma_desc_lo(smem_u32(smem + sa * P.a_stage_bytes), 0) + (uint32_t)a_off * row16;
           uint32_t a_row = a_lo0;                       // tap (r, 0)
+          if (TPS == 3) {
+            // one weight stage per filter row: one wait, one election, twelve MMAs, one commit
+            for (int r = 0; r < P.kh; ++r, a_row += (uint32_t)P.Wp * row16) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t b_row0 = umma_desc_lo(smem_u32(smem_b + sb * kStageB), lboB);
+              if (elect_one()) {
+#pragma unroll
+                for (int s3 = 0; s3 < 3; ++s3) {
+#pragma unroll
+                  for (int kk = 0; kk < KC / 16; ++kk) {
+                    umma_f16(tmem_d, umma_desc_pack(hiA, a_row + s3 * row16 + kk * 2),
+                             umma_desc_pack(hiB, b_row0 + s3 * (kBBytes >> 4) + kk * kstepB), idesc,
+                             acc);
+                    acc = 1;
+                  }
+                }
+                umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              acc = 1;
+              if (++sb == P.SB) { sb = 0; pb ^= 1u; }
+            }
+          } else {
           for (int r = 0; r < P.kh; ++r, a_row += (uint32_t)P.Wp * row16) {
             uint32_t a_tap = a_row;
             for (int s = 0; s < P.kw; ++s, a_tap += row16) {
@@ -264,6 +298,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               acc = 1;
               if (++sb == P.SB) { sb = 0; pb ^= 1u; }
             }
+          }
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();

@@ -419,12 +419,12 @@ void conv_set_deep_b_ring(int on) { g_deep_b_ring = on != 0; }
 static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
-template <int KC, int BN, bool B_MN>
+template <int KC, int BN, bool B_MN, int TPS = 1>
 static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_bytes,
                           cudaStream_t st) {
   static int attr_smem = 0;
   if (attr_smem < smem_bytes) {
-    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN>,
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN, false, TPS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_smem = 227 * 1024;
   }
@@ -466,7 +466,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
     grid -= grid % n_tiles;           // every CTA must keep one N-slice for its lifetime
     if (grid < n_tiles) P.b_resident = 0, grid = tiles < num_sms() ? tiles : num_sms();
   }
-  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN>, dim3(grid), dim3(kConvThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
+  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN, false, TPS>, dim3(grid), dim3(kConvThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }
@@ -559,9 +559,20 @@ static int launch_hconv_cl_bn(const HconvJob& J, const HconvParams& P, int BN, i
   return SEG_E_UNSUPPORTED;
 }
 
+static int g_hconv_rowstage = 0;       // seg_set_option key 14: one filter row per weight stage
+void hconv_set_rowstage(int on) { g_hconv_rowstage = on != 0; }
+
 template <int KC, bool B_MN>
 static int launch_hconv_bn(const HconvJob& J, const HconvParams& P, int BN, int smem,
-                           cudaStream_t st) {
+                           cudaStream_t st, int tps = 1) {
+  if (tps == 3) {                      // planned only for KC = 64, BN = 64 / 128
+    if (KC != 64) return SEG_E_UNSUPPORTED;
+    switch (BN) {
+      case 128: return launch_hconv_t<64, 128, B_MN, 3>(J, P, smem, st);
+      case 64: return launch_hconv_t<64, 64, B_MN, 3>(J, P, smem, st);
+    }
+    return SEG_E_UNSUPPORTED;
+  }
   switch (BN) {
     case 256: return launch_hconv_t<KC, 256, B_MN>(J, P, smem, st);
     case 128: return launch_hconv_t<KC, 128, B_MN>(J, P, smem, st);
@@ -711,6 +722,22 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
     const int rc2 = J.b_mn ? launch_hconv_cl_bn<true>(J, P, BN, smem, st)
                            : launch_hconv_cl_bn<false>(J, P, BN, smem, st);
     if (rc2 != SEG_E_UNSUPPORTED) return rc2;
+  }
+  // one filter row (3 taps) per weight stage: a third of the barrier round trips in the
+  // issue loop; the ring is re-planned in row units
+  if (g_hconv_rowstage && !res && KC == 64 && (BN == 64 || BN == 128) && J.kw == 3) {
+    const int stage = 3 * BN * KC * 2;
+    int sb = (budget - 3 * P.a_stage_bytes) / stage;
+    if (sb > kHconvMaxSB) sb = kHconvMaxSB;
+    if (sb > J.kh * chunks) sb = J.kh * chunks;
+    int sa = sb >= 2 ? (budget - sb * stage) / P.a_stage_bytes : 0;
+    if (sa > kHconvMaxSA) sa = kHconvMaxSA;
+    if (sb >= 2 && sa >= 2) {
+      P.SA = sa; P.SB = sb;
+      const int smem3 = sa * P.a_stage_bytes + sb * stage + 2048;
+      return J.b_mn ? launch_hconv_bn<64, true>(J, P, BN, smem3, st, 3)
+                    : launch_hconv_bn<64, false>(J, P, BN, smem3, st, 3);
+    }
   }
   if (J.b_mn) {
     switch (KC) {

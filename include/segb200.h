@@ -104,7 +104,8 @@ SEG_API const char* seg_last_error_string(void);
  * on adjacent M tiles, each fetching half of every streamed weight tile and multicasting it
  * to both (default 0).  key 14: halo kernel with one filter row (three taps) per streamed
  * weight stage for k x 3 kernels: a third of the barrier waits, commits and elections in the
- * single-thread MMA issue loop (default 0: not yet measured). */
+ * single-thread MMA issue loop (default 1; plain convolutions only, not the tap-table
+ * sub-kernels of strided transposed convolutions). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */

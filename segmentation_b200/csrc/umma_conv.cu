@@ -559,7 +559,7 @@ static int launch_hconv_cl_bn(const HconvJob& J, const HconvParams& P, int BN, i
   return SEG_E_UNSUPPORTED;
 }
 
-static int g_hconv_rowstage = 0;       // seg_set_option key 14: one filter row per weight stage
+static int g_hconv_rowstage = 1;       // seg_set_option key 14: one filter row per weight stage
 void hconv_set_rowstage(int on) { g_hconv_rowstage = on != 0; }
 
 template <int KC, bool B_MN>
@@ -725,7 +725,8 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   }
   // one filter row (3 taps) per weight stage: a third of the barrier round trips in the
   // issue loop; the ring is re-planned in row units
-  if (g_hconv_rowstage && !res && KC == 64 && (BN == 64 || BN == 128) && J.kw == 3) {
+  if (g_hconv_rowstage && !res && KC == 64 && (BN == 64 || BN == 128) && J.kw == 3 &&
+      !J.tap_rows) {                   // (sub-kernels with a tap table: not yet validated)
     const int stage = 3 * BN * KC * 2;
     int sb = (budget - 3 * P.a_stage_bytes) / stage;
     if (sb > kHconvMaxSB) sb = kHconvMaxSB;

@@ -74,3 +74,27 @@ def test_sass_contains_tcgen05_and_tma():
                           text=True).stdout
     for mnemonic in ('UTCHMMA', 'UTMALDG', 'IM2COL', 'LDTM'):
         assert mnemonic in sass, mnemonic
+
+
+def test_option_keys_are_documented_and_accepted_without_gpu(lib):
+    """Every OPT_* key of the ctypes binding is documented in the header ("key N") and
+    accepted by seg_set_option (a host-side switch: no device needed); an unknown key is an
+    error, not a silent no-op."""
+    from segmentation_b200 import native
+    keys = {k: v for k, v in vars(native).items() if k.startswith('OPT_') and isinstance(v, int)}
+    assert len(set(keys.values())) == len(keys), keys            # no two names share a key
+    doc = set(int(n) for n in re.findall(r'\bkeys?\s+(\d+)', open(HEADER).read()))
+    doc |= set(int(n) for n in re.findall(r'key \d+ / key (\d+)', open(HEADER).read()))
+    for name, key in keys.items():
+        assert key in doc, (name, key)
+    defaults = {native.OPT_HALO_CONV: 1, native.OPT_HALO_ROW_ALIGN: 0, native.OPT_TILE_CONV: 1,
+                native.OPT_TILE_CONV_MIN_EFF: 70, native.OPT_TILE_WGRAD: 1,
+                native.OPT_TILE_WGRAD_MIN_EFF: 40, native.OPT_PDL: 1, native.OPT_WGRAD_CLUSTER: 1,
+                native.OPT_WGRAD_MIN_TILES: 8, native.OPT_HALO_WAVEQ: 0, native.OPT_POOL_ROWS: 1,
+                native.OPT_DEEP_B_RING: 1, native.OPT_HALO_CLUSTER: 0, native.OPT_HALO_ROWSTAGE: 1}
+    assert set(defaults) == set(keys.values())
+    lib.seg_set_option.restype = ctypes.c_int32
+    lib.seg_set_option.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    for key, value in defaults.items():                          # re-apply the defaults
+        assert lib.seg_set_option(key, value) == 0, key
+    assert lib.seg_set_option(99, 1) != 0

@@ -105,7 +105,10 @@ SEG_API const char* seg_last_error_string(void);
  * to both (default 0).  key 14: halo kernel with one filter row (three taps) per streamed
  * weight stage for k x 3 kernels: a third of the barrier waits, commits and elections in the
  * single-thread MMA issue loop (default 1; plain convolutions only, not the tap-table
- * sub-kernels of strided transposed convolutions). */
+ * sub-kernels of strided transposed convolutions).  key 15: the spatial-tile weight-gradient
+ * kernel hands its partial sums to L2 as TMA tensor reduce-adds (one [ci x 32 co] box per tap
+ * and column block) instead of one bulk reduce-add per accumulator row (default 0: built
+ * after the round's GPU budget ran out, not yet run). */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
 /* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
  * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */

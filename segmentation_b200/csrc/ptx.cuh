@@ -343,6 +343,16 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t ssrc, 
                "r"(ssrc), "r"(bytes)
                : "memory");
 }
+// TMA tensor reduce-add of one shared-memory box into a 3-D fp32 tensor (clipped at the
+// tensor bounds like a tensor store)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, uint32_t ssrc, int c0, int c1,
+                                                  int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group"
+      " [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(ssrc), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

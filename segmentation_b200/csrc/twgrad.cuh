@@ -51,10 +51,17 @@ struct TwgradParams {
 constexpr int kTwTH = 8, kTwTW = 16, kTwPW = kTwTW + 2, kTwPH = kTwTH + 2;
 constexpr int kTwMaxStages = 8;
 
-template <int AW, int BN>
+// TRED (seg_set_option key 15, not yet measured): the partial sums leave the CTA as TMA
+// TENSOR reduce-adds - one [AW ci] x [32 co] fp32 box per (tap, 32-column block), 4 per MMA
+// and 18-20 per CTA, issued by one thread per group of four epilogue warps - instead of one
+// 256-byte bulk reduce-add per accumulator row and MMA (640 per CTA, whose per-lane issue
+// was measured at ~9 k of the epilogue's ~25 k cycles).  tmDW: dW as a 3-D tensor
+// {SC, BC, 9} with 128-byte-swizzled boxes {32, AW, 1} (clipped at BC and SC).
+template <int AW, int BN, bool TRED = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
-              const __grid_constant__ CUtensorMap tmZ, const TwgradParams P) {
+              const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmDW,
+              const TwgradParams P) {
   constexpr int rowA = AW * 2;                          // bytes per staged X pixel
   constexpr int kAtomN = BN < 64 ? BN : 64;
   constexpr int rowB = kAtomN * 2;                      // bytes per staged dZ pixel (per atom)
@@ -236,6 +243,47 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       // every MMA has completed, so all stages were consumed; the other epilogue warps may
       // still be summing the last dZ tiles out of them
       if (clustered || bulk_ok) named_bar_sync(2, 256);
+      if (TRED) {
+        // box layout: box (m, atom, 32-column block) = AW rows of 128 bytes, 16-byte chunk j
+        // of row cl stored at chunk j ^ (cl & 7) (the tensor map's 128-byte swizzle)
+        constexpr int kCB = BN / 32;
+        constexpr uint32_t kBoxBytes = AW * 128;
+#pragma unroll 1
+        for (int m = half; m < kNMma; m += 2) {
+#pragma unroll 1
+          for (int cc = 0; cc < BN; cc += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + m * BN + cc, r);
+            tmem_ld_wait();
+            const uint32_t row = smem_u32(smem) +
+                                 (uint32_t)((m * kAtoms + a) * kCB + (cc >> 5)) * kBoxBytes +
+                                 (uint32_t)cl * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(row + (uint32_t)((j ^ (cl & 7)) << 4),
+                     make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+          }
+          fence_proxy_async();
+          named_bar_sync(3 + half, 128);           // the four warps that staged MMA m
+          if (et == 0) {
+#pragma unroll 1
+            for (int a2 = 0; a2 < kAtoms; ++a2) {
+              const int tap2 = AW == 64 ? 2 * m + a2 : (a2 < 3 ? 3 * m + a2 : 9);
+              if (tap2 >= 9) continue;
+#pragma unroll 1
+              for (int cb = 0; cb < kCB; ++cb)
+                if (n0 + cb * 32 < P.SC)
+                  tma_reduce_add_3d(&tmDW,
+                                    smem_u32(smem) + (uint32_t)((m * kAtoms + a2) * kCB + cb) * kBoxBytes,
+                                    n0 + cb * 32, chunk * AW, tap2);
+            }
+          }
+        }
+        if (et == 0) {
+          bulk_commit_group();
+          bulk_wait_group<0>();                    // complete before the CTA exits
+        }
+      } else {
 #pragma unroll 1
       for (int m = half; m < kNMma; m += 2) {
         const int tap = AW == 64 ? 2 * m + a : (a < 3 ? 3 * m + a : 9);
@@ -282,6 +330,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       if (!clustered && bulk_ok) {
         bulk_commit_group();
         bulk_wait_group<0>();                          // complete before the CTA exits
+      }
       }
     }
   }

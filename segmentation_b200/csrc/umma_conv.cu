@@ -1043,11 +1043,30 @@ void twgrad_set_cluster(int n) { g_twgrad_cluster = n >= 8 ? 8 : (n >= 4 ? 4 : (
 void twgrad_enable(int on) { g_use_twgrad = on != 0; }
 void twgrad_set_min_eff(int pct) { g_twgrad_min_eff = pct; }
 
-template <int AW, int BN>
+static int g_twgrad_tred = 0;          // seg_set_option key 15: TMA tensor reduce-add epilogue
+void twgrad_set_tred(int on) { g_twgrad_tred = on != 0; }
+
+// dW [9][BC][SC] fp32 as a 3-D tensor {SC, BC, 9} with 128-byte-swizzled boxes {32, rows, 1}
+static int make_tmap_dw(CUtensorMap* tm, float* dw, int SC, int BC, int box_rows) {
+  SEG_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && SC % 4 == 0, SEG_E_ALIGN,
+              "dW tensor map: base and row pitch must be 16-byte aligned");
+  cuuint64_t gdim[3] = {(cuuint64_t)SC, (cuuint64_t)BC, 9};
+  cuuint64_t gstr[2] = {(cuuint64_t)SC * 4, (cuuint64_t)BC * SC * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t est[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dw, gdim, gstr, box, est,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SEG_REQUIRE(r == CUDA_SUCCESS, SEG_E_CUDA, "cuTensorMapEncodeTiled(dW) failed (%d) SC=%d BC=%d",
+              (int)r, SC, BC);
+  return SEG_OK;
+}
+
+template <int AW, int BN, bool TRED = false>
 static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    SEG_CHECK_CUDA(cudaFuncSetAttribute(twgrad_kernel<AW, BN>,
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(twgrad_kernel<AW, BN, TRED>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
@@ -1117,7 +1136,7 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
     static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (max_clusters[cs] == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, twgrad_kernel<AW, BN>, &cfg) != cudaSuccess || n < 1) {
+      if (cudaOccupancyMaxActiveClusters(&n, twgrad_kernel<AW, BN, TRED>, &cfg) != cudaSuccess || n < 1) {
         cudaGetLastError();
         n = -1;
       }
@@ -1134,7 +1153,13 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   }
   P.cluster = cs;
   P.ctas_per_combo = per;
-  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN>, dim3(combos * per), dim3(kConvThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, P));
+  CUtensorMap tmDW = tmZ;              // unused unless TRED
+  if (TRED) {
+    if (!P.staged_ok || cs > 1) return SEG_E_UNSUPPORTED;
+    rc = make_tmap_dw(&tmDW, J.dw, J.SC, J.BC, AW);
+    if (rc) return rc;
+  }
+  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN, TRED>, dim3(combos * per), dim3(kConvThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, tmDW, P));
   return SEG_OK;
 }
 
@@ -1151,6 +1176,17 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
   const int Ho = J.small_.h, Wo = J.small_.w;
   const int64_t comp = (int64_t)((Ho + kTwTH - 1) / kTwTH * kTwTH) * ((Wo + kTwTW - 1) / kTwTW * kTwTW);
   if ((int64_t)Ho * Wo * 100 < (int64_t)g_twgrad_min_eff * comp) return SEG_E_UNSUPPORTED;
+  // TMA tensor reduce-add epilogue (option 15): whole BN slices, 16-byte aligned rows
+  if (g_twgrad_tred && g_twgrad_cluster == 1 && BN >= 32 && J.SC % BN == 0 &&
+      (reinterpret_cast<uintptr_t>(J.dw) & 15) == 0) {
+    int rc2 = SEG_E_UNSUPPORTED;
+    if (AW == 64 && BN == 64) rc2 = launch_twgrad_t<64, 64, true>(J, st);
+    else if (AW == 64 && BN == 32) rc2 = launch_twgrad_t<64, 32, true>(J, st);
+    else if (AW == 32 && BN == 64) rc2 = launch_twgrad_t<32, 64, true>(J, st);
+    else if (AW == 32 && BN == 32) rc2 = launch_twgrad_t<32, 32, true>(J, st);
+    else if (AW == 16 && BN == 32) rc2 = launch_twgrad_t<16, 32, true>(J, st);
+    if (rc2 != SEG_E_UNSUPPORTED) return rc2;
+  }
   switch (AW) {
     case 64:
       switch (BN) {

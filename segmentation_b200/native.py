@@ -110,7 +110,8 @@ def load():
                      ('SEGB200_POOL_ROWS', OPT_POOL_ROWS),
                      ('SEGB200_DEEP_B', OPT_DEEP_B_RING),
                      ('SEGB200_HCONV_CLUSTER', OPT_HALO_CLUSTER),
-                     ('SEGB200_HCONV_ROWSTAGE', OPT_HALO_ROWSTAGE)):
+                     ('SEGB200_HCONV_ROWSTAGE', OPT_HALO_ROWSTAGE),
+                     ('SEGB200_TWGRAD_TRED', OPT_WGRAD_TENSOR_RED)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
     if 'SEGB200_WGRAD_MIN_TILES' in os.environ:
@@ -144,6 +145,7 @@ OPT_HALO_WAVEQ = 10    # halo kernel: halve the N tile when waves x bytes per CT
 OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep as shared memory allows
 OPT_HALO_CLUSTER = 13  # halo kernel: cluster of two CTAs multicasting the streamed weight tiles
 OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weight stage
+OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (untested)
 OPT_POOL_ROWS = 11     # row-mapped max-pool kernels (default on)
 OPT_WGRAD_CLUSTER = 8  # CTAs per cluster in the weight-gradient partial-sum reduction (1/2/4/8)
 

@@ -6,6 +6,7 @@ so the only difference is summation order -> rel-L2 <= 2e-3 for bf16 outputs
 (one bf16 rounding of the result, 2^-9 relative), 1e-4 for fp32 outputs.
 """
 import ctypes
+import os
 
 import pytest
 import torch
@@ -257,6 +258,45 @@ def test_conv_bwd(cuda, case, impl_name, impl):
         e1 = rel_l2(s1.float().cpu(), dx1.float().cpu())
         e2 = rel_l2(s2.float().cpu(), dx2.float().cpu())
         assert e1 < 1e-3 and e2 < 1e-3, (name, e1, e2)
+
+
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get('SEGB200_TEST_EXPERIMENTAL') != '1',
+                                  reason='kernel variant built after the GPU budget of its round '
+                                         'ran out: run with SEGB200_TEST_EXPERIMENTAL=1 first')
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize('case', [c for c in BWD_CASES if c[7] == 3 and c[8] == 1 and c[6] % 32 == 0],
+                         ids=lambda c: c[0])
+def test_conv_wgrad_tensor_reduce_option(cuda, case):
+    """seg_set_option key 15: the spatial-tile weight-gradient kernel's TMA tensor reduce-add
+    epilogue gives the same dW / db as the default row-wise bulk reduce-add epilogue."""
+    name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
+    x, w, b = _conv_inputs(case)
+    g = _gen(7)
+    z = T.conv2d(x, w, None, s, padding)
+    dz = bfr(torch.randn(z.shape, generator=g) * 0.05)
+    cin, cin_pad, cout_pad = C1 + C2, pad16(C1 + C2), pad16(Co)
+    dz_d = dev_bf16(dz, cout_pad)
+    d = desc(k, s, conv_pads(H, W, k, s, padding), cin, Co, cin_pad, cout_pad, 0, N.IMPL_UMMA)
+    if C2:
+        x1_d, x2_d = dev_bf16(x[..., :C1]), dev_bf16(x[..., C1:])
+    else:
+        x1_d, x2_d = dev_bf16(x, cin_pad), None
+    outs = []
+    try:
+        for on in (0, 1):
+            N.set_option(N.OPT_WGRAD_TENSOR_RED, on)
+            dw_d = torch.zeros(k, k, cin, Co, dtype=torch.float32, device='cuda')
+            db_d = torch.zeros(Co, dtype=torch.float32, device='cuda')
+            N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x1_d), N.vref(x2_d), N.vref(dz_d),
+                   N.ptr(dw_d), N.ptr(db_d), N.stream_ptr())
+            sync()
+            outs.append((dw_d.cpu(), db_d.cpu()))
+    finally:
+        N.set_option(N.OPT_WGRAD_TENSOR_RED, 0)
+    assert rel_l2(outs[1][0], outs[0][0]) < TOL_F32 * 5, name
+    assert rel_l2(outs[1][1], outs[0][1]) < TOL_F32 * 5, name
 
 
 # ---------------------------------------------------------------------------

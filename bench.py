@@ -12,8 +12,12 @@ data-parallel gradient all-reduce over NCCL for N>1).
   e2e   : img/s through UNetModel.train_step() — the reference's own no-argument call —
           with HOST (pinned) batches pulled from the dataset: every step issues one
           batch's H2D (images+masks) and reads the loss back (D2H) inside the timed region
-  roofline     : the single heaviest conv-family launch of the step, against the tensor
-                 peak or (arithmetic intensity below the ridge) the HBM peak
+  roofline     : the kernel FAMILY with the largest share of the step (tconv / hconv / igemm /
+                 twgrad / wgrad / pool / adam ...), CUDA-event timed per launch in this run,
+                 against the measured tensor peak or (arithmetic intensity below the ridge)
+                 the measured HBM peak; `families` lists every family; `traffic` comes from
+                 profiles/r02_traffic.json (tools/ncu_traffic.py) and is dropped when that
+                 file was produced from different kernel sources
   cpu_baseline : the oracle (torch-CPU fp32 restatement of the reference graph —
                  the reference's TensorFlow path cannot run) on
                  the host cores, BASELINE configs[0] (batch 4), bounded sample
@@ -72,9 +76,12 @@ def bind_to_gpu_numa(gpu_index):
 
 
 class SyntheticDataSet(object):
-    """images fp32 [B,256,256,3] ~ U[0,1), masks uint8 [B,256,256,1] ~ Bernoulli(.5)
-    (reference utils/datasets.py:174-190 tensor contract); a small pool of pinned
-    host batches is cycled."""
+    """images fp32 [B,256,256,3] (reference utils/datasets.py:174-190 tensor contract):
+    smooth random fields in [0,1) (a coarse 32x32 grid upsampled bilinearly + noise);
+    masks uint8 [B,256,256,1] = (red channel > 0.5), i.e. a learnable per-pixel target, so
+    that the loss the bench prints says something about the backward pass (with
+    Bernoulli(.5) labels it sits at ln 2 whatever the gradients are).  A small pool of
+    pinned host batches is cycled."""
     use_feed, has_masks = False, True
 
     def __init__(self, batch_size, seed, pool=4, pinned=True):
@@ -84,8 +91,12 @@ class SyntheticDataSet(object):
         g = np.random.default_rng(seed)
         self.pool = []
         for _ in range(pool):
-            x = torch.from_numpy(g.random((batch_size, S, S, 3), dtype=np.float32))
-            y = torch.from_numpy(g.integers(0, 2, (batch_size, S, S, 1)).astype(np.uint8))
+            coarse = torch.from_numpy(g.random((batch_size, 3, S // 32, S // 32), dtype=np.float32))
+            smooth = torch.nn.functional.interpolate(coarse, size=(S, S), mode='bilinear',
+                                                     align_corners=False)
+            noise = torch.from_numpy(g.random((batch_size, 3, S, S), dtype=np.float32))
+            x = (0.8 * smooth + 0.2 * noise).permute(0, 2, 3, 1).contiguous()
+            y = (x[..., 0:1] > 0.5).to(torch.uint8).contiguous()
             if pinned:
                 x, y = x.pin_memory(), y.pin_memory()
             self.pool.append((x, y))
@@ -219,6 +230,52 @@ def cpu_oracle_rate(steps, warmup, batch=4):
     return batch / med, cores, sample, med
 
 
+def parity_check(dev):
+    """Correctness signal of the run (untimed; part of the cpu_baseline leg, the one place
+    besides tests/ and smoke() that may execute oracle/): BASELINE config 1 (batch 4) -
+    the oracle's parameters and one synthetic batch go through ONE fwd + loss + bwd of the
+    CUDA path and of the bf16-emulating oracle; loss and the flat parameter gradient are
+    compared.  Tolerances are the ones tests/test_gpu_unet.py states."""
+    import numpy as np
+    import torch
+    from oracle import nets, tf_ops as T
+    from segmentation_b200.models.unet import UNetModel
+
+    class DS(object):
+        batch_size, use_feed, has_masks = 4, False, True
+
+        def set_tf_sess(self, s):
+            pass
+
+    ds = SyntheticDataSet(4, seed=123, pool=1, pinned=False)
+    x, y = ds.pool[0]
+    model = UNetModel(dataset=DS(), n_classes=NCLS, input_dims=S, n_kernels=NK, learning_rate=1e-4,
+                      load_snapshot=False, save_dir=None, seed=0)
+    p = nets.unet_params(n_kernels=NK, n_classes=NCLS, seed=0)
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    ex = model._get_exec(4, True)
+    ex.stage(x.to(dev), y.to(dev))
+    ex.forward()
+    ex.loss(True)
+    ex.backward()
+    torch.cuda.synchronize()
+    loss = float(ex.loss_sum.item()) / ex.loss_pixels
+    fwd = lambda q, xx: nets.unet_forward(q, xx, prec=T.BF16)
+    loss_ref, logits_ref, grads = nets.loss_and_grads(fwd, p, x, y)
+    names = nets.trainable_names(p)
+    g_ref = torch.cat([grads[k].flatten() for k in names]).double()
+    g_gpu = torch.cat([model.store.params[k].grad().flatten() for k in names]).double().cpu()
+    cos = float((g_ref * g_gpu).sum() / (g_ref.norm() * g_gpu.norm()))
+    rel = float((g_ref - g_gpu).norm() / g_ref.norm())
+    lg = float((ex.logits.cpu().double() - logits_ref.double()).norm() / logits_ref.double().norm())
+    ok = abs(loss - float(loss_ref)) < 2e-3 and lg < 1e-2 and cos > 0.995
+    return {'config': 'U-Net 256x256 nk32 batch 4 (BASELINE configs[0]), one fwd+loss+bwd, '
+                      'vs the bf16-emulating oracle', 'loss': loss, 'loss_oracle': float(loss_ref),
+            'logits_rel_l2': lg, 'grad_cosine': cos, 'grad_rel_l2': rel,
+            'grad_checksum': float(g_gpu.sum()), 'grad_checksum_oracle': float(g_ref.sum()),
+            'pass': bool(ok)}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -282,6 +339,7 @@ def run_ours(args):
     before = N.LAUNCHES
     model.train_step(dev_batches[0])
     launches_per_step = N.LAUNCHES - before
+    loss_first = model.seg_loss_op
     for i in range(1, W):
         model.train_step(dev_batches[i % len(dev_batches)])
 
@@ -338,7 +396,7 @@ def run_ours(args):
         # nor optimizer launches (those belong to the train step)
         N.TIMELINE = []
         ex.stage(*dev_batches[0])
-        for _ in range(3):                       # fwd + loss + bwd only: parameters untouched
+        for _ in range(3):
             torch.cuda.synchronize()
             # a spin kernel first: the host enqueues the whole pass behind it, so every event
             # pair brackets back-to-back GPU execution (no host launch latency inside)
@@ -347,9 +405,13 @@ def run_ours(args):
             ex.forward()
             ex.loss(True)
             ex.backward()
-            model.store.grad.zero_()
+            # the optimizer groups' Adam launches with lr_t = 0 (the timed regions are over;
+            # the parameters stay where they are)
+            for grp in model.opt_groups:
+                N.set_tag('adam')
+                model.store.adam_launch(0.0, chunk_range=grp['chunks'])
         torch.cuda.synchronize()
-        tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
+        tl = [(n, tag, a.elapsed_time(b), fam, fl, by) for (n, tag, a, b, fam, fl, by) in N.TIMELINE]
         N.TIMELINE = None
         out_dir = os.path.join(ROOT, 'gpurun_out')
         if os.path.isdir(out_dir):
@@ -357,7 +419,7 @@ def run_ours(args):
                 json.dump(tl, f)
         ex.graph, ex.use_graph = saved, True
         ex.use_side = saved_side
-        roof = dominant_kernel(tl, model, ex)
+        roof = family_roofline(tl)
 
     if world > 1:
         dist.barrier()                           # every rank is done with its GPU work
@@ -373,9 +435,12 @@ def run_ours(args):
     e2e = imgs / (ms_e2e * 1e-3)
     h2d = BATCH * S * S * 3 * 4 + BATCH * S * S
     if args.skip_cpu:
-        cpu_rate, cores, sample = None, 0, 'skipped (--skip-cpu)'
+        cpu_rate, cores, sample, parity = None, 0, 'skipped (--skip-cpu)', None
     else:
         os.sched_setaffinity(0, _ALL_CORES)      # the CPU baseline gets every host core
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        parity = parity_check(dev)
         cpu_rate, cores, sample, _ = cpu_oracle_rate(2, 1)
     # executed FLOPs per image: conv1_2 on its skip window (fwd if enabled, bwd always)
     y0c, x0c, hc, wc = ex.crop[4]
@@ -393,6 +458,7 @@ def run_ours(args):
                    'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
                    'l2': 'per-step working set (>1 GB activations+gradients) exceeds the 126 MB L2; '
                          '4 distinct input batches cycled',
+                   'labels': 'mask = (red channel > 0.5) of smooth random images',
                    'impl': 'umma' if model.impl == 0 else 'simt', 'cuda_graph': True,
                    'dead_code': 'conv1_2 is evaluated on the 72x72 window that feeds concat4 (its '
                                 'only consumer): identical outputs, loss and gradients',
@@ -423,7 +489,11 @@ def run_ours(args):
         'cpu_baseline': {'value': cpu_rate, 'unit': 'img/s', 'cores': cores, 'kind': 'port',
                          'sample': sample},
         'clocks': clk,
-        'loss': loss,
+        # labels are a function of the image (mask = red > 0.5): the loss starts at ~ln 2 and
+        # must fall; parity_check compares loss + gradients with the oracle (config 1)
+        'loss': loss, 'loss_first': loss_first, 'loss_last': loss,
+        'train_steps_between': model.global_step - 1,
+        'parity_check': parity,
     }
     _emit(line)
     if world > 1:
@@ -431,90 +501,105 @@ def run_ours(args):
         os._exit(0)
 
 
-def conv_work(layer, x_shape, y_shape, which):
-    """Algorithmic work of one conv-family launch.
-    FLOPs: 2*N*Ho*Wo*Cout*Cin*kh*kw for a conv, 2*N*Hi*Wi*Cin*Cout*kh*kw for a transposed
-    conv.  Bytes: each tensor the launch must read or write once, bf16, real channels:
-    fwd x+y, dgrad dy+dx, wgrad x+dy (weights / weight gradients are negligible)."""
-    k, n = layer.k, x_shape[0]
-    px = y_shape[1] * y_shape[2] if layer.kind == 'conv' else x_shape[1] * x_shape[2]
-    flops = 2.0 * n * px * layer.cout * layer.cin * k * k
-    small = n * x_shape[1] * x_shape[2] * layer.cin * 2.0
-    big = n * y_shape[1] * y_shape[2] * layer.cout * 2.0
-    return flops, small + big
+TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
-# summarised in profiles/r01_ncu_kernels.md (bytes); keyed like roofline['kernel']
-NCU_TRAFFIC = {'conv1_1 wgrad': 103.24e6, 'conv1_2 fwd': 89.37e6, 'conv2_2 wgrad': 64.24e6,
-               'conv2_2 fwd': 32.68e6}
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, one pass over one eager
+    step: tools/ncu_traffic.py), keyed 'layer kind'.  Valid only for the kernel sources it
+    was measured on: the file carries the digest of segmentation_b200/csrc + the build
+    flags, and a mismatch drops the numbers (traffic: null) instead of reporting stale ones."""
+    try:
+        from segmentation_b200 import build as B
+        t = json.load(open(TRAFFIC_FILE))
+        if t.get('csrc_digest') != B._digest():
+            return None, 'profiles/r02_traffic.json is stale (kernel sources changed since)'
+        return t, 'profiles/r02_traffic.json (ncu, same kernel sources)'
+    except Exception as e:                       # noqa: BLE001
+        return None, 'no traffic profile (%s)' % type(e).__name__
 
 
-def dominant_kernel(timeline, model, ex):
-    """The conv-family launch with the largest duration: achieved TFLOP/s against the
-    measured bf16 peak, or - when its arithmetic intensity is below the ridge of the two
-    measured peaks - achieved GB/s of algorithmic bytes against the measured HBM peak."""
+KIND_OF = {'seg_conv2d_fwd': 'fwd', 'seg_conv2d_dgrad': 'dgrad', 'seg_conv2d_wgrad': 'wgrad',
+           'seg_deconv2d_fwd': 'fwd', 'seg_deconv2d_dgrad': 'dgrad', 'seg_deconv2d_wgrad': 'wgrad',
+           'seg_stem_fwd': 'fwd', 'seg_stem_wgrad': 'wgrad'}
+
+
+def launch_key(fn, tag):
+    return '%s %s' % (tag, KIND_OF.get(fn, fn.replace('seg_', '')))
+
+
+def family_roofline(timeline):
+    """Per kernel family of one serialised step (every launch CUDA-event timed in THIS run):
+    time, share, algorithmic TFLOP/s and GB/s (engine.py notes the SURVEY-8d work of each
+    call), and the fraction of the measured peak that bounds it - the tensor peak when the
+    family's arithmetic intensity is above the ridge of the two measured peaks, else the HBM
+    peak.  `kernel` / `achieved` / `frac` at the top level are those of the family with the
+    largest share of the step."""
     pk = peaks()
-    shapes = {}
-    A = ex.act
-    x_in = (ex.B, ex.H, ex.W, model.input_channel)
-    for name, layer in model.layers.items():
-        if name == 'output':
-            shapes[name] = (A['conv9_2'].shape, ex.logits.shape)
-        elif name.startswith('upconv'):
-            j = int(name[-1])
-            below = 'conv%d_2' % (4 + j) if j > 1 else 'conv5_2'
-            shapes[name] = (A[below].shape, A[name].shape)
-        elif name == 'conv1_1':
-            shapes[name] = (x_in, A[name].shape)
-        elif name == 'conv1_2':
-            shapes[name] = (A['conv1_1'].shape, A['conv1_2'].shape)
-        else:
-            ys = A[name].shape
-            shapes[name] = ((ys[0], ys[1] + 2, ys[2] + 2, layer.cin), ys)
-    kind_of = {'seg_conv2d_fwd': 'fwd', 'seg_conv2d_dgrad': 'dgrad', 'seg_conv2d_wgrad': 'wgrad',
-               'seg_deconv2d_fwd': 'fwd', 'seg_deconv2d_dgrad': 'dgrad',
-               'seg_deconv2d_wgrad': 'wgrad'}
-    total = sum(t for _, _, t in timeline)
-    per = []
-    for fn, tag, ms in timeline:
-        if fn not in kind_of or tag not in model.layers:
-            continue
-        xs, ys = shapes[tag]
-        fl, by = conv_work(model.layers[tag], xs, ys, kind_of[fn])
-        if tag == 'conv1_2' and (kind_of[fn] != 'fwd' or getattr(ex, 'c12_crop', False)):
-            # runs on the 72x72 skip crop only (exact: no consumer / zero gradient outside)
-            y0, x0, h, w = ex.crop[4]
-            lay = model.layers[tag]
-            fl = 2.0 * ys[0] * h * w * lay.cout * lay.cin * 9
-            by = ys[0] * ((h + 2) * (w + 2) * lay.cin + h * w * lay.cout) * 2.0
-        per.append((tag, kind_of[fn], ms, fl, by))
-    if not per:
-        return None
-    tag, kind, ms, fl, by = max(per, key=lambda p: p[2])
     ridge = pk['tf_burst'] * 1e12 / (pk['hbm_gbs'] * 1e9)
-    conv_ms = sum(p[2] for p in per)
-    tf = fl / (ms * 1e-3) / 1e12
-    gbs = by / (ms * 1e-3) / 1e9
-    if fl / by >= ridge:
-        out = {'bound': 'tensor', 'achieved': tf, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s',
-               'frac': tf / pk['tf_burst']}
-    else:
-        out = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-               'frac': gbs / pk['hbm_gbs']}
-    out.update({'kernel': '%s %s' % (tag, kind),
-                'traffic': NCU_TRAFFIC.get('%s %s' % (tag, kind)), 'traffic_unit': 'bytes/launch',
-                'launch_ms': ms,
-                'flops_per_launch': fl, 'bytes_per_launch': by, 'flop_per_byte': fl / by,
-                'tflops': tf, 'peak_source': pk['src'] + ' burst',
-                'share_of_step': ms / total if total > 0 else None,
-                'conv_family_share_of_step': conv_ms / total if total > 0 else None,
-                'conv_family_tflops': sum(p[3] for p in per) / (conv_ms * 1e-3) / 1e12,
-                'serial_step_ms': total,
-                'top5': [{'kernel': '%s %s' % (p[0], p[1]), 'ms': p[2],
-                          'tflops': p[3] / (p[2] * 1e-3) / 1e12,
-                          'gbs': p[4] / (p[2] * 1e-3) / 1e9}
-                         for p in sorted(per, key=lambda q: -q[2])[:5]]})
+    traffic, traffic_src = load_traffic()
+    tmap = (traffic or {}).get('launches', {})
+    total = sum(e[2] for e in timeline)
+    fams, launches = {}, []
+    for fn, tag, ms, fam, fl, by in timeline:
+        f = fams.setdefault(fam, {'ms': 0.0, 'flops': 0.0, 'bytes': 0.0, 'launches': 0,
+                                  'traffic': 0.0, 'traffic_known': True})
+        f['ms'] += ms; f['flops'] += fl; f['bytes'] += by; f['launches'] += 1
+        t = tmap.get(launch_key(fn, tag))
+        if t is None:
+            f['traffic_known'] = False
+        else:
+            f['traffic'] += t['dram_bytes']
+        launches.append({'kernel': launch_key(fn, tag), 'family': fam, 'ms': ms,
+                         'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
+                         'gbs': by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                         'flops': fl, 'bytes': by,
+                         'traffic': t['dram_bytes'] if t is not None else None})
+
+    def bound_of(fl, by, ms):
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        if by > 0 and fl / by >= ridge:
+            return {'bound': 'tensor', 'achieved': tf, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s',
+                    'frac': tf / pk['tf_burst']}
+        return {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': gbs / pk['hbm_gbs']}
+
+    fam_list = []
+    for name, f in fams.items():
+        e = {'family': name, 'launches': f['launches'], 'us': f['ms'] * 1e3,
+             'share': f['ms'] / total if total > 0 else None,
+             'tflops': f['flops'] / (f['ms'] * 1e-3) / 1e12 if f['ms'] > 0 else 0.0,
+             'gbs': f['bytes'] / (f['ms'] * 1e-3) / 1e9 if f['ms'] > 0 else 0.0,
+             'flops': f['flops'], 'bytes': f['bytes'],
+             'traffic': f['traffic'] if (traffic is not None and f['traffic_known']) else None}
+        e.update(bound_of(f['flops'], f['bytes'], f['ms']))
+        fam_list.append(e)
+    fam_list.sort(key=lambda e: -e['us'])
+    if not fam_list:
+        return None
+    top = fam_list[0]
+    n_top = max(top['launches'], 1)
+    out = {'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
+           'unit': top['unit'], 'frac': top['frac'],
+           # per launch, like `achieved` (family totals / its launch count)
+           'traffic': top['traffic'] / n_top if top['traffic'] is not None else None,
+           'traffic_unit': 'bytes/launch (family average)', 'traffic_source': traffic_src,
+           'kernel': top['family'], 'kernel_launches': top['launches'],
+           'launch_ms': top['us'] / 1e3 / n_top,
+           'flops_per_launch': top['flops'] / n_top, 'bytes_per_launch': top['bytes'] / n_top,
+           'share_of_step': top['share'], 'peak_source': pk['src'] + ' burst',
+           'ridge_flop_per_byte': ridge, 'serial_step_ms': total,
+           'timing': 'CUDA events around every launch of one eager, single-stream step (3rd of 3 '
+                     'passes) in this run; event pairs add ~2 us per launch',
+           'families': fam_list,
+           'top5_launches': sorted(launches, key=lambda l: -l['ms'])[:5]}
+    conv = [e for e in fam_list if e['family'] in ('tconv', 'hconv', 'igemm', 'twgrad', 'wgrad',
+                                                   'stem', 'simt')]
+    if conv:
+        cms = sum(e['us'] for e in conv) / 1e3
+        out['conv_family_share_of_step'] = cms / total
+        out['conv_family_tflops'] = sum(e['flops'] for e in conv) / (cms * 1e-3) / 1e12
     return out
 
 

@@ -81,39 +81,33 @@ SEG_API int32_t seg_version(void);
 /* 0 iff the current device is compute capability 10.0 (sm_100a kernels). */
 SEG_API int32_t seg_device_check(void);
 SEG_API const char* seg_last_error_string(void);
-/* Tuning / test switches (process-wide).  key 1: use the halo-tile tcgen05 conv kernel
- * where it applies (default 1; 0 forces the TMA-im2col kernel).  key 2: smem row
- * alignment of the halo kernel's row staging in pixels (0 = natural, 8 = swizzle repeat).
- * key 3: use the spatial-tile tcgen05 conv kernel for 3x3 stride-1 fwd / dgrad (default 1).
- * key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles below which that kernel
- * declines a shape (default 70).  key 5 / key 6: the same two switches for the spatial-tile
- * weight-gradient kernel (defaults 1 and 40).  key 7: launch the hot-path kernels with
- * programmatic stream serialization (PDL) so that a kernel's prologue overlaps its
- * predecessor's tail (default 1); every such kernel executes griddepcontrol.wait before
- * its first global-memory access.  key 8: thread-block-cluster size (1, 2, 4 or 8;
- * default 1 = off) over which the spatial-tile weight-gradient kernel sums its per-CTA partial
- * results through distributed shared memory before the global fp32 reductions.  key 9: minimum
- * number of 8x16 pixel tiles per CTA of that kernel (default 8): smaller layers use fewer
- * CTAs (fewer partial sums to reduce, SMs left to the concurrent input-gradient stream).
- * key 10: let the halo kernel halve its N tile when that lowers waves x bytes ingested per
- * CTA (wave quantisation on 148 SMs; default 0 - measured slower on the U-Net step).  key 11: row-mapped max-pool kernels
- * (one block row per pool row, contiguous 16-byte stores; default 1).  key 12: when the
- * weights of a halo / spatial-tile convolution stream through a shared-memory ring (they do
- * not fit resident), make that ring as deep as shared memory allows next to three input
- * stages (default 1; 0 = 64 KB / 48 KB rings).  key 13: halo kernel in clusters of two CTAs
- * on adjacent M tiles, each fetching half of every streamed weight tile and multicasting it
- * to both (default 0).  key 14: halo kernel with one filter row (three taps) per streamed
- * weight stage for k x 3 kernels: a third of the barrier waits, commits and elections in the
- * single-thread MMA issue loop (default 1; plain convolutions only, not the tap-table
- * sub-kernels of strided transposed convolutions).  key 15: the spatial-tile weight-gradient
- * kernel hands its partial sums to L2 as TMA tensor reduce-adds (one [ci x 32 co] box per tap
- * and column block) instead of one bulk reduce-add per accumulator row (default 0: built
- * after the round's GPU budget ran out, not yet run). */
+/* Mangled name of the tile kernel the calling thread's most recent conv-family / launch_k
+ * call was planned onto ("" if none): the plan (tconv / hconv / igemm / twgrad / wgrad
+ * instantiation) is chosen from the shape, and profiles attribute time per kernel family. */
+SEG_API const char* seg_last_kernel_name(void);
+/* Plan-selection switches for tests and A/B measurements (process-wide; set them before
+ * the first launch, not concurrently with launches - the hot path itself never calls this).
+ * Every default is the measured-best plan; production code does not need this entry point.
+ *   key 1: halo-tile tcgen05 conv kernel where it applies (default 1; 0 forces TMA-im2col).
+ *   key 2: smem row alignment of the halo kernel's row staging in pixels (0 = natural).
+ *   key 3: spatial-tile tcgen05 conv kernel for 3x3 stride-1 fwd / dgrad (default 1).
+ *   key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles (default 70).
+ *   key 5 / key 6: the same two switches for the spatial-tile weight-gradient kernel
+ *          (defaults 1 and 40).
+ *   key 7: programmatic dependent launch of the hot-path kernels (default 1); every such
+ *          kernel executes griddepcontrol.wait before its first global-memory access.
+ *   key 9: minimum number of 8x16 pixel tiles per CTA of the spatial-tile weight-gradient
+ *          kernel (default 8): smaller layers use fewer CTAs.
+ *   key 11: row-mapped max-pool kernels (default 1).
+ *   key 12: streamed-weight rings as deep as shared memory allows (default 1).
+ *   key 14: halo kernel with one filter row (three taps) per streamed weight stage
+ *          (default 1; plain k x 3 convolutions).
+ *   key 15: spatial-tile weight-gradient epilogue as TMA tensor reduce-adds (one [ci x 32 co]
+ *          box per tap and column block) instead of one bulk reduce-add per accumulator row
+ *          (default 1: 1.056 -> 1.042 ms per U-Net step).
+ * (Keys 8, 10 and 13 of round 1 - cluster/DSMEM weight-gradient reduction, wave-quantised
+ * halo tiles, two-CTA multicast halo clusters - were measured slower and are gone.) */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
-/* Test hook: device buffer of 3*16*4 int64 that CTA 0 of the halo conv kernel fills with
- * clock64() marks per role (producer / MMA issuer / epilogue) and tile; null disables. */
-SEG_API int32_t seg_debug_prof_buffer(void* device_buf);
-
 /* ---- convolution: replaces Conv2D(+BiasAdd+Relu), Conv2DBackpropInput,
  * Conv2DBackpropFilter emitted for slim.convolution2d
  * (models/unet.py:111-167, models/fcn.py:110-128, models/deconvolution.py:109-174) */
@@ -222,6 +216,18 @@ SEG_API int32_t seg_batchnorm_bwd_apply(const seg_view* dy, const seg_view* x, c
 SEG_API int32_t seg_dropout(const seg_view* x, uint64_t seed, uint32_t stream_id, float keep_prob,
                     const seg_view* y, void* stream);
 
+/* Batched, CUDA-graph-replayable form of the same op: image n of x uses the Philox stream
+ *   stream_id0 + n * per_image_step + (step_dev ? *step_dev * step_mul : 0),
+ * step_dev a device uint32 the host bumps between graph replays (fresh masks every training
+ * step, models/deconvolution.py:128-129).  per_image_step != 0: the element index restarts
+ * at every image, so T MC-dropout passes of one tile (BASELINE config 5) are ONE launch with
+ * one stream per pass; per_image_step == 0: one stream over the whole batch (== seg_dropout).
+ * h*w*c must be a multiple of 8. */
+SEG_API int32_t seg_dropout_ex(const seg_view* x, uint64_t seed, uint32_t stream_id0,
+                               uint32_t per_image_step, const uint32_t* step_dev,
+                               uint32_t step_mul, float keep_prob, const seg_view* y,
+                               void* stream);
+
 /* ---- loss: one_hot + softmax_cross_entropy_with_logits + reduce_mean and its
  * gradient (models/basemodel.py:59-70,194,360).  logits fp32 [n,h,w,c]; labels
  * uint8 view (c == 1; may be a centre crop of the full mask, models/unet.py:71-72).
@@ -283,21 +289,6 @@ SEG_API int32_t seg_pack_patches(const float* x, int32_t c, int32_t h, int32_t w
                          int32_t kw, int32_t stride, int32_t pad_t, int32_t pad_l,
                          const seg_view* y, void* stream);
 SEG_API int32_t seg_fill_zero(void* ptr, int64_t bytes, void* stream);
-
-/* ---- self-test hooks used by tests/ (tcgen05 descriptor probes) */
-SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, const void* a,
-                       const void* b, float* d, void* stream);
-/* MMA issue/retire rate of `iters` x 9 taps x kc/16 tcgen05.mma (M=128, N=bn) per CTA;
- * out[2*cta] = cycles to issue, out[2*cta+1] = cycles to retire (tools/probe_rate.py) */
-SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,
-                           int32_t iters, int32_t a_mn, int32_t ctas, int64_t* out, void* stream);
-
-/* fp32 global-reduction rate: `ctas` CTAs each add `elems` floats from shared memory into
- * dst + (cta % regions) * elems with red.global.v4 (mode 0 coalesced, 1 row-per-thread) or
- * cp.reduce.async.bulk (mode 2: 256-byte rows, 3: op_bytes per operation); out[2*cta] /
- * out[2*cta+1] = cycles to issue / to complete (tools/probe_red.py) */
-SEG_API int32_t seg_probe_red_rate(int32_t mode, int32_t ctas, int32_t elems, int32_t regions,
-                           int32_t op_bytes, float* dst, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,6 @@
-"""Build libsegb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+"""Build libsegb200.so (the C-ABI CUDA library) and libsegb200_probes.so (the same kernel
+objects + the self-test / micro-benchmark hooks of include/segb200_probes.h) in-tree with nvcc
+for sm_100a.
 
     python -m segmentation_b200.build [--force]
 
@@ -15,7 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsegb200.so')
-SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu', 'probe.cu']
+PROBES_LIB = os.path.join(HERE, 'libsegb200_probes.so')
+SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu']
+PROBE_SOURCES = ['probe.cu', 'probe_api.cu']      # linked into libsegb200_probes.so only
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
@@ -32,7 +36,8 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join('..', '..', 'include', 'segb200.h')]
+    files = sorted(os.listdir(CSRC)) + [os.path.join('..', '..', 'include', 'segb200.h'),
+                                        os.path.join('..', '..', 'include', 'segb200_probes.h')]
     for f in files:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):
@@ -46,7 +51,8 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, 'stamp')
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(PROBES_LIB) and \
+            os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
 
@@ -60,12 +66,14 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed for %s:\n%s' % (src, r.stderr[-8000:]))
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError('link failed:\n' + r.stderr[-4000:])
+    with ThreadPoolExecutor(max_workers=len(SOURCES) + len(PROBE_SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES + PROBE_SOURCES))
+    n = len(SOURCES)
+    for lib, members in ((LIB, objs[:n]), (PROBES_LIB, objs)):
+        cmd = [nvcc, '-shared', '-o', lib] + members + ['-gencode', 'arch=compute_100a,code=sm_100a']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('link failed:\n' + r.stderr[-4000:])
     with open(stamp, 'w') as f:
         f.write(dig)
     if verbose:

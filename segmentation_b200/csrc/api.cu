@@ -30,21 +30,11 @@ int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
                       const seg_view& dx, const seg_view* mask, cudaStream_t st);
 int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
                       cudaStream_t st);
-int umma_probe(int mode, int M, int N, int K, const void* a, const void* b, float* d,
-               cudaStream_t st);
-int umma_probe_shift(int K, const void* a, const void* b, int shift, int use_bo, int split,
-                     float* d, cudaStream_t st);
 
-int probe_red_rate(int mode, int ctas, int elems, int regions, int op_bytes, float* dst,
-                   long long* out, cudaStream_t st);
-int umma_probe_rate(int kc, int bn, int b_mn, int wp, int shifted, int iters, int a_mn, int ctas,
-                    long long* out, cudaStream_t st);
 
 void hconv_set_row_align(int a);
-void hconv_set_waveq(int on);
 void pool_set_rows(int on);
 void conv_set_deep_b_ring(int on);
-void hconv_set_cluster(int on);
 void hconv_set_rowstage(int on);
 void twgrad_set_tred(int on);
 void hconv_set_prof(void* p);
@@ -53,7 +43,6 @@ void tconv_enable(int on);
 void tconv_set_min_eff(int pct);
 void twgrad_enable(int on);
 void twgrad_set_min_eff(int pct);
-void twgrad_set_cluster(int n);
 void twgrad_set_min_tiles(int n);
 
 static bool desc_ok(const seg_conv_desc* d) {
@@ -62,7 +51,11 @@ static bool desc_ok(const seg_conv_desc* d) {
          d->cout_pad % 8 == 0;
 }
 
+#ifndef SEGB200_KERNEL_PROF
+#define SEGB200_KERNEL_PROF 0
+#endif
 int g_pdl = 1;              // seg_set_option key 7
+thread_local const void* g_last_kernel_fn = nullptr;
 
 }  // namespace segb
 
@@ -74,10 +67,23 @@ SEG_API int32_t seg_version(void) { return 100; }
 
 SEG_API const char* seg_last_error_string(void) { return g_err; }
 
+SEG_API const char* seg_last_kernel_name(void) {
+  const char* name = nullptr;
+  if (g_last_kernel_fn == nullptr || cudaFuncGetName(&name, g_last_kernel_fn) != cudaSuccess ||
+      name == nullptr) {
+    cudaGetLastError();
+    return "";
+  }
+  return name;
+}
+
+#if SEGB200_KERNEL_PROF
+// profiling builds only (-DSEGB200_KERNEL_PROF=1, tools/layer_prof.py); see segb200_probes.h
 SEG_API int32_t seg_debug_prof_buffer(void* device_buf) {
   hconv_set_prof(device_buf);
   return SEG_OK;
 }
+#endif
 
 SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
   switch (key) {
@@ -88,12 +94,9 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 5: twgrad_enable(value); return SEG_OK;
     case 6: twgrad_set_min_eff(value); return SEG_OK;
     case 7: g_pdl = value != 0; return SEG_OK;
-    case 8: twgrad_set_cluster(value); return SEG_OK;
     case 9: twgrad_set_min_tiles(value); return SEG_OK;
-    case 10: hconv_set_waveq(value); return SEG_OK;
     case 11: pool_set_rows(value); return SEG_OK;
     case 12: conv_set_deep_b_ring(value); return SEG_OK;
-    case 13: hconv_set_cluster(value); return SEG_OK;
     case 14: hconv_set_rowstage(value); return SEG_OK;
     case 15: twgrad_set_tred(value); return SEG_OK;
   }
@@ -259,31 +262,6 @@ SEG_API int32_t seg_deconv2d_wgrad(const seg_conv_desc* d, const seg_view* x, co
   P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
   P.BC = d->cout; P.SC = d->cin;
   return simt_wgrad(P, st);
-}
-
-SEG_API int32_t seg_probe_umma(int32_t mode, int32_t m, int32_t n, int32_t k, const void* a,
-                       const void* b, float* d, void* stream) {
-  SEG_REQUIRE(a && b && d && m > 0 && n % 16 == 0 && k % 16 == 0, SEG_E_BAD_SHAPE,
-              "probe_umma: bad argument");
-  if (mode & 0x100)   // row-shift experiment: bits 16..23 = shift, bit 9 = base_offset field,
-                      // bits 24..31 = split row of a two-box load (0 = single box)
-    return umma_probe_shift(k, a, b, (mode >> 16) & 0xff, (mode >> 9) & 1, (mode >> 24) & 0xff, d,
-                            (cudaStream_t)stream);
-  return umma_probe(mode, m, n, k, a, b, d, (cudaStream_t)stream);
-}
-
-SEG_API int32_t seg_probe_red_rate(int32_t mode, int32_t ctas, int32_t elems, int32_t regions,
-                           int32_t op_bytes, float* dst, int64_t* out, void* stream) {
-  SEG_REQUIRE(dst && out, SEG_E_BAD_SHAPE, "probe_red_rate: null argument");
-  return probe_red_rate(mode, ctas, elems, regions, op_bytes, dst,
-                        reinterpret_cast<long long*>(out), (cudaStream_t)stream);
-}
-
-SEG_API int32_t seg_probe_mma_rate(int32_t kc, int32_t bn, int32_t b_mn, int32_t wp, int32_t shifted,
-                           int32_t iters, int32_t a_mn, int32_t ctas, int64_t* out, void* stream) {
-  SEG_REQUIRE(out, SEG_E_BAD_SHAPE, "probe_mma_rate: null out");
-  return umma_probe_rate(kc, bn, b_mn, wp, shifted, iters, a_mn, ctas,
-                         reinterpret_cast<long long*>(out), (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -40,6 +40,9 @@ void set_error(const char* fmt, ...);
 // still running; every kernel launched through here calls pdl_wait() before it touches
 // global memory.
 extern int g_pdl;
+// the kernel most recently launched through launch_k / launch_kc on this thread
+// (seg_last_kernel_name: which tile kernel / instantiation a call was planned onto)
+extern thread_local const void* g_last_kernel_fn;
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_kc(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                     cudaStream_t st, int cluster, Args&&... args) {
@@ -65,6 +68,7 @@ static inline cudaError_t launch_kc(void (*kern)(KArgs...), dim3 grid, dim3 bloc
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
+  g_last_kernel_fn = reinterpret_cast<const void*>(kern);
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>

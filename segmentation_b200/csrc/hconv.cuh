@@ -61,24 +61,18 @@ __device__ __forceinline__ void prof_mark(long long* prof, int role, int tile_i,
 }
 constexpr int kHconvMaxSB = 40;
 
-// CL: clusters of two CTAs that work on two adjacent M tiles of the same N slice.  Each
-// CTA fetches HALF of every streamed weight tile and multicasts it to both, so a CTA's TMA
-// unit issues half the weight rows (the producers of the small deep layers are bound by the
-// ~5 cycles the unit spends per 128-byte row, profiles/r01_ncu_kernels.md §5).  A weight
-// stage is re-armed once BOTH CTAs' MMAs have read it (multicast tcgen05.commit, barrier
-// count 2).  Streamed weights only (the launcher never combines CL with resident B).
 // TPS: filter taps per weight stage (1, or 3 = one filter row of a k x 3 kernel per stage:
 // a third of the full/empty barrier waits, commits and elections in the single-thread issue
 // loop, whose ~80 instructions per tap - not the tensor pipe - set the pace of the small
 // deep layers, profiles/r01_ncu_kernels.md §5).  Streamed weights only.
-template <int KC, int BN, bool B_MN, bool CL = false, int TPS = 1>
+template <int KC, int BN, bool B_MN, int TPS = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const HconvParams P) {
   constexpr int SWZ = KC * 2;
   constexpr int kBBytes = BN * KC * 2;
   constexpr int kStageB = TPS * kBBytes;          // one weight stage
-  static_assert(TPS == 1 || (TPS == 3 && !CL), "weight stages hold one tap or one filter row");
+  static_assert(TPS == 1 || TPS == 3, "weight stages hold one tap or one filter row");
   constexpr int kAtomN = BN < 64 ? BN : 64;
   constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                             : 2 * BN <= 256 ? 256 : 512;
@@ -103,21 +97,17 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
   const int n_tiles = P.N_total / BN;
   const int halo = (P.kh - 1) * P.Wp + P.kw - 1;
-  // schedule units: one tile, or (CL) one pair of adjacent M tiles per cluster
-  const uint32_t crank = CL ? cluster_ctarank() : 0u;
-  const int total_tiles = CL ? ((m_tiles + 1) >> 1) * n_tiles : m_tiles * n_tiles;
-  const int first_unit = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto tile_m0 = [&](int unit) {
-    return (CL ? (unit / n_tiles) * 2 + (int)crank : unit / n_tiles) * kBlockM;
-  };
+  const int total_tiles = m_tiles * n_tiles;
+  const int first_unit = (int)blockIdx.x;
+  const int unit_step = (int)gridDim.x;
+  auto tile_m0 = [&](int unit) { return (unit / n_tiles) * kBlockM; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL ? 2 : 1); }
+    for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_mbar_init();
   }
@@ -125,7 +115,6 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CL) cluster_sync_all();   // the peer's barriers are initialised before anything lands
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // everything above overlaps the previous kernel's tail
 
@@ -179,20 +168,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 uint8_t* sbp = smem_b + sb * kStageB + u * kBBytes;
                 const int bt_u = bt + (P.tap_flip ? -u : u);
                 const int tap_row = P.use_tap_rows ? P.tap_rows[t + u] : bt_u * P.b_rows_per_tap;
-                if (CL) {
-                  // this CTA's half of the tile (tmB boxes are half tiles), to both CTAs
-                  if (B_MN) {
-                    const int row = tap_row + j * KC + (int)crank * (KC / 2);
-#pragma unroll
-                    for (int a = 0; a < BN / kAtomN; ++a)
-                      tma_load_2d_mc(&tmB, &b_full[sb],
-                                     sbp + a * (KC * kAtomN * 2) + crank * ((KC / 2) * kAtomN * 2),
-                                     n0 + a * kAtomN, row, (uint16_t)3);
-                  } else {
-                    tma_load_2d_mc(&tmB, &b_full[sb], sbp + crank * ((BN / 2) * SWZ), j * KC,
-                                   tap_row + n0 + (int)crank * (BN / 2), (uint16_t)3);
-                  }
-                } else if (B_MN) {
+                if (B_MN) {
                   const int row = tap_row + j * KC;
 #pragma unroll
                   for (int a = 0; a < BN / kAtomN; ++a)
@@ -286,8 +262,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                            umma_desc_pack(hiB, b_lo0 + kk * kstepB), idesc, acc);
                   acc = 1;
                 }
-                if (CL) umma_commit_mc(&b_empty[sb], (uint16_t)3);
-                else if (!P.b_resident) umma_commit(&b_empty[sb]);
+                if (!P.b_resident) umma_commit(&b_empty[sb]);
 #if SEGB200_KERNEL_PROF
                 // per-tap issue timestamps of tiles 2 and 3 (role 3 of the timeline hook)
                 if (P.prof != nullptr && blockIdx.x == 0 && (ti == 2 || ti == 3) && j == 0)
@@ -404,7 +379,6 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (CL) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

@@ -863,6 +863,50 @@ __global__ void dropout_kernel(const bf16* x, bf16* y, int64_t numel, uint32_t s
   }
 }
 
+// Batched / graph-replayable form: image n of x uses Philox stream
+//   stream_id0 + n * per_image_step + (step_dev ? *step_dev * step_mul : 0);
+// per_image_step != 0: the element index restarts at every image (T MC passes of one tile
+// in one launch, each pass its own stream); per_image_step == 0: one stream, dense index
+// over the whole batch (identical to dropout_kernel).  One thread = 8 consecutive elements
+// (two Philox counters, one 16-byte load / store); img_elems % 8 == 0.
+__global__ void dropout_ex_kernel(const bf16* x, bf16* y, int64_t img_elems, int n_img,
+                                  uint32_t seed_lo, uint32_t seed_hi, uint32_t stream_id0,
+                                  uint32_t per_image_step, const uint32_t* step_dev,
+                                  uint32_t step_mul, float keep, float inv_keep) {
+  const uint32_t base = stream_id0 + (step_dev ? __ldg(step_dev) * step_mul : 0u);
+  const int64_t per_img = img_elems / 8;
+  const int64_t total = per_img * n_img;
+  GRID_STRIDE(t, total) {
+    int64_t q8 = t;                   // 8-element group index inside its Philox stream
+    uint32_t sid = base;
+    if (per_image_step) {
+      const int64_t n = t / per_img;
+      q8 = t - n * per_img;
+      sid = base + (uint32_t)n * per_image_step;
+    }
+    const uint4 in = *reinterpret_cast<const uint4*>(x + t * 8);
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t ctr = (uint64_t)q8 * 2 + h;
+      const Philox4 r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), sid, 0u, seed_lo,
+                                      seed_hi);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t pair = w[h * 2 + j];
+        const float u0 = (float)(r.v[2 * j] >> 8) * 5.9604644775390625e-8f;
+        const float u1 = (float)(r.v[2 * j + 1] >> 8) * 5.9604644775390625e-8f;
+        const float v0 = __uint_as_float(pair << 16), v1 = __uint_as_float(pair & 0xffff0000u);
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(u0 < keep ? v0 * inv_keep : 0.f,
+                                                        u1 < keep ? v1 * inv_keep : 0.f);
+        o[h * 2 + j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + t * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------ loss / heads
 // one thread per pixel, C <= 64 channels held in registers chunk-wise
 __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* loss_sum,
@@ -1724,6 +1768,24 @@ SEG_API int32_t seg_dropout(const seg_view* x, uint64_t seed, uint32_t stream_id
       reinterpret_cast<const bf16*>(x->ptr), reinterpret_cast<bf16*>(y->ptr), numel,
       (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32), stream_id, keep_prob,
       1.f / keep_prob);
+  SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_dropout_ex(const seg_view* x, uint64_t seed, uint32_t stream_id0,
+                               uint32_t per_image_step, const uint32_t* step_dev,
+                               uint32_t step_mul, float keep_prob, const seg_view* y,
+                               void* stream) {
+  SEG_REQUIRE(x && y && view_dense(*x) && view_dense(*y), SEG_E_BAD_SHAPE,
+              "dropout_ex: dense views required");
+  const int64_t img = (int64_t)x->h * x->w * x->c;
+  SEG_REQUIRE(img % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0,
+              SEG_E_ALIGN, "dropout_ex: h*w*c must be a multiple of 8 and the tensors 16-byte aligned");
+  dropout_ex_kernel<<<grid_for(img / 8 * x->n, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x->ptr), reinterpret_cast<bf16*>(y->ptr), img, x->n,
+      (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32), stream_id0, per_image_step, step_dev,
+      step_mul, keep_prob, 1.f / keep_prob);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
 }

@@ -26,9 +26,6 @@
 // loop; whole 128-byte lines are 2.7x faster (tools/probe_red.py).  So each thread
 // stages its row in the (by then idle) pipeline shared memory and hands BN-float row
 // segments to TMA reduce-add (cp.reduce.async.bulk .add.f32).
-// Optional (seg_set_option key 8, default off: cluster launches cost more SM
-// co-scheduling than they save): CTAs of one combo form a thread-block cluster, and
-// rank r first sums column slice r of all members through distributed shared memory.
 #pragma once
 #include "umma_conv.cuh"
 
@@ -44,15 +41,14 @@ struct TwgradParams {
   float* dw;
   float* db;                   // nullable
   int stages, stage_bytes, x_bytes, off_bars;
-  int cluster;                 // CTAs per cluster (1: none); all CTAs of a cluster share a combo
   int staged_ok;               // the pipeline stages can hold the staged accumulators
 };
 
 constexpr int kTwTH = 8, kTwTW = 16, kTwPW = kTwTW + 2, kTwPH = kTwTH + 2;
 constexpr int kTwMaxStages = 8;
 
-// TRED (seg_set_option key 15, not yet measured): the partial sums leave the CTA as TMA
-// TENSOR reduce-adds - one [AW ci] x [32 co] fp32 box per (tap, 32-column block), 4 per MMA
+// TRED (seg_set_option key 15, default on; 1.056 -> 1.042 ms / U-Net step): the partial sums
+// leave the CTA as TMA TENSOR reduce-adds - one [AW ci] x [32 co] fp32 box per (tap, 32-column block), 4 per MMA
 // and 18-20 per CTA, issued by one thread per group of four epilogue warps - instead of one
 // 256-byte bulk reduce-add per accumulator row and MMA (640 per CTA, whose per-lane issue
 // was measured at ~9 k of the epilogue's ~25 k cycles).  tmDW: dW as a 3-D tensor
@@ -95,9 +91,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
   const int total_tiles = P.batch * P.tiles_y * P.tiles_x;
   const int my_tiles = sub < total_tiles ? (total_tiles - sub + P.ctas_per_combo - 1) / P.ctas_per_combo : 0;
   const bool do_db = P.db != nullptr && chunk == 0;
-  const bool clustered = P.cluster > 1;
   constexpr int kPitch = kCols + 4;                    // floats per staged accumulator row
-  float* s_db = reinterpret_cast<float*>(smem + P.off_bars + 512);   // [BN] per-CTA bias sums
   const bool vec_ok = (P.SC & 3) == 0 && (reinterpret_cast<uintptr_t>(P.dw) & 15) == 0;
   const bool bulk_ok = vec_ok && P.staged_ok && n0 + BN <= P.SC;   // whole row segments
 
@@ -190,7 +184,6 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       const int quad = warp & 3;
       const int half = (warp - 2) >> 2;
       const int et = quad * 32 + lane;                 // 0..127 within each group of four warps
-      if (clustered && half == 0 && et < BN) s_db[et] = 0.f;
       if (do_db && half == 0) {
         // thread -> one 16-byte chunk (8 channels) of the dZ rows r with r % kRG == rg
         constexpr int kChunks = BN / 8;                // 16-byte chunks per pixel (all atoms)
@@ -224,13 +217,11 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
         for (int o = 16; o >= kChunks && o > 0; o >>= 1)
 #pragma unroll
           for (int e = 0; e < 8; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], o);
-        if (clustered) named_bar_sync(1, 128);         // s_db zeroed by all epilogue warps
         if (lane < kChunks || kChunks > 32) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int co = n0 + ch * 8 + e;
-            if (clustered) atomicAdd(s_db + ch * 8 + e, s[e]);
-            else if (co < P.SC) atomicAdd(P.db + co, s[e]);
+            if (co < P.SC) atomicAdd(P.db + co, s[e]);
           }
         }
       }
@@ -242,7 +233,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       tc_fence_after();
       // every MMA has completed, so all stages were consumed; the other epilogue warps may
       // still be summing the last dZ tiles out of them
-      if (clustered || bulk_ok) named_bar_sync(2, 256);
+      if (bulk_ok) named_bar_sync(2, 256);
       if (TRED) {
         // box layout: box (m, atom, 32-column block) = AW rows of 128 bytes, 16-byte chunk j
         // of row cl stored at chunk j ^ (cl & 7) (the tensor map's 128-byte swizzle)
@@ -294,7 +285,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + m * BN + cc, r);
           tmem_ld_wait();
-          if (clustered || bulk_ok) {
+          if (bulk_ok) {
             // stage row L, columns [m*BN+cc, +32) of the partial sum: S[L][kPitch]
             const uint32_t sa = smem_u32(smem) + (uint32_t)((L * kPitch + m * BN + cc) * 4);
 #pragma unroll
@@ -318,7 +309,7 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
             }
           }
         }
-        if (!clustered && bulk_ok) {
+        if (bulk_ok) {
           // one TMA reduce-add of this thread's BN-float row segment: L2 receives whole
           // 128-byte lines (row-per-thread red.v4 was measured 2.7x slower, probe_red.py)
           fence_proxy_async();
@@ -327,63 +318,12 @@ twgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
                                 BN * 4);
         }
       }
-      if (!clustered && bulk_ok) {
+      if (bulk_ok) {
         bulk_commit_group();
         bulk_wait_group<0>();                          // complete before the CTA exits
       }
       }
     }
-  }
-
-  if (clustered) {
-    // ---- cluster reduction: rank r owns accumulator columns [r*W, (r+1)*W) ----
-    if (my_tiles <= 0 && warp >= 2 && warp < 6) {      // (the launch gives every CTA a tile)
-      const int L = (warp & 3) * 32 + lane;
-      for (int c = 0; c < kCols; c += 4)
-        sts128(smem_u32(smem) + (uint32_t)((L * kPitch + c) * 4), make_uint4(0u, 0u, 0u, 0u));
-      if (L < BN) s_db[L] = 0.f;
-    }
-    __syncwarp();
-    cluster_sync_all();                                // every member's S (and s_db) is complete
-    if (warp >= 2 && warp < 6) {
-      const int L = (warp & 3) * 32 + lane;
-      const int a = L / AW, cl = L % AW;
-      const int ci = chunk * AW + cl;
-      const uint32_t rank = cluster_ctarank();
-      const int W = kCols / P.cluster;
-      const uint32_t s_row = smem_u32(smem) + (uint32_t)(L * kPitch * 4);
-#pragma unroll 1
-      for (int c = (int)rank * W; c < (int)(rank + 1) * W; c += 4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int q = 0; q < P.cluster; ++q) {
-          const float4 v = ld_dsmem_f4(dsmem_addr(s_row + (uint32_t)c * 4, (uint32_t)q));
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        const int m = c / BN, cc = c - m * BN;
-        const int tap = AW == 64 ? 2 * m + a : (a < 3 ? 3 * m + a : 9);
-        if (tap < 9 && ci < P.BC) {
-          float* dst = P.dw + ((int64_t)tap * P.BC + ci) * P.SC;
-          const int sc = n0 + cc;
-          if (vec_ok) {
-            if (sc < P.SC) red_add_v4(dst + sc, acc.x, acc.y, acc.z, acc.w);
-          } else {
-            const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (sc + j < P.SC) atomicAdd(dst + sc + j, v4[j]);
-          }
-        }
-      }
-      // bias gradient: rank 0 sums the members' per-channel sums
-      if (do_db && rank == 0 && L < BN) {
-        float t = 0.f;
-        for (int q = 0; q < P.cluster; ++q)
-          t += ld_dsmem_f1(dsmem_addr(smem_u32(s_db + L), (uint32_t)q));
-        if (n0 + L < P.SC) atomicAdd(P.db + n0 + L, t);
-      }
-    }
-    cluster_sync_all();                                // nobody exits while peers read its smem
   }
 
   tc_fence_before();

@@ -416,7 +416,6 @@ static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test h
 void hconv_set_prof(void* p) { g_prof_buf = reinterpret_cast<long long*>(p); }
 static int g_deep_b_ring = 1;       // seg_set_option key 12: streamed-B rings as deep as smem allows
 void conv_set_deep_b_ring(int on) { g_deep_b_ring = on != 0; }
-static int g_hconv_waveq = 0;       // seg_set_option key 10 (measured 1.172 -> 1.194 ms/step: off)
 static int g_hconv_row_align = 0;   // 0: natural (128-byte) row alignment, 8: pad rows to 8 px
 
 template <int KC, int BN, bool B_MN, int TPS = 1>
@@ -424,7 +423,7 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
                           cudaStream_t st) {
   static int attr_smem = 0;
   if (attr_smem < smem_bytes) {
-    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN, false, TPS>,
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN, TPS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_smem = 227 * 1024;
   }
@@ -466,97 +465,9 @@ static int launch_hconv_t(const HconvJob& J, const HconvParams& P0, int smem_byt
     grid -= grid % n_tiles;           // every CTA must keep one N-slice for its lifetime
     if (grid < n_tiles) P.b_resident = 0, grid = tiles < num_sms() ? tiles : num_sms();
   }
-  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN, false, TPS>, dim3(grid), dim3(kConvThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
+  SEG_CHECK_CUDA(launch_k(hconv_kernel<KC, BN, B_MN, TPS>, dim3(grid), dim3(kConvThreads), (size_t)(smem_bytes), st, tmA1, tmA2, tmB, P));
   SEG_LAUNCH_CHECK();
   return SEG_OK;
-}
-
-// Cluster-of-two variant (hconv.cuh, CL): streamed weights, KC = 64.  Returns
-// SEG_E_UNSUPPORTED (nothing launched) if no cluster can be resident.
-static int g_hconv_cluster = 0;        // seg_set_option key 13
-void hconv_set_cluster(int on) { g_hconv_cluster = on != 0; }
-
-template <int BN, bool B_MN>
-static int launch_hconv_cl_t(const HconvJob& J, const HconvParams& P0, int smem_bytes,
-                             cudaStream_t st) {
-  constexpr int KC = 64;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SEG_CHECK_CUDA(cudaFuncSetAttribute(hconv_kernel<KC, BN, B_MN, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
-  constexpr int kAtomN = BN < 64 ? BN : 64;
-  HconvParams P = P0;
-  CUtensorMap tmA1, tmA2, tmB;
-  int rc;
-  if (P.flat) {
-    rc = make_tmap_2d(&tmA1, J.a1.ptr, J.a1.c, (int64_t)J.batch * P.Hp * P.Wp, J.a1.sw, KC,
-                      P.box_rows, KC * 2);
-    if (rc) return rc;
-    if (J.a2.ptr) {
-      rc = make_tmap_2d(&tmA2, J.a2.ptr, J.a2.c, (int64_t)J.batch * P.Hp * P.Wp, J.a2.sw, KC,
-                        P.box_rows, KC * 2);
-      if (rc) return rc;
-    } else {
-      tmA2 = tmA1;
-    }
-  } else {
-    rc = make_tmap_rows(&tmA1, J.a1, KC, P.row_px, KC * 2);
-    if (rc) return rc;
-    if (J.a2.ptr) {
-      rc = make_tmap_rows(&tmA2, J.a2, KC, P.row_px, KC * 2);
-      if (rc) return rc;
-    } else {
-      tmA2 = tmA1;
-    }
-  }
-  // half-tile boxes: each CTA of the pair fetches one half and multicasts it
-  if (B_MN)
-    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, kAtomN, KC / 2, kAtomN * 2);
-  else
-    rc = make_tmap_2d(&tmB, J.w, J.w_cols, J.w_rows, J.w_cols, KC, BN / 2, KC * 2);
-  if (rc) return rc;
-  const int m_tiles = (P.P_total + kBlockM - 1) / kBlockM;
-  const int units = ((m_tiles + 1) / 2) * (J.N_total / BN);
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(num_sms() & ~1);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = 227 * 1024 - 1024;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, hconv_kernel<KC, BN, B_MN, true>, &cfg) != cudaSuccess ||
-        n < 1) {
-      cudaGetLastError();
-      n = -1;
-    }
-    max_clusters = n;
-  }
-  if (max_clusters < 1) return SEG_E_UNSUPPORTED;
-  int clusters = units < max_clusters ? units : max_clusters;
-  if (clusters > num_sms() / 2) clusters = num_sms() / 2;
-  P.b_resident = 0;
-  SEG_CHECK_CUDA(launch_kc(hconv_kernel<KC, BN, B_MN, true>, dim3(2 * clusters), dim3(kConvThreads),
-                           (size_t)(smem_bytes), st, 2, tmA1, tmA2, tmB, P));
-  SEG_LAUNCH_CHECK();
-  return SEG_OK;
-}
-
-template <bool B_MN>
-static int launch_hconv_cl_bn(const HconvJob& J, const HconvParams& P, int BN, int smem,
-                              cudaStream_t st) {
-  switch (BN) {
-    case 128: return launch_hconv_cl_t<128, B_MN>(J, P, smem, st);
-    case 64: return launch_hconv_cl_t<64, B_MN>(J, P, smem, st);
-    case 32: return launch_hconv_cl_t<32, B_MN>(J, P, smem, st);
-  }
-  return SEG_E_UNSUPPORTED;
 }
 
 static int g_hconv_rowstage = 1;       // seg_set_option key 14: one filter row per weight stage
@@ -694,21 +605,6 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
     BN >>= 1;
     plan(BN, &SA, &SB, &res);
   }
-  // wave quantisation: these layers are bound by what a CTA ingests per tile (A once per
-  // chunk, B once per chunk and tap), so compare waves x bytes for BN and BN/2 - e.g. 196
-  // tiles of BN=128 on 148 SMs cost two full tile times, 392 of BN=64 three half ones
-  if (BN > 64 && g_hconv_waveq) {
-    auto cost = [&](int bn) {
-      const int64_t tiles = m_tiles * (J.N_total / bn);
-      const int64_t waves = (tiles + num_sms() - 1) / num_sms();
-      return (double)waves * chunks * ((double)P.a_stage_bytes + (double)taps * bn * KC * 2);
-    };
-    int sa2, sb2, res2;
-    if (cost(BN / 2) < 0.95 * cost(BN) && plan(BN / 2, &sa2, &sb2, &res2) && sa2 >= 2) {
-      BN >>= 1;
-      SA = sa2; SB = sb2; res = res2;
-    }
-  }
   P.SA = SA; P.SB = SB; P.b_resident = res;
   const int smem = SA * P.a_stage_bytes + SB * BN * KC * 2 + 2048;
   static const bool dbg = getenv("SEGB200_DEBUG_PLAN") != nullptr;
@@ -717,12 +613,6 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
             "SB=%d res=%d stage=%d tiles=%lld\n", P.P_total, J.N_total, J.kh, J.kw, chunks, KC, P.flat,
             P.Wp, BN, SA, SB, res, P.a_stage_bytes,
             (long long)(ceil_div64(P.P_total, (int64_t)kBlockM) * (J.N_total / BN)));
-  if (g_hconv_cluster && !res && KC == 64 && BN >= 32 && BN <= 128 &&
-      ceil_div64(P.P_total, kBlockM) >= 2) {
-    const int rc2 = J.b_mn ? launch_hconv_cl_bn<true>(J, P, BN, smem, st)
-                           : launch_hconv_cl_bn<false>(J, P, BN, smem, st);
-    if (rc2 != SEG_E_UNSUPPORTED) return rc2;
-  }
   // one filter row (3 taps) per weight stage: a third of the barrier round trips in the
   // issue loop; the ring is re-planned in row units
   if (g_hconv_rowstage && !res && KC == 64 && (BN == 64 || BN == 128) && J.kw == 3 &&
@@ -1038,12 +928,10 @@ static bool g_use_twgrad = true;
 static int g_twgrad_min_eff = 40;
 static int g_twgrad_min_tiles = 8;   // pixel tiles per CTA below which the grid is narrowed
 void twgrad_set_min_tiles(int n) { g_twgrad_min_tiles = n < 1 ? 1 : n; }
-static int g_twgrad_cluster = 1;     // CTAs per cluster for the partial-sum reduction (1: off)
-void twgrad_set_cluster(int n) { g_twgrad_cluster = n >= 8 ? 8 : (n >= 4 ? 4 : (n >= 2 ? 2 : 1)); }
 void twgrad_enable(int on) { g_use_twgrad = on != 0; }
 void twgrad_set_min_eff(int pct) { g_twgrad_min_eff = pct; }
 
-static int g_twgrad_tred = 0;          // seg_set_option key 15: TMA tensor reduce-add epilogue
+static int g_twgrad_tred = 1;          // seg_set_option key 15: TMA tensor reduce-add epilogue
 void twgrad_set_tred(int on) { g_twgrad_tred = on != 0; }
 
 // dW [9][BC][SC] fp32 as a 3-D tensor {SC, BC, 9} with 128-byte-swizzled boxes {32, rows, 1}
@@ -1113,53 +1001,17 @@ static int launch_twgrad_t(const WgradJob& J, cudaStream_t st) {
   P.stages = stages;
   P.off_bars = stages * P.stage_bytes;
   const int smem = P.off_bars + 1024 + 1024;
-  // Cluster of CTAs of one combo: reduce the partial sums through distributed shared
-  // memory before they go to L2 (twgrad.cuh).  The cluster size must divide the CTAs per
-  // combo, split the accumulator columns into multiples of 4, the staged accumulators
-  // must fit into the pipeline stages, and the whole grid must be co-resident.
   constexpr int kCols = (AW == 64 ? 5 : 3) * BN;
-  int cs = g_twgrad_cluster;
-  while (cs > 1 && (cs > per || kCols % (4 * cs) != 0)) cs >>= 1;
+  // the idle pipeline stages hold the staged accumulators of the epilogue
   P.staged_ok = 128 * (kCols + 4) * 4 <= stages * P.stage_bytes ? 1 : 0;
-  if (!P.staged_ok) cs = 1;
-  if (cs > 1) {
-    per -= per % cs;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(combos * per);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (max_clusters[cs] == 0) {
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, twgrad_kernel<AW, BN, TRED>, &cfg) != cudaSuccess || n < 1) {
-        cudaGetLastError();
-        n = -1;
-      }
-      max_clusters[cs] = n;
-    }
-    if (max_clusters[cs] < 1) {
-      cs = 1;
-      per = num_sms() / combos < 1 ? 1 : num_sms() / combos;
-      if (per > tiles) per = tiles;
-    } else {
-      // keep the grid within one resident wave of clusters
-      while (per > cs && combos * per > max_clusters[cs] * cs) per -= cs;
-    }
-  }
-  P.cluster = cs;
   P.ctas_per_combo = per;
   CUtensorMap tmDW = tmZ;              // unused unless TRED
   if (TRED) {
-    if (!P.staged_ok || cs > 1) return SEG_E_UNSUPPORTED;
+    if (!P.staged_ok) return SEG_E_UNSUPPORTED;
     rc = make_tmap_dw(&tmDW, J.dw, J.SC, J.BC, AW);
     if (rc) return rc;
   }
-  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN, TRED>, dim3(combos * per), dim3(kConvThreads), (size_t)(smem), st, cs, tmX1, tmX2, tmZ, tmDW, P));
+  SEG_CHECK_CUDA(launch_kc(twgrad_kernel<AW, BN, TRED>, dim3(combos * per), dim3(kConvThreads), (size_t)(smem), st, 1, tmX1, tmX2, tmZ, tmDW, P));
   return SEG_OK;
 }
 
@@ -1177,7 +1029,7 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
   const int64_t comp = (int64_t)((Ho + kTwTH - 1) / kTwTH * kTwTH) * ((Wo + kTwTW - 1) / kTwTW * kTwTW);
   if ((int64_t)Ho * Wo * 100 < (int64_t)g_twgrad_min_eff * comp) return SEG_E_UNSUPPORTED;
   // TMA tensor reduce-add epilogue (option 15): whole BN slices, 16-byte aligned rows
-  if (g_twgrad_tred && g_twgrad_cluster == 1 && BN >= 32 && J.SC % BN == 0 &&
+  if (g_twgrad_tred && BN >= 32 && J.SC % BN == 0 &&
       (reinterpret_cast<uintptr_t>(J.dw) & 15) == 0) {
     int rc2 = SEG_E_UNSUPPORTED;
     if (AW == 64 && BN == 64) rc2 = launch_twgrad_t<64, 64, true>(J, st);
@@ -1210,7 +1062,6 @@ static int launch_twgrad(const WgradJob& J, cudaStream_t st) {
 }
 
 void hconv_set_row_align(int a) { g_hconv_row_align = a; }
-void hconv_set_waveq(int on) { g_hconv_waveq = on != 0; }
 
 static bool g_use_hconv = true;
 void hconv_enable(int on) { g_use_hconv = on != 0; }

@@ -182,6 +182,10 @@ class ParamStore(object):
         if b <= a:
             return
         chunks = ctypes.c_void_p(self.chunks.data_ptr() + a * 8)
+        if N.TIMELINE is not None:
+            # 4 B grad + 3 x 4 B state read + 3 x 4 B written + 2 B shadow per parameter
+            ce = N.load().seg_adam_chunk_elems()
+            N.note_work(0, min((b - a) * ce, self.numel) * 30.0)
         N.call('seg_adam_multi', N.ptr(self.master), N.ptr(self.grad), N.ptr(self.m),
                N.ptr(self.v), N.ptr(self.shadow), N.ptr(self.segments),
                N.ptr(self.shadow_offsets), chunks, b - a, lr_t,
@@ -240,6 +244,17 @@ class ConvLayer(object):
         return N.SegConvDesc(k, k, s, pt, pl, pb, pr, self.cin, self.cout, self.cin_pad,
                              self.cout_pad, flags, impl)
 
+    def work(self, small, big, big_bytes=2):
+        """(flops, bytes) of one fwd / dgrad / wgrad launch of this layer between the
+        tensor on its input side (`small`: x or dx) and on its output side (`big`: y or dz):
+        2*N*Ho*Wo*Cout*Cin*kh*kw (conv) / 2*N*Hi*Wi*Cin*Cout*kh*kw (transposed conv); both
+        tensors once, at their real channel counts."""
+        n = small.shape[0]
+        px = big.shape[1] * big.shape[2] if self.kind == 'conv' else small.shape[1] * small.shape[2]
+        flops = 2.0 * n * px * self.cout * self.cin * self.k * self.k
+        in_b = n * small.shape[1] * small.shape[2] * self.cin * 2.0
+        return flops, in_b + n * big.shape[1] * big.shape[2] * self.cout * float(big_bytes)
+
     def epi_flags(self, out_f32=False):
         f = N.EPI_BIAS
         if self.relu:
@@ -252,6 +267,7 @@ class ConvLayer(object):
     def forward(self, x, y, x2=None, impl=N.IMPL_UMMA, out_f32=False):
         st = N.stream_ptr()
         N.set_tag(self.name)
+        N.note_work(*self.work(x, y, 4 if out_f32 else 2))
         if self.kind == 'conv':
             d = self.desc(x.shape[1], x.shape[2], self.epi_flags(out_f32), impl)
             N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x), N.vref(x2),
@@ -285,6 +301,7 @@ class ConvLayer(object):
         if dx is None:
             return
         st = N.stream_ptr()
+        N.note_work(*self.work(dx, dz))
         if self.kind == 'conv':
             d = self.desc(x.shape[1], x.shape[2], 0, impl)
             N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(self.w.shadow()),
@@ -308,13 +325,16 @@ class ConvLayer(object):
         st = N.stream_ptr()
         if self.kind == 'conv':
             # BiasAddGrad is fused into the wgrad GEMM
+            N.note_work(*self.work(x, dz))
             d = self.desc(x.shape[1], x.shape[2], 0, impl)
             N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(x2), N.vref(dz),
                    N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
         else:
             dzb = dz_bias if dz_bias is not None else (dz if dz.shape[3] == self.cout
                                                        else dz[..., :self.cout])
+            N.note_work(0, dzb.shape[0] * dzb.shape[1] * dzb.shape[2] * self.cout * 2.0)
             N.call('seg_bias_grad', N.vref(dzb), N.ptr(self.b.grad()), st)
+            N.note_work(*self.work(x, dz))
             d = self.desc(dz.shape[1], dz.shape[2], 0, impl)
             N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(x), N.vref(dz),
                    N.ptr(self.w.grad()), st)
@@ -407,16 +427,24 @@ class SideStream(object):
 # thin op wrappers
 # ---------------------------------------------------------------------------
 def pack_input(x_f32, y):
+    N.note_work(0, x_f32.numel() * 4.0 + y.numel() * 2.0)
     N.call('seg_pack_input', N.ptr(x_f32), x_f32.shape[3], N.vref(y), N.stream_ptr())
 
 
 def maxpool_fwd(x, y, argmax, k=2, s=2):
+    N.note_work(0, x.numel() * 2.0 + y.numel() * 2.0 + argmax.numel())
     N.call('seg_maxpool_fwd', N.vref(x), k, s, N.vref(y), N.ptr(argmax), N.stream_ptr())
 
 
 def maxpool_bwd(dy, argmax, dx, k=2, s=2, add=None, add_y0=0, add_x0=0, mask=None, pooled=None):
     """`pooled`: the forward pool output; lets the kernel skip reading `mask` (the pool
     input) wherever no `add` gradient arrives."""
+    # dy + argmax slots (+ pool output for the mask) in, dx out, + the skip window's add / mask
+    N.note_work(0, dy.numel() * 2.0 + argmax.numel() + dx.numel() * 2.0 +
+                (pooled.numel() * 2.0 if pooled is not None else
+                 (mask.numel() * 2.0 if mask is not None else 0.0)) +
+                (add.numel() * 2.0 * (2 if (mask is not None and pooled is not None) else 1)
+                 if add is not None else 0.0))
     if pooled is not None:
         N.call('seg_maxpool_bwd_y', N.vref(dy), N.ptr(argmax), k, s, N.vref(add), add_y0, add_x0,
                N.vref(mask), N.vref(pooled), N.vref(dx), N.stream_ptr())
@@ -434,6 +462,9 @@ def head1x1_xent(x, layer, labels, logits, loss_sum, dx):
     """Fused training head: 1x1 conv `layer` (<= 4 classes) + softmax x-entropy + the
     layer's weight / bias gradient + the input gradient dx, one pass over x."""
     N.set_tag(layer.name)
+    px = x.shape[0] * x.shape[1] * x.shape[2]
+    N.note_work(3 * 2.0 * px * layer.cin * layer.cout,
+                px * (layer.cin * 2.0 * 2 + layer.cout * 4.0 + 1))
     N.call('seg_head1x1_xent', N.vref(x), N.ptr(layer.w.shadow()), layer.cout_pad,
            N.ptr(layer.b.value()), N.vref(labels), layer.cout, N.vref(logits), N.ptr(loss_sum),
            N.vref(dx), N.ptr(layer.w.grad()), N.ptr(layer.b.grad()), N.stream_ptr())
@@ -476,6 +507,15 @@ def resize_bilinear_bwd(dy, dx):
 
 def dropout(x, y, seed, stream_id, keep_prob=0.5):
     N.call('seg_dropout', N.vref(x), seed, stream_id, keep_prob, N.vref(y), N.stream_ptr())
+
+
+def dropout_ex(x, y, seed, stream_id0, per_image_step=0, step_dev=None, step_mul=0,
+               keep_prob=0.5):
+    """One launch for the whole batch: image n uses Philox stream
+    stream_id0 + n*per_image_step + step_dev[0]*step_mul (step_dev: device int32/uint32
+    scalar read at run time, so a captured CUDA graph gets fresh masks on every replay)."""
+    N.call('seg_dropout_ex', N.vref(x), seed, stream_id0, per_image_step, N.ptr(step_dev),
+           step_mul, keep_prob, N.vref(y), N.stream_ptr())
 
 
 def mc_mean_var(probs, mean, var):

@@ -89,6 +89,11 @@ class BaseModel(object):
         self._loss_sum = None
         self._last_pixels = 1
         self.mc_seed = 0
+        # global_step as a device scalar: kernels whose behaviour follows the step (dropout
+        # streams) read it at run time, so captured CUDA graphs stay valid across replays
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._last_train_exec = None              # executor of the most recent train_step
+        self._log_file = None
         self.world_size = 1
         self._allreduce = None                    # set by parallel.DataParallel: f(group index)
         self.opt_splits = ()                      # layers that start a new optimizer group
@@ -148,15 +153,37 @@ class BaseModel(object):
             if path is None:
                 raise IOError('no checkpoint')
             sd = dict(np.load(path, allow_pickle=False))
-            self.global_step = int(sd.pop('global_step', 0))
-            self.store.step = int(sd.pop('adam_step', self.global_step))
-            self.store.load_state_dict(sd)
-            for k, buf in (('segAdam', self.store.m), ('segAdam_1', self.store.v)):
-                if ('__flat__/' + k) in sd:
-                    buf.copy_(torch.from_numpy(sd['__flat__/' + k]).to(self.device))
-            print('Success! Resuming from global step {}'.format(self.global_step))
-        except Exception:
+            # validate everything before touching the model (tf.train.Saver.restore checks
+            # names and shapes before it assigns): a mismatched file leaves the freshly
+            # initialised model, step counters included, exactly as it was
+            st = self.store
+            for name, p in st.params.items():
+                if name not in sd:
+                    raise KeyError('variable %s missing from %s' % (name, path))
+                if int(np.prod(sd[name].shape)) != p.numel or \
+                        tuple(sd[name].shape) not in (tuple(p.shape), (p.numel,)):
+                    raise ValueError('variable %s: snapshot shape %s != %s' %
+                                     (name, tuple(sd[name].shape), tuple(p.shape)))
+            for name, t in st.state.items():
+                if name in sd and tuple(sd[name].shape) != tuple(t.shape):
+                    raise ValueError('state %s: snapshot shape %s != %s' %
+                                     (name, tuple(sd[name].shape), tuple(t.shape)))
+            for k in ('__flat__/segAdam', '__flat__/segAdam_1'):
+                if k in sd and sd[k].shape != (st.numel,):
+                    raise ValueError('%s: %s != (%d,)' % (k, sd[k].shape, st.numel))
+            gs = int(sd.pop('global_step', 0))
+            adam_step = int(sd.pop('adam_step', gs))
+        except (IOError, OSError, KeyError, ValueError) as e:
             print('Failed to load snapshot; proceed with training')
+            self._snapshot_error = e
+            return
+        self.global_step, st.step = gs, adam_step
+        st.load_state_dict(sd)
+        for k, buf in (('segAdam', st.m), ('segAdam_1', st.v)):
+            if ('__flat__/' + k) in sd:
+                buf.copy_(torch.from_numpy(sd['__flat__/' + k]).to(self.device))
+        self._sync_step_dev()
+        print('Success! Resuming from global step {}'.format(self.global_step))
 
     def _latest_checkpoint(self):
         if self.save_dir is None or not os.path.isdir(self.save_dir):
@@ -175,6 +202,8 @@ class BaseModel(object):
         if self.mode == 'INFERENCE':
             print('snapshot() with INFERENCE mode invalid')
             return
+        if self.save_dir is None or self.save_path is None:
+            raise Exception('snapshot() needs save_dir (the model was built with save_dir=None)')
         sd = self.store.state_dict()
         sd['global_step'] = np.int64(self.global_step)
         sd['adam_step'] = np.int64(self.store.step)
@@ -201,6 +230,23 @@ class BaseModel(object):
             arr = torch.from_numpy(np.ascontiguousarray(arr))
         return arr.to(self.device, dtype, non_blocking=True).contiguous()
 
+    def _sync_step_dev(self):
+        self.step_dev.fill_(self.global_step)
+
+    def _log_step(self):
+        """Every `summary_iter` steps: one JSON line {"step", "loss"} appended to
+        <log_dir>/train_log.jsonl (the reference writes a TF summary at that cadence,
+        models/basemodel.py:74,486-489)."""
+        if self.log_dir is None or self.global_step % self.summary_iter != 0:
+            return
+        if self._log_file is None:
+            if not os.path.exists(self.log_dir):
+                os.makedirs(self.log_dir)
+            self._log_file = open(os.path.join(self.log_dir, 'train_log.jsonl'), 'a')
+        import json
+        self._log_file.write(json.dumps({'step': self.global_step, 'loss': self.seg_loss_op}) + '\n')
+        self._log_file.flush()
+
     def load_weights(self, state_dict):
         """Inject parameters given under their TF variable names / layouts."""
         self.store.load_state_dict(state_dict)
@@ -217,8 +263,10 @@ class BaseModel(object):
             # launch, so it overlaps the step's kernels (the reference's queue runners
             # prefetch the same way, utils/datasets.py:94-196).
             ex = self._get_exec(self.dataset.batch_size, True)
+            self._last_train_exec = ex
             ex.train_step_from(self.dataset)
             self.global_step += 1
+            self._log_step()
             return
         imgs, masks = batch
         # host (pinned or pageable) or device tensors: staged straight into the
@@ -226,13 +274,15 @@ class BaseModel(object):
         x = torch.from_numpy(imgs) if isinstance(imgs, np.ndarray) else imgs
         y = torch.from_numpy(masks) if isinstance(masks, np.ndarray) else masks
         ex = self._get_exec(x.shape[0], True)
+        self._last_train_exec = ex
         ex.train_step(x, y)
         self.global_step += 1
+        self._log_step()
 
     @property
     def seg_loss_op(self):
         """Mean cross-entropy of the most recent train_step (host float)."""
-        ex = self._exec.get((self.batch_size, True))
+        ex = self._last_train_exec
         if ex is None:
             return float('nan')
         return ex.loss_value(0)
@@ -242,7 +292,7 @@ class BaseModel(object):
         """Mean cross-entropy of the step BEFORE the most recent train_step: a training
         loop that logs this keeps one step in flight on the GPU instead of draining the
         stream after every step (every step's loss is still copied to the host)."""
-        ex = self._exec.get((self.batch_size, True))
+        ex = self._last_train_exec
         if ex is None:
             return float('nan')
         return ex.loss_value(1)
@@ -254,6 +304,7 @@ class BaseModel(object):
         labelmap [B,H',W',1]] as float32 numpy arrays."""
         x = self._to_device(imgs, torch.float32)
         ex = self._get_exec(x.shape[0], False)
+        self._sync_step_dev()
         probs, labels = ex.infer(x)
         torch.cuda.current_stream().synchronize()
         return [probs.cpu().numpy(), labels.cpu().numpy()]
@@ -269,6 +320,7 @@ class BaseModel(object):
         x = self._to_device(imgs, torch.float32)
         y = self._to_device(masks, torch.uint8)
         ex = self._get_exec(x.shape[0], False)
+        self._sync_step_dev()
         loss = ex.eval_loss(x, y)
         print('TEST LOSS', loss, self.global_step)
         return loss
@@ -443,6 +495,7 @@ class ExecBase(object):
         m = self.m
         lr_t = m.store.next_lr_t(m.learning_rate)
         m.store.lr_t_dev.fill_(lr_t)
+        m._sync_step_dev()
         if self.use_graph and self.graph is None and self.calls >= 1:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()

@@ -183,8 +183,12 @@ class _DeconvExec(ExecBase):
         m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl
         if bn_training is None:
             bn_training = self.training
-        if dropout is None and m.bayesian:
-            dropout = (m.mc_seed, m.global_step)          # fresh masks every step
+        # bayesian=True without explicit streams: fresh masks every step, stream offset =
+        # global_step read from the device scalar m.step_dev at run time, so the captured
+        # CUDA graph of a train step does not bake one step's masks in
+        self._from_dev = dropout is None and m.bayesian
+        if self._from_dev:
+            dropout = (m.mc_seed, 0)
         self._dropout = dropout
         self._per_image = per_image
 
@@ -215,12 +219,12 @@ class _DeconvExec(ExecBase):
         m.y_hat = self.logits
 
     def _drop(self, t, site):
+        """One launch per site: stream (off [+ image]) * 8 + site (+ 8 * global_step, read
+        from the device, when the streams follow the training step)."""
         seed, off = self._dropout
-        if self._per_image:
-            for i in range(self.B):
-                E.dropout(t[i:i + 1], t[i:i + 1], seed, (off + i) * 8 + site)
-        else:
-            E.dropout(t, t, seed, off * 8 + site)
+        E.dropout_ex(t, t, seed, off * 8 + site, per_image_step=8 if self._per_image else 0,
+                     step_dev=self.m.step_dev if self._from_dev else None,
+                     step_mul=8 if self._from_dev else 0)
 
     def backward(self):
         m, L, A, G, impl = self.m, self.m.layers, self.act, self.g, self.m.impl
@@ -259,8 +263,3 @@ class _DeconvExec(ExecBase):
         # strided 5x5 wgrad: CUDA-core correlation kernel (the tcgen05 wgrad covers
         # stride 1 and k == stride)
         L['conv1_0'].backward(A['x'], G['conv1_0'], dx=None, impl=S)
-
-    def train_step(self, x, mask):
-        if self.m.bayesian:
-            self.use_graph = False       # dropout streams change every step
-        ExecBase.train_step(self, x, mask)

@@ -236,10 +236,9 @@ class _UNetExec(ExecBase):
         def conv(name, src, x2=None):
             L[name].forward(src, A[name], x2=x2, impl=impl)
             if dropout is not None and name in self.MC_SITES:
-                seed, off = dropout
-                for t in range(self.B):       # one Philox stream per MC pass
-                    E.dropout(A[name][t:t + 1], A[name][t:t + 1], seed,
-                              (off + t) * 8 + self.MC_SITES[name])
+                seed, off = dropout            # one launch, one Philox stream per MC pass
+                E.dropout_ex(A[name], A[name], seed, off * 8 + self.MC_SITES[name],
+                             per_image_step=8)
 
         conv('conv1_1', A['x'])
         # conv1_2 feeds only the last skip connection (reference models/unet.py:118-120,161):

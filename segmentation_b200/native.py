@@ -44,7 +44,6 @@ SIGNATURES = {
     'seg_version': [],
     'seg_device_check': [],
     'seg_set_option': [_I32, _I32],
-    'seg_debug_prof_buffer': [_P],
     'seg_conv2d_fwd': [_DP, _VP, _VP, _P, _P, _VP, _P],
     'seg_conv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _VP, _VP, _P],
     'seg_conv2d_dgrad_slice': [_DP, _VP, _P, ctypes.c_int32, _VP, _VP, _P],
@@ -69,6 +68,7 @@ SIGNATURES = {
     'seg_batchnorm_bwd_reduce': [_VP, _VP, _P, _P, _P, _P, _P],
     'seg_batchnorm_bwd_apply': [_VP, _VP, _P, _P, _P, _P, _I64, _I32, _VP, _P],
     'seg_dropout': [_VP, _U64, _U32, _F, _VP, _P],
+    'seg_dropout_ex': [_VP, _U64, _U32, _U32, _P, _U32, _F, _VP, _P],
     'seg_softmax_xent_fwd_bwd': [_VP, _VP, _P, _VP, _P],
     'seg_sigmoid_argmax': [_VP, _P, _P, _P],
     'seg_mc_mean_var': [_P, _I32, _I64, _P, _P, _P],
@@ -78,12 +78,44 @@ SIGNATURES = {
     'seg_pack_input': [_P, _I32, _VP, _P],
     'seg_pack_patches': [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _P],
     'seg_fill_zero': [_P, _I64, _P],
+}
+
+# self-test / micro-benchmark hooks: include/segb200_probes.h, libsegb200_probes.so
+PROBE_SIGNATURES = {
     'seg_probe_umma': [_I32, _I32, _I32, _I32, _P, _P, _P, _P],
     'seg_probe_mma_rate': [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     'seg_probe_red_rate': [_I32, _I32, _I32, _I32, _I32, _P, _P, _P],
 }
+PROBES_LIB_PATH = os.path.join(_HERE, 'libsegb200_probes.so')
 
 _lib = None
+_probes = None
+
+
+def load_probes():
+    """The probes library (same kernels + the seg_probe_* hooks); used by tests/ and tools/."""
+    global _probes
+    if _probes is None:
+        if not os.path.exists(PROBES_LIB_PATH):
+            raise SegError('%s not found: build it with `python -m segmentation_b200.build`'
+                           % PROBES_LIB_PATH)
+        lib = ctypes.CDLL(PROBES_LIB_PATH)
+        for name, args in PROBE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int32
+        lib.seg_last_error_string.argtypes = []
+        lib.seg_last_error_string.restype = ctypes.c_char_p
+        _probes = lib
+    return _probes
+
+
+def call_probe(name, *args):
+    lib = load_probes()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        msg = lib.seg_last_error_string()
+        raise SegError('%s failed (status %d): %s' % (name, status, msg.decode() if msg else ''))
 
 
 def load():
@@ -101,23 +133,20 @@ def load():
         fn.restype = ctypes.c_int32
     lib.seg_last_error_string.argtypes = []
     lib.seg_last_error_string.restype = ctypes.c_char_p
+    lib.seg_last_kernel_name.argtypes = []
+    lib.seg_last_kernel_name.restype = ctypes.c_char_p
     _lib = lib
     if os.environ.get('SEGB200_PDL', '1') == '0':
         lib.seg_set_option(OPT_PDL, 0)
     for env, key in (('SEGB200_TCONV_MIN_EFF', OPT_TILE_CONV_MIN_EFF),
                      ('SEGB200_TWGRAD_MIN_EFF', OPT_TILE_WGRAD_MIN_EFF),
-                     ('SEGB200_HCONV_WAVEQ', OPT_HALO_WAVEQ),
                      ('SEGB200_POOL_ROWS', OPT_POOL_ROWS),
                      ('SEGB200_DEEP_B', OPT_DEEP_B_RING),
-                     ('SEGB200_HCONV_CLUSTER', OPT_HALO_CLUSTER),
                      ('SEGB200_HCONV_ROWSTAGE', OPT_HALO_ROWSTAGE),
-                     ('SEGB200_TWGRAD_TRED', OPT_WGRAD_TENSOR_RED)):
+                     ('SEGB200_TWGRAD_TRED', OPT_WGRAD_TENSOR_RED),
+                     ('SEGB200_WGRAD_MIN_TILES', OPT_WGRAD_MIN_TILES)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
-    if 'SEGB200_WGRAD_MIN_TILES' in os.environ:
-        lib.seg_set_option(OPT_WGRAD_MIN_TILES, int(os.environ['SEGB200_WGRAD_MIN_TILES']))
-    if 'SEGB200_WGRAD_CLUSTER' in os.environ:
-        lib.seg_set_option(OPT_WGRAD_CLUSTER, int(os.environ['SEGB200_WGRAD_CLUSTER']))
     return lib
 
 
@@ -137,17 +166,26 @@ def set_tag(tag):
     _TAG[0] = tag
 
 
+_WORK = [0.0, 0.0]    # algorithmic (flops, bytes) of the next call, noted by the engine wrappers
+
+
+def note_work(flops, nbytes):
+    """Algorithmic work of the next C-ABI call (conv 2*N*Ho*Wo*Cout*Cin*kh*kw,
+    every tensor read or written once at its real channel count); recorded with the call's
+    timeline entry when a timeline is being taken, otherwise dropped."""
+    if TIMELINE is not None:
+        _WORK[0], _WORK[1] = float(flops), float(nbytes)
+
+
+# seg_set_option keys: test / A-B switches over the plan selection (include/segb200.h)
 OPT_HALO_CONV, OPT_HALO_ROW_ALIGN, OPT_TILE_CONV, OPT_TILE_CONV_MIN_EFF = 1, 2, 3, 4
 OPT_TILE_WGRAD, OPT_TILE_WGRAD_MIN_EFF = 5, 6
 OPT_PDL = 7           # programmatic dependent launch of the hot-path kernels (default on)
 OPT_WGRAD_MIN_TILES = 9  # pixel tiles per CTA below which the weight-gradient grid is narrowed
-OPT_HALO_WAVEQ = 10    # halo kernel: halve the N tile when waves x bytes per CTA drops
-OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep as shared memory allows
-OPT_HALO_CLUSTER = 13  # halo kernel: cluster of two CTAs multicasting the streamed weight tiles
-OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weight stage
-OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (untested)
 OPT_POOL_ROWS = 11     # row-mapped max-pool kernels (default on)
-OPT_WGRAD_CLUSTER = 8  # CTAs per cluster in the weight-gradient partial-sum reduction (1/2/4/8)
+OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep as shared memory allows
+OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weight stage
+OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (default on)
 
 
 def set_option(key, value):
@@ -165,7 +203,30 @@ def call(name, *args):
     e0.record()
     check(getattr(load(), name)(*args), name)
     e1.record()
-    TIMELINE.append((name, _TAG[0], e0, e1))
+    TIMELINE.append((name, _TAG[0], e0, e1, kernel_family(name), _WORK[0], _WORK[1]))
+    _WORK[0] = _WORK[1] = 0.0
+
+
+_FAMILY_OF_CALL = (('seg_maxpool', 'pool'), ('seg_adam', 'adam'), ('seg_head1x1', 'head'),
+                   ('seg_softmax', 'loss'), ('seg_pack', 'pack'), ('seg_bias_grad', 'bias_grad'),
+                   ('seg_batchnorm', 'batchnorm'), ('seg_dropout', 'dropout'),
+                   ('seg_bilinear', 'bilinear'), ('seg_resize', 'resize'))
+_CONV_CALLS = ('seg_conv2d_', 'seg_deconv2d_')
+
+
+def kernel_family(call_name):
+    """Kernel family a C-ABI call ran on: for the convolution family the tile kernel the
+    plan picked (tconv / hconv / igemm / twgrad / wgrad / stem, from seg_last_kernel_name;
+    'simt' for the CUDA-core kernels), else a name derived from the entry point."""
+    if call_name.startswith(_CONV_CALLS):
+        import re
+        k = load().seg_last_kernel_name().decode()
+        m = re.search(r'(tconv|hconv|igemm|twgrad|wgrad|stem\w*?)_kernel', k)
+        return m.group(1) if m else 'simt'
+    for prefix, fam in _FAMILY_OF_CALL:
+        if call_name.startswith(prefix):
+            return fam
+    return 'other'
 
 
 def stream_ptr():

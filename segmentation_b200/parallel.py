@@ -66,9 +66,20 @@ class DataParallel(object):
     update of the back of the network overlap the backward pass of the front."""
 
     def __init__(self, model, group=None):
+        from . import engine as E
+        bn = [n for n, l in getattr(model, 'layers', {}).items() if isinstance(l, E.BatchNorm)]
+        if bn:
+            # batch statistics would be per-rank (not the statistics of the global batch) and
+            # the moving averages would drift apart after the initial broadcast
+            raise Exception('DataParallel: batch-coupled layers (%s) are not supported; images '
+                            'must be independent in forward and backward (SURVEY 8e)' % ', '.join(bn))
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group)
+        # executors built (and graphs captured) before wrapping have no all-reduce and a
+        # grad_scale of 1 baked in
+        model._exec.clear()
+        model._last_train_exec = None
         model.world_size = self.world
         st = model.store
         dist.broadcast(st.master, src=0, group=group)

@@ -77,8 +77,8 @@ def test_probe_umma_gemm(cuda, mode):
         a_d = a.to(torch.bfloat16).cuda()
         b_d = (b.t().contiguous() if mode == 1 else b).to(torch.bfloat16).cuda()
         d = torch.full((M, Nn), float('nan'), dtype=torch.float32, device='cuda')
-        N.call('seg_probe_umma', mode, M, Nn, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d),
-               N.stream_ptr())
+        N.call_probe('seg_probe_umma', mode, M, Nn, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d),
+                     N.stream_ptr())
         sync()
         err = rel_l2(d.cpu(), ref)
         report('probe', {'mode': mode, 'M': M, 'N': Nn, 'K': K, 'err': err})
@@ -150,14 +150,13 @@ def test_conv_fwd(cuda, case, impl_name, impl):
 CLUSTER_CASES = [c for c in CONV_CASES if c[0] in ('c512', 'v3_128_256', 'concat')]
 
 
-@pytest.mark.parametrize('opt', ['cluster', 'rowstage'])
+@pytest.mark.parametrize('opt', ['rowstage'])
 @pytest.mark.parametrize('case', CLUSTER_CASES, ids=[c[0] for c in CLUSTER_CASES])
 def test_conv_fwd_halo_plan_options(cuda, case, opt):
-    """Alternative plans of the halo kernel for streamed weights: seg_set_option key 13
-    (clusters of two CTAs, each fetching half of every weight tile and multicasting it) and
-    key 14 (one filter row = three taps per weight stage).  Same numbers as the default
-    plan; layers whose weights stay resident in shared memory ignore both options."""
-    key = N.OPT_HALO_CLUSTER if opt == 'cluster' else N.OPT_HALO_ROWSTAGE
+    """Plans of the halo kernel for streamed weights: seg_set_option key 14 (one filter row =
+    three taps per weight stage, the default) against one tap per stage.  Same numbers;
+    layers whose weights stay resident in shared memory ignore the option."""
+    key = N.OPT_HALO_ROWSTAGE
     name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
     x, w, b = _conv_inputs(case)
     cin, cin_pad, cout_pad = C1 + C2, pad16(C1 + C2), pad16(Co)
@@ -180,7 +179,7 @@ def test_conv_fwd_halo_plan_options(cuda, case, opt):
             sync()
             outs.append(y_d.float().cpu())
     finally:
-        N.set_option(key, 0)
+        N.set_option(key, 1)
     ref = torch.relu(T.conv2d(x, w, b, s, padding)) if relu else T.conv2d(x, w, b, s, padding)
     assert rel_l2(outs[1], ref) < TOL_BF16, name
     # same K order per output: the plans differ in staging only
@@ -260,17 +259,11 @@ def test_conv_bwd(cuda, case, impl_name, impl):
         assert e1 < 1e-3 and e2 < 1e-3, (name, e1, e2)
 
 
-EXPERIMENTAL = pytest.mark.skipif(os.environ.get('SEGB200_TEST_EXPERIMENTAL') != '1',
-                                  reason='kernel variant built after the GPU budget of its round '
-                                         'ran out: run with SEGB200_TEST_EXPERIMENTAL=1 first')
-
-
-@EXPERIMENTAL
 @pytest.mark.parametrize('case', [c for c in BWD_CASES if c[7] == 3 and c[8] == 1 and c[6] % 32 == 0],
                          ids=lambda c: c[0])
 def test_conv_wgrad_tensor_reduce_option(cuda, case):
     """seg_set_option key 15: the spatial-tile weight-gradient kernel's TMA tensor reduce-add
-    epilogue gives the same dW / db as the default row-wise bulk reduce-add epilogue."""
+    epilogue (the default) gives the same dW / db as the row-wise bulk reduce-add epilogue."""
     name, Nb, H, W, C1, C2, Co, k, s, padding, relu, f32 = case
     x, w, b = _conv_inputs(case)
     g = _gen(7)
@@ -294,7 +287,7 @@ def test_conv_wgrad_tensor_reduce_option(cuda, case):
             sync()
             outs.append((dw_d.cpu(), db_d.cpu()))
     finally:
-        N.set_option(N.OPT_WGRAD_TENSOR_RED, 0)
+        N.set_option(N.OPT_WGRAD_TENSOR_RED, 1)
     assert rel_l2(outs[1][0], outs[0][0]) < TOL_F32 * 5, name
     assert rel_l2(outs[1][1], outs[0][1]) < TOL_F32 * 5, name
 

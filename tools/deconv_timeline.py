@@ -16,7 +16,7 @@ for _ in range(2):
     N.TIMELINE = []
     ex.infer(x)
     torch.cuda.synchronize()
-    tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
+    tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b, *_) in N.TIMELINE]
     N.TIMELINE = None
 tot = sum(t for _, _, t in tl)
 print('total %.2f ms' % tot)

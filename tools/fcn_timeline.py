@@ -17,7 +17,7 @@ for _ in range(2):
     N.TIMELINE = []
     ex.forward(); ex.loss(True); ex.backward()
     torch.cuda.synchronize()
-    tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b) in N.TIMELINE]
+    tl = [(n, tag, a.elapsed_time(b)) for (n, tag, a, b, *_) in N.TIMELINE]
     N.TIMELINE = None
     m.store.grad.zero_()
 tot = sum(t for _, _, t in tl)

@@ -44,8 +44,9 @@ for name in want:
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1000 / 20
         prof.zero_()
-        N.call('seg_debug_prof_buffer', N.ptr(prof)); fn(); torch.cuda.synchronize()
-        N.call('seg_debug_prof_buffer', None)
+        # profiling build only (SEGB200_KERNEL_PROF=1 python -m segmentation_b200.build --force)
+        N.load().seg_debug_prof_buffer(N.ptr(prof)); fn(); torch.cuda.synchronize()
+        N.load().seg_debug_prof_buffer(None)
         pall = prof.cpu()
         taps = pall[3 * 64:].view(4, 16)
         p = pall[:3 * 64].view(3, 16, 4)

@@ -13,7 +13,7 @@ def run(kc, bn, b_mn, wp, shifted, a_mn=0, ctas=1, stress=()):
     out = torch.zeros(2 * ctas + 8192 * ctas + 64, dtype=torch.int64, device='cuda')
     fl = sum(FLAGS[s] for s in stress)
     for _ in range(2):
-        N.call('seg_probe_mma_rate', kc, bn, b_mn, wp, shifted, ITERS, a_mn | (fl << 4), ctas, N.ptr(out), N.stream_ptr())
+        N.call_probe('seg_probe_mma_rate', kc, bn, b_mn, wp, shifted, ITERS, a_mn | (fl << 4), ctas, N.ptr(out), N.stream_ptr())
     torch.cuda.synchronize()
     o = out[:2 * ctas].cpu().view(ctas, 2).double()
     n_mma = ITERS * 9 * (kc // 16)

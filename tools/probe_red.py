@@ -13,7 +13,7 @@ def run(mode, ctas, elems, regions, op_bytes=256):
         dst.zero_()
         torch.cuda.synchronize()
         e0.record()
-        N.call('seg_probe_red_rate', mode, ctas, elems, regions, op_bytes, N.ptr(dst), N.ptr(out), N.stream_ptr())
+        N.call_probe('seg_probe_red_rate', mode, ctas, elems, regions, op_bytes, N.ptr(dst), N.ptr(out), N.stream_ptr())
         e1.record()
         torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3

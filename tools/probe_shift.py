@@ -13,7 +13,7 @@ for K in (64, 32, 16):
         for shift in (0, 1, 2, 3, 5, 7, 8, 9, 16, 17, 30):
             d = torch.full((128, 64), float('nan'), device='cuda')
             mode = 0x100 | (use_bo << 9) | (shift << 16)
-            N.call('seg_probe_umma', mode, 128, 64, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d), N.stream_ptr())
+            N.call_probe('seg_probe_umma', mode, 128, 64, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d), N.stream_ptr())
             torch.cuda.synchronize()
             ref = a[shift:shift + 128].float() @ b.float().t()
             err = float((d.cpu() - ref).norm() / ref.norm())
@@ -28,7 +28,7 @@ for K in (64, 32, 16):
         for shift in (0, 3, 17):
             d = torch.full((128, 64), float('nan'), device='cuda')
             mode = 0x100 | (shift << 16) | (split << 24)
-            N.call('seg_probe_umma', mode, 128, 64, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d), N.stream_ptr())
+            N.call_probe('seg_probe_umma', mode, 128, 64, K, N.ptr(a_d), N.ptr(b_d), N.ptr(d), N.stream_ptr())
             torch.cuda.synchronize()
             ref = a[shift:shift + 128].float() @ b.float().t()
             err = float((d.cpu() - ref).norm() / ref.norm())

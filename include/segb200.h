@@ -105,6 +105,8 @@ SEG_API const char* seg_last_kernel_name(void);
  *   key 15: spatial-tile weight-gradient epilogue as TMA tensor reduce-adds (one [ci x 32 co]
  *          box per tap and column block) instead of one bulk reduce-add per accumulator row
  *          (default 1: 1.056 -> 1.042 ms per U-Net step).
+ *   key 16: first-layer kernel (3x3 stride-1 convolution of the 4-channel (R,G,B,1) input of
+ *          seg_stage_input, forward and weight gradient; default 1).
  * (Keys 8, 10 and 13 of round 1 - cluster/DSMEM weight-gradient reduction, wave-quantised
  * halo tiles, two-CTA multicast halo clusters - were measured slower and are gone.) */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);
@@ -276,6 +278,36 @@ SEG_API int32_t seg_adam_multi(float* param, float* grad, float* m, float* v, vo
                        const float* lr_t_dev, float beta1, float beta2, float eps,
                        float grad_scale, void* stream);
 
+/* ---- input staging (BaseModel._init_input, models/basemodel.py:145-177, fed by
+ * utils/datasets.py:176-190): source pixels -> y4, a dense bf16 [n,h,w,4] tensor holding
+ * (R, G, B, 1) per pixel - the layout the first-layer convolution kernel reads (its fourth
+ * weight row is zero; in the weight gradient the constant channel yields the bias gradient).
+ *   x_kind 0: x is fp32 [n,src_h,src_w,c] in [0,1];  1: uint8, divided by 255 in fp32
+ *             (utils/datasets.py:178 / :41) before the bf16 rounding.
+ *   crop_yx (device int32 [n][2], nullable): top-left corner of image n's h x w window in
+ *             the source (the joint image+mask random crop of utils/datasets.py:184-185; the
+ *             caller draws the offsets).  Null: src_h == h and src_w == w.
+ *   mask_src (nullable, uint8 [n,src_h,src_w]) -> mask_dst (uint8 [n,h,w], same window):
+ *             mask_kind 0 copies class labels, 1 maps 255 -> 1 and everything else -> 0
+ *             (uint8(mask / 255), utils/datasets.py:179,172).
+ *   ctl (host struct, nullable): per-step scalars written by the same launch, so that a
+ *             training step is [this kernel, one CUDA-graph replay]: *loss_sum is published
+ *             to host_ring[2*(publish_step&3)] = {loss_sum, bits of publish_step} (pinned
+ *             host memory, device-accessible) when publish_step >= 0, then zeroed;
+ *             *lr_t_dev = lr_t; *step_dev = step.  Null members are skipped. */
+typedef struct seg_stage_ctl {
+  float* loss_sum;
+  float* host_ring;
+  int32_t publish_step;
+  float lr_t;
+  float* lr_t_dev;
+  int32_t step;
+  int32_t* step_dev;
+} seg_stage_ctl;
+SEG_API int32_t seg_stage_input(const void* x, int32_t x_kind, int32_t c, int32_t src_h,
+                                int32_t src_w, const int32_t* crop_yx, const seg_view* y4,
+                                const uint8_t* mask_src, int32_t mask_kind, uint8_t* mask_dst,
+                                const seg_stage_ctl* ctl, void* stream);
 /* ---- layout helpers */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with channels zero-padded to y.c */
 SEG_API int32_t seg_pack_input(const float* x, int32_t c, const seg_view* y, void* stream);

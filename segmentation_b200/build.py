@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libsegb200.so')
 PROBES_LIB = os.path.join(HERE, 'libsegb200_probes.so')
-SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu']
+SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'umma_conv.cu', 'fconv.cu']
 PROBE_SOURCES = ['probe.cu', 'probe_api.cu']      # linked into libsegb200_probes.so only
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',

@@ -37,6 +37,7 @@ void pool_set_rows(int on);
 void conv_set_deep_b_ring(int on);
 void hconv_set_rowstage(int on);
 void twgrad_set_tred(int on);
+void fconv_enable(int on);
 void hconv_set_prof(void* p);
 void hconv_enable(int on);
 void tconv_enable(int on);
@@ -99,6 +100,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 12: conv_set_deep_b_ring(value); return SEG_OK;
     case 14: hconv_set_rowstage(value); return SEG_OK;
     case 15: twgrad_set_tred(value); return SEG_OK;
+    case 16: fconv_enable(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

@@ -1169,6 +1169,67 @@ __global__ void pack_input16_kernel(const float* __restrict__ x, int C, bf16* __
   }
 }
 
+// Input staging of one step (seg_stage_input): source pixels (fp32 in [0,1], or uint8 to be
+// divided by 255 as utils/datasets.py:176-178 does) -> 4 bf16 per pixel (R, G, B, 1) - the
+// layout the first-layer kernel (fconv.cuh) reads - with an optional per-image crop window
+// (utils/datasets.py:184-185) and the mask that goes with it; thread 0 also runs the step's
+// scalar housekeeping so that a training step needs no other node in front of its graph.
+struct StageArgs {
+  const void* x;
+  int kind, C, src_h, src_w;
+  const int32_t* crop_yx;
+  uint2* y;
+  int n, H, W;
+  const uint8_t* mask_src;
+  int mask_kind;
+  uint8_t* mask_dst;
+  seg_stage_ctl ctl;
+  int has_ctl;
+};
+
+__global__ void stage_input4_kernel(const StageArgs A) {
+  pdl_trigger();
+  pdl_wait();
+  if (A.has_ctl && blockIdx.x == 0 && threadIdx.x == 0) {
+    const seg_stage_ctl& c = A.ctl;
+    if (c.loss_sum) {
+      if (c.host_ring && c.publish_step >= 0) {
+        // loss of the step that just finished -> pinned host ring {loss_sum, step id}
+        volatile float* slot = c.host_ring + 2 * (c.publish_step & 3);
+        slot[0] = *c.loss_sum;
+        slot[1] = __int_as_float(c.publish_step);
+      }
+      *c.loss_sum = 0.f;
+    }
+    if (c.lr_t_dev) *c.lr_t_dev = c.lr_t;
+    if (c.step_dev) *c.step_dev = c.step;
+  }
+  const int64_t pixels = (int64_t)A.n * A.H * A.W;
+  const float one = 1.0f;
+  GRID_STRIDE(m, pixels) {
+    const int xx = (int)(m % A.W);
+    const int64_t t = m / A.W;
+    const int yy = (int)(t % A.H);
+    const int n = (int)(t / A.H);
+    int cy = 0, cx = 0;
+    if (A.crop_yx) { cy = __ldg(A.crop_yx + 2 * n); cx = __ldg(A.crop_yx + 2 * n + 1); }
+    const int64_t src = ((int64_t)n * A.src_h + yy + cy) * A.src_w + xx + cx;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (A.kind == 0) {
+      const float* xp = reinterpret_cast<const float*>(A.x) + src * A.C;
+      for (int c = 0; c < A.C; ++c) v[c] = __ldg(xp + c);
+    } else {
+      const uint8_t* xp = reinterpret_cast<const uint8_t*>(A.x) + src * A.C;
+      for (int c = 0; c < A.C; ++c) v[c] = (float)__ldg(xp + c) / 255.0f;
+    }
+    A.y[m] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], one));
+    if (A.mask_src) {
+      const uint8_t mk = __ldg(A.mask_src + src);
+      A.mask_dst[m] = A.mask_kind ? (uint8_t)(mk == 255) : mk;
+    }
+  }
+}
+
 // fp32 NHWC [n,H,W,C] -> bf16 [n,Ho,Wo,CP]: the kh x kw x C patch of every output pixel is
 // packed into the channel axis, channel (r*kw+s)*C+c of pixel (oy,ox) =
 // x[n, oy*stride+r-pad_t, ox*stride+s-pad_l, c] (zero outside the image and beyond
@@ -1890,6 +1951,30 @@ SEG_API int32_t seg_pack_patches(const float* x, int32_t c, int32_t h, int32_t w
   const int64_t total = pixels * (y->c / 8);
   SEG_CHECK_CUDA(launch_k(pack_patches_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0,
                           (cudaStream_t)stream, x, c, h, w, kh, kw, stride, pad_t, pad_l, *y));
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_stage_input(const void* x, int32_t x_kind, int32_t c, int32_t src_h,
+                                int32_t src_w, const int32_t* crop_yx, const seg_view* y4,
+                                const uint8_t* mask_src, int32_t mask_kind, uint8_t* mask_dst,
+                                const seg_stage_ctl* ctl, void* stream) {
+  SEG_REQUIRE(x && y4 && y4->c == 4 && view_dense(*y4) && c >= 1 && c <= 3 &&
+                  (x_kind == 0 || x_kind == 1) && src_h >= y4->h && src_w >= y4->w &&
+                  (reinterpret_cast<uintptr_t>(y4->ptr) & 7) == 0,
+              SEG_E_BAD_SHAPE, "stage_input: need a dense 4-channel bf16 destination, 1..3 source "
+              "channels and a source at least as large as the destination");
+  SEG_REQUIRE(!mask_src || mask_dst, SEG_E_BAD_SHAPE, "stage_input: mask_dst missing");
+  SEG_REQUIRE(crop_yx || (src_h == y4->h && src_w == y4->w), SEG_E_BAD_SHAPE,
+              "stage_input: a larger source needs crop offsets");
+  StageArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = x; A.kind = x_kind; A.C = c; A.src_h = src_h; A.src_w = src_w; A.crop_yx = crop_yx;
+  A.y = reinterpret_cast<uint2*>(y4->ptr); A.n = y4->n; A.H = y4->h; A.W = y4->w;
+  A.mask_src = mask_src; A.mask_kind = mask_kind; A.mask_dst = mask_dst;
+  if (ctl) { A.ctl = *ctl; A.has_ctl = 1; }
+  const int64_t pixels = (int64_t)A.n * A.H * A.W;
+  SEG_CHECK_CUDA(launch_k(stage_input4_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)0,
+                          (cudaStream_t)stream, A));
   return SEG_OK;
 }
 

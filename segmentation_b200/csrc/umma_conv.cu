@@ -1069,8 +1069,21 @@ void hconv_enable(int on) { g_use_hconv = on != 0; }
 // ---------------------------------------------------------------------------
 // op-level entry points used by api.cu
 // ---------------------------------------------------------------------------
+// fconv.cu: first-layer kernel; SEG_E_UNSUPPORTED = not its shape, nothing launched
+int fconv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
+              const float* bias, const seg_view& y, cudaStream_t st);
+int fconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
+                const seg_view& dz, float* dw, float* db, cudaStream_t st);
+
 int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
                   const float* bias, const seg_view& y, cudaStream_t st) {
+  if (x.c == 4 && d.cin == 3) {
+    const int rc = fconv_fwd(d, x, x2, w, bias, y, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+    SEG_REQUIRE(false, SEG_E_UNSUPPORTED,
+                "conv_fwd: a 4-channel (R,G,B,1) input needs the first-layer kernel's shape "
+                "(3x3, stride 1, dense tensors, 32 or 64 padded output channels)");
+  }
   IgemmJob J;
   memset(&J, 0, sizeof(J));
   J.a1 = x;
@@ -1194,6 +1207,12 @@ int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, c
 
 int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                     const seg_view& dz, float* dw, float* db, cudaStream_t st) {
+  if (x.c == 4 && d.cin == 3) {
+    const int rc = fconv_wgrad(d, x, x2, dz, dw, db, st);
+    if (rc != SEG_E_UNSUPPORTED) return rc;
+    SEG_REQUIRE(false, SEG_E_UNSUPPORTED,
+                "conv_wgrad: a 4-channel (R,G,B,1) input needs the first-layer kernel's shape");
+  }
   WgradJob J;
   memset(&J, 0, sizeof(J));
   J.big = x;

@@ -453,6 +453,25 @@ def maxpool_bwd(dy, argmax, dx, k=2, s=2, add=None, add_y0=0, add_x0=0, mask=Non
            N.vref(mask), N.vref(dx), N.stream_ptr())
 
 
+def stage_input(x, y4, mask_src=None, mask_dst=None, crop_yx=None, mask_kind=None, ctl=None):
+    """seg_stage_input: x fp32 [B,Hs,Ws,C] in [0,1] or uint8 (divided by 255 on the device,
+    reference utils/datasets.py:176-178) -> y4 bf16 [B,H,W,4] = (R,G,B,1), the first-layer
+    kernel's input; optional per-image crop (device int32 [B,2], :184-185), the mask that
+    goes with it, and the per-step scalars of `ctl` (a native.SegStageCtl)."""
+    kind = 1 if x.dtype == torch.uint8 else 0
+    assert x.is_contiguous() and (kind == 1 or x.dtype == torch.float32)
+    if mask_kind is None:
+        mask_kind = kind                     # raw 0/255 masks travel with raw uint8 images
+    if mask_src is not None:
+        assert mask_src.is_contiguous() and mask_src.dtype == torch.uint8
+        assert mask_dst.is_contiguous() and mask_dst.dtype == torch.uint8
+        assert mask_src.shape[1] == x.shape[1] and mask_src.shape[2] == x.shape[2]
+    N.note_work(0, y4.shape[0] * y4.shape[1] * y4.shape[2] * (x.shape[3] * x.element_size() + 8.0))
+    N.call('seg_stage_input', N.ptr(x), kind, x.shape[3], x.shape[1], x.shape[2], N.ptr(crop_yx),
+           N.vref(y4), N.ptr(mask_src), int(mask_kind), N.ptr(mask_dst),
+           ctypes.byref(ctl) if ctl is not None else None, N.stream_ptr())
+
+
 def softmax_xent(logits, labels, loss_sum, dlogits=None):
     N.call('seg_softmax_xent_fwd_bwd', N.vref(logits), N.vref(labels), N.ptr(loss_sum),
            N.vref(dlogits), N.stream_ptr())

@@ -268,14 +268,17 @@ class BaseModel(object):
             self.global_step += 1
             self._log_step()
             return
-        imgs, masks = batch
+        imgs, masks = batch[0], batch[1]
+        crop = batch[2] if len(batch) > 2 else None      # uint8 batches: per-image crop corners
         # host (pinned or pageable) or device tensors: staged straight into the
         # executor's static input buffers (H2D on the compute stream)
         x = torch.from_numpy(imgs) if isinstance(imgs, np.ndarray) else imgs
         y = torch.from_numpy(masks) if isinstance(masks, np.ndarray) else masks
+        if isinstance(crop, np.ndarray):
+            crop = torch.from_numpy(crop)
         ex = self._get_exec(x.shape[0], True)
         self._last_train_exec = ex
-        ex.train_step(x, y)
+        ex.train_step(x, y, crop)
         self.global_step += 1
         self._log_step()
 
@@ -332,6 +335,15 @@ class ExecBase(object):
     backward(); this base owns input staging, loss, head, the CUDA-graph
     captured train step and inference."""
 
+    @staticmethod
+    def first_layer_x4(model, layer):
+        """True if `layer` (the model's first convolution) can run on the first-layer kernel:
+        a plain 3x3 stride-1 convolution of an RGB input onto 32 or 64 padded channels
+        (csrc/fconv.cuh).  SEGB200_FIRST_LAYER=0 keeps the 16-channel padded input."""
+        return (type(layer) is E.ConvLayer and layer.kind == 'conv' and layer.k == 3 and
+                layer.stride == 1 and model.input_channel == 3 and layer.cout_pad in (32, 64) and
+                os.environ.get('SEGB200_FIRST_LAYER', '1') != '0')
+
     def _init_io(self, model, B, H, W, oh, ow, n_out, dlogits_pad, training):
         dev = model.device
         self.m, self.B, self.training = model, B, training
@@ -341,6 +353,15 @@ class ExecBase(object):
         # may land while a step is running
         self.x_f32 = torch.zeros(B, H, W, model.input_channel, dtype=torch.float32, device=dev)
         self.mask_in = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
+        # x4: the executor's first layer takes the (R,G,B,1) input of seg_stage_input (set by
+        # the child before _init_io).  One staging launch then does everything a step needs
+        # in front of its graph: pack, mask, loss publication + zeroing, lr_t, global step.
+        self.x4 = bool(getattr(self, 'x4', False))
+        self.x_u8 = None               # uint8 landing buffer (raw-image batches), on demand
+        self._src = (self.x_f32, self.mask_in, None)   # what the next staging launch reads
+        self._loss_prezeroed = False
+        self._loss_ring = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
         self.mask = torch.zeros(B, H, W, 1, dtype=torch.uint8, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ev_staged = torch.cuda.Event()
@@ -383,8 +404,13 @@ class ExecBase(object):
         self.m.y_hat_sig, self.m.output = self.probs, self.labelmap
         return self.probs, self.labelmap
 
+    def zero_loss(self):
+        """loss_sum = 0, unless the step's staging launch already did it."""
+        if not self._loss_prezeroed:
+            E.fill_zero(self.loss_sum)
+
     def loss(self, with_grad):
-        E.fill_zero(self.loss_sum)
+        self.zero_loss()
         E.softmax_xent(self.logits, self.mask_view(), self.loss_sum,
                        self.dlogits if with_grad else None)
 
@@ -433,34 +459,70 @@ class ExecBase(object):
             self._pack_now()
 
     def _pack_now(self):
-        """Default: C zero-padded to 16 channels.  Executors whose first layer is a
-        PatchConvLayer override this with its patch packing."""
-        E.pack_input(self.x_f32, self.act['x'])
+        """Default: the first-layer kernel's (R,G,B,1) layout when the executor uses it,
+        else C zero-padded to 16 channels.  Executors whose first layer is a PatchConvLayer
+        override this with its patch packing."""
+        if self.x4:
+            E.stage_input(self.x_f32, self.act['x'])
+        else:
+            E.pack_input(self.x_f32, self.act['x'])
 
-    def _stage_async(self, x, mask):
-        """Copy a batch into the landing buffers: host tensors go over the copy stream
-        (pinned memory makes this asynchronous), device tensors over the compute stream."""
+    def _stage_async(self, x, mask, crop_yx=None):
+        """Make a batch available to the next step.  Host tensors are copied into the landing
+        buffers over the copy stream (pinned memory makes this asynchronous); device tensors
+        go over the compute stream, or - x4 executors, contiguous fp32 / uint8 - are read in
+        place by the step's staging launch.  uint8 images (raw decoded files, reference
+        utils/datasets.py:19-45,176-190) may be larger than the model input: `crop_yx`
+        (int32 [B,2]) then gives each image's crop corner, and the masks are raw 0/255."""
         cur = torch.cuda.current_stream()
-        if x.is_cuda:
-            cur.wait_event(self.ev_staged)           # a prefetch still landing there
-            self.x_f32.copy_(x, non_blocking=True)
-            self.mask_in.copy_(mask, non_blocking=True)
+        raw = x.dtype == torch.uint8
+        if raw or crop_yx is not None:
+            if not self.x4:
+                raise Exception('uint8 / cropped batches need the first-layer (x4) input path')
+        if self.x4 and x.is_cuda and x.is_contiguous() and mask.is_cuda and mask.is_contiguous() \
+                and (raw or x.dtype == torch.float32):
+            cy = None if crop_yx is None else crop_yx.to(device=x.device, dtype=torch.int32)
+            cur.wait_event(self.ev_staged)
+            self._src = (x, mask, cy)
             self.ev_staged.record(cur)
             return
-        cs = self.copy_stream
-        cs.wait_event(self.ev_consumed)              # previous batch packed
-        with torch.cuda.stream(cs):
-            self.x_f32.copy_(x, non_blocking=True)
-            self.mask_in.copy_(mask, non_blocking=True)
-            self.ev_staged.record(cs)
+        if raw:
+            if self.x_u8 is None or tuple(self.x_u8.shape) != tuple(x.shape):
+                self.x_u8 = torch.zeros(tuple(x.shape), dtype=torch.uint8, device=self.m.device)
+                self.mask_u8 = torch.zeros(tuple(mask.shape), dtype=torch.uint8,
+                                           device=self.m.device)
+                self.crop_dev = torch.zeros(x.shape[0], 2, dtype=torch.int32, device=self.m.device)
+            land_x, land_m = self.x_u8, self.mask_u8
+        else:
+            land_x, land_m = self.x_f32, self.mask_in
+        if x.is_cuda:
+            cur.wait_event(self.ev_staged)           # a prefetch still landing there
+            land_x.copy_(x, non_blocking=True)
+            land_m.copy_(mask, non_blocking=True)
+            if raw and crop_yx is not None:
+                self.crop_dev.copy_(crop_yx, non_blocking=True)
+            self.ev_staged.record(cur)
+        else:
+            cs = self.copy_stream
+            cs.wait_event(self.ev_consumed)              # previous batch packed
+            with torch.cuda.stream(cs):
+                land_x.copy_(x, non_blocking=True)
+                land_m.copy_(mask, non_blocking=True)
+                if raw and crop_yx is not None:
+                    self.crop_dev.copy_(crop_yx, non_blocking=True)
+                self.ev_staged.record(cs)
+        self._src = (land_x, land_m, self.crop_dev if (raw and crop_yx is not None) else None)
 
     def _prefetch(self, dataset):
         batch = self._pf_host if self._pf_host is not None else dataset.next_batch()
         self._pf_host = None
-        imgs, masks = batch
+        imgs, masks = batch[0], batch[1]
+        crop = batch[2] if len(batch) > 2 else None
         x = torch.from_numpy(imgs) if isinstance(imgs, np.ndarray) else imgs
         y = torch.from_numpy(masks) if isinstance(masks, np.ndarray) else masks
-        self._stage_async(x, y)
+        if isinstance(crop, np.ndarray):
+            crop = torch.from_numpy(crop)
+        self._stage_async(x, y, crop)
         self._pf = batch
 
     def train_step_from(self, dataset):
@@ -472,30 +534,44 @@ class ExecBase(object):
         self._launch_step()
         self._prefetch(dataset)
 
-    def train_step(self, x, mask):
+    def train_step(self, x, mask, crop_yx=None):
         if self._pf is not None:                     # keep the prefetched batch for later
             self._pf_host, self._pf = self._pf, None
-        self._stage_async(x, mask)
+        self._stage_async(x, mask, crop_yx)
         self._launch_step()
 
     def _launch_step(self):
         m = self.m
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ev_staged)
-        self._pack_now()
-        self.mask.copy_(self.mask_in, non_blocking=True)
+        lr_t = m.store.next_lr_t(m.learning_rate)
+        if self.x4:
+            # ONE launch in front of the step's graph: input pack (+ /255, crop), mask, the
+            # previous step's loss to the pinned ring, loss_sum = 0, lr_t and global step
+            x, mask, crop = self._src
+            ctl = N.SegStageCtl(self.loss_sum.data_ptr(), self._loss_ring.data_ptr(),
+                                self.calls - 1, float(lr_t), m.store.lr_t_dev.data_ptr(),
+                                int(m.global_step), m.step_dev.data_ptr())
+            E.stage_input(x, self.act['x'], mask_src=mask, mask_dst=self.mask, crop_yx=crop,
+                          ctl=ctl)
+            self._stage_ev[self.calls & 1].record(cur)
+            self._src = (self.x_f32, self.mask_in, None)
+            self._loss_prezeroed = True
+        else:
+            self._pack_now()
+            self.mask.copy_(self.mask_in, non_blocking=True)
+            m.store.lr_t_dev.fill_(lr_t)
+            m._sync_step_dev()
         self.ev_consumed.record(cur)
         self._prepacked = True
         try:
             self._run_step()
         finally:
             self._prepacked = False
+            self._loss_prezeroed = False
 
     def _run_step(self):
         m = self.m
-        lr_t = m.store.next_lr_t(m.learning_rate)
-        m.store.lr_t_dev.fill_(lr_t)
-        m._sync_step_dev()
         if self.use_graph and self.graph is None and self.calls >= 1:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -511,21 +587,34 @@ class ExecBase(object):
             self.graph.replay()
         else:
             self._step_body()
-        # the step's loss goes to pinned host memory behind the step (4 bytes, asynchronous):
-        # the host can read step i's loss while step i+1 runs (BaseModel.seg_loss_lagged)
-        slot = self.calls & 1
-        self._loss_host[slot].copy_(self.loss_sum[0], non_blocking=True)
-        self._loss_ev[slot].record(torch.cuda.current_stream())
+        if not self.x4:
+            # the step's loss goes to pinned host memory behind the step (4 bytes,
+            # asynchronous): the host can read step i's loss while step i+1 runs
+            # (BaseModel.seg_loss_lagged).  x4 executors: the NEXT step's staging launch
+            # publishes it, no node behind the graph at all.
+            slot = self.calls & 1
+            self._loss_host[slot].copy_(self.loss_sum[0], non_blocking=True)
+            self._loss_ev[slot].record(torch.cuda.current_stream())
         self.calls += 1
 
     def loss_value(self, lag=0):
-        """Mean loss of the most recent step (lag=0) or of the one before it (lag=1), read
-        from the pinned copy once that step's event has completed."""
+        """Mean loss of the most recent step (lag=0) or of the one before it (lag=1).
+        x4 executors: step n's loss is published to the pinned ring by the staging launch of
+        step n+1 (the latest step's is read from the device after a stream sync); otherwise
+        it is read from the pinned copy once that step's event has completed."""
         if self.calls == 0:
             return float('nan')
         n = self.calls - 1 - (lag if self.calls > lag else 0)
-        self._loss_ev[n & 1].synchronize()
-        return float(self._loss_host[n & 1]) / self.loss_pixels
+        if not self.x4:
+            self._loss_ev[n & 1].synchronize()
+            return float(self._loss_host[n & 1]) / self.loss_pixels
+        if n == self.calls - 1:
+            return float(self.loss_sum.item()) / self.loss_pixels
+        self._stage_ev[(n + 1) & 1].synchronize()
+        slot = 2 * (n & 3)
+        if int(self._loss_ring.view(torch.int32)[slot + 1]) != n:
+            raise Exception('loss ring: slot %d does not hold step %d' % (slot // 2, n))
+        return float(self._loss_ring[slot]) / self.loss_pixels
 
     def infer(self, x):
         self.stage(x, None)

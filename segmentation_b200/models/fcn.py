@@ -104,7 +104,8 @@ class _FCNExec(ExecBase):
             self.act[name] = torch.zeros(B, h, w, c, dtype=BF16, device=dev)
             return self.act[name]
 
-        buf('x', H, W, L['conv1'].cin_pad)
+        self.x4 = self.first_layer_x4(model, L['conv1'])
+        buf('x', H, W, 4 if self.x4 else L['conv1'].cin_pad)
         chans = [nk, nk * 2, nk * 4, nk * 8, nk * 8]
         h, w = H, W
         for i, c in enumerate(chans, 1):

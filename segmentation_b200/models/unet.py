@@ -146,10 +146,11 @@ class _UNetExec(ExecBase):
             return self.act[name]
 
         self.patch_l1 = isinstance(L['conv1_1'], E.PatchConvLayer)
+        self.x4 = self.first_layer_x4(model, L['conv1_1'])
         if self.patch_l1:
             buf('x', H - 2, W - 2, L['conv1_1'].cin_pad)
         else:
-            buf('x', H, W, L['conv1_1'].cin_pad)
+            buf('x', H, W, 4 if self.x4 else L['conv1_1'].cin_pad)
         # ---- encoder geometry
         h, w = H - 2, W - 2
         buf('conv1_1', h, w, nk)
@@ -201,7 +202,7 @@ class _UNetExec(ExecBase):
         if self.patch_l1:
             self.m.layers['conv1_1'].pack(self.x_f32, self.act['x'])
         else:
-            E.pack_input(self.x_f32, self.act['x'])
+            super(_UNetExec, self)._pack_now()
 
     # ------------------------------------------------------------- buffers
     def skip_view(self, j):
@@ -292,7 +293,7 @@ class _UNetExec(ExecBase):
                 self.m.layers['output'].forward(self.act['conv9_2'], self.logits, impl=self.m.impl,
                                                 out_f32=True)
             return super(_UNetExec, self).loss(with_grad)
-        E.fill_zero(self.loss_sum)
+        self.zero_loss()
         E.head1x1_xent(self.act['conv9_2'], self.m.layers['output'], self.mask_view(), self.logits,
                        self.loss_sum, self.g['conv9_2'])
 

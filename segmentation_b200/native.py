@@ -33,6 +33,14 @@ class SegConvDesc(ctypes.Structure):
                  'cin_pad', 'cout_pad', 'flags', 'impl')]
 
 
+class SegStageCtl(ctypes.Structure):
+    """seg_stage_ctl: per-step scalars written by the staging launch (include/segb200.h)."""
+    _fields_ = [('loss_sum', ctypes.c_void_p), ('host_ring', ctypes.c_void_p),
+                ('publish_step', ctypes.c_int32), ('lr_t', ctypes.c_float),
+                ('lr_t_dev', ctypes.c_void_p), ('step', ctypes.c_int32),
+                ('step_dev', ctypes.c_void_p)]
+
+
 _VP = ctypes.POINTER(SegView)
 _DP = ctypes.POINTER(SegConvDesc)
 _P = ctypes.c_void_p
@@ -76,6 +84,8 @@ SIGNATURES = {
     'seg_adam_multi': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P, _F, _F, _F, _F, _P],
     'seg_head1x1_xent': [_VP, _P, _I32, _P, _VP, _I32, _VP, _P, _VP, _P, _P, _P],
     'seg_pack_input': [_P, _I32, _VP, _P],
+    'seg_stage_input': [_P, _I32, _I32, _I32, _I32, _P, _VP, _P, _I32, _P,
+                        ctypes.POINTER(SegStageCtl), _P],
     'seg_pack_patches': [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _P],
     'seg_fill_zero': [_P, _I64, _P],
 }
@@ -144,6 +154,7 @@ def load():
                      ('SEGB200_DEEP_B', OPT_DEEP_B_RING),
                      ('SEGB200_HCONV_ROWSTAGE', OPT_HALO_ROWSTAGE),
                      ('SEGB200_TWGRAD_TRED', OPT_WGRAD_TENSOR_RED),
+                     ('SEGB200_FIRST_LAYER', OPT_FIRST_LAYER),
                      ('SEGB200_WGRAD_MIN_TILES', OPT_WGRAD_MIN_TILES)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
@@ -186,6 +197,7 @@ OPT_POOL_ROWS = 11     # row-mapped max-pool kernels (default on)
 OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep as shared memory allows
 OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weight stage
 OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (default on)
+OPT_FIRST_LAYER = 16   # first-layer kernel on the (R,G,B,1) staged input (default on)
 
 
 def set_option(key, value):
@@ -208,7 +220,7 @@ def call(name, *args):
 
 
 _FAMILY_OF_CALL = (('seg_maxpool', 'pool'), ('seg_adam', 'adam'), ('seg_head1x1', 'head'),
-                   ('seg_softmax', 'loss'), ('seg_pack', 'pack'), ('seg_bias_grad', 'bias_grad'),
+                   ('seg_softmax', 'loss'), ('seg_pack', 'pack'), ('seg_stage', 'pack'), ('seg_bias_grad', 'bias_grad'),
                    ('seg_batchnorm', 'batchnorm'), ('seg_dropout', 'dropout'),
                    ('seg_bilinear', 'bilinear'), ('seg_resize', 'resize'))
 _CONV_CALLS = ('seg_conv2d_', 'seg_deconv2d_')
@@ -216,12 +228,12 @@ _CONV_CALLS = ('seg_conv2d_', 'seg_deconv2d_')
 
 def kernel_family(call_name):
     """Kernel family a C-ABI call ran on: for the convolution family the tile kernel the
-    plan picked (tconv / hconv / igemm / twgrad / wgrad / stem, from seg_last_kernel_name;
+    plan picked (fconv / tconv / hconv / igemm / twgrad / wgrad, from seg_last_kernel_name;
     'simt' for the CUDA-core kernels), else a name derived from the entry point."""
     if call_name.startswith(_CONV_CALLS):
         import re
         k = load().seg_last_kernel_name().decode()
-        m = re.search(r'(tconv|hconv|igemm|twgrad|wgrad|stem\w*?)_kernel', k)
+        m = re.search(r'(fconv|tconv|hconv|igemm|twgrad|wgrad)_kernel', k)
         return m.group(1) if m else 'simt'
     for prefix, fam in _FAMILY_OF_CALL:
         if call_name.startswith(prefix):

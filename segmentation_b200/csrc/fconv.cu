@@ -21,7 +21,8 @@ static bool fconv_shape_ok(const seg_conv_desc& d, const seg_view& x, const seg_
          (d.cout_pad == 32 || d.cout_pad == 64) &&
          (reinterpret_cast<uintptr_t>(x.ptr) & 7) == 0 &&
          (int64_t)out.n * out.h * out.w < (int64_t)1 << 30 &&
-         out.h == x.h + d.pad_t + d.pad_b - 2 && out.w == x.w + d.pad_l + d.pad_r - 2;
+         out.h == x.h + d.pad_t + d.pad_b - 2 && out.w == x.w + d.pad_l + d.pad_r - 2 &&
+         out.w > 1 && out.h * out.w > 1;
 }
 
 template <int BN, bool WGRAD>
@@ -55,6 +56,17 @@ static void fill_params(FconvParams* P, const seg_conv_desc& d, const seg_view& 
   P->pad_t = d.pad_t; P->pad_l = d.pad_l;
   P->M_total = out.n * out.h * out.w;
   P->tiles = (P->M_total + 127) / 128;
+  // exact unsigned division of values < 2^31 by multiply-high + shift
+  auto magic = [](uint32_t d, uint32_t* mul, uint32_t* shr) {
+    if (d == 1) { *mul = 0xFFFFFFFFu; *shr = 0; return; }      // handled below: x*1
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    const uint32_t p = 31 + l;
+    *mul = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
+    *shr = p - 32;
+  };
+  magic((uint32_t)out.w, &P->div_wo_mul, &P->div_wo_shr);
+  magic((uint32_t)(out.h * out.w), &P->div_hw_mul, &P->div_hw_shr);
   P->cin_pad = d.cin_pad; P->cout_pad = d.cout_pad; P->cout = d.cout;
 }
 

@@ -4,20 +4,23 @@
 // models/fcn.py:110): arithmetic intensity 25 flop/B, i.e. HBM-bound, and with the input
 // padded to 16 channels for the generic spatial-tile kernels it was also TMA-row bound
 // (32-byte pixel rows) - 10 % of the U-Net step for 0.5 % of its FLOPs.  Here the input
-// lives in HBM as 4 bf16 per pixel, (R, G, B, 1): 8 bytes.  Builder warps gather the 3x3x4
-// patch of each of a tile's 128 consecutive output pixels (nine 8-byte loads, served by
-// L1/L2 after the first touch) straight into the canonical K-major SWIZZLE_128B operand
-// layout in shared memory - one 128-byte row per pixel, k-slot = r*12 + s*4 + c, 36 of 48
-// used (c = 3 is the constant 1, its weight rows are zero) - so the tile is ONE 128 x BN x 48
-// MMA group and nothing padded is ever read from or written to HBM.  Output pixels are
+// lives in HBM as 4 bf16 per pixel, (R, G, B, 1): 8 bytes.  Four builder warps gather the
+// 3x3x4 patch of each of a tile's 128 consecutive output pixels with nine 8-byte cp.async
+// copies per pixel (no register staging, so several tiles are in flight per CTA; L1/L2 serve
+// the 9-fold reuse) straight into the canonical K-major SWIZZLE_128B operand layout in
+// shared memory - one 128-byte row per pixel, k-slot = r*12 + s*4 + c (c = 3: weight rows
+// zero), slots 36 and 37 a constant 1 whose weight rows hold the bias split into two bf16
+// (hi + lo: the bias add costs the epilogue nothing) - so a tile is ONE 128 x BN x 48 MMA
+// group and nothing padded is ever read from or written to HBM.  Output pixels are
 // flattened over (n, y, x), so an output tile is 128 consecutive rows of the dense
-// [pixels][BN] activation: one TMA store box per epilogue warp.
+// [pixels][BN] activation: TMEM -> relu + bf16 (one cvt per pair) -> one TMA store box per
+// epilogue warp; eight epilogue warps, the two of a TMEM lane quadrant take tiles alternately.
 //
 // Weight gradient: the same patch tile read MN-major (pixels are the GEMM K axis) times the
 // dZ tile fetched by one TMA load, accumulated in TMEM over all of the CTA's tiles:
-// dW[k-slot][co] += sum_px patch[px][k-slot] * dZ[px][co].  The k-slot of the centre tap's
-// constant-1 channel accumulates sum_px dZ - the bias gradient - for free.  One red.add of
-// 27 x BN (+ BN) floats per CTA at the end.
+// dW[k-slot][co] += sum_px patch[px][k-slot] * dZ[px][co].  The constant-1 slot 36
+// accumulates sum_px dZ - the bias gradient - for free.  One red.add of 27 x BN (+ BN)
+// floats per CTA at the end.
 #pragma once
 #include "umma_conv.cuh"
 
@@ -27,8 +30,10 @@ struct FconvParams {
   const uint2* x4;          // [N][H][W] pixels of 4 bf16 (R, G, B, 1), dense
   int H, W, Ho, Wo;
   int pad_t, pad_l;
-  int M_total;              // N * Ho * Wo
+  int M_total;              // N * Ho * Wo (< 2^30)
   int tiles;                // ceil(M_total / 128)
+  uint32_t div_wo_mul, div_wo_shr;      // m / Wo and m / (Ho*Wo) as __umulhi(m, mul) >> shr
+  uint32_t div_hw_mul, div_hw_shr;
   const bf16* w;            // bf16 shadow [3][3][cin_pad][cout_pad]
   int cin_pad, cout_pad, cout;
   const float* bias;
@@ -37,9 +42,10 @@ struct FconvParams {
   float* db;                // nullable
 };
 
-constexpr int kFcThreads = 448;          // MMA issuer, TMA/alloc warp, 4 epilogue, 8 builder warps
+constexpr int kFcThreads = 448;          // MMA issuer, TMA/alloc warp, 8 epilogue, 4 builder warps
 constexpr int kFcStages = 4;
 constexpr int kFcABytes = 128 * 128;     // one patch tile: 128 pixels x 128-byte row
+constexpr int kFcRows = 37;              // accumulator rows of the weight gradient that are used
 
 template <int BN, bool WGRAD>
 struct FconvCfg {
@@ -48,7 +54,7 @@ struct FconvCfg {
   static constexpr int kWBytes = BN * 128;              // weights, K-major 128-byte rows (fwd)
   static constexpr int kStgBytes = 32 * rowB;           // one epilogue warp's store box (fwd)
   static constexpr int kOffBars = kFcStages * kFcABytes +
-                                  (WGRAD ? kFcStages * kZBytes : kWBytes + 8 * kStgBytes);
+                                  (WGRAD ? kFcStages * kZBytes : kWBytes + 16 * kStgBytes);
   static constexpr int kSmemBytes = kOffBars + 256 + 1024 /*base alignment*/;
   static constexpr int kTmemCols = WGRAD ? (BN < 32 ? 32 : BN) : 2 * BN;
 };
@@ -85,7 +91,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmIO);
     for (int i = 0; i < S; ++i) {
-      mbar_init(&a_full[i], 4);
+      mbar_init(&a_full[i], 128);
       mbar_init(&a_empty[i], 1);
       mbar_init(&z_full[i], 1);
     }
@@ -93,10 +99,17 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  // zero the patch ring once: the builders only ever write the first five 16-byte chunks of
-  // a row, the sixth (k-slots 40..47, read by the third k-step) must stay zero
+  // initialise the patch ring once: the builders only ever write the first 72 bytes of a row
+  // (k-slots 0..35); slots 36 and 37 are the constant 1, slots 38..47 (read by the third
+  // k-step) stay zero
   for (int i = threadIdx.x; i < S * kFcABytes / 16; i += kFcThreads)
     sts128(smem_u32(a_ring) + i * 16, make_uint4(0u, 0u, 0u, 0u));
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * 128; i += kFcThreads) {
+    const uint32_t row = smem_u32(a_ring) + (uint32_t)i * 128u;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + ((4u ^ ((uint32_t)i & 7u)) << 4) + 8u),
+                 "r"(0x3F803F80u) : "memory");
+  }
   pdl_wait();                 // everything above overlaps the previous kernel's tail
   if (!WGRAD) {
     // weights -> K-major SWIZZLE_128B rows: row = output channel, k-slot = r*12 + s*4 + c
@@ -104,8 +117,13 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
       const int co = idx >> 6, k = idx & 63;
       const int r = k / 12, rem = k - r * 12, s = rem >> 2, c = rem & 3;
       bf16 v = __float2bfloat16(0.f);
-      if (k < 36 && c < 3 && co < P.cout_pad)
+      if (k < 36 && c < 3 && co < P.cout_pad) {
         v = P.w[((int64_t)(r * 3 + s) * P.cin_pad + c) * P.cout_pad + co];
+      } else if ((k == 36 || k == 37) && (P.flags & SEG_EPI_BIAS) && co < P.cout) {
+        const float bv = __ldg(P.bias + co);
+        const bf16 hi = __float2bfloat16(bv);
+        v = k == 36 ? hi : __float2bfloat16(bv - __bfloat162float(hi));
+      }
       *reinterpret_cast<bf16*>(w_smem + co * 128 + (((k >> 3) ^ (co & 7)) << 4) + (k & 7) * 2) = v;
     }
   }
@@ -126,6 +144,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           const int s = i % S, as = i & 1;
           mbar_wait(&tempty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
           mbar_wait(&a_full[s], (uint32_t)(i / S) & 1u);
+          fence_proxy_async();           // the builders' cp.async writes -> tensor-core reads
           tc_fence_after();
           const uint32_t a0 = umma_desc_lo(smem_u32(a_ring + s * kFcABytes), 0);
 #pragma unroll
@@ -146,6 +165,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           const uint32_t ph = (uint32_t)(i / S) & 1u;
           mbar_wait(&a_full[s], ph);
           mbar_wait(&z_full[s], ph);
+          fence_proxy_async();
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_ring + s * kFcABytes);
           const uint32_t z_addr = smem_u32(z_ring + s * Cfg::kZBytes);
@@ -170,61 +190,66 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         tma_load_2d(&tmIO, &z_full[s], z_ring + s * Cfg::kZBytes, 0, tile * 128);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ============================== epilogue ==============================
     const int quad = warp & 3;                       // TMEM lanes [32*quad, +32)
+    const int half = (warp - 2) >> 2;                // which warp of the quadrant's pair
     if (!WGRAD) {
+      // warp (quad, half) takes the tiles i with (i & 1) == half: accumulator stage `half`
       constexpr int NCH = BN / 32;
-      float bl[NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        bl[c] = ((P.flags & SEG_EPI_BIAS) && 32 * c + lane < P.cout) ? __ldg(P.bias + 32 * c + lane)
-                                                                      : 0.f;
       uint8_t* my_stg = stg + (warp - 2) * 2 * Cfg::kStgBytes;
-      for (int i = 0; i < n_my; ++i) {
-        const int as = i & 1;
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN;
+      int j = 0;
+      for (int i = half; i < n_my; i += 2, ++j) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        uint8_t* box = my_stg + (i & 1) * Cfg::kStgBytes;
+        uint8_t* box = my_stg + (j & 1) * Cfg::kStgBytes;
         if (lane == 0) bulk_wait_group_read<1>();    // the store that last read this box
         __syncwarp();
-        mbar_wait(&tfull[as], (uint32_t)(i >> 1) & 1u);
+        mbar_wait(&tfull[half], (uint32_t)j & 1u);
         tc_fence_after();
         const uint32_t row = smem_u32(box) + (uint32_t)lane * rowB;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c * 32, r);
+          tmem_ld_32x32(tsrc + c * 32, r);
           tmem_ld_wait();
+          if (c == NCH - 1) {                        // the stage is drained: next tile may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[half]);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[e] = __uint_as_float(r[q * 8 + e]) + __shfl_sync(0xffffffffu, bl[c], q * 8 + e);
-              if (P.flags & SEG_EPI_RELU) v[e] = fmaxf(v[e], 0.f);
-            }
             uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
+            if (P.flags & SEG_EPI_RELU) {
+              o.x = pack_bf16x2_relu(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+              o.y = pack_bf16x2_relu(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+              o.z = pack_bf16x2_relu(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+              o.w = pack_bf16x2_relu(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+            } else {
+              o.x = pack_bf16x2(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+            }
             const uint32_t chunk = (uint32_t)(c * 4 + q);
             const uint32_t pos = BN == 32 ? (chunk ^ ((uint32_t)(lane >> 1) & 3u))
                                           : (chunk ^ ((uint32_t)lane & 7u));
             sts128(row + (pos << 4), o);
           }
         }
-        tc_fence_before();
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&tempty[as]);
           tma_store_2d(&tmIO, box, 0, tile * 128 + quad * 32);
           bulk_commit_group();
         }
       }
       if (lane == 0) bulk_wait_group<0>();
-    } else if (n_my > 0) {
+    } else if (n_my > 0 && half == 0) {
+      // partial sums of this CTA: accumulator rows 0..36 (k-slots + the constant-1 slot) ->
+      // shared memory [37][BN] fp32 (the patch ring is idle once every MMA has completed);
+      // the cluster-wide reduction below adds them to dW / db
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
       const int L = quad * 32 + lane;                // accumulator row = k-slot
@@ -233,77 +258,75 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, r);
         tmem_ld_wait();
-        if (L < 36) {
-          const int rr = L / 12, rem = L - rr * 12, ss = rem >> 2, ch = rem & 3;
-          if (ch < 3) {
-            float* dst = P.dw + ((int64_t)((rr * 3 + ss) * 3 + ch)) * P.cout + c * 32;
+        if (L < kFcRows) {
+          const uint32_t dst = smem_u32(a_ring) + (uint32_t)((L * BN + c * 32) * 4);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < P.cout) atomicAdd(dst + j, __uint_as_float(r[j]));
-          } else if (L == 19 && P.db != nullptr) {   // centre tap, constant-1 channel
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < P.cout) atomicAdd(P.db + c * 32 + j, __uint_as_float(r[j]));
-          }
+          for (int j = 0; j < 32; j += 4)
+            sts128(dst + j * 4, make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
         }
       }
     }
   } else {
     // ========================== patch-tile builders ==========================
-    // two groups of four warps take the CTA's tiles alternately; thread = one output pixel.
-    // The nine 8-byte loads of a group's NEXT tile are in flight while the current one is
-    // written to shared memory.
-    const int g = (warp - 6) >> 2;
-    const int t = ((warp - 6) & 3) * 32 + lane;
+    // four warps, thread = one output pixel of the tile: nine 8-byte cp.async copies (zero
+    // filled outside the image) straight to the pixel's swizzled operand row, then one
+    // deferred mbarrier arrival that fires when they have landed.  Nothing waits for data
+    // here, so the builders run up to kFcStages tiles ahead of the tensor core.
+    const int t = (warp - 10) * 32 + lane;
     const int HoWo = P.Ho * P.Wo;
-    auto load = [&](int i, uint2 (&v)[9]) {
+    const uint32_t x7 = (uint32_t)t & 7u;
+    for (int i = 0; i < n_my; ++i) {
       const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + t;
       const bool live = m < P.M_total;
-      const int mm = live ? m : 0;
-      const int n = mm / HoWo;
-      const int rem = mm - n * HoWo;
-      const int oy = rem / P.Wo;
-      const int ox = rem - oy * P.Wo;
+      const uint32_t mm = live ? (uint32_t)m : 0u;
+      const int n = (int)(__umulhi(mm, P.div_hw_mul) >> P.div_hw_shr);
+      const uint32_t rem = mm - (uint32_t)(n * HoWo);
+      const int oy = (int)(__umulhi(rem, P.div_wo_mul) >> P.div_wo_shr);
+      const int ox = (int)rem - oy * P.Wo;
       const int iy0 = oy - P.pad_t, ix0 = ox - P.pad_l;
+      const int s = i % S;
+      mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);
+      const uint32_t row = smem_u32(a_ring + s * kFcABytes) + (uint32_t)t * 128u;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int iy = iy0 + r;
         const bool yok = live && (unsigned)iy < (unsigned)P.H;
-        const uint2* rowp = P.x4 + ((int64_t)(n * P.H + iy) * P.W + ix0);
+        const int iyc = yok ? iy : 0;
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const bool ok = yok && (unsigned)(ix0 + s) < (unsigned)P.W;
-          v[r * 3 + s] = ok ? __ldg(rowp + s) : make_uint2(0u, 0u);
+        for (int sx = 0; sx < 3; ++sx) {
+          const int ix = ix0 + sx;
+          const bool ok = yok && (unsigned)ix < (unsigned)P.W;
+          const uint2* src = P.x4 + ((int64_t)(n * P.H + iyc) * P.W + (ok ? ix : 0));
+          const int q = r * 3 + sx;                  // 8-byte piece q of the row
+          cp_async_8(row + ((((uint32_t)q >> 1) ^ x7) << 4) + (uint32_t)(q & 1) * 8u, src,
+                     ok ? 8u : 0u);
         }
       }
-    };
-    uint2 cur[9], nxt[9];
-    int i = g;
-    if (i < n_my) load(i, cur);
-    for (; i < n_my; i += 2) {
-      const bool more = i + 2 < n_my;
-      if (more) load(i + 2, nxt);
-      const int s = i % S;
-      mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);
-      const uint32_t row = smem_u32(a_ring + s * kFcABytes) + (uint32_t)t * 128u;
-      const uint32_t x7 = (uint32_t)t & 7u;
-      sts128(row + ((0u ^ x7) << 4), make_uint4(cur[0].x, cur[0].y, cur[1].x, cur[1].y));
-      sts128(row + ((1u ^ x7) << 4), make_uint4(cur[2].x, cur[2].y, cur[3].x, cur[3].y));
-      sts128(row + ((2u ^ x7) << 4), make_uint4(cur[4].x, cur[4].y, cur[5].x, cur[5].y));
-      sts128(row + ((3u ^ x7) << 4), make_uint4(cur[6].x, cur[6].y, cur[7].x, cur[7].y));
-      sts128(row + ((4u ^ x7) << 4), make_uint4(cur[8].x, cur[8].y, 0u, 0u));
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[s]);
-      if (more) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) cur[q] = nxt[q];
-      }
+      cp_async_arrive_noinc(&a_full[s]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (WGRAD) {
+    // Every CTA adds its [37][BN] partial sum to dW / db: consecutive threads take
+    // consecutive elements, so a warp's red.add covers whole 128-byte lines (one row of the
+    // accumulator per thread - 28 lines per instruction - cost 20 us here; a DSMEM
+    // pre-reduction over clusters of 8 CTAs was slower still: cluster scheduling, 47 vs 29 us)
+    const uint32_t base = smem_u32(a_ring);
+    for (uint32_t e = threadIdx.x; e < (uint32_t)(kFcRows * BN); e += kFcThreads) {
+      const float v = lds32f(base + e * 4u);
+      const int L = (int)(e / BN), co = (int)(e % BN);
+      if (co < P.cout) {
+        if (L < 36) {
+          const int rr = L / 12, rem = L - rr * 12, ss = rem >> 2, ch = rem & 3;
+          if (ch < 3) atomicAdd(P.dw + ((int64_t)((rr * 3 + ss) * 3 + ch)) * P.cout + co, v);
+        } else if (P.db != nullptr) {                // the constant-1 slot: sum of dZ
+          atomicAdd(P.db + co, v);
+        }
+      }
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);

@@ -80,6 +80,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------
+// cp.async (LDGSTS): 8-byte global -> shared copy without register staging; src_bytes = 0
+// writes zeros.  cp_async_arrive_noinc: the mbarrier receives one arrival (counted against
+// its expected count) once all prior cp.async of the executing thread have landed.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_8(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// relu + round-to-nearest-even pack of two floats into bf16x2 (lo in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// ----------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

@@ -60,7 +60,7 @@ def main():
     ks.sort(key=lambda e: e['ts'])
     os.remove(trace)
     # split into steps at the pack kernel (first kernel of a step)
-    starts = [i for i, e in enumerate(ks) if 'pack_input' in e['name']]
+    starts = [i for i, e in enumerate(ks) if 'pack_input' in e['name'] or 'stage_input' in e['name']]
     if len(starts) < 5:
         print('could not find step boundaries (%d pack kernels)' % len(starts))
         starts = [0, len(ks)]

@@ -1185,6 +1185,7 @@ struct StageArgs {
   uint8_t* mask_dst;
   seg_stage_ctl ctl;
   int has_ctl;
+  int vec4;
 };
 
 __global__ void stage_input4_kernel(const StageArgs A) {
@@ -1206,6 +1207,30 @@ __global__ void stage_input4_kernel(const StageArgs A) {
   }
   const int64_t pixels = (int64_t)A.n * A.H * A.W;
   const float one = 1.0f;
+  if (A.vec4) {
+    // dense fp32 RGB, no crop: four pixels per thread = three 16-byte loads, two 16-byte
+    // stores (+ 4 mask bytes)
+    const float4* x4 = reinterpret_cast<const float4*>(A.x);
+    GRID_STRIDE(q, pixels / 4) {
+      const float4 a = __ldg(x4 + 3 * q), b = __ldg(x4 + 3 * q + 1), c = __ldg(x4 + 3 * q + 2);
+      uint4* dst = reinterpret_cast<uint4*>(A.y + 4 * q);
+      dst[0] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, one), pack_bf16x2(a.w, b.x),
+                          pack_bf16x2(b.y, one));
+      dst[1] = make_uint4(pack_bf16x2(b.z, b.w), pack_bf16x2(c.x, one), pack_bf16x2(c.y, c.z),
+                          pack_bf16x2(c.w, one));
+      if (A.mask_src) {
+        uint32_t mk = __ldg(reinterpret_cast<const uint32_t*>(A.mask_src) + q);
+        if (A.mask_kind) {
+          uint32_t o = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o |= (uint32_t)(((mk >> (8 * k)) & 0xffu) == 255u) << (8 * k);
+          mk = o;
+        }
+        reinterpret_cast<uint32_t*>(A.mask_dst)[q] = mk;
+      }
+    }
+    return;
+  }
   GRID_STRIDE(m, pixels) {
     const int xx = (int)(m % A.W);
     const int64_t t = m / A.W;
@@ -1328,19 +1353,33 @@ __global__ void channel_sum_vec8_kernel(seg_view a, float* out0, float* out1) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
   if (pl < lanes) {
-    for (int64_t m = (int64_t)blockIdx.x * lanes + pl; m < pixels; m += (int64_t)gridDim.x * lanes) {
-      const int xx = m % a.w;
-      const int64_t t = m / a.w;
-      const int yy = t % a.h;
-      const int n = t / a.h;
-      const uint4 u = *reinterpret_cast<const uint4*>(view_at(a, n, yy, xx) + g * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    // four pixels per trip, their 16-byte loads issued before any is consumed: these are
+    // small tensors (a few MB), so the kernel is bound by load latency, not bandwidth
+    const int64_t step = (int64_t)gridDim.x * lanes;
+    for (int64_t m0 = (int64_t)blockIdx.x * lanes + pl; m0 < pixels; m0 += 4 * step) {
+      uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
-        s0[2 * j] += lo;
-        s0[2 * j + 1] += hi;
-        if (MODE == 0) { s1[2 * j] += lo * lo; s1[2 * j + 1] += hi * hi; }
+      for (int k = 0; k < 4; ++k) {
+        const int64_t m = m0 + k * step;
+        u[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (m < pixels) {
+          const int xx = m % a.w;
+          const int64_t t = m / a.w;
+          const int yy = t % a.h;
+          const int n = t / a.h;
+          u[k] = *reinterpret_cast<const uint4*>(view_at(a, n, yy, xx) + g * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+          s0[2 * j] += lo;
+          s0[2 * j + 1] += hi;
+          if (MODE == 0) { s1[2 * j] += lo * lo; s1[2 * j + 1] += hi * hi; }
+        }
       }
     }
   }
@@ -1729,8 +1768,8 @@ static int launch_channel_reduce(const seg_view& a, const seg_view& b, const flo
   const int block = 256;
   if ((mode == 0 || mode == 2) && vec8_ok(a) && a.c / 8 <= block) {
     const int lanes_v = block / (a.c / 8);
-    int64_t gv = ceil_div64(pixels, (int64_t)lanes_v * 8);
-    const int64_t capv = (int64_t)num_sms() * 4;
+    int64_t gv = ceil_div64(pixels, (int64_t)lanes_v * 4);
+    const int64_t capv = (int64_t)num_sms() * 8;
     if (gv > capv) gv = capv;
     if (gv < 1) gv = 1;
     const size_t shb = (size_t)2 * block * 8 * sizeof(float);
@@ -1973,8 +2012,13 @@ SEG_API int32_t seg_stage_input(const void* x, int32_t x_kind, int32_t c, int32_
   A.mask_src = mask_src; A.mask_kind = mask_kind; A.mask_dst = mask_dst;
   if (ctl) { A.ctl = *ctl; A.has_ctl = 1; }
   const int64_t pixels = (int64_t)A.n * A.H * A.W;
-  SEG_CHECK_CUDA(launch_k(stage_input4_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)0,
-                          (cudaStream_t)stream, A));
+  A.vec4 = x_kind == 0 && c == 3 && !crop_yx && pixels % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(y4->ptr) & 15) == 0 &&
+           (!mask_src || ((reinterpret_cast<uintptr_t>(mask_src) & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(mask_dst) & 3) == 0));
+  SEG_CHECK_CUDA(launch_k(stage_input4_kernel, dim3(grid_for(A.vec4 ? pixels / 4 : pixels, 256)),
+                          dim3(256), (size_t)0, (cudaStream_t)stream, A));
   return SEG_OK;
 }
 

@@ -36,14 +36,22 @@ def _x4(x):
     return y4
 
 
-def test_stage_input_fp32_bit_exact(cuda):
+@pytest.mark.parametrize('shape', [(3, 37, 29), (2, 16, 18)], ids=['scalar', 'vec4'])
+def test_stage_input_fp32_bit_exact(cuda, shape):
+    """fp32 -> (R,G,B,1) bf16 and the mask copy: the one-pixel-per-thread path (pixel count
+    not a multiple of 4) and the four-pixels-per-thread path."""
     g = _gen(0)
-    x = torch.rand(3, 37, 29, 3, generator=g)
-    y4 = _x4(x)
+    B, H, W = shape
+    x = torch.rand(B, H, W, 3, generator=g)
+    m = (torch.rand(B, H, W, 1, generator=g) * 21).to(torch.uint8)
+    y4 = torch.zeros(B, H, W, 4, dtype=BF16, device='cuda')
+    m_out = torch.full((B, H, W, 1), 99, dtype=torch.uint8, device='cuda')
+    E.stage_input(x.cuda(), y4, mask_src=m.cuda(), mask_dst=m_out)
     sync()
-    ref = torch.ones(3, 37, 29, 4, dtype=BF16)
+    ref = torch.ones(B, H, W, 4, dtype=BF16)
     ref[..., :3] = x.to(BF16)
     assert torch.equal(y4.cpu(), ref)
+    assert torch.equal(m_out.cpu(), m)
 
 
 def test_stage_input_u8_crop_mask_and_scalars(cuda):

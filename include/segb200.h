@@ -133,6 +133,30 @@ SEG_API int32_t seg_conv2d_dgrad_slice(const seg_conv_desc* d, const seg_view* d
 SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* x2,
                          const seg_view* dz, float* dw, float* db, void* stream);
 
+/* ---- first layer fused with the max-pool that follows it (models/unet.py:111-120:
+ * conv1_1 -> pool1; models/fcn.py:110-117: conv1 -> pool1).  x4 is the (R,G,B,1) input of
+ * seg_stage_input; 3x3, stride 1, cout_pad == 32, even output grid.
+ * fwd: pooled = maxpool2x2/2(relu(conv(x4) + bias)) with the uint8 window slots of
+ *   seg_maxpool_fwd in `argmax`, ONE launch; the full-resolution activation is written only
+ *   into y_win (nullable), a view of its window whose top-left output pixel is
+ *   (win_y0, win_x0) - U-Net's conv1_1 is read again only by conv1_2 on the crop that feeds
+ *   the last skip connection (models/unet.py:118-120,159-161), FCN's conv1 never.
+ * wgrad: dw, db += gradients for dz = relu_mask(pool_grad(dpool) + add), i.e.
+ *   seg_maxpool_bwd_y followed by seg_conv2d_wgrad without the full-resolution gradient ever
+ *   existing: the pool backward is evaluated inside the operand producer.  `add` (nullable):
+ *   gradient arriving from a second consumer inside the window (same geometry as y_win, which
+ *   supplies the ReLU mask there); elsewhere the mask comes from `pooled` (the forward pool
+ *   output).  Both return SEG_E_UNSUPPORTED for other shapes (use the unfused entries). */
+SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, const void* w_bf16,
+                                    const float* bias, const seg_view* y_win, int32_t win_y0,
+                                    int32_t win_x0, const seg_view* pooled, uint8_t* argmax,
+                                    void* stream);
+SEG_API int32_t seg_conv2d_pool_wgrad(const seg_conv_desc* d, const seg_view* x4,
+                                      const seg_view* dpool, const uint8_t* argmax,
+                                      const seg_view* pooled, const seg_view* add,
+                                      const seg_view* y_win, int32_t win_y0, int32_t win_x0,
+                                      float* dw, float* db, void* stream);
+
 /* ---- transposed convolution: replaces Conv2DBackpropInput (+BiasAdd+Relu) and
  * its gradients for slim.convolution2d_transpose (models/unet.py:138,145,152,159;
  * models/deconvolution.py:150,156,159,166).  Weights HWOI [kh][kw][cout][cin].

@@ -30,6 +30,14 @@ int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
                       const seg_view& dx, const seg_view* mask, cudaStream_t st);
 int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
                       cudaStream_t st);
+// fconv.cu
+int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
+                   const seg_view* y_win, int win_y0, int win_x0, const seg_view& pooled,
+                   uint8_t* argmax, cudaStream_t st);
+int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dpool,
+                     const uint8_t* argmax, const seg_view& pooled, const seg_view* add,
+                     const seg_view* y_win, int win_y0, int win_x0, float* dw, float* db,
+                     cudaStream_t st);
 
 
 void hconv_set_row_align(int a);
@@ -199,6 +207,38 @@ SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, cons
   P.kh = d->kh; P.kw = d->kw; P.stride = d->stride; P.pad_t = d->pad_t; P.pad_l = d->pad_l;
   P.BC = d->cin; P.SC = d->cout;
   return simt_wgrad(P, st);
+}
+
+SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, const void* w_bf16,
+                                    const float* bias, const seg_view* y_win, int32_t win_y0,
+                                    int32_t win_x0, const seg_view* pooled, uint8_t* argmax,
+                                    void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x4 && w_bf16 && pooled && argmax, SEG_E_BAD_SHAPE,
+              "conv2d_pool_fwd: bad argument");
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "conv2d_pool_fwd: bias missing");
+  const int rc = fconv_pool_fwd(*d, *x4, w_bf16, bias, y_win, win_y0, win_x0, *pooled, argmax,
+                                (cudaStream_t)stream);
+  SEG_REQUIRE(rc != SEG_E_UNSUPPORTED, SEG_E_UNSUPPORTED,
+              "conv2d_pool_fwd: needs the first-layer shape (3x3 stride 1 on the (R,G,B,1) input, "
+              "32 padded output channels), an even output grid and dense 16-byte aligned "
+              "pooled / argmax tensors; use seg_conv2d_fwd + seg_maxpool_fwd otherwise");
+  return rc;
+}
+
+SEG_API int32_t seg_conv2d_pool_wgrad(const seg_conv_desc* d, const seg_view* x4,
+                                      const seg_view* dpool, const uint8_t* argmax,
+                                      const seg_view* pooled, const seg_view* add,
+                                      const seg_view* y_win, int32_t win_y0, int32_t win_x0,
+                                      float* dw, float* db, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x4 && dpool && argmax && pooled && dw, SEG_E_BAD_SHAPE,
+              "conv2d_pool_wgrad: bad argument");
+  const int rc = fconv_pool_wgrad(*d, *x4, *dpool, argmax, *pooled, add, y_win, win_y0, win_x0, dw,
+                                  db, (cudaStream_t)stream);
+  SEG_REQUIRE(rc != SEG_E_UNSUPPORTED, SEG_E_UNSUPPORTED,
+              "conv2d_pool_wgrad: needs the shape of seg_conv2d_pool_fwd (and, with `add`, a "
+              "window view of the activation of the same size); use seg_maxpool_bwd_y + "
+              "seg_conv2d_wgrad otherwise");
+  return rc;
 }
 
 SEG_API int32_t seg_deconv2d_fwd(const seg_conv_desc* d, const seg_view* x, const void* w_bf16,

@@ -1,26 +1,41 @@
-// First-layer tcgen05 convolution (3x3, stride 1, RGB input): forward and weight gradient.
+// First-layer tcgen05 convolution (3x3, stride 1, RGB input): forward and weight gradient,
+// each optionally fused with the 2x2/2 max-pool that follows the layer.
 //
 // The first layer of every reference graph convolves 3 input channels (models/unet.py:111,
 // models/fcn.py:110): arithmetic intensity 25 flop/B, i.e. HBM-bound, and with the input
 // padded to 16 channels for the generic spatial-tile kernels it was also TMA-row bound
 // (32-byte pixel rows) - 10 % of the U-Net step for 0.5 % of its FLOPs.  Here the input
 // lives in HBM as 4 bf16 per pixel, (R, G, B, 1): 8 bytes.  Four builder warps gather the
-// 3x3x4 patch of each of a tile's 128 consecutive output pixels with nine 8-byte cp.async
-// copies per pixel (no register staging, so several tiles are in flight per CTA; L1/L2 serve
-// the 9-fold reuse) straight into the canonical K-major SWIZZLE_128B operand layout in
-// shared memory - one 128-byte row per pixel, k-slot = r*12 + s*4 + c (c = 3: weight rows
-// zero), slots 36 and 37 a constant 1 whose weight rows hold the bias split into two bf16
-// (hi + lo: the bias add costs the epilogue nothing) - so a tile is ONE 128 x BN x 48 MMA
-// group and nothing padded is ever read from or written to HBM.  Output pixels are
-// flattened over (n, y, x), so an output tile is 128 consecutive rows of the dense
-// [pixels][BN] activation: TMEM -> relu + bf16 (one cvt per pair) -> one TMA store box per
-// epilogue warp; eight epilogue warps, the two of a TMEM lane quadrant take tiles alternately.
+// 3x3x4 patch of each of a tile's 128 output pixels with nine 8-byte cp.async copies per
+// pixel (no register staging, so several tiles are in flight per CTA; L1/L2 serve the
+// 9-fold reuse) straight into the canonical K-major SWIZZLE_128B operand layout in shared
+// memory - one 128-byte row per pixel, k-slot = r*12 + s*4 + c (c = 3: weight rows zero),
+// slots 36 and 37 a constant 1 whose weight rows hold the bias split into two bf16 (hi + lo:
+// the bias add costs the epilogue nothing) - so a tile is ONE 128 x BN x 48 MMA group and
+// nothing padded is ever read from or written to HBM.
+//
+// Plain forward: a tile is 128 consecutive output pixels (flattened over n, y, x), i.e. 128
+// consecutive rows of the dense [pixels][BN] activation: TMEM -> relu + bf16 (one cvt per
+// pair) -> one TMA store box per epilogue warp; eight epilogue warps, the two of a TMEM lane
+// quadrant take tiles alternately.
+//
+// Forward + max-pool (POOL; models/unet.py:111-120, models/fcn.py:110-117): a tile is two
+// output rows x 64 columns, pixel (2Y+dy, 64tx + 2xp + dx) in accumulator row
+// 4xp + 2dy + dx, so a 2x2 pool window is four adjacent TMEM lanes: two butterfly shuffles
+// on the packed bf16 pairs give every lane its window's maximum and the slot of the first
+// maximum (row-major scan order, as seg_maxpool_fwd), and the four lanes write the pooled
+// pixel's four 16-byte chunks (+ two 16-byte chunks of uint8 slots).  The full-resolution
+// activation is written only inside a caller-given window (U-Net: the crop conv1_2 reads;
+// FCN: nothing) - 66 MB of stores and the pool kernel's 66 MB of loads disappear.
 //
 // Weight gradient: the same patch tile read MN-major (pixels are the GEMM K axis) times the
-// dZ tile fetched by one TMA load, accumulated in TMEM over all of the CTA's tiles:
-// dW[k-slot][co] += sum_px patch[px][k-slot] * dZ[px][co].  The constant-1 slot 36
-// accumulates sum_px dZ - the bias gradient - for free.  One red.add of 27 x BN (+ BN)
-// floats per CTA at the end.
+// dZ tile, accumulated in TMEM over all of the CTA's tiles:
+// dW[k-slot][co] += sum_px patch[px][k-slot] * dZ[px][co]; the constant-1 slot 36
+// accumulates sum_px dZ - the bias gradient - for free.  One coalesced red.add of 28 x BN
+// floats per CTA at the end.  The dZ tile is one TMA load, or (POOL) is BUILT in shared
+// memory from the pooled gradient, the argmax slots and the ReLU mask - the max-pool
+// backward (seg_maxpool_bwd_y semantics, skip-gradient window included) fused into the
+// operand producer, so the full-resolution gradient never exists in HBM.
 #pragma once
 #include "umma_conv.cuh"
 
@@ -31,41 +46,80 @@ struct FconvParams {
   int H, W, Ho, Wo;
   int pad_t, pad_l;
   int M_total;              // N * Ho * Wo (< 2^30)
-  int tiles;                // ceil(M_total / 128)
-  uint32_t div_wo_mul, div_wo_shr;      // m / Wo and m / (Ho*Wo) as __umulhi(m, mul) >> shr
-  uint32_t div_hw_mul, div_hw_shr;
+  int tiles;
+  // exact division by multiply-high + shift (values < 2^31); mul == 0: divisor 1.
+  //   plain: a = Wo, b = Ho*Wo (pixel index -> n, oy, ox)
+  //   POOL:  a = tiles_x, b = Hp*tiles_x (tile index -> n, Y, tx)
+  uint32_t div_a, div_a_mul, div_a_shr;
+  uint32_t div_b, div_b_mul, div_b_shr;
   const bf16* w;            // bf16 shadow [3][3][cin_pad][cout_pad]
   int cin_pad, cout_pad, cout;
   const float* bias;
   int flags;
   float* dw;                // fp32 master layout [3][3][3][cout]
   float* db;                // nullable
+  // ---- POOL variants (BN = 32)
+  int Hp, Wp;               // pooled grid = Ho/2 x Wo/2
+  bf16* y;                  // full-resolution activation: written inside the window (forward),
+  int64_t y_sn, y_sh, y_sw; //   ReLU-mask source inside the window (weight gradient)
+  int win_y0, win_x0, win_y1, win_x1;   // the window, output coordinates [y0,y1) x [x0,x1)
+  bf16* pooled;             // dense [N][Hp][Wp][BN]: pool output (forward) / mask source (wgrad)
+  uint8_t* amax;            // dense [N][Hp][Wp][BN] window slots
+  const bf16* dpool;        // dense [N][Hp][Wp][BN] gradient w.r.t. the pool output
+  const bf16* add;          // nullable: gradient arriving inside the window, positioned at its
+  int64_t add_sn, add_sh, add_sw;       //   corner (seg_maxpool_bwd's `add`)
 };
 
-constexpr int kFcThreads = 448;          // MMA issuer, TMA/alloc warp, 8 epilogue, 4 builder warps
-constexpr int kFcStages = 4;
+constexpr int kFcThreads = 448;          // MMA issuer, alloc/TMA warp, 8 epilogue, 4 builder warps
 constexpr int kFcABytes = 128 * 128;     // one patch tile: 128 pixels x 128-byte row
 constexpr int kFcRows = 37;              // accumulator rows of the weight gradient that are used
+constexpr int kFcRawDepth = 4;           // pooled weight gradient: raw tiles in flight per thread
+constexpr int kFcRawBytes = 128 * 48;    // dpool 16 B + pooled 16 B + slots 8 B (+8) per thread
 
-template <int BN, bool WGRAD>
+template <int BN, bool WGRAD, bool POOL>
 struct FconvCfg {
+  static constexpr int S = (WGRAD && POOL) ? 3 : 4;     // pipeline stages
   static constexpr int rowB = BN * 2;
   static constexpr int kZBytes = 128 * rowB;            // one dZ tile (wgrad)
   static constexpr int kWBytes = BN * 128;              // weights, K-major 128-byte rows (fwd)
   static constexpr int kStgBytes = 32 * rowB;           // one epilogue warp's store box (fwd)
-  static constexpr int kOffBars = kFcStages * kFcABytes +
-                                  (WGRAD ? kFcStages * kZBytes : kWBytes + 16 * kStgBytes);
+  static constexpr int kOffRaw = S * kFcABytes + S * kZBytes;
+  static constexpr int kOffBars =
+      S * kFcABytes + (WGRAD ? S * kZBytes + (POOL ? kFcRawDepth * kFcRawBytes : 0)
+                             : kWBytes + (POOL ? 0 : 16 * kStgBytes));
   static constexpr int kSmemBytes = kOffBars + 256 + 1024 /*base alignment*/;
   static constexpr int kTmemCols = WGRAD ? (BN < 32 ? 32 : BN) : 2 * BN;
 };
 
-template <int BN, bool WGRAD>
+__device__ __forceinline__ uint32_t fc_div(uint32_t x, uint32_t mul, uint32_t shr) {
+  return mul ? (__umulhi(x, mul) >> shr) : x;
+}
+// per-half (a > b) ? 0xffff : 0 on packed bf16 pairs
+__device__ __forceinline__ uint32_t bf16x2_gt_mask(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ void cp_async_16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc),
+               "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int BN, bool WGRAD, bool POOL>
 __global__ void __launch_bounds__(kFcThreads, 2)
 fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
-  using Cfg = FconvCfg<BN, WGRAD>;
-  constexpr int S = kFcStages;
+  using Cfg = FconvCfg<BN, WGRAD, POOL>;
+  constexpr int S = Cfg::S;
   constexpr int rowB = Cfg::rowB;
   static_assert(BN == 32 || BN == 64, "first-layer kernel: 32 or 64 output channels per tile");
+  static_assert(!POOL || BN == 32, "pooled variants: 32 output channels");
 
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -73,8 +127,9 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
   uint8_t* z_ring = smem + S * kFcABytes;               // wgrad
+  uint8_t* raw_ring = smem + Cfg::kOffRaw;              // wgrad + pool
   uint8_t* w_smem = smem + S * kFcABytes;               // fwd
-  uint8_t* stg = w_smem + Cfg::kWBytes;                 // fwd
+  uint8_t* stg = w_smem + Cfg::kWBytes;                 // fwd (plain)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + S;
@@ -87,13 +142,21 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
   const int lane = threadIdx.x & 31;
   const int n_my = ((int)blockIdx.x < P.tiles)
                        ? (P.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+  // POOL: tile -> (image, pooled row, column block)
+  auto tile_pos = [&](int tile, int& n, int& Y, int& tx) {
+    n = (int)fc_div((uint32_t)tile, P.div_b_mul, P.div_b_shr);
+    const uint32_t rem = (uint32_t)tile - (uint32_t)n * P.div_b;
+    Y = (int)fc_div(rem, P.div_a_mul, P.div_a_shr);
+    tx = (int)(rem - (uint32_t)Y * P.div_a);
+  };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmIO);
+    if (!POOL) tma_prefetch_desc(&tmIO);
     for (int i = 0; i < S; ++i) {
       mbar_init(&a_full[i], 128);
       mbar_init(&a_empty[i], 1);
-      mbar_init(&z_full[i], 1);
+      mbar_init(&z_full[i], POOL ? 4 : 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_mbar_init();
@@ -180,28 +243,27 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
       }
     }
   } else if (warp == 1) {
-    // ======================= dZ tile producer (wgrad) =======================
-    if (WGRAD && elect_one()) {
+    // ==================== dZ tile producer (plain wgrad: TMA) ====================
+    if (WGRAD && !POOL && elect_one()) {
       for (int i = 0; i < n_my; ++i) {
         const int s = i % S;
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);
         mbar_expect_tx(&z_full[s], Cfg::kZBytes);
-        tma_load_2d(&tmIO, &z_full[s], z_ring + s * Cfg::kZBytes, 0, tile * 128);
+        tma_load_2d(&tmIO, &z_full[s], z_ring + s * Cfg::kZBytes, 0, tile_of(i) * 128);
       }
     }
   } else if (warp < 10) {
-    // ============================== epilogue ==============================
     const int quad = warp & 3;                       // TMEM lanes [32*quad, +32)
     const int half = (warp - 2) >> 2;                // which warp of the quadrant's pair
-    if (!WGRAD) {
+    if (!WGRAD && !POOL) {
+      // ====================== epilogue: plain forward ======================
       // warp (quad, half) takes the tiles i with (i & 1) == half: accumulator stage `half`
       constexpr int NCH = BN / 32;
       uint8_t* my_stg = stg + (warp - 2) * 2 * Cfg::kStgBytes;
       const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN;
       int j = 0;
       for (int i = half; i < n_my; i += 2, ++j) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int tile = tile_of(i);
         uint8_t* box = my_stg + (j & 1) * Cfg::kStgBytes;
         if (lane == 0) bulk_wait_group_read<1>();    // the store that last read this box
         __syncwarp();
@@ -246,10 +308,172 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         }
       }
       if (lane == 0) bulk_wait_group<0>();
-    } else if (n_my > 0 && half == 0) {
+    } else if (!WGRAD && POOL) {
+      // ================= epilogue: forward + 2x2 max-pool =================
+      // lane = accumulator row 4*xp + 2*dy + dx of its quadrant: 8 pool windows per warp
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN;
+      const bool dx = (lane & 1) != 0, dy = (lane & 2) != 0;
+      const int k = lane & 3;
+      const int xp = quad * 8 + (lane >> 2);
+      int j = 0;
+      for (int i = half; i < n_my; i += 2, ++j) {
+        int n, Y, tx;
+        tile_pos(tile_of(i), n, Y, tx);
+        mbar_wait(&tfull[half], (uint32_t)j & 1u);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(tsrc, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[half]);
+        uint32_t p[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          p[w] = (P.flags & SEG_EPI_RELU)
+                     ? pack_bf16x2_relu(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]))
+                     : pack_bf16x2(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
+        const int oy = 2 * Y + (dy ? 1 : 0);
+        const int ox = 64 * tx + 2 * xp + (dx ? 1 : 0);
+        if (ox < P.Wo && oy >= P.win_y0 && oy < P.win_y1 && ox >= P.win_x0 && ox < P.win_x1) {
+          uint4* dst = reinterpret_cast<uint4*>(P.y + n * P.y_sn + oy * P.y_sh + ox * P.y_sw);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        }
+        // window maximum and slot of its first maximum (scan order (0,0),(0,1),(1,0),(1,1):
+        // a later element wins only if strictly greater); every lane ends with both
+        uint32_t sb[8];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const uint32_t a = p[w];
+          const uint32_t b = __shfl_xor_sync(0xffffffffu, a, 1);
+          const uint32_t left = dx ? b : a, right = dx ? a : b;
+          const uint32_t g1 = bf16x2_gt_mask(right, left);
+          const uint32_t m01 = (right & g1) | (left & ~g1);
+          const uint32_t c2 = __shfl_xor_sync(0xffffffffu, m01, 2);
+          const uint32_t g1o = __shfl_xor_sync(0xffffffffu, g1, 2);
+          const uint32_t top = dy ? c2 : m01, bot = dy ? m01 : c2;
+          const uint32_t itop = dy ? g1o : g1, ibot = dy ? g1 : g1o;
+          const uint32_t g2 = bf16x2_gt_mask(bot, top);
+          p[w] = (bot & g2) | (top & ~g2);
+          const uint32_t i0 = (ibot & g2) | (itop & ~g2);
+          const uint32_t sl = (i0 & 0x00010001u) | (g2 & 0x00020002u);    // slot per 16-bit half
+          const uint32_t two = (sl & 0xffu) | ((sl >> 8) & 0xff00u);      // -> two bytes
+          if (w & 1) sb[w >> 1] |= two << 16; else sb[w >> 1] = two;
+        }
+        const int col = 32 * tx + xp;
+        if (col < P.Wp) {
+          const int64_t pix = ((int64_t)(n * P.Hp + Y) * P.Wp + col) * BN;
+          // lane k of the window writes 16-byte chunk k of the pooled pixel
+          uint4 o;
+          o.x = k == 0 ? p[0] : k == 1 ? p[4] : k == 2 ? p[8] : p[12];
+          o.y = k == 0 ? p[1] : k == 1 ? p[5] : k == 2 ? p[9] : p[13];
+          o.z = k == 0 ? p[2] : k == 1 ? p[6] : k == 2 ? p[10] : p[14];
+          o.w = k == 0 ? p[3] : k == 1 ? p[7] : k == 2 ? p[11] : p[15];
+          *reinterpret_cast<uint4*>(P.pooled + pix + 8 * k) = o;
+          if (k < 2) {
+            uint4 s4;
+            s4.x = k == 0 ? sb[0] : sb[4];
+            s4.y = k == 0 ? sb[1] : sb[5];
+            s4.z = k == 0 ? sb[2] : sb[6];
+            s4.w = k == 0 ? sb[3] : sb[7];
+            *reinterpret_cast<uint4*>(P.amax + pix + 16 * k) = s4;
+          }
+        }
+      }
+    } else if (WGRAD && POOL && half == 1) {
+      // ============ dZ tile builders: max-pool backward into the operand ============
+      // thread = (pool window xp, 16-byte chunk q of its 32 channels): the pooled gradient,
+      // the window slots and the pooled activation (ReLU mask: the input at the argmax IS
+      // the pooled value) arrive through per-thread cp.async groups kFcRawDepth tiles ahead;
+      // the thread expands them to its four pixels' 16-byte chunks of the dZ tile (rows of
+      // 64 bytes, SWIZZLE_64B, the MN-major B operand).  Inside the skip-gradient window the
+      // arriving gradient is added and the mask comes from the activation itself.
+      const int u = (warp - 6) * 32 + lane;
+      const int xp = u >> 2, q = u & 3;
+      const uint32_t raw0 = smem_u32(raw_ring) + (uint32_t)u * 48u;
+      auto fetch = [&](int i) {
+        if (i < n_my) {
+          int n, Y, tx;
+          tile_pos(tile_of(i), n, Y, tx);
+          const int col = 32 * tx + xp;
+          const bool live = col < P.Wp;
+          const int64_t idx = ((int64_t)(n * P.Hp + Y) * P.Wp + (live ? col : 0)) * BN + 8 * q;
+          const uint32_t dst = raw0 + (uint32_t)(i % kFcRawDepth) * kFcRawBytes;
+          cp_async_16(dst, P.dpool + idx, live ? 16u : 0u);
+          cp_async_16(dst + 16, P.pooled + idx, live ? 16u : 0u);
+          cp_async_8(dst + 32, P.amax + idx, live ? 8u : 0u);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int i = 0; i < kFcRawDepth; ++i) fetch(i);
+      for (int i = 0; i < n_my; ++i) {
+        cp_async_wait<kFcRawDepth - 1>();
+        const uint32_t src = raw0 + (uint32_t)(i % kFcRawDepth) * kFcRawBytes;
+        const uint4 dp = lds128(src), pl = lds128(src + 16);
+        uint2 am;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(am.x), "=r"(am.y) : "r"(src + 32)
+                     : "memory");
+        int n, Y, tx;
+        tile_pos(tile_of(i), n, Y, tx);
+        const uint32_t dpw[4] = {dp.x, dp.y, dp.z, dp.w};
+        const uint32_t plw[4] = {pl.x, pl.y, pl.z, pl.w};
+        // ReLU mask from the pooled activation, per 16-bit half
+        uint32_t pos[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) pos[w] = bf16x2_gt_mask(plw[w], 0u);
+        const int s = i % S;
+        mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);
+        const uint32_t zt = smem_u32(z_ring + s * Cfg::kZBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // slot == kk, per byte -> per 16-bit half masks
+          uint32_t o[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t two = ((w < 2 ? am.x : am.y) >> (16 * (w & 1))) & 0xffffu;
+            const uint32_t lo = (two & 0xffu) == (uint32_t)kk ? 0x0000ffffu : 0u;
+            const uint32_t hi = (two >> 8) == (uint32_t)kk ? 0xffff0000u : 0u;
+            o[w] = dpw[w] & (lo | hi) & pos[w];
+          }
+          const int oy = 2 * Y + (kk >> 1);
+          const int ox = 64 * tx + 2 * xp + (kk & 1);
+          if (P.add != nullptr && oy >= P.win_y0 && oy < P.win_y1 && ox >= P.win_x0 &&
+              ox < P.win_x1) {
+            // inside the window: g = routed + add (fp32, one bf16 rounding), mask = y > 0
+            const uint4 av = *reinterpret_cast<const uint4*>(
+                P.add + n * P.add_sn + (oy - P.win_y0) * P.add_sh + (ox - P.win_x0) * P.add_sw +
+                8 * q);
+            const uint4 yv = *reinterpret_cast<const uint4*>(P.y + n * P.y_sn + oy * P.y_sh +
+                                                             ox * P.y_sw + 8 * q);
+            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const uint32_t two = ((w < 2 ? am.x : am.y) >> (16 * (w & 1))) & 0xffffu;
+              const uint32_t sel = ((two & 0xffu) == (uint32_t)kk ? 0x0000ffffu : 0u) |
+                                   ((two >> 8) == (uint32_t)kk ? 0xffff0000u : 0u);
+              const uint32_t routed = dpw[w] & sel;
+              const float glo = bf16_lo(routed) + bf16_lo(aw[w]);
+              const float ghi = bf16_hi(routed) + bf16_hi(aw[w]);
+              o[w] = pack_bf16x2(glo, ghi) & bf16x2_gt_mask(yw[w], 0u);
+            }
+          }
+          const uint32_t m = (uint32_t)(4 * xp + kk);            // dZ tile row
+          sts128(zt + m * rowB + (((uint32_t)q ^ ((m >> 1) & 3u)) << 4),
+                 make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&z_full[s]);
+        fetch(i + kFcRawDepth);                      // this thread's raw slot is free again
+      }
+    } else if (WGRAD && n_my > 0 && half == 0) {
       // partial sums of this CTA: accumulator rows 0..36 (k-slots + the constant-1 slot) ->
       // shared memory [37][BN] fp32 (the patch ring is idle once every MMA has completed);
-      // the cluster-wide reduction below adds them to dW / db
+      // the reduction below adds them to dW / db
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
       const int L = quad * 32 + lane;                // accumulator row = k-slot
@@ -271,18 +495,27 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
     // four warps, thread = one output pixel of the tile: nine 8-byte cp.async copies (zero
     // filled outside the image) straight to the pixel's swizzled operand row, then one
     // deferred mbarrier arrival that fires when they have landed.  Nothing waits for data
-    // here, so the builders run up to kFcStages tiles ahead of the tensor core.
+    // here, so the builders run up to S tiles ahead of the tensor core.
     const int t = (warp - 10) * 32 + lane;
-    const int HoWo = P.Ho * P.Wo;
     const uint32_t x7 = (uint32_t)t & 7u;
     for (int i = 0; i < n_my; ++i) {
-      const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + t;
-      const bool live = m < P.M_total;
-      const uint32_t mm = live ? (uint32_t)m : 0u;
-      const int n = (int)(__umulhi(mm, P.div_hw_mul) >> P.div_hw_shr);
-      const uint32_t rem = mm - (uint32_t)(n * HoWo);
-      const int oy = (int)(__umulhi(rem, P.div_wo_mul) >> P.div_wo_shr);
-      const int ox = (int)rem - oy * P.Wo;
+      int n, oy, ox;
+      bool live;
+      if (POOL) {
+        int Y, tx;
+        tile_pos(tile_of(i), n, Y, tx);
+        oy = 2 * Y + ((t >> 1) & 1);
+        ox = 64 * tx + 2 * (t >> 2) + (t & 1);
+        live = ox < P.Wo;
+      } else {
+        const int m = tile_of(i) * 128 + t;
+        live = m < P.M_total;
+        const uint32_t mm = live ? (uint32_t)m : 0u;
+        n = (int)fc_div(mm, P.div_b_mul, P.div_b_shr);
+        const uint32_t rem = mm - (uint32_t)n * P.div_b;
+        oy = (int)fc_div(rem, P.div_a_mul, P.div_a_shr);
+        ox = (int)(rem - (uint32_t)oy * P.div_a);
+      }
       const int iy0 = oy - P.pad_t, ix0 = ox - P.pad_l;
       const int s = i % S;
       mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);

@@ -10,6 +10,7 @@ What the pieces replace in the reference:
 """
 import ctypes
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -276,6 +277,44 @@ class ConvLayer(object):
             d = self.desc(y.shape[1], y.shape[2], self.epi_flags(out_f32), impl)
             N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(x), N.ptr(self.w.shadow()),
                    N.ptr(self.b.value()), N.vref(y), st)
+
+    # ---- first layer fused with its 2x2 max-pool (seg_conv2d_pool_fwd / _wgrad) ----
+    def pool_fusable(self, x, pooled, impl=N.IMPL_UMMA):
+        """True if conv + 2x2/2 max-pool of this layer can run as one launch: the first-layer
+        kernel's shape (x is the (R,G,B,1) input), 32 padded output channels, even output
+        grid.  SEGB200_FUSE_POOL1=0 disables it."""
+        if impl != N.IMPL_UMMA or self.kind != 'conv' or type(self) is not ConvLayer:
+            return False
+        if self.k != 3 or self.stride != 1 or self.cin != 3 or x.shape[3] != 4 or self.cout_pad != 32:
+            return False
+        oh, ow = self.out_hw(x.shape[1], x.shape[2])
+        return (oh % 2 == 0 and ow % 2 == 0 and tuple(pooled.shape[1:]) == (oh // 2, ow // 2, 32)
+                and os.environ.get('SEGB200_FUSE_POOL1', '1') != '0')
+
+    def forward_pool(self, x, pooled, argmax, y_win=None, win_y0=0, win_x0=0):
+        st = N.stream_ptr()
+        N.set_tag(self.name)
+        oh, ow = self.out_hw(x.shape[1], x.shape[2])
+        px = x.shape[0] * oh * ow
+        # algorithmic work: the convolution; bytes = input + pooled output + slots (+ window)
+        N.note_work(2.0 * px * self.cout * self.cin * 9,
+                    x.numel() * 2.0 + pooled.numel() * 3.0 + (y_win.numel() * 2.0 if y_win is not None else 0))
+        d = self.desc(x.shape[1], x.shape[2], self.epi_flags(False), N.IMPL_UMMA)
+        N.call('seg_conv2d_pool_fwd', ctypes.byref(d), N.vref(x), N.ptr(self.w.shadow()),
+               N.ptr(self.b.value()), N.vref(y_win), int(win_y0), int(win_x0), N.vref(pooled),
+               N.ptr(argmax), st)
+
+    def wgrad_pool(self, x, dpool, argmax, pooled, add=None, y_win=None, win_y0=0, win_x0=0):
+        st = N.stream_ptr()
+        N.set_tag(self.name)
+        oh, ow = self.out_hw(x.shape[1], x.shape[2])
+        px = x.shape[0] * oh * ow
+        N.note_work(2.0 * px * self.cout * self.cin * 9,
+                    x.numel() * 2.0 + pooled.numel() * 5.0 + (add.numel() * 4.0 if add is not None else 0))
+        d = self.desc(x.shape[1], x.shape[2], 0, N.IMPL_UMMA)
+        N.call('seg_conv2d_pool_wgrad', ctypes.byref(d), N.vref(x), N.vref(dpool), N.ptr(argmax),
+               N.vref(pooled), N.vref(add), N.vref(y_win), int(win_y0), int(win_x0),
+               N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
 
     # ---- backward ----------------------------------------------------------
     def backward(self, x, dz, dx=None, x2=None, dx2=None, mask=None, mask2=None,

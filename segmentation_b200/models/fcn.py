@@ -140,9 +140,15 @@ class _FCNExec(ExecBase):
         m, L, A, impl, v = self.m, self.m.layers, self.act, self.m.impl, self.v
         self.pack()
         src = A['x']
+        # conv1 + pool1 as one launch (first-layer kernel): conv1's full-resolution
+        # activation has no other consumer (models/fcn.py:110-117)
+        self.fuse_pool1 = self.x4 and L['conv1'].pool_fusable(A['x'], A['pool1'], impl)
         for i in range(1, 6):
-            L['conv%d' % i].forward(src, A['conv%d' % i], impl=impl)
-            E.maxpool_fwd(A['conv%d' % i], A['pool%d' % i], self.amax['pool%d' % i])
+            if i == 1 and self.fuse_pool1:
+                L['conv1'].forward_pool(A['x'], A['pool1'], self.amax['pool1'])
+            else:
+                L['conv%d' % i].forward(src, A['conv%d' % i], impl=impl)
+                E.maxpool_fwd(A['conv%d' % i], A['pool%d' % i], self.amax['pool%d' % i])
             src = A['pool%d' % i]
         L['conv6'].forward(A['pool5'], A['conv6'], impl=impl)
         L['conv7'].forward(A['conv6'], A['conv7'], impl=impl)
@@ -194,6 +200,12 @@ class _FCNExec(ExecBase):
         for i in range(5, 0, -1):
             conv, pool = 'conv%d' % i, 'pool%d' % i
             second = G.get(pool + '_b')
+            if i == 1 and getattr(self, 'fuse_pool1', False):
+                # pool1 backward + conv1 weight gradient in one launch
+                N.set_tag(conv)
+                L[conv].wgrad_pool(A['x'], G[pool], self.amax[pool], A[pool])
+                self.layer_done(conv)
+                continue
             if second is not None:
                 E.maxpool_bwd2(G[pool], second, self.amax[pool], G[conv], mask=A[conv])
             else:

@@ -241,7 +241,20 @@ class _UNetExec(ExecBase):
                 E.dropout_ex(A[name], A[name], seed, off * 8 + self.MC_SITES[name],
                              per_image_step=8)
 
-        conv('conv1_1', A['x'])
+        # conv1_1 + pool1 as ONE launch where the first-layer kernel applies: the full-resolution
+        # conv1_1 activation is needed again only inside the window conv1_2 reads
+        y0, x0, h, w = self.crop[4]
+        self.fuse_pool1 = (self.x4 and not self.patch_l1 and
+                           L['conv1_1'].pool_fusable(A['x'], A['pool1'], impl))
+        if self.fuse_pool1:
+            if self.c12_crop:
+                win, wy, wx = A['conv1_1'][:, y0:y0 + h + 2, x0:x0 + w + 2, :], y0, x0
+            else:
+                win, wy, wx = A['conv1_1'], 0, 0
+            L['conv1_1'].forward_pool(A['x'], A['pool1'], self.amax['pool1'], y_win=win,
+                                      win_y0=wy, win_x0=wx)
+        else:
+            conv('conv1_1', A['x'])
         # conv1_2 feeds only the last skip connection (reference models/unet.py:118-120,161):
         # it runs on the side stream, filling the SMs the small deep layers leave idle
         fwd_at = int(os.environ.get('SEGB200_FWD_SIDE', '1'))   # 0: off; i: fork before stage i+1
@@ -266,7 +279,8 @@ class _UNetExec(ExecBase):
 
         if fwd_at <= 1:
             conv1_2()
-        E.maxpool_fwd(A['conv1_1'], A['pool1'], self.amax['pool1'])
+        if not self.fuse_pool1:
+            E.maxpool_fwd(A['conv1_1'], A['pool1'], self.amax['pool1'])
         for i in range(2, 6):
             if fwd_at == i:
                 conv1_2()
@@ -369,6 +383,16 @@ class _UNetExec(ExecBase):
         # first group, a chain nothing else is left to overlap.  Optionally (tail_split
         # batch slices) the weight gradient of slice k runs on the side stream while the
         # pool backward of slice k+1 runs here; partial sums meet in the fp32 reductions.
+        if getattr(self, 'fuse_pool1', False):
+            # pool1's backward evaluated inside the operand producer of conv1_1's weight
+            # gradient: one launch, the full-resolution gradient never exists
+            N.set_tag('conv1_1')
+            L['conv1_1'].wgrad_pool(A['x'], G['pool1'], self.amax['pool1'], A['pool1'],
+                                    add=G['conv1_1_part'], y_win=x_win, win_y0=y0, win_x0=x0)
+            self.layer_done('conv1_1')
+            if side is not None:
+                side.join()
+            return
         ts = self.tail_split if (side is not None and self.B % max(self.tail_split, 1) == 0) else 1
         nb = self.B // ts
         for k in range(ts):

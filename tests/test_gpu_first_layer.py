@@ -172,3 +172,106 @@ def test_first_layer_wgrad(cuda, case):
         e_b = rel_l2(db.cpu(), db_ref)
         report('first_layer_wgrad', {'case': name, 'impl': impl_name, 'dw': e_w, 'db': e_b})
         assert e_w < TOL_F32 and e_b < TOL_F32, (name, impl_name, e_w, e_b)
+
+
+# ---------------------------------------------------------------------------
+# first layer fused with its 2x2 max-pool (seg_conv2d_pool_fwd / seg_conv2d_pool_wgrad)
+# ---------------------------------------------------------------------------
+POOL_CASES = [
+    # name, N, H, W, Cout, padding, window (y0, x0, h, w) in output coordinates or None
+    ('unet_like', 2, 44, 70, 32, 'VALID', (9, 13, 20, 30)),
+    ('wide', 1, 20, 200, 32, 'VALID', (0, 0, 18, 198)),          # window = whole output
+    ('fcn_like', 2, 32, 48, 32, 'SAME', None),
+    ('cout24', 1, 18, 134, 24, 'VALID', (3, 60, 8, 70)),
+]
+
+
+def _pool_setup(case, seed):
+    name, Nb, H, W, Co, padding, win = case
+    x, w, b = _inputs((name, Nb, H, W, Co, padding), seed=seed)
+    pads = conv_pads(H, W, 3, 1, padding)
+    Ho, Wo = H + pads[0] + pads[2] - 2, W + pads[1] + pads[3] - 2
+    return x, w, b, pads, Ho, Wo
+
+
+@pytest.mark.parametrize('case', POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_first_layer_pool_forward(cuda, case):
+    """pooled values and argmax slots bit-exact against the unfused C-ABI path (same MMA per
+    pixel, then seg_maxpool_fwd), the window of the activation bit-exact as well; pooled
+    values against the oracle within the bf16 tolerance."""
+    name, Nb, H, W, Co, padding, win = case
+    x, w, b, pads, Ho, Wo = _pool_setup(case, 7)
+    x4 = _x4(x)
+    sh, bd = shadow_conv(w, 16, 32), b.cuda()
+    d = desc(3, 1, pads, 3, Co, 16, 32, N.EPI_BIAS | N.EPI_RELU, N.IMPL_UMMA)
+    st = N.stream_ptr()
+    y_ref = torch.zeros(Nb, Ho, Wo, 32, dtype=BF16, device='cuda')
+    N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x4), None, N.ptr(sh), N.ptr(bd), N.vref(y_ref), st)
+    p_ref = torch.zeros(Nb, Ho // 2, Wo // 2, 32, dtype=BF16, device='cuda')
+    a_ref = torch.zeros(Nb, Ho // 2, Wo // 2, 32, dtype=torch.uint8, device='cuda')
+    E.maxpool_fwd(y_ref, p_ref, a_ref)
+    y = torch.full((Nb, Ho, Wo, 32), -7.0, dtype=BF16, device='cuda')
+    pooled = torch.full_like(p_ref, float('nan'))
+    amax = torch.full_like(a_ref, 9)
+    ywin = None if win is None else y[:, win[0]:win[0] + win[2], win[1]:win[1] + win[3], :]
+    N.call('seg_conv2d_pool_fwd', ctypes.byref(d), N.vref(x4), N.ptr(sh), N.ptr(bd), N.vref(ywin),
+           win[0] if win else 0, win[1] if win else 0, N.vref(pooled), N.ptr(amax), st)
+    sync()
+    assert 'fconv' in N.load().seg_last_kernel_name().decode()
+    assert torch.equal(pooled.cpu().view(torch.int16), p_ref.cpu().view(torch.int16))
+    assert torch.equal(amax.cpu(), a_ref.cpu())
+    if win is not None:
+        y0, x0, h, ww = win
+        assert torch.equal(y[:, y0:y0 + h, x0:x0 + ww].cpu().view(torch.int16),
+                           y_ref[:, y0:y0 + h, x0:x0 + ww].cpu().view(torch.int16))
+        outside = y.clone()
+        outside[:, y0:y0 + h, x0:x0 + ww] = -7.0
+        assert bool((outside == -7.0).all())                 # nothing written outside the window
+    ref = torch.relu(T.conv2d(bfr(x), w, b, 1, padding))
+    pr = T.max_pool(bfr(ref), 2, 2)
+    assert rel_l2(pooled.float().cpu()[..., :Co], pr) < TOL_BF16
+
+
+@pytest.mark.parametrize('case', POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_first_layer_pool_wgrad(cuda, case):
+    """dW / db of the fused pool-backward + weight-gradient launch against the unfused C-ABI
+    path (seg_maxpool_bwd_y, then seg_conv2d_wgrad on the materialised gradient)."""
+    name, Nb, H, W, Co, padding, win = case
+    x, w, b, pads, Ho, Wo = _pool_setup(case, 11)
+    x4 = _x4(x)
+    sh, bd = shadow_conv(w, 16, 32), b.cuda()
+    d = desc(3, 1, pads, 3, Co, 16, 32, N.EPI_BIAS | N.EPI_RELU, N.IMPL_UMMA)
+    st = N.stream_ptr()
+    y = torch.zeros(Nb, Ho, Wo, 32, dtype=BF16, device='cuda')
+    N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x4), None, N.ptr(sh), N.ptr(bd), N.vref(y), st)
+    pooled = torch.zeros(Nb, Ho // 2, Wo // 2, 32, dtype=BF16, device='cuda')
+    amax = torch.zeros(Nb, Ho // 2, Wo // 2, 32, dtype=torch.uint8, device='cuda')
+    E.maxpool_fwd(y, pooled, amax)
+    g = _gen(13)
+    dpool = torch.zeros_like(pooled)
+    dpool[..., :Co] = (torch.randn(Nb, Ho // 2, Wo // 2, Co, generator=g) * 0.3).to(BF16).cuda()
+    add = ywin = None
+    if win is not None:
+        y0, x0, h, ww = win
+        add = torch.zeros(Nb, h, ww, 32, dtype=BF16, device='cuda')
+        add[..., :Co] = (torch.randn(Nb, h, ww, Co, generator=g) * 0.3).to(BF16).cuda()
+        ywin = y[:, y0:y0 + h, x0:x0 + ww, :]
+    # unfused: materialise dz, then the first-layer weight gradient
+    dz = torch.zeros_like(y)
+    E.maxpool_bwd(dpool, amax, dz, add=add, add_y0=win[0] if win else 0, add_x0=win[1] if win else 0,
+                  mask=y, pooled=pooled)
+    dw_ref = torch.zeros(3, 3, 3, Co, dtype=torch.float32, device='cuda')
+    db_ref = torch.zeros(Co, dtype=torch.float32, device='cuda')
+    d0 = desc(3, 1, pads, 3, Co, 16, 32, 0, N.IMPL_UMMA)
+    N.call('seg_conv2d_wgrad', ctypes.byref(d0), N.vref(x4), None, N.vref(dz), N.ptr(dw_ref),
+           N.ptr(db_ref), st)
+    dw = torch.zeros_like(dw_ref)
+    db = torch.zeros_like(db_ref)
+    N.call('seg_conv2d_pool_wgrad', ctypes.byref(d0), N.vref(x4), N.vref(dpool), N.ptr(amax),
+           N.vref(pooled), N.vref(add), N.vref(ywin), win[0] if win else 0, win[1] if win else 0,
+           N.ptr(dw), N.ptr(db), st)
+    sync()
+    assert 'fconv' in N.load().seg_last_kernel_name().decode()
+    e_w, e_b = rel_l2(dw.cpu(), dw_ref.cpu()), rel_l2(db.cpu(), db_ref.cpu())
+    report('first_layer_pool_wgrad', {'case': name, 'dw': e_w, 'db': e_b})
+    assert e_w < 2e-5 and e_b < 2e-5, (name, e_w, e_b)

@@ -1,2 +1,2 @@
 cd /root/repo; mkdir -p gpurun_out
-for d in 0 8 12 13 14 15 24 28 31; do echo "dbg=$d"; SEGB200_FCONV_DBG=$d python tools/fconv_prof.py 2>&1 | grep wgrad; done
+timeout 300 python -m pytest tests/test_gpu_first_layer.py -m gpu -x -q 2>&1 | tail -15

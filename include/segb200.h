@@ -141,21 +141,22 @@ SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, cons
  *   into y_win (nullable), a view of its window whose top-left output pixel is
  *   (win_y0, win_x0) - U-Net's conv1_1 is read again only by conv1_2 on the crop that feeds
  *   the last skip connection (models/unet.py:118-120,159-161), FCN's conv1 never.
- * wgrad: dw, db += gradients for dz = relu_mask(pool_grad(dpool) + add), i.e.
- *   seg_maxpool_bwd_y followed by seg_conv2d_wgrad without the full-resolution gradient ever
- *   existing: the pool backward is evaluated inside the operand producer.  `add` (nullable):
- *   gradient arriving from a second consumer inside the window (same geometry as y_win, which
- *   supplies the ReLU mask there); elsewhere the mask comes from `pooled` (the forward pool
- *   output).  Both return SEG_E_UNSUPPORTED for other shapes (use the unfused entries). */
+ * wgrad: dw, db += gradients for dz = relu_mask(pool_grad(dpool)), i.e. seg_maxpool_bwd_y
+ *   followed by seg_conv2d_wgrad without the full-resolution gradient ever existing: the pool
+ *   backward is evaluated inside the operand producer (the ReLU mask comes from `pooled`, the
+ *   forward pool output: the input at the argmax IS the pooled value).  A gradient arriving
+ *   from a second consumer of the activation (U-Net: conv1_2's input gradient on the window)
+ *   is a separate linear term: mask it with the activation (seg_conv2d_dgrad's mask_src) and
+ *   run seg_conv2d_wgrad on the window - x4 may be a crop view of the staged input.
+ * Both return SEG_E_UNSUPPORTED for other shapes (use the unfused entries). */
 SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, const void* w_bf16,
                                     const float* bias, const seg_view* y_win, int32_t win_y0,
                                     int32_t win_x0, const seg_view* pooled, uint8_t* argmax,
                                     void* stream);
 SEG_API int32_t seg_conv2d_pool_wgrad(const seg_conv_desc* d, const seg_view* x4,
                                       const seg_view* dpool, const uint8_t* argmax,
-                                      const seg_view* pooled, const seg_view* add,
-                                      const seg_view* y_win, int32_t win_y0, int32_t win_x0,
-                                      float* dw, float* db, void* stream);
+                                      const seg_view* pooled, float* dw, float* db,
+                                      void* stream);
 
 /* ---- transposed convolution: replaces Conv2DBackpropInput (+BiasAdd+Relu) and
  * its gradients for slim.convolution2d_transpose (models/unet.py:138,145,152,159;

@@ -35,8 +35,7 @@ int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, con
                    const seg_view* y_win, int win_y0, int win_x0, const seg_view& pooled,
                    uint8_t* argmax, cudaStream_t st);
 int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dpool,
-                     const uint8_t* argmax, const seg_view& pooled, const seg_view* add,
-                     const seg_view* y_win, int win_y0, int win_x0, float* dw, float* db,
+                     const uint8_t* argmax, const seg_view& pooled, float* dw, float* db,
                      cudaStream_t st);
 
 
@@ -227,16 +226,13 @@ SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, 
 
 SEG_API int32_t seg_conv2d_pool_wgrad(const seg_conv_desc* d, const seg_view* x4,
                                       const seg_view* dpool, const uint8_t* argmax,
-                                      const seg_view* pooled, const seg_view* add,
-                                      const seg_view* y_win, int32_t win_y0, int32_t win_x0,
-                                      float* dw, float* db, void* stream) {
+                                      const seg_view* pooled, float* dw, float* db,
+                                      void* stream) {
   SEG_REQUIRE(desc_ok(d) && x4 && dpool && argmax && pooled && dw, SEG_E_BAD_SHAPE,
               "conv2d_pool_wgrad: bad argument");
-  const int rc = fconv_pool_wgrad(*d, *x4, *dpool, argmax, *pooled, add, y_win, win_y0, win_x0, dw,
-                                  db, (cudaStream_t)stream);
+  const int rc = fconv_pool_wgrad(*d, *x4, *dpool, argmax, *pooled, dw, db, (cudaStream_t)stream);
   SEG_REQUIRE(rc != SEG_E_UNSUPPORTED, SEG_E_UNSUPPORTED,
-              "conv2d_pool_wgrad: needs the shape of seg_conv2d_pool_fwd (and, with `add`, a "
-              "window view of the activation of the same size); use seg_maxpool_bwd_y + "
+              "conv2d_pool_wgrad: needs the shape of seg_conv2d_pool_fwd; use seg_maxpool_bwd_y + "
               "seg_conv2d_wgrad otherwise");
   return rc;
 }

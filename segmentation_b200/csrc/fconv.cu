@@ -18,7 +18,8 @@ void fconv_enable(int on) { g_use_fconv = on != 0; }
 static bool fconv_geom_ok(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, int out_n,
                           int out_h, int out_w) {
   return g_use_fconv && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.cin == 3 && x.c == 4 &&
-         !(x2 && x2->ptr) && view_dense(x) && (d.cout_pad == 32 || d.cout_pad == 64) &&
+         !(x2 && x2->ptr) && x.sw == 4 && x.sh % 4 == 0 && x.sn % 4 == 0 &&
+         (d.cout_pad == 32 || d.cout_pad == 64) &&
          (reinterpret_cast<uintptr_t>(x.ptr) & 7) == 0 && out_n == x.n &&
          (int64_t)out_n * out_h * out_w < (int64_t)1 << 30 &&
          out_h == x.h + d.pad_t + d.pad_b - 2 && out_w == x.w + d.pad_l + d.pad_r - 2 &&
@@ -70,6 +71,7 @@ static void fill_params(FconvParams* P, const seg_conv_desc& d, const seg_view& 
                         int out_w, bool pool) {
   memset(P, 0, sizeof(*P));
   P->x4 = reinterpret_cast<const uint2*>(x.ptr);
+  P->x_sn = x.sn / 4; P->x_sh = x.sh / 4;
   P->H = x.h; P->W = x.w; P->Ho = out_h; P->Wo = out_w;
   P->pad_t = d.pad_t; P->pad_l = d.pad_l;
   P->M_total = x.n * out_h * out_w;
@@ -130,7 +132,7 @@ int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, con
                    uint8_t* argmax, cudaStream_t st) {
   const int oh = x.h + d.pad_t + d.pad_b - 2, ow = x.w + d.pad_l + d.pad_r - 2;
   if (!pool_geom_ok(d, x, oh, ow, pooled) || (d.flags & SEG_EPI_OUT_F32) || !argmax ||
-      (reinterpret_cast<uintptr_t>(argmax) & 15) != 0)
+      (reinterpret_cast<uintptr_t>(argmax) & 7) != 0)
     return SEG_E_UNSUPPORTED;
   FconvParams P;
   fill_params(&P, d, x, oh, ow, true);
@@ -154,8 +156,7 @@ int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, con
 }
 
 int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dpool,
-                     const uint8_t* argmax, const seg_view& pooled, const seg_view* add,
-                     const seg_view* y_win, int win_y0, int win_x0, float* dw, float* db,
+                     const uint8_t* argmax, const seg_view& pooled, float* dw, float* db,
                      cudaStream_t st) {
   const int oh = x.h + d.pad_t + d.pad_b - 2, ow = x.w + d.pad_l + d.pad_r - 2;
   if (!pool_geom_ok(d, x, oh, ow, pooled) || !pool_geom_ok(d, x, oh, ow, dpool) || !argmax ||
@@ -168,19 +169,6 @@ int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& 
   P.dpool = reinterpret_cast<const bf16*>(dpool.ptr);
   P.pooled = reinterpret_cast<bf16*>(pooled.ptr);
   P.amax = const_cast<uint8_t*>(argmax);
-  if (add && add->ptr) {
-    if (!y_win || !y_win->ptr || !window_view_ok(*add) || !window_view_ok(*y_win) ||
-        add->n != x.n || y_win->n != x.n || add->h != y_win->h || add->w != y_win->w ||
-        win_y0 < 0 || win_x0 < 0 || win_y0 + add->h > oh || win_x0 + add->w > ow)
-      return SEG_E_UNSUPPORTED;
-    P.add = reinterpret_cast<const bf16*>(add->ptr);
-    P.add_sn = add->sn; P.add_sh = add->sh; P.add_sw = add->sw;
-    P.y = reinterpret_cast<bf16*>(y_win->ptr) - (int64_t)win_y0 * y_win->sh -
-          (int64_t)win_x0 * y_win->sw;
-    P.y_sn = y_win->sn; P.y_sh = y_win->sh; P.y_sw = y_win->sw;
-    P.win_y0 = win_y0; P.win_x0 = win_x0;
-    P.win_y1 = win_y0 + add->h; P.win_x1 = win_x0 + add->w;
-  }
   return launch_fconv_t<32, true, true>(P, nullptr, st);
 }
 

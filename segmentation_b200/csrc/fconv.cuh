@@ -21,10 +21,13 @@
 //
 // Forward + max-pool (POOL; models/unet.py:111-120, models/fcn.py:110-117): a tile is two
 // output rows x 64 columns, pixel (2Y+dy, 64tx + 2xp + dx) in accumulator row
-// 4xp + 2dy + dx, so a 2x2 pool window is four adjacent TMEM lanes: two butterfly shuffles
-// on the packed bf16 pairs give every lane its window's maximum and the slot of the first
-// maximum (row-major scan order, as seg_maxpool_fwd), and the four lanes write the pooled
-// pixel's four 16-byte chunks (+ two 16-byte chunks of uint8 slots).  The full-resolution
+// 4xp + 2dy + dx, so a 2x2 pool window is four adjacent TMEM lanes: the warp transposes
+// through a small shared-memory staging area (lane k of a window reads 16-byte chunk k of
+// its four pixels), scans the four candidates on packed bf16 pairs for the maximum and the
+// slot of the first maximum (row-major scan order, as seg_maxpool_fwd) and writes chunk k of
+// the pooled pixel and its 8 slot bytes (a butterfly-shuffle version that kept every lane's
+// whole pixel cost ~500 instructions per warp and tile - 41 us; this one ~100).  The
+// full-resolution
 // activation is written only inside a caller-given window (U-Net: the crop conv1_2 reads;
 // FCN: nothing) - 66 MB of stores and the pool kernel's 66 MB of loads disappear.
 //
@@ -33,16 +36,19 @@
 // dW[k-slot][co] += sum_px patch[px][k-slot] * dZ[px][co]; the constant-1 slot 36
 // accumulates sum_px dZ - the bias gradient - for free.  One coalesced red.add of 28 x BN
 // floats per CTA at the end.  The dZ tile is one TMA load, or (POOL) is BUILT in shared
-// memory from the pooled gradient, the argmax slots and the ReLU mask - the max-pool
-// backward (seg_maxpool_bwd_y semantics, skip-gradient window included) fused into the
-// operand producer, so the full-resolution gradient never exists in HBM.
+// memory from the pooled gradient, the argmax slots and the ReLU mask (the input at the
+// argmax IS the pooled value) - the max-pool backward fused into the operand producer, so
+// the full-resolution gradient never exists in HBM.  (A gradient arriving from a second
+// consumer of the activation - U-Net's conv1_2 window - is a separate, linear term: the
+// caller runs the plain weight gradient on that window.)
 #pragma once
 #include "umma_conv.cuh"
 
 namespace segb {
 
 struct FconvParams {
-  const uint2* x4;          // [N][H][W] pixels of 4 bf16 (R, G, B, 1), dense
+  const uint2* x4;          // pixels of 4 bf16 (R, G, B, 1): pixel (n, y, x) at x4[n*x_sn + y*x_sh + x]
+  int64_t x_sn, x_sh;       //   (a crop of the staged input is a view: pointer offset + strides)
   int H, W, Ho, Wo;
   int pad_t, pad_l;
   int M_total;              // N * Ho * Wo (< 2^30)
@@ -60,14 +66,12 @@ struct FconvParams {
   float* db;                // nullable
   // ---- POOL variants (BN = 32)
   int Hp, Wp;               // pooled grid = Ho/2 x Wo/2
-  bf16* y;                  // full-resolution activation: written inside the window (forward),
-  int64_t y_sn, y_sh, y_sw; //   ReLU-mask source inside the window (weight gradient)
+  bf16* y;                  // forward: full-resolution activation, written inside the window
+  int64_t y_sn, y_sh, y_sw;
   int win_y0, win_x0, win_y1, win_x1;   // the window, output coordinates [y0,y1) x [x0,x1)
   bf16* pooled;             // dense [N][Hp][Wp][BN]: pool output (forward) / mask source (wgrad)
   uint8_t* amax;            // dense [N][Hp][Wp][BN] window slots
   const bf16* dpool;        // dense [N][Hp][Wp][BN] gradient w.r.t. the pool output
-  const bf16* add;          // nullable: gradient arriving inside the window, positioned at its
-  int64_t add_sn, add_sh, add_sw;       //   corner (seg_maxpool_bwd's `add`)
 };
 
 constexpr int kFcThreads = 448;          // MMA issuer, alloc/TMA warp, 8 epilogue, 4 builder warps
@@ -75,6 +79,7 @@ constexpr int kFcABytes = 128 * 128;     // one patch tile: 128 pixels x 128-byt
 constexpr int kFcRows = 37;              // accumulator rows of the weight gradient that are used
 constexpr int kFcRawDepth = 4;           // pooled weight gradient: raw tiles in flight per thread
 constexpr int kFcRawBytes = 128 * 48;    // dpool 16 B + pooled 16 B + slots 8 B (+8) per thread
+constexpr int kFcPoolStg = 32 * 80;      // pooled forward: one warp's transpose staging (80-byte rows)
 
 template <int BN, bool WGRAD, bool POOL>
 struct FconvCfg {
@@ -86,7 +91,7 @@ struct FconvCfg {
   static constexpr int kOffRaw = S * kFcABytes + S * kZBytes;
   static constexpr int kOffBars =
       S * kFcABytes + (WGRAD ? S * kZBytes + (POOL ? kFcRawDepth * kFcRawBytes : 0)
-                             : kWBytes + (POOL ? 0 : 16 * kStgBytes));
+                             : kWBytes + (POOL ? 8 * kFcPoolStg : 16 * kStgBytes));
   static constexpr int kSmemBytes = kOffBars + 256 + 1024 /*base alignment*/;
   static constexpr int kTmemCols = WGRAD ? (BN < 32 ? 32 : BN) : 2 * BN;
 };
@@ -341,45 +346,42 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           for (int q = 0; q < 4; ++q)
             dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
         }
-        // window maximum and slot of its first maximum (scan order (0,0),(0,1),(1,0),(1,1):
-        // a later element wins only if strictly greater); every lane ends with both
-        uint32_t sb[8];
+        // transpose through shared memory: lane k of a window gets chunk k of its 4 pixels
+        const uint32_t sw = smem_u32(stg) + (uint32_t)(warp - 2) * kFcPoolStg;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-          const uint32_t a = p[w];
-          const uint32_t b = __shfl_xor_sync(0xffffffffu, a, 1);
-          const uint32_t left = dx ? b : a, right = dx ? a : b;
-          const uint32_t g1 = bf16x2_gt_mask(right, left);
-          const uint32_t m01 = (right & g1) | (left & ~g1);
-          const uint32_t c2 = __shfl_xor_sync(0xffffffffu, m01, 2);
-          const uint32_t g1o = __shfl_xor_sync(0xffffffffu, g1, 2);
-          const uint32_t top = dy ? c2 : m01, bot = dy ? m01 : c2;
-          const uint32_t itop = dy ? g1o : g1, ibot = dy ? g1 : g1o;
-          const uint32_t g2 = bf16x2_gt_mask(bot, top);
-          p[w] = (bot & g2) | (top & ~g2);
-          const uint32_t i0 = (ibot & g2) | (itop & ~g2);
-          const uint32_t sl = (i0 & 0x00010001u) | (g2 & 0x00020002u);    // slot per 16-bit half
-          const uint32_t two = (sl & 0xffu) | ((sl >> 8) & 0xff00u);      // -> two bytes
-          if (w & 1) sb[w >> 1] |= two << 16; else sb[w >> 1] = two;
+        for (int q = 0; q < 4; ++q)
+          sts128(sw + (uint32_t)lane * 80u + q * 16,
+                 make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]));
+        __syncwarp();
+        uint4 v[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          v[jj] = lds128(sw + (uint32_t)((lane & ~3) + jj) * 80u + (uint32_t)k * 16u);
+        __syncwarp();
+        // maximum and slot of the first maximum in scan order (0,0),(0,1),(1,0),(1,1): a
+        // later candidate wins only if strictly greater
+        uint32_t best[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+        uint32_t slot[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int jj = 1; jj < 4; ++jj) {
+          const uint32_t c[4] = {v[jj].x, v[jj].y, v[jj].z, v[jj].w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t g = bf16x2_gt_mask(c[w], best[w]);
+            best[w] = (c[w] & g) | (best[w] & ~g);
+            slot[w] = ((0x00010001u * (uint32_t)jj) & g) | (slot[w] & ~g);
+          }
         }
         const int col = 32 * tx + xp;
         if (col < P.Wp) {
           const int64_t pix = ((int64_t)(n * P.Hp + Y) * P.Wp + col) * BN;
-          // lane k of the window writes 16-byte chunk k of the pooled pixel
-          uint4 o;
-          o.x = k == 0 ? p[0] : k == 1 ? p[4] : k == 2 ? p[8] : p[12];
-          o.y = k == 0 ? p[1] : k == 1 ? p[5] : k == 2 ? p[9] : p[13];
-          o.z = k == 0 ? p[2] : k == 1 ? p[6] : k == 2 ? p[10] : p[14];
-          o.w = k == 0 ? p[3] : k == 1 ? p[7] : k == 2 ? p[11] : p[15];
-          *reinterpret_cast<uint4*>(P.pooled + pix + 8 * k) = o;
-          if (k < 2) {
-            uint4 s4;
-            s4.x = k == 0 ? sb[0] : sb[4];
-            s4.y = k == 0 ? sb[1] : sb[5];
-            s4.z = k == 0 ? sb[2] : sb[6];
-            s4.w = k == 0 ? sb[3] : sb[7];
-            *reinterpret_cast<uint4*>(P.amax + pix + 16 * k) = s4;
-          }
+          *reinterpret_cast<uint4*>(P.pooled + pix + 8 * k) =
+              make_uint4(best[0], best[1], best[2], best[3]);
+          uint32_t two[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) two[w] = (slot[w] & 0xffu) | ((slot[w] >> 8) & 0xff00u);
+          *reinterpret_cast<uint2*>(P.amax + pix + 8 * k) =
+              make_uint2(two[0] | (two[1] << 16), two[2] | (two[3] << 16));
         }
       }
     } else if (WGRAD && POOL && half == 1) {
@@ -388,8 +390,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
       // the window slots and the pooled activation (ReLU mask: the input at the argmax IS
       // the pooled value) arrive through per-thread cp.async groups kFcRawDepth tiles ahead;
       // the thread expands them to its four pixels' 16-byte chunks of the dZ tile (rows of
-      // 64 bytes, SWIZZLE_64B, the MN-major B operand).  Inside the skip-gradient window the
-      // arriving gradient is added and the mask comes from the activation itself.
+      // 64 bytes, SWIZZLE_64B, the MN-major B operand).
       const int u = (warp - 6) * 32 + lane;
       const int xp = u >> 2, q = u & 3;
       const uint32_t raw0 = smem_u32(raw_ring) + (uint32_t)u * 48u;
@@ -437,29 +438,6 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
             const uint32_t lo = (two & 0xffu) == (uint32_t)kk ? 0x0000ffffu : 0u;
             const uint32_t hi = (two >> 8) == (uint32_t)kk ? 0xffff0000u : 0u;
             o[w] = dpw[w] & (lo | hi) & pos[w];
-          }
-          const int oy = 2 * Y + (kk >> 1);
-          const int ox = 64 * tx + 2 * xp + (kk & 1);
-          if (P.add != nullptr && oy >= P.win_y0 && oy < P.win_y1 && ox >= P.win_x0 &&
-              ox < P.win_x1) {
-            // inside the window: g = routed + add (fp32, one bf16 rounding), mask = y > 0
-            const uint4 av = *reinterpret_cast<const uint4*>(
-                P.add + n * P.add_sn + (oy - P.win_y0) * P.add_sh + (ox - P.win_x0) * P.add_sw +
-                8 * q);
-            const uint4 yv = *reinterpret_cast<const uint4*>(P.y + n * P.y_sn + oy * P.y_sh +
-                                                             ox * P.y_sw + 8 * q);
-            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
-            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const uint32_t two = ((w < 2 ? am.x : am.y) >> (16 * (w & 1))) & 0xffffu;
-              const uint32_t sel = ((two & 0xffu) == (uint32_t)kk ? 0x0000ffffu : 0u) |
-                                   ((two >> 8) == (uint32_t)kk ? 0xffff0000u : 0u);
-              const uint32_t routed = dpw[w] & sel;
-              const float glo = bf16_lo(routed) + bf16_lo(aw[w]);
-              const float ghi = bf16_hi(routed) + bf16_hi(aw[w]);
-              o[w] = pack_bf16x2(glo, ghi) & bf16x2_gt_mask(yw[w], 0u);
-            }
           }
           const uint32_t m = (uint32_t)(4 * xp + kk);            // dZ tile row
           sts128(zt + m * rowB + (((uint32_t)q ^ ((m >> 1) & 3u)) << 4),
@@ -529,7 +507,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         for (int sx = 0; sx < 3; ++sx) {
           const int ix = ix0 + sx;
           const bool ok = yok && (unsigned)ix < (unsigned)P.W;
-          const uint2* src = P.x4 + ((int64_t)(n * P.H + iyc) * P.W + (ok ? ix : 0));
+          const uint2* src = P.x4 + (n * P.x_sn + iyc * P.x_sh + (ok ? ix : 0));
           const int q = r * 3 + sx;                  // 8-byte piece q of the row
           cp_async_8(row + ((((uint32_t)q >> 1) ^ x7) << 4) + (uint32_t)(q & 1) * 8u, src,
                      ok ? 8u : 0u);

@@ -304,17 +304,15 @@ class ConvLayer(object):
                N.ptr(self.b.value()), N.vref(y_win), int(win_y0), int(win_x0), N.vref(pooled),
                N.ptr(argmax), st)
 
-    def wgrad_pool(self, x, dpool, argmax, pooled, add=None, y_win=None, win_y0=0, win_x0=0):
+    def wgrad_pool(self, x, dpool, argmax, pooled):
         st = N.stream_ptr()
         N.set_tag(self.name)
         oh, ow = self.out_hw(x.shape[1], x.shape[2])
         px = x.shape[0] * oh * ow
-        N.note_work(2.0 * px * self.cout * self.cin * 9,
-                    x.numel() * 2.0 + pooled.numel() * 5.0 + (add.numel() * 4.0 if add is not None else 0))
+        N.note_work(2.0 * px * self.cout * self.cin * 9, x.numel() * 2.0 + pooled.numel() * 5.0)
         d = self.desc(x.shape[1], x.shape[2], 0, N.IMPL_UMMA)
         N.call('seg_conv2d_pool_wgrad', ctypes.byref(d), N.vref(x), N.vref(dpool), N.ptr(argmax),
-               N.vref(pooled), N.vref(add), N.vref(y_win), int(win_y0), int(win_x0),
-               N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
+               N.vref(pooled), N.ptr(self.w.grad()), N.ptr(self.b.grad()), st)
 
     # ---- backward ----------------------------------------------------------
     def backward(self, x, dz, dx=None, x2=None, dx2=None, mask=None, mask2=None,

@@ -257,7 +257,9 @@ class _UNetExec(ExecBase):
             conv('conv1_1', A['x'])
         # conv1_2 feeds only the last skip connection (reference models/unet.py:118-120,161):
         # it runs on the side stream, filling the SMs the small deep layers leave idle
-        fwd_at = int(os.environ.get('SEGB200_FWD_SIDE', '1'))   # 0: off; i: fork before stage i+1
+        # 0: off; i: fork before stage i+1.  With conv1_1 + pool1 fused nothing is left for
+        # conv1_2 to overlap with at the start: inline is faster (0.942 vs 0.954 ms/step)
+        fwd_at = int(os.environ.get('SEGB200_FWD_SIDE', '0' if self.fuse_pool1 else '1'))
         fwd_side = self.side if (self.use_side and dropout is None and fwd_at > 0) else None
 
         def conv1_2():
@@ -375,10 +377,19 @@ class _UNetExec(ExecBase):
         y0, x0, h, w = self.crop[4]
         if skipside is not None:
             skipside.join()
+        fused = getattr(self, 'fuse_pool1', False)
         if not (skipside is not None and self.early_conv1_2):
-            bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'])
+            # fused first layer: conv1_2's input gradient is ReLU-masked here (not by pool1's
+            # backward, which never materialises) ...
+            bw('conv1_2', x_win, G['skip4'], dx=G['conv1_1_part'], mask=x_win if fused else None)
         else:
+            assert not fused
             self.layer_done('conv1_2')
+        if fused:
+            # ... and enters conv1_1's weight gradient as its own linear term: the plain
+            # first-layer weight gradient on the window (input = a crop view of the staged x)
+            L['conv1_1'].backward(A['x'][:, y0:y0 + h + 4, x0:x0 + w + 4, :], G['conv1_1_part'],
+                                  dx=None, impl=impl, side=side)
         # The step ends with pool1's backward -> conv1_1's weight gradient -> Adam of the
         # first group, a chain nothing else is left to overlap.  Optionally (tail_split
         # batch slices) the weight gradient of slice k runs on the side stream while the
@@ -387,8 +398,7 @@ class _UNetExec(ExecBase):
             # pool1's backward evaluated inside the operand producer of conv1_1's weight
             # gradient: one launch, the full-resolution gradient never exists
             N.set_tag('conv1_1')
-            L['conv1_1'].wgrad_pool(A['x'], G['pool1'], self.amax['pool1'], A['pool1'],
-                                    add=G['conv1_1_part'], y_win=x_win, win_y0=y0, win_x0=x0)
+            L['conv1_1'].wgrad_pool(A['x'], G['pool1'], self.amax['pool1'], A['pool1'])
             self.layer_done('conv1_1')
             if side is not None:
                 side.join()

@@ -250,16 +250,9 @@ def test_first_layer_pool_wgrad(cuda, case):
     g = _gen(13)
     dpool = torch.zeros_like(pooled)
     dpool[..., :Co] = (torch.randn(Nb, Ho // 2, Wo // 2, Co, generator=g) * 0.3).to(BF16).cuda()
-    add = ywin = None
-    if win is not None:
-        y0, x0, h, ww = win
-        add = torch.zeros(Nb, h, ww, 32, dtype=BF16, device='cuda')
-        add[..., :Co] = (torch.randn(Nb, h, ww, Co, generator=g) * 0.3).to(BF16).cuda()
-        ywin = y[:, y0:y0 + h, x0:x0 + ww, :]
     # unfused: materialise dz, then the first-layer weight gradient
     dz = torch.zeros_like(y)
-    E.maxpool_bwd(dpool, amax, dz, add=add, add_y0=win[0] if win else 0, add_x0=win[1] if win else 0,
-                  mask=y, pooled=pooled)
+    E.maxpool_bwd(dpool, amax, dz, mask=y, pooled=pooled)
     dw_ref = torch.zeros(3, 3, 3, Co, dtype=torch.float32, device='cuda')
     db_ref = torch.zeros(Co, dtype=torch.float32, device='cuda')
     d0 = desc(3, 1, pads, 3, Co, 16, 32, 0, N.IMPL_UMMA)
@@ -268,10 +261,39 @@ def test_first_layer_pool_wgrad(cuda, case):
     dw = torch.zeros_like(dw_ref)
     db = torch.zeros_like(db_ref)
     N.call('seg_conv2d_pool_wgrad', ctypes.byref(d0), N.vref(x4), N.vref(dpool), N.ptr(amax),
-           N.vref(pooled), N.vref(add), N.vref(ywin), win[0] if win else 0, win[1] if win else 0,
-           N.ptr(dw), N.ptr(db), st)
+           N.vref(pooled), N.ptr(dw), N.ptr(db), st)
     sync()
     assert 'fconv' in N.load().seg_last_kernel_name().decode()
     e_w, e_b = rel_l2(dw.cpu(), dw_ref.cpu()), rel_l2(db.cpu(), db_ref.cpu())
     report('first_layer_pool_wgrad', {'case': name, 'dw': e_w, 'db': e_b})
     assert e_w < 2e-5 and e_b < 2e-5, (name, e_w, e_b)
+
+
+def test_first_layer_wgrad_on_crop_view(cuda):
+    """The plain first-layer weight gradient on a crop VIEW of the staged input (U-Net: the
+    window of conv1_1 whose gradient arrives from conv1_2, models/unet.py:118-120): equals
+    the gradient computed on a dense copy of the crop."""
+    g = _gen(21)
+    Nb, H, W, Co = 2, 40, 52, 32
+    x = torch.rand(Nb, H, W, 3, generator=g)
+    x4 = _x4(x)
+    y0, x0, h, w = 7, 11, 22, 30                          # input window; output (h-2) x (w-2)
+    dz = (torch.randn(Nb, h - 2, w - 2, Co, generator=g) * 0.2).to(BF16).cuda()
+    d0 = desc(3, 1, (0, 0, 0, 0), 3, Co, 16, 32, 0, N.IMPL_UMMA)
+    out = []
+    for src in (x4[:, y0:y0 + h, x0:x0 + w, :], x4[:, y0:y0 + h, x0:x0 + w, :].contiguous()):
+        dw = torch.zeros(3, 3, 3, Co, dtype=torch.float32, device='cuda')
+        db = torch.zeros(Co, dtype=torch.float32, device='cuda')
+        N.call('seg_conv2d_wgrad', ctypes.byref(d0), N.vref(src), None, N.vref(dz), N.ptr(dw),
+               N.ptr(db), N.stream_ptr())
+        sync()
+        assert 'fconv' in N.load().seg_last_kernel_name().decode()
+        out.append((dw.cpu(), db.cpu()))
+    assert rel_l2(out[0][0], out[1][0]) < 1e-6 and rel_l2(out[0][1], out[1][1]) < 1e-6
+    xr = bfr(x)[:, y0:y0 + h, x0:x0 + w].double()
+    dw_ref = torch.zeros(3, 3, 3, Co, dtype=torch.float64)
+    for r in range(3):
+        for s in range(3):
+            dw_ref[r, s] = torch.einsum('nhwc,nhwo->co', xr[:, r:r + h - 2, s:s + w - 2, :],
+                                        dz.float().cpu().double())
+    assert rel_l2(out[0][0], dw_ref) < TOL_F32

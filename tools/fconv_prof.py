@@ -61,3 +61,35 @@ for fn, name in ((fwd, 'fwd'), (wgrad, 'wgrad')):
     byt = B * Ho * Wo * CO * 2 + B * H * W * 8
     print('%s %s: median %.1f us  min %.1f us  -> %.0f GB/s (algorithmic %d MB)'
           % (name, PAD, ts[len(ts) // 2], ts[0], byt / ts[len(ts) // 2] / 1e3, byt >> 20))
+
+# ---- fused with the 2x2 max-pool (seg_conv2d_pool_fwd / seg_conv2d_pool_wgrad)
+if Ho % 2 == 0 and Wo % 2 == 0:
+    pooled = torch.zeros(B, Ho // 2, Wo // 2, CO, dtype=torch.bfloat16, device='cuda')
+    amax = torch.zeros(B, Ho // 2, Wo // 2, CO, dtype=torch.uint8, device='cuda')
+    dpool = (torch.randn(B, Ho // 2, Wo // 2, CO, device='cuda') * 0.1).to(torch.bfloat16)
+    wy, wx, wh, ww = (Ho - 74) // 2, (Wo - 74) // 2, 74, 74
+    ywin = y[:, wy:wy + wh, wx:wx + ww, :]
+    add = (torch.randn(B, wh, ww, CO, device='cuda') * 0.1).to(torch.bfloat16)
+
+    def pfwd():
+        N.call('seg_conv2d_pool_fwd', ctypes.byref(d), N.vref(x4), N.ptr(w), N.ptr(b), N.vref(ywin),
+               wy, wx, N.vref(pooled), N.ptr(amax), st)
+
+    def pwgrad():
+        N.call('seg_conv2d_pool_wgrad', ctypes.byref(d), N.vref(x4), N.vref(dpool), N.ptr(amax),
+               N.vref(pooled), N.ptr(dw), N.ptr(db), st)
+
+    for fn, name in ((pfwd, 'pool fwd'), (pwgrad, 'pool wgrad')):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        print('%s %s: median %.1f us  min %.1f us' % (name, PAD, ts[len(ts) // 2], ts[0]))

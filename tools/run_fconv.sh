@@ -1,2 +1,2 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_first_layer.py -m gpu -x -q 2>&1 | tail -15
+REPS=1 timeout 300 ncu --set full --import-source on --clock-control none -k regex:fconv --launch-skip 7 -c 4 -f -o gpurun_out/fconv_p python tools/fconv_prof.py > gpurun_out/fconv_ncu.log 2>&1; echo ncu=$?

@@ -107,6 +107,8 @@ SEG_API const char* seg_last_kernel_name(void);
  *          (default 1: 1.056 -> 1.042 ms per U-Net step).
  *   key 16: first-layer kernel (3x3 stride-1 convolution of the 4-channel (R,G,B,1) input of
  *          seg_stage_input, forward and weight gradient; default 1).
+ *   key 17: number of SMs the persistent tile kernels size their grids for (default 0 = all).
+ *          Data-parallel training sets it to (SM count - all-reduce CTAs): see parallel.py.
  * (Keys 8, 10 and 13 of round 1 - cluster/DSMEM weight-gradient reduction, wave-quantised
  * halo tiles, two-CTA multicast halo clusters - were measured slower and are gone.) */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);

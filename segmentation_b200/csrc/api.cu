@@ -63,6 +63,7 @@ static bool desc_ok(const seg_conv_desc* d) {
 #define SEGB200_KERNEL_PROF 0
 #endif
 int g_pdl = 1;              // seg_set_option key 7
+int g_sm_limit = 0;         // seg_set_option key 17
 thread_local const void* g_last_kernel_fn = nullptr;
 
 }  // namespace segb
@@ -108,6 +109,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 14: hconv_set_rowstage(value); return SEG_OK;
     case 15: twgrad_set_tred(value); return SEG_OK;
     case 16: fconv_enable(value); return SEG_OK;
+    case 17: g_sm_limit = value > 0 ? value : 0; return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

@@ -78,6 +78,10 @@ static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block
 }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// seg_set_option key 17: SMs the persistent tile kernels size their grids for (0 = all).
+// Data-parallel training leaves a few SMs to the all-reduce kernels: a persistent grid of one
+// CTA per SM that finds some SMs held by NCCL for the length of a bucket runs a second wave.
+extern int g_sm_limit;
 static inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -86,7 +90,7 @@ static inline int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 __device__ __forceinline__ const bf16* view_at(const seg_view& v, int n, int y, int x) {

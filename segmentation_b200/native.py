@@ -200,6 +200,7 @@ OPT_DEEP_B_RING = 12   # halo / spatial-tile conv: streamed-weight ring as deep 
 OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weight stage
 OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (default on)
 OPT_FIRST_LAYER = 16   # first-layer kernel on the (R,G,B,1) staged input (default on)
+OPT_SM_LIMIT = 17      # SMs the persistent tile kernels size their grids for (0 = all)
 
 
 def set_option(key, value):

@@ -12,8 +12,12 @@ backward completes it from the back, so buckets are contiguous slices that
 become ready one after the other; each is reduced and then updated by its own
 Adam launch on the executor's optimizer stream while the backward pass goes on.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+from . import native as N
 
 
 class GradBuckets(object):
@@ -74,6 +78,30 @@ class DataParallel(object):
             raise Exception('DataParallel: batch-coupled layers (%s) are not supported; images '
                             'must be independent in forward and backward (SURVEY 8e)' % ', '.join(bn))
         self.model = model
+        if group is None and dist.get_backend() == 'nccl' and \
+                os.environ.get('SEGB200_NCCL_PRIO', '1') != '0':
+            # The all-reduce kernels must find SM slots beside persistent 148-CTA kernels that
+            # hold every SM until they exit: on a high-priority stream NCCL's CTAs are placed
+            # first at the next kernel boundary instead of queueing behind every pending CTA of
+            # the backward pass (measured at 2 GPUs: bucket conv3-4 ready at ~900 us, started at
+            # 961 us on a default-priority stream; profiles/r02_dp.md)
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            # Optional (SEGB200_NCCL_CTAS=n, default off): hold NCCL to n CTAs and size the tile
+            # kernels' persistent grids for the remaining SMs, so that an SM held by an
+            # all-reduce does not force a second wave on every overlapped launch.  Measured at
+            # 2 GPUs: n = 4 / 8 / 16 -> 1.29 / 1.15 / 1.08 ms per step against 1.03 with NCCL's
+            # own choice (32 CTAs, ring LL): few channels cannot carry 31 MB inside the backward
+            # pass, the exposed reduction costs more than the second waves it avoids.
+            ctas = int(os.environ.get('SEGB200_NCCL_CTAS', '0'))
+            if ctas > 0:
+                try:
+                    opts.config.min_ctas = ctas
+                    opts.config.max_ctas = ctas
+                    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                    N.set_option(N.OPT_SM_LIMIT, sms - ctas)
+                except AttributeError:                   # older torch: no ncclConfig fields
+                    pass
+            group = dist.new_group(backend='nccl', pg_options=opts)
         self.group = group
         self.world = dist.get_world_size(group)
         # executors built (and graphs captured) before wrapping have no all-reduce and a

@@ -282,6 +282,25 @@ SEG_API int32_t seg_head1x1_xent(const seg_view* x, const void* w_bf16, int32_t 
 SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* labelmap,
                            void* stream);
 
+/* ---- class-map tail of the generic conv/deconvolution model, inference, ONE launch:
+ * tf.image.resize_bilinear(x, [rh, rw]) -> 2x2/stride-2 transposed conv (+bias, ReLU) to
+ * n_classes -> slim.batch_norm with the moving statistics -> 3x3 SAME conv (+bias, no
+ * activation) to n_classes -> sigmoid + argmax (models/deconvolution.py:163-174, :79-82).
+ * x bf16 [n,hs,ws,32]; w_up / w_out are the bf16 shadows of the two layers ([2][2][cout_pad]
+ * [cin_pad] and [3][3][cin_pad][cout_pad]); 2 <= n_classes <= 4.  Outputs at [n,2rh,2rw]:
+ * logits (nullable, fp32 [.,n_classes]), probs (fp32), labelmap (fp32, first index on ties).
+ * Every intermediate is rounded to bf16 exactly where the unfused entries store bf16, so
+ * the results agree with seg_resize_bilinear_fwd + seg_deconv2d_fwd + seg_batchnorm_infer +
+ * seg_conv2d_fwd + seg_sigmoid_argmax up to fp32 summation order. */
+SEG_API int32_t seg_classmap_tail_infer(const seg_view* x, int32_t rh, int32_t rw,
+                                        const void* w_up_bf16, int32_t up_cout_pad,
+                                        int32_t up_cin_pad, const float* b_up,
+                                        const float* bn_mean, const float* bn_var, float bn_eps,
+                                        const float* bn_beta, const void* w_out_bf16,
+                                        int32_t out_cin_pad, int32_t out_cout_pad,
+                                        const float* b_out, int32_t n_classes, float* logits,
+                                        float* probs, float* labelmap, void* stream);
+
 /* ---- MC-dropout statistics: probs [t][count] -> mean[count], var[count]
  * (population variance over the t passes, Welford). */
 SEG_API int32_t seg_mc_mean_var(const float* probs, int32_t t, int64_t count, float* mean, float* var,

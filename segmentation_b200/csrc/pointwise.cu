@@ -1017,6 +1017,156 @@ __global__ void sigmoid_argmax_kernel(seg_view logits, float* probs, float* labe
   }
 }
 
+// ------------------------------------------------- class-map tail (inference), one launch
+// DeconvModel ends with  resize_bilinear(H/2) -> 2x2/s2 transposed conv (+bias, ReLU) to
+// n_classes -> batch-norm -> 3x3 SAME conv to n_classes -> sigmoid / argmax
+// (reference models/deconvolution.py:163-174, head :79-82).  Unfused, the n_classes <= 4
+// channels travel through HBM as 16-channel padded full-resolution tensors four times
+// (3.5 of config 4's 6.4 ms).  Here a block owns 14 x 14 pixels of the half-resolution grid
+// (28 x 28 outputs): phase A, one thread per half-resolution pixel of the 16 x 16 haloed
+// tile: lerp of the C input channels (legacy resize arithmetic, bf16 rounding as the stored
+// tensor would have), the four sub-pixels of the transposed conv, ReLU, batch-norm (moving
+// statistics), each rounded to bf16 where the unfused path stores bf16, into a 32 x 32 x NC
+// shared-memory tile (zero outside the image: the SAME padding of the 3x3 conv); phase B:
+// 3x3 conv + sigmoid + first-index argmax per output pixel.  HBM traffic: the small input
+// and the outputs.
+constexpr int kTailT = 14;                 // half-resolution pixels per tile side
+constexpr int kTailH = kTailT + 2;         // + halo
+constexpr int kTailO = 2 * kTailH;         // bn tile side (outputs incl. halo ring)
+struct TailArgs {
+  seg_view x;                              // [n, hs, ws, C] bf16
+  int rh, rw;                              // half-resolution grid (resize target)
+  const bf16* w_up; int up_cop, up_cip;    // [2][2][cout_pad][cin_pad]
+  const float* b_up;
+  const float* bn_mean; const float* bn_var; float bn_eps; const float* bn_beta;
+  const bf16* w_out; int out_cip, out_cop; // [3][3][cin_pad][cout_pad]
+  const float* b_out;
+  float* logits; float* probs; float* labelmap;
+};
+
+template <int NC, int C>
+__global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
+  __shared__ float s_wup[4 * NC * C];             // [sub][co][ci]
+  __shared__ float s_wout[9 * NC * NC];           // [tap][ci][co]
+  __shared__ float s_aff[4 * NC];                 // b_up, bn scale, bn shift, b_out
+  __shared__ bf16 s_t[kTailO * kTailO * NC];      // bn output tile
+  pdl_trigger();
+  pdl_wait();
+  for (int i = threadIdx.x; i < 4 * NC * C; i += 256) {
+    const int ci = i % C, co = (i / C) % NC, sub = i / (C * NC);
+    s_wup[i] = __bfloat162float(A.w_up[((int64_t)sub * A.up_cop + co) * A.up_cip + ci]);
+  }
+  for (int i = threadIdx.x; i < 9 * NC * NC; i += 256) {
+    const int co = i % NC, ci = (i / NC) % NC, tap = i / (NC * NC);
+    s_wout[i] = __bfloat162float(A.w_out[((int64_t)tap * A.out_cip + ci) * A.out_cop + co]);
+  }
+  if (threadIdx.x < NC) {
+    const int c = threadIdx.x;
+    const float sc = rsqrtf(__ldg(A.bn_var + c) + A.bn_eps);
+    s_aff[c] = __ldg(A.b_up + c);
+    s_aff[NC + c] = sc;
+    s_aff[2 * NC + c] = __ldg(A.bn_beta + c) - __ldg(A.bn_mean + c) * sc;   // informational
+    s_aff[3 * NC + c] = __ldg(A.b_out + c);
+  }
+  __syncthreads();
+  const int tiles_x = (A.rw + kTailT - 1) / kTailT, tiles_y = (A.rh + kTailT - 1) / kTailT;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x - n * tiles_x * tiles_y;
+  const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+  const int ry0 = ty * kTailT - 1, rx0 = tx * kTailT - 1;   // haloed tile origin (half-res)
+  // ---- phase A: thread = one half-resolution pixel of the 16 x 16 haloed tile
+  {
+    const int ly_ = threadIdx.x / kTailH, lx_ = threadIdx.x % kTailH;
+    const int ry = ry0 + ly_, rx = rx0 + lx_;
+    const bool inside = ry >= 0 && ry < A.rh && rx >= 0 && rx < A.rw;
+    float v[C];
+    if (inside) {
+      const float sy = (float)A.x.h / (float)A.rh, sx = (float)A.x.w / (float)A.rw;
+      int y0, y1, x0, x1;
+      float fy, fx;
+      legacy_src(ry, sy, A.x.h, y0, y1, fy);
+      legacy_src(rx, sx, A.x.w, x0, x1, fx);
+      const bf16* p00 = view_at(A.x, n, y0, x0);
+      const bf16* p01 = view_at(A.x, n, y0, x1);
+      const bf16* p10 = view_at(A.x, n, y1, x0);
+      const bf16* p11 = view_at(A.x, n, y1, x1);
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p00 + c0);
+        const uint4 b = *reinterpret_cast<const uint4*>(p01 + c0);
+        const uint4 c = *reinterpret_cast<const uint4*>(p10 + c0);
+        const uint4 d = *reinterpret_cast<const uint4*>(p11 + c0);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float tl = e ? bf16_hi(aw[j]) : bf16_lo(aw[j]);
+            const float tr = e ? bf16_hi(bw[j]) : bf16_lo(bw[j]);
+            const float bl = e ? bf16_hi(cw[j]) : bf16_lo(cw[j]);
+            const float br = e ? bf16_hi(dw[j]) : bf16_lo(dw[j]);
+            const float top = tl + (tr - tl) * fx;
+            const float bot = bl + (br - bl) * fx;
+            v[c0 + 2 * j + e] = __bfloat162float(__float2bfloat16(top + (bot - top) * fy));
+          }
+      }
+    }
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int oyl = 2 * ly_ + (sub >> 1), oxl = 2 * lx_ + (sub & 1);
+#pragma unroll
+      for (int co = 0; co < NC; ++co) {
+        float r = 0.f;
+        if (inside) {
+          float acc = 0.f;
+          const float* wp = s_wup + (sub * NC + co) * C;
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci) acc += v[ci] * wp[ci];
+          acc = fmaxf(acc + s_aff[co], 0.f);
+          const float dq = __bfloat162float(__float2bfloat16(acc));    // stored deconv output
+          r = (dq - __ldg(A.bn_mean + co)) * s_aff[NC + co] + __ldg(A.bn_beta + co);
+        }
+        s_t[(oyl * kTailO + oxl) * NC + co] = __float2bfloat16(r);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: 28 x 28 output pixels of the tile interior
+  const int H = 2 * A.rh, W = 2 * A.rw;
+  for (int i = threadIdx.x; i < 4 * kTailT * kTailT; i += 256) {
+    const int oyl = i / (2 * kTailT), oxl = i - oyl * (2 * kTailT);
+    const int oy = 2 * ty * kTailT + oyl, ox = 2 * tx * kTailT + oxl;
+    if (oy >= H || ox >= W) continue;
+    float acc[NC];
+#pragma unroll
+    for (int co = 0; co < NC; ++co) acc[co] = s_aff[3 * NC + co];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const bf16* tp = s_t + ((oyl + 1 + r) * kTailO + (oxl + 1 + sx)) * NC;
+#pragma unroll
+        for (int ci = 0; ci < NC; ++ci) {
+          const float xv = __bfloat162float(tp[ci]);
+#pragma unroll
+          for (int co = 0; co < NC; ++co) acc[co] += xv * s_wout[((r * 3 + sx) * NC + ci) * NC + co];
+        }
+      }
+    const int64_t m = ((int64_t)n * H + oy) * W + ox;
+    float best = -1.f;
+    int bi = 0;
+#pragma unroll
+    for (int co = 0; co < NC; ++co) {
+      if (A.logits) A.logits[m * NC + co] = acc[co];
+      const float sg = 1.f / (1.f + expf(-acc[co]));
+      A.probs[m * NC + co] = sg;
+      if (sg > best) { best = sg; bi = co; }
+    }
+    A.labelmap[m] = (float)bi;
+  }
+}
+
 __global__ void mc_mean_var_kernel(const float* probs, int T, int64_t count, float* mean,
                                    float* var) {
   GRID_STRIDE(i, count) {
@@ -1928,6 +2078,42 @@ SEG_API int32_t seg_sigmoid_argmax(const seg_view* logits, float* probs, float* 
   sigmoid_argmax_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(*logits, probs,
                                                                                  labelmap);
   SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_classmap_tail_infer(const seg_view* x, int32_t rh, int32_t rw,
+                                        const void* w_up_bf16, int32_t up_cout_pad,
+                                        int32_t up_cin_pad, const float* b_up,
+                                        const float* bn_mean, const float* bn_var, float bn_eps,
+                                        const float* bn_beta, const void* w_out_bf16,
+                                        int32_t out_cin_pad, int32_t out_cout_pad,
+                                        const float* b_out, int32_t n_classes, float* logits,
+                                        float* probs, float* labelmap, void* stream) {
+  SEG_REQUIRE(x && w_up_bf16 && b_up && bn_mean && bn_var && bn_beta && w_out_bf16 && b_out &&
+                  probs && labelmap && rh > 0 && rw > 0,
+              SEG_E_BAD_SHAPE, "classmap_tail_infer: null argument");
+  SEG_REQUIRE(n_classes >= 2 && n_classes <= 4 && x->c == 32 && up_cin_pad >= 32 &&
+                  up_cout_pad >= n_classes && out_cin_pad >= n_classes &&
+                  out_cout_pad >= n_classes && vec8_ok(*x),
+              SEG_E_UNSUPPORTED, "classmap_tail_infer: 32 input channels (16-byte aligned view), "
+              "2..4 classes");
+  TailArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = *x; A.rh = rh; A.rw = rw;
+  A.w_up = reinterpret_cast<const bf16*>(w_up_bf16); A.up_cop = up_cout_pad; A.up_cip = up_cin_pad;
+  A.b_up = b_up;
+  A.bn_mean = bn_mean; A.bn_var = bn_var; A.bn_eps = bn_eps; A.bn_beta = bn_beta;
+  A.w_out = reinterpret_cast<const bf16*>(w_out_bf16); A.out_cip = out_cin_pad;
+  A.out_cop = out_cout_pad; A.b_out = b_out;
+  A.logits = logits; A.probs = probs; A.labelmap = labelmap;
+  const int tiles = ((rw + kTailT - 1) / kTailT) * ((rh + kTailT - 1) / kTailT);
+  const dim3 grid((unsigned)(tiles * x->n));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_classes) {
+    case 2: SEG_CHECK_CUDA(launch_k(classmap_tail_kernel<2, 32>, grid, dim3(256), (size_t)0, st, A)); break;
+    case 3: SEG_CHECK_CUDA(launch_k(classmap_tail_kernel<3, 32>, grid, dim3(256), (size_t)0, st, A)); break;
+    default: SEG_CHECK_CUDA(launch_k(classmap_tail_kernel<4, 32>, grid, dim3(256), (size_t)0, st, A)); break;
+  }
   return SEG_OK;
 }
 

@@ -509,6 +509,21 @@ def stage_input(x, y4, mask_src=None, mask_dst=None, crop_yx=None, mask_kind=Non
            ctypes.byref(ctl) if ctl is not None else None, N.stream_ptr())
 
 
+def classmap_tail_infer(x, rh, rw, up, bn, conv_out, logits, probs, labelmap):
+    """seg_classmap_tail_infer: resize_bilinear -> 2x2/s2 transposed conv `up` (+ReLU) ->
+    batch-norm `bn` (moving statistics) -> 3x3 SAME conv `conv_out` -> sigmoid / argmax, one
+    launch (reference models/deconvolution.py:163-174, :79-82)."""
+    n, h, w = x.shape[0], 2 * rh, 2 * rw
+    N.set_tag('tail')
+    N.note_work(2.0 * n * h * w * (up.cin * up.cout + 9 * conv_out.cin * conv_out.cout),
+                x.numel() * 2.0 + n * h * w * (conv_out.cout * 8.0 + 4.0))
+    N.call('seg_classmap_tail_infer', N.vref(x), rh, rw, N.ptr(up.w.shadow()), up.cout_pad,
+           up.cin_pad, N.ptr(up.b.value()), N.ptr(bn.moving_mean), N.ptr(bn.moving_var), bn.eps,
+           N.ptr(bn.beta.value()), N.ptr(conv_out.w.shadow()), conv_out.cin_pad, conv_out.cout_pad,
+           N.ptr(conv_out.b.value()), conv_out.cout, N.ptr(logits), N.ptr(probs), N.ptr(labelmap),
+           N.stream_ptr())
+
+
 def softmax_xent(logits, labels, loss_sum, dlogits=None):
     N.call('seg_softmax_xent_fwd_bwd', N.vref(logits), N.vref(labels), N.ptr(loss_sum),
            N.vref(dlogits), N.stream_ptr())

@@ -113,7 +113,8 @@ class DeconvModel(BaseModel):
         assert x.shape[0] == 1, 'infer_mc takes one tile'
         ex = self._get_exec(passes, False)
         ex.stage(x.expand(passes, -1, -1, -1), None)
-        ex.forward(dropout=(self.mc_seed if seed is None else seed, pass_offset), per_image=True)
+        ex.forward(dropout=(self.mc_seed if seed is None else seed, pass_offset), per_image=True,
+                   fused_tail=True)
         probs, _ = ex.head()
         mean = torch.empty_like(probs[0])
         var = torch.empty_like(probs[0])
@@ -179,7 +180,7 @@ class _DeconvExec(ExecBase):
         else:
             E.pack_input(self.x_f32, self.act['x'])
 
-    def forward(self, bn_training=None, dropout=None, per_image=False):
+    def forward(self, bn_training=None, dropout=None, per_image=False, fused_tail=False):
         m, L, A, impl = self.m, self.m.layers, self.act, self.m.impl
         if bn_training is None:
             bn_training = self.training
@@ -211,12 +212,32 @@ class _DeconvExec(ExecBase):
         L['deconv1_0'].forward(A['bn4'], A['deconv1_0'], impl=dimpl); bn('bn5', 'deconv1_0')
         L['deconv2_0'].forward(A['bn5'], A['deconv2_0'], impl=dimpl); bn('bn6', 'deconv2_0')
         L['deconv2_1'].forward(A['bn6'], A['deconv2_1'], impl=dimpl); bn('bn7', 'deconv2_1')
+        self._tail_done = False
+        if (fused_tail and not bn_training and impl == N.IMPL_UMMA and 2 <= m.n_classes <= 4 and
+                A['bn7'].shape[3] == 32 and os.environ.get('SEGB200_FUSED_TAIL', '1') != '0'):
+            # inference: resize -> deconv3_0 -> bn8 -> conv_out -> sigmoid/argmax in ONE launch;
+            # the class maps never travel through HBM as 16-channel padded tensors
+            E.classmap_tail_infer(A['bn7'], self.H // 2, self.W // 2, L['deconv3_0'], L['bn8'],
+                                  L['conv_out'], self.logits, self.probs, self.labelmap)
+            m.y_hat, m.y_hat_sig, m.output = self.logits, self.probs, self.labelmap
+            self._tail_done = True
+            return
         E.resize_bilinear_fwd(A['bn7'], A['resize'])
         nc = m.n_classes
         L['deconv3_0'].forward(A['resize'], A['deconv3_0'][..., :nc], impl=impl)
         bn('bn8', 'deconv3_0')
         L['conv_out'].forward(A['bn8'], self.logits, impl=impl, out_f32=True)
         m.y_hat = self.logits
+
+    def head(self):
+        if getattr(self, '_tail_done', False):          # the fused tail produced both already
+            return self.probs, self.labelmap
+        return super(_DeconvExec, self).head()
+
+    def infer(self, x):
+        self.stage(x, None)
+        self.forward(fused_tail=True)
+        return self.head()
 
     def _drop(self, t, site):
         """One launch per site: stream (off [+ image]) * 8 + site (+ 8 * global_step, read

@@ -82,6 +82,8 @@ SIGNATURES = {
     'seg_softmax_xent_fwd_bwd': [_VP, _VP, _P, _VP, _P],
     'seg_sigmoid_argmax': [_VP, _P, _P, _P],
     'seg_mc_mean_var': [_P, _I32, _I64, _P, _P, _P],
+    'seg_classmap_tail_infer': [_VP, _I32, _I32, _P, _I32, _I32, _P, _P, _P, _F, _P, _P, _I32, _I32,
+                                _P, _I32, _P, _P, _P, _P],
     'seg_adam_chunk_elems': [],
     'seg_adam_multi': [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _F, _P, _F, _F, _F, _F, _P],
     'seg_head1x1_xent': [_VP, _P, _I32, _P, _VP, _I32, _VP, _P, _VP, _P, _P, _P],

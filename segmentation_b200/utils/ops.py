@@ -52,17 +52,29 @@ def _truncated_normal(shape, stddev):
 
 
 def _var(name, shape, init):
+    """A trainable variable: an fp32 device tensor with requires_grad, so that gradients
+    of anything built from these helpers arrive in `get_variable(name).grad` after
+    `.backward()` - the torch analogue of tf.gradients over tf.get_variable."""
     if name not in _VARS:
-        _VARS[name] = torch.from_numpy(np.asarray(init(shape), dtype=np.float32)).cuda()
+        v = torch.from_numpy(np.asarray(init(shape), dtype=np.float32)).cuda()
+        v.requires_grad_(True)
+        _VARS[name] = v
     v = _VARS[name]
     assert tuple(v.shape) == tuple(shape), 'variable %s exists with another shape' % name
     return v
 
 
-def _as_bf16_padded(x):
-    """NHWC tensor -> bf16 with channels zero-padded to a multiple of 16."""
+def _state(name, shape, init):
+    """Non-trainable state (batch-norm moving statistics)."""
+    if name not in _VARS:
+        _VARS[name] = torch.from_numpy(np.asarray(init(shape), dtype=np.float32)).cuda()
+    return _VARS[name]
+
+
+def _as_bf16_padded(x, cp=None):
+    """NHWC tensor -> bf16 with channels zero-padded to a multiple of 16 (or to cp)."""
     c = x.shape[-1]
-    cp = E.pad16(c)
+    cp = E.pad16(c) if cp is None else cp
     if x.dtype == BF16 and cp == c and x.is_contiguous():
         return x
     out = torch.zeros(x.shape[:-1] + (cp,), dtype=BF16, device=x.device)
@@ -72,8 +84,143 @@ def _as_bf16_padded(x):
 
 def _shadow(w, pad_dims):
     s = torch.zeros(w.shape[:2] + tuple(pad_dims), dtype=BF16, device=w.device)
-    s[:, :, :w.shape[2], :w.shape[3]] = w.to(BF16)
+    s[:, :, :w.shape[2], :w.shape[3]] = w.detach().to(BF16)
     return s
+
+
+# Temporaries (padded inputs, bf16 shadows) are plain torch tensors: the caching allocator
+# reuses their memory in stream order, so no call here synchronises with the host.
+class _ConvFn(torch.autograd.Function):
+    """tf.nn.conv2d(SAME) + bias_add and its two gradients through the C ABI
+    (seg_conv2d_fwd / seg_conv2d_dgrad / seg_conv2d_wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, out_f32):
+        k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        xb = _as_bf16_padded(x)
+        cin_pad, cout_pad = xb.shape[-1], E.pad16(cout)
+        Nb, H, W = xb.shape[0], xb.shape[1], xb.shape[2]
+        pt, pb = E.same_pad(H, k, stride)
+        pl, pr = E.same_pad(W, k, stride)
+        Ho, Wo = -(-H // stride), -(-W // stride)
+        sh = _shadow(w, (cin_pad, cout_pad))
+        flags = N.EPI_BIAS | (N.EPI_OUT_F32 if out_f32 else 0)
+        y = torch.zeros(Nb, Ho, Wo, cout if out_f32 else cout_pad,
+                        dtype=torch.float32 if out_f32 else BF16, device=xb.device)
+        d = N.SegConvDesc(k, k, stride, pt, pl, pb, pr, cin, cout, cin_pad, cout_pad, flags,
+                          N.IMPL_UMMA)
+        N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(xb), None, N.ptr(sh), N.ptr(b.detach()),
+               N.vref(y[..., :cout]), N.stream_ptr())
+        ctx.save_for_backward(xb, sh)
+        ctx.geom = (k, stride, (pt, pl, pb, pr), cin, cout, cin_pad, cout_pad, x.dtype)
+        return y[..., :cout]
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, sh = ctx.saved_tensors
+        k, stride, pads, cin, cout, cin_pad, cout_pad, xdt = ctx.geom
+        # the tcgen05 gradients cover stride 1; strided convolutions use the CUDA-core kernels
+        impl = N.IMPL_UMMA if stride == 1 else N.IMPL_SIMT
+        d = N.SegConvDesc(k, k, stride, pads[0], pads[1], pads[2], pads[3], cin, cout, cin_pad,
+                          cout_pad, 0, impl)
+        dz = _as_bf16_padded(gy, cout_pad)
+        st = N.stream_ptr()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxp = torch.zeros_like(xb)
+            N.call('seg_conv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(sh), N.vref(dxp), None,
+                   None, None, st)
+            dx = dxp[..., :cin].to(xdt)
+        dw = torch.zeros(k, k, cin, cout, dtype=torch.float32, device=xb.device)
+        db = torch.zeros(cout, dtype=torch.float32, device=xb.device)
+        N.call('seg_conv2d_wgrad', ctypes.byref(d), N.vref(xb), None, N.vref(dz), N.ptr(dw),
+               N.ptr(db), st)
+        return dx, dw, db, None, None
+
+
+class _DeconvFn(torch.autograd.Function):
+    """tf.nn.conv2d_transpose(SAME) + bias_add and its gradients (seg_deconv2d_fwd /
+    seg_deconv2d_dgrad / seg_deconv2d_wgrad + seg_bias_grad).  w is [kh, kw, cout, cin]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, out_hw):
+        k, cout, cin = w.shape[0], w.shape[2], w.shape[3]
+        xb = _as_bf16_padded(x)
+        cin_pad, cout_pad = xb.shape[-1], E.pad16(cout)
+        tot = max(k - stride, 0)
+        pads = (tot // 2, tot // 2, tot - tot // 2, tot - tot // 2)
+        y = torch.zeros(xb.shape[0], out_hw[0], out_hw[1], cout_pad, dtype=BF16, device=xb.device)
+        # k == stride runs on the tcgen05 kernels; SAME-cropped k > stride on the gather kernel
+        impl = N.IMPL_UMMA if k == stride else N.IMPL_SIMT
+        d = N.SegConvDesc(k, k, stride, pads[0], pads[1], pads[2], pads[3], cin, cout, cin_pad,
+                          cout_pad, N.EPI_BIAS, impl)
+        sh = torch.zeros(k, k, cout_pad, cin_pad, dtype=BF16, device=xb.device)
+        sh[:, :, :cout, :cin] = w.detach().to(BF16)
+        N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(xb), N.ptr(sh), N.ptr(b.detach()),
+               N.vref(y[..., :cout]), N.stream_ptr())
+        ctx.save_for_backward(xb, sh)
+        ctx.geom = (k, stride, pads, cin, cout, cin_pad, cout_pad, impl, x.dtype)
+        return y[..., :cout]
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, sh = ctx.saved_tensors
+        k, stride, pads, cin, cout, cin_pad, cout_pad, impl, xdt = ctx.geom
+        d = N.SegConvDesc(k, k, stride, pads[0], pads[1], pads[2], pads[3], cin, cout, cin_pad,
+                          cout_pad, 0, impl)
+        dz = _as_bf16_padded(gy, cout_pad)
+        st = N.stream_ptr()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxp = torch.zeros_like(xb)
+            N.call('seg_deconv2d_dgrad', ctypes.byref(d), N.vref(dz), N.ptr(sh), N.vref(dxp), None,
+                   st)
+            dx = dxp[..., :cin].to(xdt)
+        dw = torch.zeros(k, k, cout, cin, dtype=torch.float32, device=xb.device)
+        db = torch.zeros(cout, dtype=torch.float32, device=xb.device)
+        N.call('seg_deconv2d_wgrad', ctypes.byref(d), N.vref(xb), N.vref(dz), N.ptr(dw), st)
+        N.call('seg_bias_grad', N.vref(dz[..., :cout]), N.ptr(db), st)
+        return dx, dw, db, None, None
+
+
+class _BatchNormTrainFn(torch.autograd.Function):
+    """Batch statistics, y = xhat * gamma + beta, and the batch-norm gradient
+    (seg_batchnorm_stats / _finalize / _apply, seg_batchnorm_bwd_reduce / _bwd_apply)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mm, mv, eps, momentum):
+        c = x.shape[-1]
+        xb = _as_bf16_padded(x)
+        y = torch.zeros_like(xb)
+        st = N.stream_ptr()
+        xs, ys = xb[..., :c], y[..., :c]
+        s = torch.zeros(4, c, dtype=torch.float32, device=x.device)
+        N.call('seg_batchnorm_stats', N.vref(xs), N.ptr(s[0]), N.ptr(s[1]), st)
+        count = x.shape[0] * x.shape[1] * x.shape[2]
+        N.call('seg_batchnorm_finalize', N.ptr(s[0]), N.ptr(s[1]), count, c, eps, momentum,
+               N.ptr(s[2]), N.ptr(s[3]), N.ptr(mm), N.ptr(mv), st)
+        scale = s[3] * gamma.detach()                # gamma folded into rstd (C elements)
+        N.call('seg_batchnorm_apply', N.vref(xs), N.ptr(s[2]), N.ptr(scale), N.ptr(beta.detach()),
+               N.vref(ys), st)
+        ctx.save_for_backward(xb, s, gamma.detach())
+        ctx.meta = (c, count, x.dtype)
+        return ys
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, s, gamma = ctx.saved_tensors
+        c, count, xdt = ctx.meta
+        st = N.stream_ptr()
+        dy = _as_bf16_padded(gy, xb.shape[-1])
+        red = torch.zeros(2, c, dtype=torch.float32, device=xb.device)   # sum dy, sum dy*xhat
+        N.call('seg_batchnorm_bwd_reduce', N.vref(dy[..., :c]), N.vref(xb[..., :c]), N.ptr(s[2]),
+               N.ptr(s[3]), N.ptr(red[0]), N.ptr(red[1]), st)
+        dx = torch.zeros_like(xb)
+        N.call('seg_batchnorm_bwd_apply', N.vref(dy[..., :c]), N.vref(xb[..., :c]), N.ptr(s[2]),
+               N.ptr(s[3]), N.ptr(red[0]), N.ptr(red[1]), count, 0, N.vref(dx[..., :c]), st)
+        # y = xhat * gamma + beta: the kernels differentiate xhat + beta; gamma scales dx
+        dxs = (dx[..., :c].float() * gamma).to(xdt)
+        return dxs, red[1].clone(), red[0].clone(), None, None, None, None
 
 
 class batch_norm(object):
@@ -89,26 +236,14 @@ class batch_norm(object):
         c = x.shape[-1]
         beta = _var(self.name + '/beta', (c,), np.zeros)
         gamma = _var(self.name + '/gamma', (c,), np.ones)
-        mm = _var(self.name + '/moving_mean', (c,), np.zeros)
-        mv = _var(self.name + '/moving_variance', (c,), np.ones)
-        xb = _as_bf16_padded(x)
-        y = torch.zeros_like(xb)
-        st = N.stream_ptr()
-        xs, ys = xb[..., :c], y[..., :c]
+        mm = _state(self.name + '/moving_mean', (c,), np.zeros)
+        mv = _state(self.name + '/moving_variance', (c,), np.ones)
         if train:
-            s = torch.zeros(4, c, dtype=torch.float32, device=x.device)
-            N.call('seg_batchnorm_stats', N.vref(xs), N.ptr(s[0]), N.ptr(s[1]), st)
-            count = x.shape[0] * x.shape[1] * x.shape[2]
-            N.call('seg_batchnorm_finalize', N.ptr(s[0]), N.ptr(s[1]), count, c, self.epsilon,
-                   self.momentum, N.ptr(s[2]), N.ptr(s[3]), N.ptr(mm), N.ptr(mv), st)
-            scale = s[3] * gamma                     # gamma folded into rstd (C elements)
-            N.call('seg_batchnorm_apply', N.vref(xs), N.ptr(s[2]), N.ptr(scale), N.ptr(beta),
-                   N.vref(ys), st)
-        else:
-            scale = gamma * torch.rsqrt(mv + self.epsilon)
-            N.call('seg_batchnorm_apply', N.vref(xs), N.ptr(mm), N.ptr(scale), N.ptr(beta),
-                   N.vref(ys), st)
-        return ys
+            return _BatchNormTrainFn.apply(x, gamma, beta, mm, mv, self.epsilon, self.momentum)
+        # inference: a per-channel affine of the moving statistics (plain tensor algebra,
+        # differentiable as it stands)
+        scale = gamma * torch.rsqrt(mv + self.epsilon)
+        return ((x.float() - mm) * scale + beta).to(BF16)
 
 
 def concat(tensors, axis, *args, **kwargs):
@@ -126,20 +261,7 @@ def conv2d(input_, output_dim, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="co
     cin = input_.shape[-1]
     w = _var(name + '/w', (k_h, k_w, cin, output_dim), lambda s: _truncated_normal(s, stddev))
     b = _var(name + '/biases', (output_dim,), np.zeros)
-    x = _as_bf16_padded(input_)
-    cin_pad, cout_pad = x.shape[-1], E.pad16(output_dim)
-    Nb, H, W = x.shape[0], x.shape[1], x.shape[2]
-    pt, pb = E.same_pad(H, k_h, d_h)
-    pl, pr = E.same_pad(W, k_w, d_w)
-    Ho, Wo = -(-H // d_h), -(-W // d_w)
-    y = torch.zeros(Nb, Ho, Wo, cout_pad, dtype=BF16, device=x.device)
-    d = N.SegConvDesc(k_h, k_w, d_h, pt, pl, pb, pr, cin, output_dim, cin_pad, cout_pad,
-                      N.EPI_BIAS, N.IMPL_UMMA)
-    sh = _shadow(w, (cin_pad, cout_pad))
-    N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x), None, N.ptr(sh), N.ptr(b),
-           N.vref(y[..., :output_dim]), N.stream_ptr())
-    torch.cuda.current_stream().synchronize()      # `sh` is a temporary
-    return y[..., :output_dim]
+    return _ConvFn.apply(input_, w, b, d_h, False)
 
 
 def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="deconv2d",
@@ -149,22 +271,9 @@ def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name
     # filter : [height, width, output_channels, in_channels]
     w = _var(name + '/w', (k_h, k_w, cout, cin), lambda s: _RNG.normal(0, stddev, s))
     b = _var(name + '/biases', (cout,), np.zeros)
-    x = _as_bf16_padded(input_)
-    cin_pad, cout_pad = x.shape[-1], E.pad16(cout)
-    assert output_shape[1] == x.shape[1] * d_h and output_shape[2] == x.shape[2] * d_w, \
+    assert output_shape[1] == input_.shape[1] * d_h and output_shape[2] == input_.shape[2] * d_w, \
         'SAME transposed conv: output must be input * stride'
-    tot = max(k_h - d_h, 0)
-    y = torch.zeros(x.shape[0], output_shape[1], output_shape[2], cout_pad, dtype=BF16,
-                    device=x.device)
-    impl = N.IMPL_UMMA if (k_h == d_h) else N.IMPL_SIMT
-    d = N.SegConvDesc(k_h, k_w, d_h, tot // 2, tot // 2, tot - tot // 2, tot - tot // 2, cin, cout,
-                      cin_pad, cout_pad, N.EPI_BIAS, impl)
-    sh = torch.zeros(k_h, k_w, cout_pad, cin_pad, dtype=BF16, device=x.device)
-    sh[:, :, :cout, :cin] = w.to(BF16)
-    N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(x), N.ptr(sh), N.ptr(b),
-           N.vref(y[..., :cout]), N.stream_ptr())
-    torch.cuda.current_stream().synchronize()
-    deconv = y[..., :cout]
+    deconv = _DeconvFn.apply(input_, w, b, d_h, (output_shape[1], output_shape[2]))
     if with_w:
         return deconv, w, b
     return deconv
@@ -179,16 +288,9 @@ def linear(input_, output_size, scope=None, stddev=0.02, bias_start=0.0, with_w=
     sc = scope or "Linear"
     matrix = _var(sc + '/Matrix', (shape[1], output_size), lambda s: _RNG.normal(0, stddev, s))
     bias = _var(sc + '/bias', (output_size,), lambda s: np.full(s, bias_start))
-    x = _as_bf16_padded(input_.reshape(shape[0], 1, 1, shape[1]))
-    kin_pad, n_pad = x.shape[-1], E.pad16(output_size)
-    sh = torch.zeros(1, 1, kin_pad, n_pad, dtype=BF16, device=x.device)
-    sh[0, 0, :shape[1], :output_size] = matrix.to(BF16)
-    y = torch.zeros(shape[0], 1, 1, output_size, dtype=torch.float32, device=x.device)
-    d = N.SegConvDesc(1, 1, 1, 0, 0, 0, 0, shape[1], output_size, kin_pad, n_pad,
-                      N.EPI_BIAS | N.EPI_OUT_F32, N.IMPL_UMMA)
-    N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x), None, N.ptr(sh), N.ptr(bias), N.vref(y),
-           N.stream_ptr())
-    torch.cuda.current_stream().synchronize()
+    # x @ Matrix + bias as a 1x1 convolution over a [B,1,1,K] view (fp32 output)
+    y = _ConvFn.apply(input_.reshape(shape[0], 1, 1, shape[1]),
+                      matrix.reshape(1, 1, shape[1], output_size), bias, 1, True)
     out = y.reshape(shape[0], output_size)
     if with_w:
         return out, matrix, bias

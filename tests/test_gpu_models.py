@@ -217,24 +217,123 @@ def test_ops_helpers(cuda):
     g = torch.Generator().manual_seed(0)
     x = bfr(torch.randn(2, 12, 12, 8, generator=g))
     y = ops.conv2d(x.cuda(), 24, name='d_h0_conv')
-    w, b = ops.get_variable('d_h0_conv/w').cpu(), ops.get_variable('d_h0_conv/biases').cpu()
+    w = ops.get_variable('d_h0_conv/w').detach().cpu()
+    b = ops.get_variable('d_h0_conv/biases').detach().cpu()
     assert tuple(w.shape) == (5, 5, 8, 24) and float(w.abs().max()) <= 0.04 + 1e-6
     ref = T.conv2d(x, bfr(w), b, 2, 'SAME')
     assert tuple(y.shape) == (2, 6, 6, 24) and rel_l2(y.float().cpu(), ref) < 4e-3
     y2 = ops.conv2d(x.cuda(), 24, name='d_h0_conv')                  # reuse
     assert torch.equal(y2, y)
     d, dw, db = ops.deconv2d(y, [2, 12, 12, 16], name='g_h1', with_w=True)
-    ref = T.conv2d_transpose(bfr(y.float().cpu()), bfr(dw.cpu()), db.cpu(), 2, 'SAME')
-    assert tuple(d.shape) == (2, 12, 12, 16) and rel_l2(d.float().cpu(), ref) < 4e-3
+    ref = T.conv2d_transpose(bfr(y.detach().float().cpu()), bfr(dw.detach().cpu()),
+                             db.detach().cpu(), 2, 'SAME')
+    assert tuple(d.shape) == (2, 12, 12, 16) and rel_l2(d.detach().float().cpu(), ref) < 4e-3
     z = bfr(torch.randn(4, 40, generator=g))
     out, M, bias = ops.linear(z.cuda(), 10, 'g_h0_lin', with_w=True)
-    assert rel_l2(out.cpu(), z @ bfr(M.cpu()) + bias.cpu()) < 1e-4
+    assert rel_l2(out.detach().cpu(), z @ bfr(M.detach().cpu()) + bias.detach().cpu()) < 1e-4
     bn = ops.batch_norm(name='g_bn0')
     yb = bn(x.cuda(), train=True)
     ref, m_ref, v_ref = T.batch_norm(x, torch.zeros(8), torch.zeros(8), torch.ones(8), True,
                                      decay=0.9, eps=1e-5, gamma=torch.ones(8))
-    assert rel_l2(yb.float().cpu(), ref) < 4e-3
+    assert rel_l2(yb.detach().float().cpu(), ref) < 4e-3
     assert torch.allclose(ops.get_variable('g_bn0/moving_mean').cpu(), m_ref, atol=1e-5)
     assert torch.equal(ops.lrelu(torch.tensor([-1.0, 2.0])), torch.tensor([-0.2, 2.0]))
     cc = ops.conv_cond_concat(x.cuda(), torch.ones(2, 1, 1, 3).cuda())
     assert tuple(cc.shape) == (2, 12, 12, 11)
+
+
+def test_ops_helpers_are_differentiable(cuda):
+    """The utils/ops.py helpers are differentiable like their TF originals (reference
+    utils/ops.py:58-110 build tf ops): a small DCGAN-style graph conv2d (3x3/s1 and the default
+    5x5/s2) -> lrelu -> batch_norm -> deconv2d (5x5/s2 SAME and 2x2/s2) -> linear, gradients of
+    a scalar w.r.t. every variable and the input against torch autograd on the CPU oracle ops
+    with bf16 rounding (straight-through) at the same op boundaries."""
+    from segmentation_b200.utils import ops
+    ops.reset_variables(1)
+    g = torch.Generator().manual_seed(3)
+    x = bfr(torch.randn(2, 8, 8, 8, generator=g))
+    coef = torch.randn(2, 5, generator=g)
+
+    xd = x.cuda().requires_grad_(True)
+    h0 = ops.lrelu(ops.conv2d(xd, 16, k_h=3, k_w=3, d_h=1, d_w=1, stddev=0.2, name='c0'))
+    h1 = ops.conv2d(h0, 16, stddev=0.1, name='c1')
+    bn = ops.batch_norm(name='bn0')
+    h2 = ops.lrelu(bn(h1, train=True))
+    h3 = ops.deconv2d(h2, [2, 8, 8, 8], stddev=0.1, name='d0')
+    h4 = ops.deconv2d(h3, [2, 16, 16, 4], k_h=2, k_w=2, stddev=0.3, name='d1')
+    out = ops.linear(h4.reshape(2, -1).float(), 5, 'lin', stddev=0.1)
+    (out * coef.cuda()).sum().backward()
+    sync()
+
+    def ste(t):                                   # bf16 rounding, gradient passes through
+        return t + (bfr(t.detach()) - t.detach())
+
+    names = ['c0/w', 'c0/biases', 'c1/w', 'c1/biases', 'bn0/gamma', 'bn0/beta', 'd0/w', 'd0/biases',
+             'd1/w', 'd1/biases', 'lin/Matrix', 'lin/bias']
+    V = {n: ops.get_variable(n).detach().cpu().clone().requires_grad_(True) for n in names}
+    xr = x.clone().requires_grad_(True)
+    r0 = ste(T.conv2d(xr, ste(V['c0/w']), V['c0/biases'], 1, 'SAME'))
+    r0 = torch.maximum(r0, 0.2 * r0)
+    r1 = ste(T.conv2d(r0, ste(V['c1/w']), V['c1/biases'], 2, 'SAME'))
+    r2, _, _ = T.batch_norm(r1, V['bn0/beta'], torch.zeros(16), torch.ones(16), True, decay=0.9,
+                            eps=1e-5, gamma=V['bn0/gamma'])
+    r2 = ste(r2)
+    r2 = torch.maximum(r2, 0.2 * r2)
+    r3 = ste(T.conv2d_transpose(r2, ste(V['d0/w']), V['d0/biases'], 2, 'SAME'))
+    r4 = ste(T.conv2d_transpose(r3, ste(V['d1/w']), V['d1/biases'], 2, 'SAME'))
+    ro = ste(r4.reshape(2, -1)) @ ste(V['lin/Matrix']) + V['lin/bias']
+    (ro * coef).sum().backward()
+    assert rel_l2(out.detach().cpu(), ro.detach()) < 1e-2
+    rec = {}
+    for n in names:
+        rec[n] = rel_l2(ops.get_variable(n).grad.cpu(), V[n].grad)
+    rec['x'] = rel_l2(xd.grad.cpu(), xr.grad)
+    report('ops_backward', rec)
+    # the bias in front of a batch-norm has a gradient of exactly zero (the layer removes the
+    # mean): both sides hold rounding noise there, compare it with the layer's weight gradient
+    rec.pop('c1/biases')
+    noise = float(ops.get_variable('c1/biases').grad.abs().max())
+    assert noise < 1e-2 * float(ops.get_variable('c1/w').grad.abs().max()), noise
+    assert max(rec.values()) < 3e-2, rec
+
+
+def test_deconv_fused_tail_matches_unfused(cuda):
+    """DeconvModel inference: the one-launch class-map tail (seg_classmap_tail_infer: resize ->
+    deconv3_0 -> bn8 -> conv_out -> sigmoid/argmax) against the five separate C-ABI calls.
+    Every intermediate is rounded to bf16 at the same points, so logits agree to fp32
+    summation order and the label maps wherever the class margin exceeds that noise."""
+    import os
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.deconvolution import DeconvModel
+    S, nk, B = 256, 32, 3
+    model = DeconvModel(mode='INFERENCE', n_classes=2, input_dims=S, n_kernels=nk,
+                        load_snapshot=False, save_dir=None)
+    p = _nonzero_biases(nets.deconv_params(n_kernels=nk, n_classes=2, seed=9))
+    g = np.random.default_rng(4)
+    for k in p:
+        if k.endswith('moving_mean'):
+            p[k] = torch.from_numpy(g.normal(0.2, 0.05, p[k].shape).astype(np.float32))
+        if k.endswith('moving_variance'):
+            p[k] = torch.from_numpy(g.uniform(0.05, 0.3, p[k].shape).astype(np.float32))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x = g.random((B, S, S, 3), dtype=np.float32)
+    ex = model._get_exec(B, False)
+    probs_f, lab_f = model.infer(x)
+    assert ex._tail_done
+    logits_f = ex.logits.cpu().clone()
+    os.environ['SEGB200_FUSED_TAIL'] = '0'
+    try:
+        probs_u, lab_u = model.infer(x)
+        assert not ex._tail_done
+        logits_u = ex.logits.cpu().clone()
+    finally:
+        del os.environ['SEGB200_FUSED_TAIL']
+    e = rel_l2(logits_f, logits_u)
+    dmax = float((logits_f - logits_u).abs().max())
+    margin = (logits_u[..., 0] - logits_u[..., 1]).abs()
+    safe = margin > 4 * dmax + 1e-6
+    report('deconv_fused_tail', {'logits_rel_l2': e, 'logits_max_abs': dmax,
+                                 'unsafe': int((~safe).sum()), 'pixels': int(safe.numel())})
+    assert e < 2e-3, e
+    assert np.allclose(probs_f, probs_u, atol=0.25 * dmax + 1e-6)
+    assert bool((torch.from_numpy(lab_f)[..., 0][safe] == torch.from_numpy(lab_u)[..., 0][safe]).all())

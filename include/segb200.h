@@ -136,8 +136,9 @@ SEG_API int32_t seg_conv2d_wgrad(const seg_conv_desc* d, const seg_view* x, cons
                          const seg_view* dz, float* dw, float* db, void* stream);
 
 /* ---- first layer fused with the max-pool that follows it (models/unet.py:111-120:
- * conv1_1 -> pool1; models/fcn.py:110-117: conv1 -> pool1).  x4 is the (R,G,B,1) input of
- * seg_stage_input; 3x3, stride 1, cout_pad == 32, even output grid.
+ * conv1_1 -> pool1; models/fcn.py:110-117: conv1 -> pool1; models/deconvolution.py:109-118:
+ * conv1_0 -> bn1 -> pool1).  x4 is the (R,G,B,1) input of seg_stage_input; 3x3 stride 1 or
+ * (forward entries) 5x5 stride 2, cout_pad == 32, even output grid; argmax nullable.
  * fwd: pooled = maxpool2x2/2(relu(conv(x4) + bias)) with the uint8 window slots of
  *   seg_maxpool_fwd in `argmax`, ONE launch; the full-resolution activation is written only
  *   into y_win (nullable), a view of its window whose top-left output pixel is
@@ -155,6 +156,17 @@ SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, 
                                     const float* bias, const seg_view* y_win, int32_t win_y0,
                                     int32_t win_x0, const seg_view* pooled, uint8_t* argmax,
                                     void* stream);
+/* inference form with slim.batch_norm (moving statistics) between the ReLU and the pool:
+ * pooled = maxpool2x2/2(bn(relu(conv(x4) + bias))), each stage rounded to bf16 where the
+ * unfused entries store bf16 (seg_conv2d_fwd, seg_batchnorm_infer, seg_maxpool_fwd).
+ * w_rows_per_tap: rows of the [taps * rows][cout_pad] bf16 weight matrix per filter tap -
+ * 0 = d->cin_pad (the padded HWIO shadow), 3 = the dense [kh*kw*3][cout_pad] matrix of a
+ * patch-packed first layer. */
+SEG_API int32_t seg_conv2d_bn_pool_infer(const seg_conv_desc* d, const seg_view* x4,
+                                         const void* w_bf16, int32_t w_rows_per_tap,
+                                         const float* bias, const float* bn_mean, const float* bn_var, float bn_eps,
+                                         const float* bn_beta, const seg_view* pooled,
+                                         uint8_t* argmax, void* stream);
 SEG_API int32_t seg_conv2d_pool_wgrad(const seg_conv_desc* d, const seg_view* x4,
                                       const seg_view* dpool, const uint8_t* argmax,
                                       const seg_view* pooled, float* dw, float* db,

@@ -33,7 +33,8 @@ int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view&
 // fconv.cu
 int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
                    const seg_view* y_win, int win_y0, int win_x0, const seg_view& pooled,
-                   uint8_t* argmax, cudaStream_t st);
+                   uint8_t* argmax, const float* bn_mean, const float* bn_var, float bn_eps,
+                   const float* bn_beta, int w_rows_per_tap, cudaStream_t st);
 int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dpool,
                      const uint8_t* argmax, const seg_view& pooled, float* dw, float* db,
                      cudaStream_t st);
@@ -214,15 +215,31 @@ SEG_API int32_t seg_conv2d_pool_fwd(const seg_conv_desc* d, const seg_view* x4, 
                                     const float* bias, const seg_view* y_win, int32_t win_y0,
                                     int32_t win_x0, const seg_view* pooled, uint8_t* argmax,
                                     void* stream) {
-  SEG_REQUIRE(desc_ok(d) && x4 && w_bf16 && pooled && argmax, SEG_E_BAD_SHAPE,
+  SEG_REQUIRE(desc_ok(d) && x4 && w_bf16 && pooled, SEG_E_BAD_SHAPE,
               "conv2d_pool_fwd: bad argument");
   SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE, "conv2d_pool_fwd: bias missing");
   const int rc = fconv_pool_fwd(*d, *x4, w_bf16, bias, y_win, win_y0, win_x0, *pooled, argmax,
-                                (cudaStream_t)stream);
+                                nullptr, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
   SEG_REQUIRE(rc != SEG_E_UNSUPPORTED, SEG_E_UNSUPPORTED,
-              "conv2d_pool_fwd: needs the first-layer shape (3x3 stride 1 on the (R,G,B,1) input, "
-              "32 padded output channels), an even output grid and dense 16-byte aligned "
-              "pooled / argmax tensors; use seg_conv2d_fwd + seg_maxpool_fwd otherwise");
+              "conv2d_pool_fwd: needs the first-layer shape (3x3 stride 1 or 5x5 stride 2 on the "
+              "(R,G,B,1) input, 32 padded output channels), an even output grid and dense 16-byte "
+              "aligned pooled / argmax tensors; use seg_conv2d_fwd + seg_maxpool_fwd otherwise");
+  return rc;
+}
+
+SEG_API int32_t seg_conv2d_bn_pool_infer(const seg_conv_desc* d, const seg_view* x4,
+                                         const void* w_bf16, int32_t w_rows_per_tap,
+                                         const float* bias, const float* bn_mean, const float* bn_var, float bn_eps,
+                                         const float* bn_beta, const seg_view* pooled,
+                                         uint8_t* argmax, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x4 && w_bf16 && pooled && bn_mean && bn_var && bn_beta, SEG_E_BAD_SHAPE,
+              "conv2d_bn_pool_infer: bad argument");
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE,
+              "conv2d_bn_pool_infer: bias missing");
+  const int rc = fconv_pool_fwd(*d, *x4, w_bf16, bias, nullptr, 0, 0, *pooled, argmax, bn_mean,
+                                bn_var, bn_eps, bn_beta, w_rows_per_tap, (cudaStream_t)stream);
+  SEG_REQUIRE(rc != SEG_E_UNSUPPORTED, SEG_E_UNSUPPORTED,
+              "conv2d_bn_pool_infer: needs the shape of seg_conv2d_pool_fwd");
   return rc;
 }
 

@@ -17,25 +17,27 @@ void fconv_enable(int on) { g_use_fconv = on != 0; }
 // grid.
 static bool fconv_geom_ok(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, int out_n,
                           int out_h, int out_w) {
-  return g_use_fconv && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.cin == 3 && x.c == 4 &&
+  const bool k3 = d.kh == 3 && d.kw == 3 && d.stride == 1;
+  const bool k5 = d.kh == 5 && d.kw == 5 && d.stride == 2;      // forward variants only
+  return g_use_fconv && (k3 || k5) && d.cin == 3 && x.c == 4 &&
          !(x2 && x2->ptr) && x.sw == 4 && x.sh % 4 == 0 && x.sn % 4 == 0 &&
          (d.cout_pad == 32 || d.cout_pad == 64) &&
          (reinterpret_cast<uintptr_t>(x.ptr) & 7) == 0 && out_n == x.n &&
          (int64_t)out_n * out_h * out_w < (int64_t)1 << 30 &&
-         out_h == x.h + d.pad_t + d.pad_b - 2 && out_w == x.w + d.pad_l + d.pad_r - 2 &&
-         out_w > 1 && out_h > 1;
+         out_h == (x.h + d.pad_t + d.pad_b - d.kh) / d.stride + 1 &&
+         out_w == (x.w + d.pad_l + d.pad_r - d.kw) / d.stride + 1 && out_w > 1 && out_h > 1;
 }
 static bool fconv_shape_ok(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                            const seg_view& out) {
   return fconv_geom_ok(d, x, x2, out.n, out.h, out.w) && view_dense(out) && out.c == d.cout_pad;
 }
 
-template <int BN, bool WGRAD, bool POOL>
+template <int BN, bool WGRAD, bool POOL, int KH = 3, int ST = 1>
 static int launch_fconv_t(const FconvParams& P, const void* io, cudaStream_t st) {
-  using Cfg = FconvCfg<BN, WGRAD, POOL>;
+  using Cfg = FconvCfg<BN, WGRAD, POOL, KH, ST>;
   static bool attr_done = false;
   if (!attr_done) {
-    SEG_CHECK_CUDA(cudaFuncSetAttribute(fconv_kernel<BN, WGRAD, POOL>,
+    SEG_CHECK_CUDA(cudaFuncSetAttribute(fconv_kernel<BN, WGRAD, POOL, KH, ST>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_done = true;
@@ -51,7 +53,7 @@ static int launch_fconv_t(const FconvParams& P, const void* io, cudaStream_t st)
   const int per_sm = 2 * Cfg::kSmemBytes <= 220 * 1024 ? 2 : 1;
   int grid = per_sm * num_sms();
   if (grid > P.tiles) grid = P.tiles;
-  SEG_CHECK_CUDA(launch_k(fconv_kernel<BN, WGRAD, POOL>, dim3(grid), dim3(kFcThreads),
+  SEG_CHECK_CUDA(launch_k(fconv_kernel<BN, WGRAD, POOL, KH, ST>, dim3(grid), dim3(kFcThreads),
                           (size_t)Cfg::kSmemBytes, st, tm, P));
   return SEG_OK;
 }
@@ -98,13 +100,16 @@ int fconv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, con
   P.w = reinterpret_cast<const bf16*>(w);
   P.bias = bias;
   P.flags = d.flags;
+  if (d.kh == 5)
+    return d.cout_pad == 32 ? launch_fconv_t<32, false, false, 5, 2>(P, y.ptr, st)
+                            : SEG_E_UNSUPPORTED;
   return d.cout_pad == 32 ? launch_fconv_t<32, false, false>(P, y.ptr, st)
                           : launch_fconv_t<64, false, false>(P, y.ptr, st);
 }
 
 int fconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                 const seg_view& dz, float* dw, float* db, cudaStream_t st) {
-  if (!fconv_shape_ok(d, x, x2, dz)) return SEG_E_UNSUPPORTED;
+  if (!fconv_shape_ok(d, x, x2, dz) || d.kh != 3) return SEG_E_UNSUPPORTED;
   FconvParams P;
   fill_params(&P, d, x, dz.h, dz.w, false);
   P.dw = dw;
@@ -129,9 +134,11 @@ static bool window_view_ok(const seg_view& v) {     // 16-byte chunks of 32-chan
 
 int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
                    const seg_view* y_win, int win_y0, int win_x0, const seg_view& pooled,
-                   uint8_t* argmax, cudaStream_t st) {
-  const int oh = x.h + d.pad_t + d.pad_b - 2, ow = x.w + d.pad_l + d.pad_r - 2;
-  if (!pool_geom_ok(d, x, oh, ow, pooled) || (d.flags & SEG_EPI_OUT_F32) || !argmax ||
+                   uint8_t* argmax, const float* bn_mean, const float* bn_var, float bn_eps,
+                   const float* bn_beta, int w_rows_per_tap, cudaStream_t st) {
+  const int oh = (x.h + d.pad_t + d.pad_b - d.kh) / d.stride + 1;
+  const int ow = (x.w + d.pad_l + d.pad_r - d.kw) / d.stride + 1;
+  if (!pool_geom_ok(d, x, oh, ow, pooled) || (d.flags & SEG_EPI_OUT_F32) ||
       (reinterpret_cast<uintptr_t>(argmax) & 7) != 0)
     return SEG_E_UNSUPPORTED;
   FconvParams P;
@@ -152,6 +159,9 @@ int fconv_pool_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, con
     P.win_y0 = win_y0; P.win_x0 = win_x0;
     P.win_y1 = win_y0 + y_win->h; P.win_x1 = win_x0 + y_win->w;
   }
+  P.bn_mean = bn_mean; P.bn_var = bn_var; P.bn_beta = bn_beta; P.bn_eps = bn_eps;
+  if (w_rows_per_tap > 0) P.cin_pad = w_rows_per_tap;      // weight-matrix rows per filter tap
+  if (d.kh == 5) return launch_fconv_t<32, false, true, 5, 2>(P, nullptr, st);
   return launch_fconv_t<32, false, true>(P, nullptr, st);
 }
 
@@ -159,7 +169,7 @@ int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& 
                      const uint8_t* argmax, const seg_view& pooled, float* dw, float* db,
                      cudaStream_t st) {
   const int oh = x.h + d.pad_t + d.pad_b - 2, ow = x.w + d.pad_l + d.pad_r - 2;
-  if (!pool_geom_ok(d, x, oh, ow, pooled) || !pool_geom_ok(d, x, oh, ow, dpool) || !argmax ||
+  if (d.kh != 3 || !pool_geom_ok(d, x, oh, ow, pooled) || !pool_geom_ok(d, x, oh, ow, dpool) || !argmax ||
       (reinterpret_cast<uintptr_t>(argmax) & 7) != 0)
     return SEG_E_UNSUPPORTED;
   FconvParams P;

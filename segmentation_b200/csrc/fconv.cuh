@@ -72,28 +72,40 @@ struct FconvParams {
   bf16* pooled;             // dense [N][Hp][Wp][BN]: pool output (forward) / mask source (wgrad)
   uint8_t* amax;            // dense [N][Hp][Wp][BN] window slots
   const bf16* dpool;        // dense [N][Hp][Wp][BN] gradient w.r.t. the pool output
+  // pooled forward, inference: slim.batch_norm with the moving statistics between the ReLU and
+  // the pool (models/deconvolution.py:109-118), y = (relu(conv) - mean) * rsqrt(var + eps) +
+  // beta, each stage rounded to bf16 as the unfused entries store it.  Null: none.
+  const float* bn_mean; const float* bn_var; const float* bn_beta; float bn_eps;
 };
 
 constexpr int kFcThreads = 448;          // MMA issuer, alloc/TMA warp, 8 epilogue, 4 builder warps
-constexpr int kFcABytes = 128 * 128;     // one patch tile: 128 pixels x 128-byte row
+constexpr int kFcABytes = 128 * 128;     // one K-block of a patch tile: 128 pixels x 128 bytes
 constexpr int kFcRows = 37;              // accumulator rows of the weight gradient that are used
 constexpr int kFcRawDepth = 4;           // pooled weight gradient: raw tiles in flight per thread
 constexpr int kFcRawBytes = 128 * 48;    // dpool 16 B + pooled 16 B + slots 8 B (+8) per thread
 constexpr int kFcPoolStg = 32 * 80;      // pooled forward: one warp's transpose staging (80-byte rows)
 
-template <int BN, bool WGRAD, bool POOL>
+// KH x KH filter taps, stride ST.  k-slot of (tap, channel) = tap*4 + c; the constant-1
+// slots (bias hi / lo) follow the taps; K is padded to a multiple of 16 and split into
+// K-blocks of 64 slots (one 128-byte SWIZZLE_128B row per pixel and block).
+template <int BN, bool WGRAD, bool POOL, int KH = 3, int ST = 1>
 struct FconvCfg {
-  static constexpr int S = (WGRAD && POOL) ? 3 : 4;     // pipeline stages
+  static constexpr int kOne = KH * KH * 4;                       // first constant-1 slot
+  static constexpr int kKpad = (kOne + 2 + 15) / 16 * 16;        // 48 (3x3), 112 (5x5)
+  static constexpr int kKB = (kKpad + 63) / 64;                  // K-blocks per tile
+  static constexpr int kABytes = kKB * kFcABytes;                // one patch-tile stage
+  static constexpr int S = (WGRAD && POOL) ? 3 : (kKB > 1 ? 2 : 4);   // pipeline stages
   static constexpr int rowB = BN * 2;
   static constexpr int kZBytes = 128 * rowB;            // one dZ tile (wgrad)
-  static constexpr int kWBytes = BN * 128;              // weights, K-major 128-byte rows (fwd)
+  static constexpr int kWBytes = kKB * BN * 128;        // weights, K-major 128-byte rows (fwd)
   static constexpr int kStgBytes = 32 * rowB;           // one epilogue warp's store box (fwd)
-  static constexpr int kOffRaw = S * kFcABytes + S * kZBytes;
+  static constexpr int kOffRaw = S * kABytes + S * kZBytes;
   static constexpr int kOffBars =
-      S * kFcABytes + (WGRAD ? S * kZBytes + (POOL ? kFcRawDepth * kFcRawBytes : 0)
-                             : kWBytes + (POOL ? 8 * kFcPoolStg : 16 * kStgBytes));
+      S * kABytes + (WGRAD ? S * kZBytes + (POOL ? kFcRawDepth * kFcRawBytes : 0)
+                           : kWBytes + (POOL ? 8 * kFcPoolStg : 16 * kStgBytes));
   static constexpr int kSmemBytes = kOffBars + 256 + 1024 /*base alignment*/;
   static constexpr int kTmemCols = WGRAD ? (BN < 32 ? 32 : BN) : 2 * BN;
+  static_assert(!WGRAD || kKB == 1, "weight gradient: 3x3 only");
 };
 
 __device__ __forceinline__ uint32_t fc_div(uint32_t x, uint32_t mul, uint32_t shr) {
@@ -117,11 +129,12 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, bool WGRAD, bool POOL>
+template <int BN, bool WGRAD, bool POOL, int KH = 3, int ST = 1>
 __global__ void __launch_bounds__(kFcThreads, 2)
 fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
-  using Cfg = FconvCfg<BN, WGRAD, POOL>;
+  using Cfg = FconvCfg<BN, WGRAD, POOL, KH, ST>;
   constexpr int S = Cfg::S;
+  constexpr int kAB = Cfg::kABytes;
   constexpr int rowB = Cfg::rowB;
   static_assert(BN == 32 || BN == 64, "first-layer kernel: 32 or 64 output channels per tile");
   static_assert(!POOL || BN == 32, "pooled variants: 32 output channels");
@@ -131,9 +144,9 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
-  uint8_t* z_ring = smem + S * kFcABytes;               // wgrad
+  uint8_t* z_ring = smem + S * kAB;                     // wgrad
   uint8_t* raw_ring = smem + Cfg::kOffRaw;              // wgrad + pool
-  uint8_t* w_smem = smem + S * kFcABytes;               // fwd
+  uint8_t* w_smem = smem + S * kAB;                     // fwd
   uint8_t* stg = w_smem + Cfg::kWBytes;                 // fwd (plain)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint64_t* a_full = bars;
@@ -170,29 +183,38 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
   // initialise the patch ring once: the builders only ever write the first 72 bytes of a row
   // (k-slots 0..35); slots 36 and 37 are the constant 1, slots 38..47 (read by the third
   // k-step) stay zero
-  for (int i = threadIdx.x; i < S * kFcABytes / 16; i += kFcThreads)
+  for (int i = threadIdx.x; i < S * kAB / 16; i += kFcThreads)
     sts128(smem_u32(a_ring) + i * 16, make_uint4(0u, 0u, 0u, 0u));
   __syncthreads();
-  for (int i = threadIdx.x; i < S * 128; i += kFcThreads) {
-    const uint32_t row = smem_u32(a_ring) + (uint32_t)i * 128u;
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + ((4u ^ ((uint32_t)i & 7u)) << 4) + 8u),
-                 "r"(0x3F803F80u) : "memory");
+  {
+    // the two constant-1 slots: byte kOne*2 of the pixel's K row = K-block kOne/64, 16-byte
+    // chunk (kOne%64)/8 (swizzled), second half
+    constexpr uint32_t kBlk = Cfg::kOne / 64, kChunk = (Cfg::kOne % 64) / 8;
+    static_assert((Cfg::kOne % 8) == 4, "constant-1 slots sit in the second half of a chunk");
+    for (int i = threadIdx.x; i < S * 128; i += kFcThreads) {
+      const uint32_t st_ = (uint32_t)i / 128u, t_ = (uint32_t)i % 128u;
+      const uint32_t row = smem_u32(a_ring) + st_ * kAB + kBlk * kFcABytes + t_ * 128u;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + ((kChunk ^ (t_ & 7u)) << 4) + 8u),
+                   "r"(0x3F803F80u) : "memory");
+    }
   }
   pdl_wait();                 // everything above overlaps the previous kernel's tail
   if (!WGRAD) {
     // weights -> K-major SWIZZLE_128B rows: row = output channel, k-slot = r*12 + s*4 + c
-    for (int idx = threadIdx.x; idx < BN * 64; idx += kFcThreads) {
-      const int co = idx >> 6, k = idx & 63;
-      const int r = k / 12, rem = k - r * 12, s = rem >> 2, c = rem & 3;
+    for (int idx = threadIdx.x; idx < BN * Cfg::kKB * 64; idx += kFcThreads) {
+      const int co = idx / (Cfg::kKB * 64), k = idx % (Cfg::kKB * 64);
+      const int tap = k >> 2, c = k & 3;
       bf16 v = __float2bfloat16(0.f);
-      if (k < 36 && c < 3 && co < P.cout_pad) {
-        v = P.w[((int64_t)(r * 3 + s) * P.cin_pad + c) * P.cout_pad + co];
-      } else if ((k == 36 || k == 37) && (P.flags & SEG_EPI_BIAS) && co < P.cout) {
+      if (k < Cfg::kOne && c < 3 && co < P.cout_pad) {
+        v = P.w[((int64_t)tap * P.cin_pad + c) * P.cout_pad + co];
+      } else if ((k == Cfg::kOne || k == Cfg::kOne + 1) && (P.flags & SEG_EPI_BIAS) && co < P.cout) {
         const float bv = __ldg(P.bias + co);
         const bf16 hi = __float2bfloat16(bv);
-        v = k == 36 ? hi : __float2bfloat16(bv - __bfloat162float(hi));
+        v = k == Cfg::kOne ? hi : __float2bfloat16(bv - __bfloat162float(hi));
       }
-      *reinterpret_cast<bf16*>(w_smem + co * 128 + (((k >> 3) ^ (co & 7)) << 4) + (k & 7) * 2) = v;
+      const int blk = k >> 6, kk = k & 63;
+      *reinterpret_cast<bf16*>(w_smem + blk * (BN * 128) + co * 128 +
+                               (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2) = v;
     }
   }
   fence_proxy_async();
@@ -214,11 +236,13 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           mbar_wait(&a_full[s], (uint32_t)(i / S) & 1u);
           fence_proxy_async();           // the builders' cp.async writes -> tensor-core reads
           tc_fence_after();
-          const uint32_t a0 = umma_desc_lo(smem_u32(a_ring + s * kFcABytes), 0);
+          const uint32_t a0 = umma_desc_lo(smem_u32(a_ring + s * kAB), 0);
 #pragma unroll
-          for (int kk = 0; kk < 3; ++kk)
-            umma_f16(tmem_base + as * BN, umma_desc_pack(hi, a0 + kk * 2),
-                     umma_desc_pack(hi, b0 + kk * 2), idesc, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < Cfg::kKpad / 16; ++kk)
+            umma_f16(tmem_base + as * BN,
+                     umma_desc_pack(hi, a0 + (kk >> 2) * (kFcABytes >> 4) + (kk & 3) * 2),
+                     umma_desc_pack(hi, b0 + (kk >> 2) * ((BN * 128) >> 4) + (kk & 3) * 2), idesc,
+                     kk != 0 ? 1u : 0u);
           umma_commit(&a_empty[s]);
           umma_commit(&tfull[as]);
         }
@@ -235,7 +259,7 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           mbar_wait(&z_full[s], ph);
           fence_proxy_async();
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_ring + s * kFcABytes);
+          const uint32_t a_addr = smem_u32(a_ring + s * kAB);
           const uint32_t z_addr = smem_u32(z_ring + s * Cfg::kZBytes);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -320,6 +344,14 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
       const bool dx = (lane & 1) != 0, dy = (lane & 2) != 0;
       const int k = lane & 3;
       const int xp = quad * 8 + (lane >> 2);
+      float bn_m[8], bn_s[8], bn_b[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool on = P.bn_mean != nullptr && 8 * k + e < P.cout;
+        bn_m[e] = on ? __ldg(P.bn_mean + 8 * k + e) : 0.f;
+        bn_s[e] = on ? rsqrtf(__ldg(P.bn_var + 8 * k + e) + P.bn_eps) : 1.f;
+        bn_b[e] = on ? __ldg(P.bn_beta + 8 * k + e) : 0.f;
+      }
       int j = 0;
       for (int i = half; i < n_my; i += 2, ++j) {
         int n, Y, tx;
@@ -358,6 +390,22 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         for (int jj = 0; jj < 4; ++jj)
           v[jj] = lds128(sw + (uint32_t)((lane & ~3) + jj) * 80u + (uint32_t)k * 16u);
         __syncwarp();
+        if (P.bn_mean != nullptr) {
+          // batch-norm (moving statistics) on this lane's 8 channels of the four candidates
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            uint32_t c4[4] = {v[jj].x, v[jj].y, v[jj].z, v[jj].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int ch = 8 * k + 2 * w;
+              const float lo = (bf16_lo(c4[w]) - bn_m[2 * w]) * bn_s[2 * w] + bn_b[2 * w];
+              const float hi = (bf16_hi(c4[w]) - bn_m[2 * w + 1]) * bn_s[2 * w + 1] + bn_b[2 * w + 1];
+              (void)ch;
+              c4[w] = pack_bf16x2(lo, hi);
+            }
+            v[jj] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+          }
+        }
         // maximum and slot of the first maximum in scan order (0,0),(0,1),(1,0),(1,1): a
         // later candidate wins only if strictly greater
         uint32_t best[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
@@ -377,11 +425,13 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
           const int64_t pix = ((int64_t)(n * P.Hp + Y) * P.Wp + col) * BN;
           *reinterpret_cast<uint4*>(P.pooled + pix + 8 * k) =
               make_uint4(best[0], best[1], best[2], best[3]);
-          uint32_t two[4];
+          if (P.amax != nullptr) {
+            uint32_t two[4];
 #pragma unroll
-          for (int w = 0; w < 4; ++w) two[w] = (slot[w] & 0xffu) | ((slot[w] >> 8) & 0xff00u);
-          *reinterpret_cast<uint2*>(P.amax + pix + 8 * k) =
-              make_uint2(two[0] | (two[1] << 16), two[2] | (two[3] << 16));
+            for (int w = 0; w < 4; ++w) two[w] = (slot[w] & 0xffu) | ((slot[w] >> 8) & 0xff00u);
+            *reinterpret_cast<uint2*>(P.amax + pix + 8 * k) =
+                make_uint2(two[0] | (two[1] << 16), two[2] | (two[3] << 16));
+          }
         }
       }
     } else if (WGRAD && POOL && half == 1) {
@@ -494,23 +544,24 @@ fconv_kernel(const __grid_constant__ CUtensorMap tmIO, const FconvParams P) {
         oy = (int)fc_div(rem, P.div_a_mul, P.div_a_shr);
         ox = (int)(rem - (uint32_t)oy * P.div_a);
       }
-      const int iy0 = oy - P.pad_t, ix0 = ox - P.pad_l;
+      const int iy0 = oy * ST - P.pad_t, ix0 = ox * ST - P.pad_l;
       const int s = i % S;
       mbar_wait(&a_empty[s], ((uint32_t)(i / S) & 1u) ^ 1u);
-      const uint32_t row = smem_u32(a_ring + s * kFcABytes) + (uint32_t)t * 128u;
+      const uint32_t row = smem_u32(a_ring + s * kAB) + (uint32_t)t * 128u;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
+      for (int r = 0; r < KH; ++r) {
         const int iy = iy0 + r;
         const bool yok = live && (unsigned)iy < (unsigned)P.H;
         const int iyc = yok ? iy : 0;
 #pragma unroll
-        for (int sx = 0; sx < 3; ++sx) {
+        for (int sx = 0; sx < KH; ++sx) {
           const int ix = ix0 + sx;
           const bool ok = yok && (unsigned)ix < (unsigned)P.W;
           const uint2* src = P.x4 + (n * P.x_sn + iyc * P.x_sh + (ok ? ix : 0));
-          const int q = r * 3 + sx;                  // 8-byte piece q of the row
-          cp_async_8(row + ((((uint32_t)q >> 1) ^ x7) << 4) + (uint32_t)(q & 1) * 8u, src,
-                     ok ? 8u : 0u);
+          const int q = r * KH + sx;                 // 8-byte piece q of the pixel's K row
+          cp_async_8(row + (uint32_t)(q >> 4) * kFcABytes +
+                         (((((uint32_t)q & 15u) >> 1) ^ x7) << 4) + (uint32_t)(q & 1) * 8u,
+                     src, ok ? 8u : 0u);
         }
       }
       cp_async_arrive_noinc(&a_full[s]);

@@ -509,6 +509,30 @@ def stage_input(x, y4, mask_src=None, mask_dst=None, crop_yx=None, mask_kind=Non
            ctypes.byref(ctl) if ctl is not None else None, N.stream_ptr())
 
 
+def conv_bn_pool_infer(layer, bn, x4, pooled, argmax=None):
+    """seg_conv2d_bn_pool_infer: first convolution (`layer`: a ConvLayer or PatchConvLayer of an
+    RGB input, 3x3/s1 or 5x5/s2) + ReLU + batch-norm `bn` (moving statistics) + 2x2/2 max-pool in
+    one launch on the (R,G,B,1) staged input (reference models/deconvolution.py:109-118)."""
+    patch = isinstance(layer, PatchConvLayer)
+    k = layer.patch_k if patch else layer.k
+    s = layer.patch_stride if patch else layer.stride
+    padding = layer.patch_padding if patch else layer.padding
+    h, w = x4.shape[1], x4.shape[2]
+    if padding == 'SAME':
+        (pt, pb), (pl, pr) = same_pad(h, k, s), same_pad(w, k, s)
+    else:
+        pt = pb = pl = pr = 0
+    cout = layer.cout
+    d = N.SegConvDesc(k, k, s, pt, pl, pb, pr, 3, cout, 16, layer.cout_pad,
+                      N.EPI_BIAS | (N.EPI_RELU if layer.relu else 0), N.IMPL_UMMA)
+    N.set_tag(layer.name)
+    px = pooled.shape[0] * pooled.shape[1] * pooled.shape[2] * 4
+    N.note_work(2.0 * px * cout * 3 * k * k, x4.numel() * 2.0 + pooled.numel() * 2.0)
+    N.call('seg_conv2d_bn_pool_infer', ctypes.byref(d), N.vref(x4), N.ptr(layer.w.shadow()),
+           3 if patch else 0, N.ptr(layer.b.value()), N.ptr(bn.moving_mean), N.ptr(bn.moving_var),
+           bn.eps, N.ptr(bn.beta.value()), N.vref(pooled), N.ptr(argmax), N.stream_ptr())
+
+
 def classmap_tail_infer(x, rh, rw, up, bn, conv_out, logits, probs, labelmap):
     """seg_classmap_tail_infer: resize_bilinear -> 2x2/s2 transposed conv `up` (+ReLU) ->
     batch-norm `bn` (moving statistics) -> 3x3 SAME conv `conv_out` -> sigmoid / argmax, one

@@ -100,7 +100,15 @@ class DeconvModel(BaseModel):
         """Forward graph; `training` selects batch statistics vs moving statistics
         in the batch-norm layers (reference `models/deconvolution.py:101,116`)."""
         x = self._to_device(input_op, torch.float32)
-        ex = self._get_exec(x.shape[0], False)
+        if training:
+            # batch statistics: an executor with the unfused first layer (the inference
+            # executor evaluates conv1_0 + bn1 + pool1 with the moving statistics in one launch)
+            key = (x.shape[0], 'forward-batchstats')
+            if key not in self._exec:
+                self._exec[key] = _DeconvExec(self, x.shape[0], False, fuse_head=False)
+            ex = self._exec[key]
+        else:
+            ex = self._get_exec(x.shape[0], False)
         ex.stage(x, None)
         ex.forward(bn_training=training)
         return ex.logits
@@ -126,7 +134,7 @@ class DeconvModel(BaseModel):
 class _DeconvExec(ExecBase):
     SITES = {'bn2': 0, 'bn4': 1, 'bn5': 2}
 
-    def __init__(self, model, B, training):
+    def __init__(self, model, B, training, fuse_head=True):
         dev, nk, nc = model.device, model.n_kernels, model.n_classes
         H, W = model.input_dims
         L = model.layers
@@ -150,14 +158,28 @@ class _DeconvExec(ExecBase):
             return h, w
 
         self.patch_l1 = isinstance(L['conv1_0'], E.PatchConvLayer)
-        if self.patch_l1:
+        # inference: conv1_0 + bn1 + pool1 as ONE launch of the first-layer kernel on the
+        # (R,G,B,1) staged input (no patch tensor, no full-resolution conv1_0 / bn1 tensors)
+        self.head_fused = (fuse_head and not training and model.impl == N.IMPL_UMMA and
+                           model.input_channel == 3
+                           and L['conv1_0'].cout_pad == 32 and (H // 2) % 2 == 0 and (W // 2) % 2 == 0
+                           and os.environ.get('SEGB200_FUSED_HEAD1', '1') != '0')
+        self.x4 = self.head_fused
+        if self.head_fused:
+            buf('x', H, W, 4)
+            h, w = -(-H // 2), -(-W // 2)
+        elif self.patch_l1:
             h, w = L['conv1_0'].patch_out_hw(H, W)
             buf('x', h, w, L['conv1_0'].cin_pad)
         else:
             buf('x', H, W, L['conv1_0'].cin_pad)
             h, w = L['conv1_0'].out_hw(H, W)
-        pair('conv1_0', 'bn1', h, w, nk)
-        h, w = pool('pool1', 'bn1', 2)
+        if self.head_fused:
+            h, w = h // 2, w // 2
+            buf('pool1', h, w, nk)
+        else:
+            pair('conv1_0', 'bn1', h, w, nk)
+            h, w = pool('pool1', 'bn1', 2)
         h, w = pair('conv2_0', 'bn2', h - 2, w - 2, nk * 2)
         h, w = pool('pool2', 'bn2', 3)
         h, w = pair('conv3_0', 'bn3', h - 2, w - 2, nk * 4)
@@ -175,7 +197,9 @@ class _DeconvExec(ExecBase):
         self.step_seed = 0
 
     def _pack_now(self):
-        if self.patch_l1:
+        if self.head_fused:
+            E.stage_input(self.x_f32, self.act['x'])
+        elif self.patch_l1:
             self.m.layers['conv1_0'].pack(self.x_f32, self.act['x'])
         else:
             E.pack_input(self.x_f32, self.act['x'])
@@ -199,8 +223,12 @@ class _DeconvExec(ExecBase):
                 self._drop(A[name], self.SITES[name])
 
         self.pack()
-        L['conv1_0'].forward(A['x'], A['conv1_0'], impl=impl); bn('bn1', 'conv1_0')
-        E.maxpool_fwd(A['bn1'], A['pool1'], self.amax['pool1'], 2, 2)
+        if self.head_fused and not bn_training:
+            E.conv_bn_pool_infer(L['conv1_0'], L['bn1'], A['x'], A['pool1'])
+        else:
+            assert not self.head_fused, 'inference executor: batch statistics not available'
+            L['conv1_0'].forward(A['x'], A['conv1_0'], impl=impl); bn('bn1', 'conv1_0')
+            E.maxpool_fwd(A['bn1'], A['pool1'], self.amax['pool1'], 2, 2)
         L['conv2_0'].forward(A['pool1'], A['conv2_0'], impl=impl); bn('bn2', 'conv2_0')
         E.maxpool_fwd(A['bn2'], A['pool2'], self.amax['pool2'], 3, 3)
         L['conv3_0'].forward(A['pool2'], A['conv3_0'], impl=impl); bn('bn3', 'conv3_0')

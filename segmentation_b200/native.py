@@ -58,6 +58,7 @@ SIGNATURES = {
     'seg_conv2d_wgrad': [_DP, _VP, _VP, _VP, _P, _P, _P],
     'seg_conv2d_pool_fwd': [_DP, _VP, _P, _P, _VP, _I32, _I32, _VP, _P, _P],
     'seg_conv2d_pool_wgrad': [_DP, _VP, _VP, _P, _VP, _P, _P, _P],
+    'seg_conv2d_bn_pool_infer': [_DP, _VP, _P, _I32, _P, _P, _P, _F, _P, _VP, _P, _P],
     'seg_deconv2d_fwd': [_DP, _VP, _P, _P, _VP, _P],
     'seg_deconv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _P],
     'seg_deconv2d_wgrad': [_DP, _VP, _VP, _P, _P],

@@ -297,3 +297,43 @@ def test_first_layer_wgrad_on_crop_view(cuda):
             dw_ref[r, s] = torch.einsum('nhwc,nhwo->co', xr[:, r:r + h - 2, s:s + w - 2, :],
                                         dz.float().cpu().double())
     assert rel_l2(out[0][0], dw_ref) < TOL_F32
+
+
+@pytest.mark.parametrize('geom', [(5, 2, 'SAME', 2, 64, 96), (3, 1, 'VALID', 2, 38, 70)],
+                         ids=['k5s2_same', 'k3s1_valid'])
+def test_first_layer_bn_pool_infer(cuda, geom):
+    """conv (5x5/s2 SAME as DeconvModel's conv1_0, or 3x3/s1) + ReLU + batch-norm (moving
+    statistics) + 2x2 max-pool in one launch against the oracle (reference
+    models/deconvolution.py:109-118), both weight layouts (padded HWIO shadow, dense
+    patch-packed matrix)."""
+    k, s, padding, Nb, H, W = geom
+    Co = 32
+    g = _gen(31)
+    x = torch.rand(Nb, H, W, 3, generator=g)
+    w = bfr(torch.randn(k, k, 3, Co, generator=g) * 0.1)
+    b = torch.randn(Co, generator=g) * 0.1
+    mm = torch.rand(Co, generator=g) * 0.3
+    mv = torch.rand(Co, generator=g) * 0.3 + 0.05
+    beta = torch.randn(Co, generator=g) * 0.1
+    eps = 1e-3
+    pads = conv_pads(H, W, k, s, padding)
+    Ho = (H + pads[0] + pads[2] - k) // s + 1
+    Wo = (W + pads[1] + pads[3] - k) // s + 1
+    x4 = _x4(x)
+    conv = bfr(torch.relu(T.conv2d(bfr(x), w, b, s, padding)))
+    bn = bfr((conv - mm) * torch.rsqrt(mv + eps) + beta)
+    ref = T.max_pool(bn, 2, 2)
+    d = desc(k, s, pads, 3, Co, 16, 32, N.EPI_BIAS | N.EPI_RELU, N.IMPL_UMMA)
+    dense = torch.zeros(k * k * 3 + 5, 32, dtype=BF16)          # patch-packed [k*k*3 (+pad)][32]
+    dense[:k * k * 3, :Co] = w.reshape(k * k * 3, Co).to(BF16)
+    bd, mmd, mvd, betad = b.cuda(), mm.cuda(), mv.cuda(), beta.cuda()   # keep the buffers alive
+    for name, sh, rows in (('shadow', shadow_conv(w, 16, 32), 0), ('dense', dense.cuda(), 3)):
+        pooled = torch.full((Nb, Ho // 2, Wo // 2, 32), float('nan'), dtype=BF16, device='cuda')
+        N.call('seg_conv2d_bn_pool_infer', ctypes.byref(d), N.vref(x4), N.ptr(sh), rows,
+               N.ptr(bd), N.ptr(mmd), N.ptr(mvd), eps, N.ptr(betad),
+               N.vref(pooled), None, N.stream_ptr())
+        sync()
+        assert 'fconv' in N.load().seg_last_kernel_name().decode()
+        e = rel_l2(pooled.float().cpu()[..., :Co], ref)
+        report('first_layer_bn_pool', {'geom': list(geom), 'weights': name, 'err': e})
+        assert e < TOL_BF16, (geom, name, e)

@@ -328,6 +328,19 @@ def test_deconv_fused_tail_matches_unfused(cuda):
         logits_u = ex.logits.cpu().clone()
     finally:
         del os.environ['SEGB200_FUSED_TAIL']
+    # ... and the one-launch head (conv1_0 + bn1 + pool1 on the (R,G,B,1) input) against the
+    # patch-packed convolution + batch-norm + pool launches
+    os.environ['SEGB200_FUSED_HEAD1'] = '0'
+    try:
+        model._exec.clear()
+        model.infer(x)
+        ex2 = model._get_exec(B, False)
+        assert not ex2.head_fused and ex.head_fused
+        e_head = rel_l2(ex2.logits.cpu(), logits_f)
+    finally:
+        del os.environ['SEGB200_FUSED_HEAD1']
+    report('deconv_fused_head', {'logits_rel_l2': e_head})
+    assert e_head < 1e-2, e_head
     e = rel_l2(logits_f, logits_u)
     dmax = float((logits_f - logits_u).abs().max())
     margin = (logits_u[..., 0] - logits_u[..., 1]).abs()

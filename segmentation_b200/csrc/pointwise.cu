@@ -1046,7 +1046,7 @@ struct TailArgs {
 
 template <int NC, int C>
 __global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
-  __shared__ float s_wup[4 * NC * C];             // [sub][co][ci]
+  __shared__ __align__(16) float s_wup[4 * NC * C];   // [sub][co][ci]
   __shared__ float s_wout[9 * NC * NC];           // [tap][ci][co]
   __shared__ float s_aff[4 * NC];                 // b_up, bn scale, bn shift, b_out
   __shared__ bf16 s_t[kTailO * kTailO * NC];      // bn output tile
@@ -1119,10 +1119,19 @@ __global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
       for (int co = 0; co < NC; ++co) {
         float r = 0.f;
         if (inside) {
-          float acc = 0.f;
-          const float* wp = s_wup + (sub * NC + co) * C;
+          // weights read as float4 (one shared-memory load per four products, all lanes the
+          // same address); four partial sums shorten the dependency chain
+          const float4* wp = reinterpret_cast<const float4*>(s_wup + (sub * NC + co) * C);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < C; ++ci) acc += v[ci] * wp[ci];
+          for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 w4 = wp[c4];
+            a0 += v[4 * c4] * w4.x;
+            a1 += v[4 * c4 + 1] * w4.y;
+            a2 += v[4 * c4 + 2] * w4.z;
+            a3 += v[4 * c4 + 3] * w4.w;
+          }
+          float acc = (a0 + a1) + (a2 + a3);
           acc = fmaxf(acc + s_aff[co], 0.f);
           const float dq = __bfloat162float(__float2bfloat16(acc));    // stored deconv output
           r = (dq - __ldg(A.bn_mean + co)) * s_aff[NC + co] + __ldg(A.bn_beta + co);
@@ -1134,6 +1143,9 @@ __global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
   __syncthreads();
   // ---- phase B: 28 x 28 output pixels of the tile interior
   const int H = 2 * A.rh, W = 2 * A.rw;
+  float wo[9 * NC * NC];
+#pragma unroll
+  for (int i = 0; i < 9 * NC * NC; ++i) wo[i] = s_wout[i];
   for (int i = threadIdx.x; i < 4 * kTailT * kTailT; i += 256) {
     const int oyl = i / (2 * kTailT), oxl = i - oyl * (2 * kTailT);
     const int oy = 2 * ty * kTailT + oyl, ox = 2 * tx * kTailT + oxl;
@@ -1150,7 +1162,7 @@ __global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
         for (int ci = 0; ci < NC; ++ci) {
           const float xv = __bfloat162float(tp[ci]);
 #pragma unroll
-          for (int co = 0; co < NC; ++co) acc[co] += xv * s_wout[((r * 3 + sx) * NC + ci) * NC + co];
+          for (int co = 0; co < NC; ++co) acc[co] += xv * wo[((r * 3 + sx) * NC + ci) * NC + co];
         }
       }
     const int64_t m = ((int64_t)n * H + oy) * W + ox;

@@ -113,7 +113,7 @@ class DeconvModel(BaseModel):
         ex.forward(bn_training=training)
         return ex.logits
 
-    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0):
+    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0, return_probs=True):
         """T stochastic passes of one tile as one batch (dropout sites of the
         reference graph, Philox stream (pass_offset+t)*8+site), mean / variance of
         the sigmoid probabilities.  Returns [mean, var, probs[T]]."""
@@ -128,7 +128,12 @@ class DeconvModel(BaseModel):
         var = torch.empty_like(probs[0])
         E.mc_mean_var(probs, mean, var)
         torch.cuda.current_stream().synchronize()
-        return [mean.cpu().numpy(), var.cpu().numpy(), probs.cpu().numpy()]
+        # return_probs=False: mean and variance maps only (BASELINE config 5's output); the T
+        # probability maps are T x larger than both and their device->host copy dominates
+        out = [mean.cpu().numpy(), var.cpu().numpy()]
+        if return_probs:
+            out.append(probs.cpu().numpy())
+        return out
 
 
 class _DeconvExec(ExecBase):

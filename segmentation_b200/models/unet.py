@@ -107,7 +107,7 @@ class UNetModel(BaseModel):
         ex.forward()
         return ex.logits
 
-    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0):
+    def infer_mc(self, imgs, passes=16, seed=None, pass_offset=0, return_probs=True):
         """Bayesian mode (BASELINE config 5): `passes` stochastic forward passes of
         ONE tile executed as one batch, MC-dropout (keep .5) after conv2_2,
         conv4_2, conv6_2 (build-defined placement — the reference's UNetModel
@@ -124,7 +124,12 @@ class UNetModel(BaseModel):
         var = torch.empty_like(probs[0])
         E.mc_mean_var(probs, mean, var)
         torch.cuda.current_stream().synchronize()
-        return [mean.cpu().numpy(), var.cpu().numpy(), probs.cpu().numpy()]
+        # return_probs=False: mean and variance maps only (BASELINE config 5's output); the T
+        # probability maps are T x larger than both and their device->host copy dominates
+        out = [mean.cpu().numpy(), var.cpu().numpy()]
+        if return_probs:
+            out.append(probs.cpu().numpy())
+        return out
 
 
 class _UNetExec(ExecBase):

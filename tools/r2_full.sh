@@ -21,3 +21,6 @@ r=d['roofline']
 print('roofline', r['kernel'], r['bound'], '%.3f'%r['frac'], 'serial', r['serial_step_ms'])
 for f in r['families']: print('  %-10s n=%2d %7.1f us %5.1f%% %7.1f TF/s %7.0f GB/s %s %.3f'%(f['family'],f['launches'],f['us'],100*f['share'],f['tflops'],f['gbs'],f['bound'],f['frac']))
 PY
+python tools/ncu_traffic.py gpurun_out/step_ncu.csv gpurun_out/step_calls.json > gpurun_out/ncu_traffic.log 2>&1; echo "traffic exit=$?"; tail -2 gpurun_out/ncu_traffic.log
+cp profiles/r02_traffic.json profiles/r02_launches.md gpurun_out/ 2>/dev/null
+timeout 300 python tools/configs_check.py 2 4 5u 5d 2>&1 | grep config

@@ -1,0 +1,64 @@
+"""-m gpu: the device-side input path (reference utils/datasets.py:176-190) through
+the model API: a train step fed with raw uint8 images + 0/255 masks + per-image crop corners
+equals the step fed with the fp32 / {0,1} tensors the reference's host pipeline would have
+produced for the same draw: the staged bf16 input and the mask are bit-identical, so the first
+step's loss is too; later steps agree to the noise of the unordered fp32 gradient reductions."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from segmentation_b200.models.unet import UNetModel
+from segmentation_b200.utils.datasets import ArrayImageMaskDataSet
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(ds, S):
+    os.environ['SEGB200_IMPL'] = 'umma'
+    return UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=32, learning_rate=1e-3,
+                     load_snapshot=False, save_dir=None, seed=0)
+
+
+def test_uint8_cropped_batches_equal_host_preprocessing(cuda):
+    g = np.random.default_rng(0)
+    n, Hs, Ws, S, B = 6, 230, 250, 188, 2
+    images = g.integers(0, 256, (n, Hs, Ws, 3), dtype=np.uint8)
+    masks = (g.random((n, Hs, Ws, 1)) > 0.5).astype(np.uint8) * 255
+    ds = ArrayImageMaskDataSet(images, masks, batch_size=B, crop_size=S, seed=1)
+    raw_model, ref_model = _model(ds, S), _model(ds, S)
+    assert raw_model._get_exec(B, True).x4, 'first-layer (x4) input path expected'
+    draws = np.random.default_rng(7)
+    for step in range(3):
+        idx = draws.integers(0, n, B)
+        crop = np.stack([draws.integers(0, Hs - S + 1, B), draws.integers(0, Ws - S + 1, B)], 1)
+        crop = crop.astype(np.int32)
+        xr, yr = ds.reference_batch(idx, crop)
+        raw_model.train_step((images[idx], masks[idx], crop))
+        ref_model.train_step((xr, yr))
+        a, b = raw_model.seg_loss_op, ref_model.seg_loss_op
+        assert np.isfinite(a) and (a == b if step == 0 else abs(a - b) < 1e-4), (step, a, b)
+    sa, sb = raw_model.store.state_dict(), ref_model.store.state_dict()
+    for k in sa:
+        assert np.allclose(sa[k], sb[k], rtol=1e-3, atol=1e-5), k
+
+
+def test_dataset_driven_steps_with_prefetch(cuda):
+    """train_step() with no argument pulls (images, masks, crop) batches from the dataset, the
+    next batch's upload overlapping the step; two models over identically seeded datasets stay
+    in agreement (to the noise of the unordered fp32 gradient reductions) and the loss is finite."""
+    g = np.random.default_rng(3)
+    n, Hs, S, B = 8, 200, 188, 2
+    images = g.integers(0, 256, (n, Hs, Hs, 3), dtype=np.uint8)
+    masks = (images[..., 0:1] > 127).astype(np.uint8) * 255
+    m1 = _model(ArrayImageMaskDataSet(images, masks, batch_size=B, crop_size=S, seed=4), S)
+    m2 = _model(ArrayImageMaskDataSet(images, masks, batch_size=B, crop_size=S, seed=4), S)
+    l1 = []
+    for _ in range(6):
+        m1.train_step()
+        m2.train_step()
+        l1.append(m1.seg_loss_lagged)
+        assert abs(m1.seg_loss_op - m2.seg_loss_op) < 1e-4
+    assert all(np.isfinite(v) for v in l1)
+    assert m1.global_step == 6 and m2.global_step == 6

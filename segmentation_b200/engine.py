@@ -420,11 +420,13 @@ class SideStream(object):
     enqueued so far on the current stream; join(): the current stream waits for the side
     stream.  Works inside CUDA-graph capture (fork/join become graph edges)."""
 
-    def __init__(self, device, lanes=1):
+    def __init__(self, device, lanes=1, priority=0):
         """`lanes` > 1: successive fork()s rotate over that many streams, so that narrow
         kernels of different layers (weight-gradient grids of 30-128 CTAs) can overlap each
-        other as well as the current stream."""
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, lanes))]
+        other as well as the current stream.  `priority` < 0: a high-priority stream (its
+        kernels' CTAs are placed first when SM slots free up; captured into graph nodes)."""
+        self.streams = [torch.cuda.Stream(device=device, priority=priority)
+                        for _ in range(max(1, lanes))]
         self.stream = self.streams[0]
         self._used = [False] * len(self.streams)
         self._next = 0

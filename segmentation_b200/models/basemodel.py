@@ -370,7 +370,17 @@ class ExecBase(object):
         self._pf_host = None           # host batch fetched from the dataset but not staged
         self._prepacked = False
         self.side = E.SideStream(dev, lanes=int(os.environ.get('SEGB200_WGRAD_LANES', '1')))   # weight gradients
-        self.opt = E.SideStream(dev)              # all-reduce + Adam per optimizer group
+        # Adam per optimizer group.  SEGB200_OPT_PRIO=1 makes it a high-priority stream (its
+        # blocks are placed first when SM slots free up); measured: one GPU 0.963 vs 0.942 ms
+        # (the prioritised Adam takes SMs from the critical-path kernels), 8 GPUs no gain once
+        # the all-reduces have their own stream - off.
+        self.opt = E.SideStream(dev, priority=-1 if os.environ.get('SEGB200_OPT_PRIO', '0') != '0'
+                                else 0)
+        # data parallel: the all-reduce of a group is issued from its own stream, so that the
+        # next group's reduction does not queue behind this group's Adam (8-GPU timeline: the
+        # conv3-4 bucket was ready at ~930 us and started at 1013 us, behind the bottleneck
+        # group's Adam; 1.140 -> 1.080 ms/step, profiles/r02_dp.md)
+        self.comm = E.SideStream(dev)
         self.skipside = E.SideStream(dev)         # skip-connection halves of the concat input gradients
         self.use_side = os.environ.get('SEGB200_WGRAD_STREAM', '1') != '0'
         self._opt_active = False
@@ -427,6 +437,7 @@ class ExecBase(object):
                 self.group_ready(i)
             self.side.join()
             self.skipside.join()
+            self.comm.join()
             self.opt.join()
         finally:
             self._opt_active = False
@@ -441,8 +452,13 @@ class ExecBase(object):
         if not self._opt_active or i not in self._pending:
             return
         self._pending.discard(i)
-        with self.opt.fork(also=(self.side, self.skipside)):
-            if m._allreduce is not None:
+        split = m._allreduce is not None and os.environ.get('SEGB200_COMM_STREAM', '1') != '0'
+        if split:
+            with self.comm.fork(also=(self.side, self.skipside)):
+                m._allreduce(i)
+        with self.opt.fork(also=(self.side, self.skipside, self.comm) if split
+                           else (self.side, self.skipside)):
+            if m._allreduce is not None and not split:
                 m._allreduce(i)
             m.store.adam_launch(0.0, grad_scale=1.0 / m.world_size, from_device=True,
                                 chunk_range=m.opt_groups[i]['chunks'])

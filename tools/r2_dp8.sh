@@ -1,15 +1,17 @@
 #!/bin/bash
-# 8-GPU data-parallel A/B: NCCL's own choice vs NVLS with few CTAs + SM budget
+# 8-GPU data-parallel A/B of the optimizer-stream priority and the separate all-reduce stream
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-8}
 run() {  # label, env...
   local label=$1; shift
   P=$((29500 + RANDOM % 1000))
-  env "$@" timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 200 --warmup 10 --skip-cpu > gpurun_out/bench_dp${N}_$label.json 2> gpurun_out/bench_dp${N}_$label.err
+  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 200 --warmup 10 --skip-cpu > gpurun_out/bench_dp${N}_$label.json 2> gpurun_out/bench_dp${N}_$label.err
   python -c "
 import json; d=json.load(open('gpurun_out/bench_dp${N}_$label.json')); print('$label N=%d ms/step %.4f value %.0f e2e %.0f (%.4f ms)'%(d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'], d['e2e']['ms_per_step']))" 2>&1 | tail -1
 }
-run ctas8 SEGB200_NCCL_CTAS=8
-run ctas16 SEGB200_NCCL_CTAS=16
-run default SEGB200_NCCL_CTAS=0
+run comm1_prio1 SEGB200_COMM_STREAM=1 SEGB200_OPT_PRIO=1
+run comm0_prio1 SEGB200_COMM_STREAM=0 SEGB200_OPT_PRIO=1
+run comm1_prio0 SEGB200_COMM_STREAM=1 SEGB200_OPT_PRIO=0
+P=$((29500 + RANDOM % 1000))
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P tools/graph_timeline.py > gpurun_out/graph_timeline_dp.log 2>&1; echo "timeline exit=$?"

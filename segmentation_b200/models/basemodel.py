@@ -428,6 +428,7 @@ class ExecBase(object):
     def _step_body(self):
         m = self.m
         self._opt_active = True
+        self._sm_reserved = False
         self._pending = set(range(len(m.opt_groups)))
         try:
             self.forward()
@@ -441,6 +442,9 @@ class ExecBase(object):
             self.opt.join()
         finally:
             self._opt_active = False
+            if self._sm_reserved:
+                N.set_option(N.OPT_SM_LIMIT, 0)
+                self._sm_reserved = False
 
     def group_ready(self, i):
         """Every gradient of optimizer group i has been enqueued (weight gradients on the
@@ -453,6 +457,13 @@ class ExecBase(object):
             return
         self._pending.discard(i)
         split = m._allreduce is not None and os.environ.get('SEGB200_COMM_STREAM', '1') != '0'
+        reserve = int(os.environ.get('SEGB200_DP_SM_RESERVE', '0'))
+        if m._allreduce is not None and reserve > 0 and not self._sm_reserved:
+            # from the first bucket on, the tile kernels' persistent grids leave `reserve` SMs
+            # to the all-reduce kernels (grid sizes are fixed at graph capture)
+            sms = torch.cuda.get_device_properties(m.device).multi_processor_count
+            N.set_option(N.OPT_SM_LIMIT, sms - reserve)
+            self._sm_reserved = True
         if split:
             with self.comm.fork(also=(self.side, self.skipside)):
                 m._allreduce(i)

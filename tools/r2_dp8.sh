@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU data-parallel A/B of the optimizer-stream priority and the separate all-reduce stream
+# 8-GPU data-parallel A/B: SMs reserved for the all-reduce kernels during the backward pass
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-8}
@@ -10,8 +10,6 @@ run() {  # label, env...
   python -c "
 import json; d=json.load(open('gpurun_out/bench_dp${N}_$label.json')); print('$label N=%d ms/step %.4f value %.0f e2e %.0f (%.4f ms)'%(d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'], d['e2e']['ms_per_step']))" 2>&1 | tail -1
 }
-run comm1_prio1 SEGB200_COMM_STREAM=1 SEGB200_OPT_PRIO=1
-run comm0_prio1 SEGB200_COMM_STREAM=0 SEGB200_OPT_PRIO=1
-run comm1_prio0 SEGB200_COMM_STREAM=1 SEGB200_OPT_PRIO=0
-P=$((29500 + RANDOM % 1000))
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P tools/graph_timeline.py > gpurun_out/graph_timeline_dp.log 2>&1; echo "timeline exit=$?"
+run reserve0 SEGB200_DP_SM_RESERVE=0
+run reserve24 SEGB200_DP_SM_RESERVE=24
+run reserve12 SEGB200_DP_SM_RESERVE=12

@@ -507,7 +507,8 @@ class ExecBase(object):
             if not self.x4:
                 raise Exception('uint8 / cropped batches need the first-layer (x4) input path')
         if self.x4 and x.is_cuda and x.is_contiguous() and mask.is_cuda and mask.is_contiguous() \
-                and (raw or x.dtype == torch.float32):
+                and mask.dtype == torch.uint8 and (raw or x.dtype == torch.float32) \
+                and (crop_yx is not None or tuple(x.shape[1:3]) == (self.H, self.W)):
             cy = None if crop_yx is None else crop_yx.to(device=x.device, dtype=torch.int32)
             cur.wait_event(self.ev_staged)
             self._src = (x, mask, cy)

@@ -107,3 +107,52 @@ def test_patch_conv_layer_shadow_is_the_hwio_tensor_read_as_a_matrix():
     assert st.segments.view(-1, 6)[0].tolist() == [0, 864, 32, 32, 27, 32]
     big = E.PatchConvLayer(E.ParamStore(torch.device('cpu')), 'conv1_0', 5, 2, 'SAME', 3, 32)
     assert (big.cin, big.cin_pad) == (75, 80) and big.patch_out_hw(1024, 1024) == (512, 512)
+
+
+def test_array_image_mask_dataset_matches_reference_preprocessing():
+    """utils/datasets.py (device-side input path): the batches it hands the model
+    and its host restatement of reference utils/datasets.py:176-190 (x/255, uint8(mask/255),
+    joint crop)."""
+    import numpy as np
+    from segmentation_b200.utils.datasets import ArrayImageMaskDataSet, load_images
+    g = np.random.default_rng(0)
+    imgs = g.integers(0, 256, (5, 40, 48, 3), dtype=np.uint8)
+    msk = g.choice(np.array([0, 255], dtype=np.uint8), (5, 40, 48, 1))
+    ds = ArrayImageMaskDataSet(imgs, msk, batch_size=3, crop_size=32, seed=1, pinned=False)
+    x, y, c = ds.next_batch()
+    assert tuple(x.shape) == (3, 40, 48, 3) and x.dtype.__str__() == 'torch.uint8'
+    assert tuple(y.shape) == (3, 40, 48, 1) and tuple(c.shape) == (3, 2)
+    assert int(c[:, 0].max()) <= 8 and int(c[:, 1].max()) <= 16 and int(c.min()) >= 0
+    idx, crop = np.array([0, 4, 2]), np.array([[0, 0], [8, 16], [3, 5]], dtype=np.int32)
+    xr, yr = ds.reference_batch(idx, crop)
+    assert xr.dtype == np.float32 and xr.shape == (3, 32, 32, 3) and yr.shape == (3, 32, 32, 1)
+    assert np.array_equal(xr[1], imgs[4, 8:40, 16:48].astype(np.float32) / np.float32(255))
+    assert set(np.unique(yr)) <= {0, 1}
+    assert np.array_equal(yr[2][..., 0] == 1, msk[2, 3:35, 5:37, 0] == 255)
+    sel, cr = load_images(imgs, 4, 32, rng=np.random.default_rng(2))
+    assert sel.shape == (4, 40, 48, 3) and cr.shape == (4, 2)
+
+
+def test_fast_division_constants_of_the_first_layer_kernel():
+    """csrc/fconv.cu computes (mul, shr) so that x // d == (x * mul) >> (32 + shr) for every
+    x < 2^31 (pixel / tile index -> image, row, column on the device): the same construction
+    in Python, checked at the divisors the models use and at the range ends."""
+    def magic(d):
+        if d == 1:
+            return 0, 0
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        p = 31 + l
+        return ((1 << p) + d - 1) // d, p - 32
+
+    import random
+    rnd = random.Random(0)
+    for d in [2, 3, 4, 7, 8, 62, 127, 254, 255, 256, 508, 512, 2048, 64516, 262144, 16129 * 4, 999983]:
+        mul, shr = magic(d)
+        assert mul < (1 << 32)
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 30) - 1, (1 << 30), (1 << 31) - 1]
+        xs += [rnd.randrange(1 << 31) for _ in range(2000)]
+        xs += [k * d + e for k in (1, 5, 1000, ((1 << 31) - 1) // d) for e in (-1, 0, 1) if 0 <= k * d + e < (1 << 31)]
+        for x in xs:
+            assert ((x * mul) >> 32) >> shr == x // d, (d, x)

@@ -183,6 +183,21 @@ SEG_API int32_t seg_deconv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, c
 SEG_API int32_t seg_deconv2d_wgrad(const seg_conv_desc* d, const seg_view* x, const seg_view* dz,
                            float* dw, void* stream);
 
+/* ---- inference forms with the slim.batch_norm that follows the layer folded into the
+ * layer (models/deconvolution.py:120-170: conv/deconv -> ReLU -> batch_norm, is_training
+ * False): y = relu(op(x) + bias) * post_scale + post_shift with post_scale / post_shift
+ * (cout_pad floats each) from seg_batchnorm_fold.  The activation is normalised from the
+ * fp32 accumulator, i.e. without the bf16 rounding the unfused pair (seg_conv2d_fwd,
+ * seg_batchnorm_infer) has in between.  tcgen05 path only; SEG_E_UNSUPPORTED where the
+ * halo-tile kernel cannot take the geometry (use the unfused pair). */
+SEG_API int32_t seg_conv2d_fwd_affine(const seg_conv_desc* d, const seg_view* x, const void* w_bf16,
+                                      const float* bias, const float* post_scale,
+                                      const float* post_shift, const seg_view* y, void* stream);
+SEG_API int32_t seg_deconv2d_fwd_affine(const seg_conv_desc* d, const seg_view* x,
+                                        const void* w_bf16, const float* bias,
+                                        const float* post_scale, const float* post_shift,
+                                        const seg_view* y, void* stream);
+
 /* db[c] += sum over pixels of dz[...,c]  (BiasAddGrad).  Caller zeroes db. */
 SEG_API int32_t seg_bias_grad(const seg_view* dz, float* db, void* stream);
 
@@ -196,6 +211,14 @@ SEG_API int32_t seg_bias_grad(const seg_view* dz, float* db, void* stream);
  * (zero outside) — covers the U-Net skip crop (models/unet.py:140-141). */
 SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const seg_view* y,
                         uint8_t* argmax, void* stream);
+/* inference: y = batch_norm(maxpool(x)) with the moving statistics of the batch-norm that
+ * PRECEDES the pool in the model (models/deconvolution.py:126-138: conv -> bn -> pool).  The
+ * normalisation has a positive slope and every rounding is monotonic, so the result equals
+ * seg_maxpool_fwd(seg_batchnorm_infer(x)) bit for bit without the normalised full-resolution
+ * tensor.  k == stride, channels [0, bn_c) are normalised, the rest copied; no argmax. */
+SEG_API int32_t seg_maxpool_bn_infer(const seg_view* x, int32_t k, const float* moving_mean,
+                                     const float* moving_var, float eps, const float* beta,
+                                     int32_t bn_c, const seg_view* y, void* stream);
 SEG_API int32_t seg_maxpool_bwd(const seg_view* dy, const uint8_t* argmax, int32_t k, int32_t s,
                         const seg_view* add, int32_t add_y0, int32_t add_x0,
                         const seg_view* mask_src, const seg_view* dx, void* stream);
@@ -242,6 +265,12 @@ SEG_API int32_t seg_batchnorm_apply(const seg_view* x, const float* mean, const 
 SEG_API int32_t seg_batchnorm_infer(const seg_view* x, const float* moving_mean,
                             const float* moving_var, float eps, const float* beta,
                             const seg_view* y, void* stream);
+/* inference form folded for a conv epilogue (seg_conv2d_fwd_affine): scale[i] =
+ * rsqrt(var[i] + eps), shift[i] = beta[i] - mean[i] * scale[i] for i < c, both 0 for
+ * c <= i < c_pad */
+SEG_API int32_t seg_batchnorm_fold(const float* moving_mean, const float* moving_var, float eps,
+                                   const float* beta, int32_t c, int32_t c_pad, float* scale,
+                                   float* shift, void* stream);
 /* bwd pass 1: dbeta[c] += sum dy, dxhat[c] += sum dy*xhat;  pass 2 writes dx and
  * applies the ReluGrad of the producing conv (x itself is the mask source). */
 SEG_API int32_t seg_batchnorm_bwd_reduce(const seg_view* dy, const seg_view* x, const float* mean,

@@ -18,14 +18,16 @@ void set_error(const char* fmt, ...) {
 
 // umma_conv.cu
 int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
-                  const float* bias, const seg_view& y, cudaStream_t st);
+                  const float* bias, const seg_view& y, cudaStream_t st,
+                  const float* post_scale = nullptr, const float* post_shift = nullptr);
 int umma_conv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w, const seg_view& dx,
                     const seg_view* dx2, const seg_view* mask, const seg_view* mask2,
                     cudaStream_t st, int cin_lo);
 int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                     const seg_view& dz, float* dw, float* db, cudaStream_t st);
 int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
-                    const seg_view& y, cudaStream_t st);
+                    const seg_view& y, cudaStream_t st, const float* post_scale = nullptr,
+                    const float* post_shift = nullptr);
 int umma_deconv_dgrad(const seg_conv_desc& d, const seg_view& dz, const void* w,
                       const seg_view& dx, const seg_view* mask, cudaStream_t st);
 int umma_deconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& dz, float* dw,
@@ -149,6 +151,35 @@ SEG_API int32_t seg_conv2d_fwd(const seg_conv_desc* d, const seg_view* x, const 
   if (simt_tiny_conv_ok(P, d->cin)) return simt_tiny_conv(P, d->cin, st);
   if (d->impl == SEG_IMPL_UMMA) return umma_conv_fwd(*d, *x, x2, w_bf16, bias, *y, st);
   return simt_direct(P, st);
+}
+
+SEG_API int32_t seg_conv2d_fwd_affine(const seg_conv_desc* d, const seg_view* x, const void* w_bf16,
+                                      const float* bias, const float* post_scale,
+                                      const float* post_shift, const seg_view* y, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && w_bf16 && y && post_scale && post_shift, SEG_E_BAD_SHAPE,
+              "conv2d_fwd_affine: bad argument");
+  SEG_REQUIRE(y->h == (x->h + d->pad_t + d->pad_b - d->kh) / d->stride + 1 &&
+                  y->w == (x->w + d->pad_l + d->pad_r - d->kw) / d->stride + 1 && y->n == x->n,
+              SEG_E_BAD_SHAPE, "conv2d_fwd_affine: output geometry mismatch (%dx%d)", y->h, y->w);
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE,
+              "conv2d_fwd_affine: bias missing");
+  SEG_REQUIRE(d->impl == SEG_IMPL_UMMA && !(d->flags & SEG_EPI_OUT_F32), SEG_E_UNSUPPORTED,
+              "conv2d_fwd_affine: tcgen05 path with a bf16 output only");
+  return umma_conv_fwd(*d, *x, nullptr, w_bf16, bias, *y, (cudaStream_t)stream, post_scale,
+                       post_shift);
+}
+
+SEG_API int32_t seg_deconv2d_fwd_affine(const seg_conv_desc* d, const seg_view* x,
+                                        const void* w_bf16, const float* bias,
+                                        const float* post_scale, const float* post_shift,
+                                        const seg_view* y, void* stream) {
+  SEG_REQUIRE(desc_ok(d) && x && w_bf16 && y && post_scale && post_shift, SEG_E_BAD_SHAPE,
+              "deconv2d_fwd_affine: bad argument");
+  SEG_REQUIRE(!(d->flags & SEG_EPI_BIAS) || bias, SEG_E_BAD_SHAPE,
+              "deconv2d_fwd_affine: bias missing");
+  SEG_REQUIRE(d->impl == SEG_IMPL_UMMA && !(d->flags & SEG_EPI_OUT_F32), SEG_E_UNSUPPORTED,
+              "deconv2d_fwd_affine: tcgen05 path with a bf16 output only");
+  return umma_deconv_fwd(*d, *x, w_bf16, bias, *y, (cudaStream_t)stream, post_scale, post_shift);
 }
 
 SEG_API int32_t seg_conv2d_dgrad(const seg_conv_desc* d, const seg_view* dz, const void* w_bf16,

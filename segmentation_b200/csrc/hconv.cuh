@@ -42,6 +42,10 @@ struct HconvParams {
   int split_n;
   const float* bias;
   int flags;
+  // optional per-column affine map applied after bias / ReLU (an inference batch-norm folded
+  // to scale and shift, seg_batchnorm_fold): N_total floats each, or null
+  const float* post_scale;
+  const float* post_shift;
   long long* prof;           // optional in-kernel timeline of CTA 0 (test hook), else null
 };
 
@@ -328,6 +332,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             v[j] = __uint_as_float(r[j]);
             if ((P.flags & SEG_EPI_BIAS) && ncol + j < D.cols) v[j] += __ldg(P.bias + ncol + j);
             if (P.flags & SEG_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (P.post_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+              v[j] = fmaf(v[j], __ldg(P.post_scale + ncol + j), __ldg(P.post_shift + ncol + j));
           }
           if ((P.flags & SEG_EPI_RELU_MASK) && D.mask) {
             const bf16* mp = D.mask + moff + ncol;

@@ -237,6 +237,78 @@ maxpool_fwd_row8_kernel(seg_view x, int k_rt, seg_view y, uint8_t* argmax) {
   }
 }
 
+// slim.batch_norm at inference (moving statistics, centre only) on one value: the single
+// expression every kernel that applies it shares, so a fused and an unfused evaluation round
+// the same way
+__device__ __forceinline__ float bn_infer_value(float v, float mean, float rstd, float beta) {
+  return (v - mean) * rstd + beta;
+}
+
+// max-pool (k == stride) followed by the inference batch-norm of the layer BEFORE it:
+// y = bn(maxpool(x)).  The affine map has a positive slope (rsqrt(var + eps)) and every
+// rounding on the way is monotonic, so this equals maxpool(bn(x)) - the order the model
+// states (models/deconvolution.py:126-138: conv -> bn -> pool) - bit for bit, while the
+// normalised full-resolution tensor is neither written nor read.  No argmax (inference).
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_bn_infer_row8_kernel(seg_view x, int k_rt, const float* __restrict__ mean,
+                             const float* __restrict__ var, float eps,
+                             const float* __restrict__ beta, int bn_c, seg_view y) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = K ? K : k_rt;
+  const int cv = y.c >> 3;
+  const int rowlen = y.w * cv;
+  const int n = blockIdx.y / y.h, p = blockIdx.y - n * y.h;
+  const bf16* xrow = view_at(x, n, p * k, 0);
+  bf16* yrow = view_at_mut(y, n, p, 0);
+  const int x_sw = (int)x.sw, y_sw = (int)y.sw;
+  const int step = gridDim.x * blockDim.x;
+  const int step_q = step / cv, step_c = step - step_q * cv;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int q = i / cv, c8 = i - q * cv;
+  for (; i < rowlen; i += step, q += step_q, c8 += step_c) {
+    if (c8 >= cv) { c8 -= cv; ++q; }
+    const int c0 = c8 * 8;
+    uint32_t best[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int dy = 0; dy < (K ? K : 8); ++dy) {
+      if (dy >= k) break;
+#pragma unroll
+      for (int dx = 0; dx < (K ? K : 8); ++dx) {
+        if (dx >= k) break;
+        const uint4 u = *reinterpret_cast<const uint4*>(xrow + dy * x.sh + (q * k + dx) * x_sw + c0);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        if (dy == 0 && dx == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = w[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = bf16x2_gt_mask(w[j], best[j]);
+            best[j] = (w[j] & m) | (best[j] & ~m);
+          }
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * j + e;
+        const float v = e ? bf16_hi(best[j]) : bf16_lo(best[j]);
+        r[e] = c < bn_c ? bn_infer_value(v, __ldg(mean + c), rsqrtf(__ldg(var + c) + eps),
+                                         __ldg(beta + c))
+                        : v;
+      }
+      o[j] = pack_bf16x2(r[0], r[1]);
+    }
+    *reinterpret_cast<uint4*>(yrow + q * y_sw + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // per-halfword mask (0xffff / 0) of the bf16 pairs in `w` that are > 0 (NaN: not > 0)
 __device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t w) {
   __nv_bfloat162 v;
@@ -773,6 +845,24 @@ __global__ void bn_apply_kernel(seg_view x, const float* mean, const float* rstd
   }
 }
 
+// inference batch-norm folded to y = x * scale + shift for a conv epilogue; columns beyond
+// the layer's c channels (the padded ones) map to zero
+__global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, const float* __restrict__ beta, int c, int c_pad,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_pad) return;
+  float sc = 0.f, sh = 0.f;
+  if (i < c) {
+    sc = rsqrtf(var[i] + eps);
+    sh = beta[i] - mean[i] * sc;
+  }
+  scale[i] = sc;
+  shift[i] = sh;
+}
+
 // 8 channels per thread, 16-byte accesses; per-channel scale / shift from L1
 __global__ void bn_apply_vec8_kernel(seg_view x, const float* __restrict__ mean,
                                      const float* __restrict__ rstd_or_var, float eps, int is_var,
@@ -799,7 +889,7 @@ __global__ void bn_apply_vec8_kernel(seg_view x, const float* __restrict__ mean,
         const int c = c0 + 2 * j + e;
         const float sc = is_var ? rsqrtf(__ldg(rstd_or_var + c) + eps) : __ldg(rstd_or_var + c);
         const float v = e ? bf16_hi(w[j]) : bf16_lo(w[j]);
-        r[e] = (v - __ldg(mean + c)) * sc + __ldg(beta + c);
+        r[e] = bn_infer_value(v, __ldg(mean + c), sc, __ldg(beta + c));
       }
       o[j] = pack_bf16x2(r[0], r[1]);
     }
@@ -1774,6 +1864,33 @@ SEG_API int32_t seg_maxpool_fwd(const seg_view* x, int32_t k, int32_t s, const s
   return SEG_OK;
 }
 
+SEG_API int32_t seg_maxpool_bn_infer(const seg_view* x, int32_t k, const float* moving_mean,
+                                     const float* moving_var, float eps, const float* beta,
+                                     int32_t bn_c, const seg_view* y, void* stream) {
+  SEG_REQUIRE(x && y && moving_mean && moving_var && beta, SEG_E_BAD_SHAPE,
+              "maxpool_bn_infer: null argument");
+  SEG_REQUIRE(k >= 1 && k <= 8 && y->h == x->h / k && y->w == x->w / k && y->c == x->c &&
+                  y->n == x->n && bn_c >= 0 && bn_c <= x->c,
+              SEG_E_BAD_SHAPE, "maxpool_bn_infer: bad geometry");
+  const int64_t f_rows = (int64_t)y->n * y->h;
+  SEG_REQUIRE(vec8_ok(*x) && vec8_ok(*y) && f_rows > 0 && f_rows <= 65535, SEG_E_UNSUPPORTED,
+              "maxpool_bn_infer: needs 16-byte aligned channel vectors and n*h_out <= 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rowlen = y->w * (y->c / 8);
+  dim3 grid, block;
+  pool_row_geometry(f_rows, rowlen, &grid, &block);
+  if (k == 2)
+    SEG_CHECK_CUDA(launch_k(maxpool_bn_infer_row8_kernel<2>, grid, block, (size_t)0, st, *x, k,
+                            moving_mean, moving_var, eps, beta, bn_c, *y));
+  else if (k == 3)
+    SEG_CHECK_CUDA(launch_k(maxpool_bn_infer_row8_kernel<3>, grid, block, (size_t)0, st, *x, k,
+                            moving_mean, moving_var, eps, beta, bn_c, *y));
+  else
+    SEG_CHECK_CUDA(launch_k(maxpool_bn_infer_row8_kernel<0>, grid, block, (size_t)0, st, *x, k,
+                            moving_mean, moving_var, eps, beta, bn_c, *y));
+  return SEG_OK;
+}
+
 // row-mapped backward launch; false: geometry outside its limits (caller uses the cell form)
 static bool launch_pool_bwd_rows(const seg_view& dy, const seg_view& dy2, const uint8_t* argmax,
                                  int k, const seg_view& add, int add_y0, int add_x0,
@@ -2000,6 +2117,18 @@ SEG_API int32_t seg_batchnorm_infer(const seg_view* x, const float* moving_mean,
     bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         *x, moving_mean, moving_var, eps, 1, beta, *y);
   SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_batchnorm_fold(const float* moving_mean, const float* moving_var, float eps,
+                                   const float* beta, int32_t c, int32_t c_pad, float* scale,
+                                   float* shift, void* stream) {
+  SEG_REQUIRE(moving_mean && moving_var && beta && scale && shift && c >= 0 && c <= c_pad,
+              SEG_E_BAD_SHAPE, "batchnorm_fold: bad argument");
+  if (c_pad == 0) return SEG_OK;
+  SEG_CHECK_CUDA(launch_k(bn_fold_kernel, dim3((c_pad + 127) / 128), dim3(128), (size_t)0,
+                          (cudaStream_t)stream, moving_mean, moving_var, eps, beta, (int)c,
+                          (int)c_pad, scale, shift));
   return SEG_OK;
 }
 

@@ -410,6 +410,8 @@ struct HconvJob {
   const float* bias;
   int flags;
   const int* tap_rows;         // optional: weight-matrix row of tap t = r*kw+s (see HconvParams)
+  const float* post_scale;     // optional affine map after bias / ReLU (see HconvParams)
+  const float* post_shift;
 };
 
 static long long* g_prof_buf = nullptr;     // in-kernel timeline buffer (test hook)
@@ -561,6 +563,7 @@ static int launch_hconv(const HconvJob& J, cudaStream_t st) {
   P.N_total = J.N_total;
   P.d0 = J.d0; P.d1 = J.d1; P.split_n = J.split_n;
   P.bias = J.bias; P.flags = J.flags;
+  P.post_scale = J.post_scale; P.post_shift = J.post_shift;
   P.prof = g_prof_buf;
 
   // shared-memory budget: B resident if every (chunk, tap) tile of one N-slice fits next
@@ -1076,7 +1079,8 @@ int fconv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
                 const seg_view& dz, float* dw, float* db, cudaStream_t st);
 
 int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2, const void* w,
-                  const float* bias, const seg_view& y, cudaStream_t st) {
+                  const float* bias, const seg_view& y, cudaStream_t st, const float* post_scale,
+                  const float* post_shift) {
   if (x.c == 4 && d.cin == 3) {
     const int rc = fconv_fwd(d, x, x2, w, bias, y, st);
     if (rc != SEG_E_UNSUPPORTED) return rc;
@@ -1099,7 +1103,8 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
   J.N_total = d.cout_pad; J.max_bn = d.cout_pad;
   J.d0 = make_dest(&y, nullptr);
   J.bias = bias; J.flags = d.flags;
-  if (g_use_tconv && d.stride == 1 && d.kh == 3 && d.kw == 3) {
+  // the folded batch-norm epilogue exists in the halo-tile kernel only
+  if (g_use_tconv && d.stride == 1 && d.kh == 3 && d.kw == 3 && !post_scale) {
     TconvJob T;
     memset(&T, 0, sizeof(T));
     T.a1 = J.a1; T.a2 = J.a2;
@@ -1124,9 +1129,12 @@ int umma_conv_fwd(const seg_conv_desc& d, const seg_view& x, const seg_view* x2,
     H.b_mn = true; H.b_rows_per_tap = J.b_rows_per_tap; H.tap_flip = false;
     H.N_total = J.N_total; H.max_bn = J.max_bn;
     H.d0 = J.d0; H.bias = bias; H.flags = d.flags;
+    H.post_scale = post_scale; H.post_shift = post_shift;
     const int rc = launch_hconv(H, st);
     if (rc != SEG_E_UNSUPPORTED) return rc;
   }
+  SEG_REQUIRE(!post_scale, SEG_E_UNSUPPORTED,
+              "conv_fwd: the folded batch-norm epilogue needs the halo-tile kernel's geometry");
   return launch_igemm(J, st);
 }
 
@@ -1239,7 +1247,8 @@ int umma_conv_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view* x
 // runs on the halo-tile kernel with a strided destination view and a tap -> weight-row
 // table.  Returns SEG_E_UNSUPPORTED if a class does not fit that kernel.
 static int deconv_fwd_parity(const seg_conv_desc& d, const seg_view& x, const void* w,
-                             const float* bias, const seg_view& y, cudaStream_t st) {
+                             const float* bias, const seg_view& y, cudaStream_t st,
+                             const float* post_scale, const float* post_shift) {
   const int s = d.stride, k = d.kh;
   const size_t esz = (d.flags & SEG_EPI_OUT_F32) ? 4 : 2;
   for (int py = 0; py < s; ++py) {
@@ -1266,6 +1275,7 @@ static int deconv_fwd_parity(const seg_conv_desc& d, const seg_view& x, const vo
       H.N_total = d.cout_pad; H.max_bn = d.cout_pad;
       H.d0 = make_dest(&yv, nullptr);
       H.bias = bias; H.flags = d.flags;
+      H.post_scale = post_scale; H.post_shift = post_shift;
       int rows[25];
       if (My * Mx > 25) return SEG_E_UNSUPPORTED;
       for (int r = 0; r < My; ++r)
@@ -1281,7 +1291,8 @@ static int deconv_fwd_parity(const seg_conv_desc& d, const seg_view& x, const vo
 
 // transposed conv, VALID: k == stride as GEMM + pixel shuffle, k > stride by output parity
 int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, const float* bias,
-                    const seg_view& y, cudaStream_t st) {
+                    const seg_view& y, cudaStream_t st, const float* post_scale,
+                    const float* post_shift) {
   SEG_REQUIRE(d.kh == d.kw && d.kh >= d.stride && d.pad_t == 0 && d.pad_l == 0 && d.pad_b == 0 &&
                   d.pad_r == 0,
               SEG_E_UNSUPPORTED, "umma deconv_fwd: square k >= stride, VALID only");
@@ -1290,8 +1301,10 @@ int umma_deconv_fwd(const seg_conv_desc& d, const seg_view& x, const void* w, co
     int rc = load_encoders();
     if (rc) return rc;
     SEG_REQUIRE(y.c <= d.cout_pad, SEG_E_BAD_SHAPE, "deconv_fwd: y.c > cout_pad");
-    return deconv_fwd_parity(d, x, w, bias, y, st);
+    return deconv_fwd_parity(d, x, w, bias, y, st, post_scale, post_shift);
   }
+  SEG_REQUIRE(!post_scale, SEG_E_UNSUPPORTED,
+              "deconv_fwd: the folded batch-norm epilogue needs k > stride (halo-tile kernel)");
   IgemmJob J;
   memset(&J, 0, sizeof(J));
   J.a1 = x;

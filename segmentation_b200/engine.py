@@ -269,6 +269,10 @@ class ConvLayer(object):
         st = N.stream_ptr()
         N.set_tag(self.name)
         N.note_work(*self.work(x, y, 4 if out_f32 else 2))
+        if y.shape[3] > self.cout:
+            # the bias vector has `cout` entries and is indexed by output column: hand the
+            # kernels the logical channels only (the padded ones stay at their zero fill)
+            y = y[..., :self.cout]
         if self.kind == 'conv':
             d = self.desc(x.shape[1], x.shape[2], self.epi_flags(out_f32), impl)
             N.call('seg_conv2d_fwd', ctypes.byref(d), N.vref(x), N.vref(x2),
@@ -277,6 +281,31 @@ class ConvLayer(object):
             d = self.desc(y.shape[1], y.shape[2], self.epi_flags(out_f32), impl)
             N.call('seg_deconv2d_fwd', ctypes.byref(d), N.vref(x), N.ptr(self.w.shadow()),
                    N.ptr(self.b.value()), N.vref(y), st)
+
+    def forward_bn_infer(self, x, y, bn, impl=N.IMPL_UMMA):
+        """Inference: this layer and the batch-norm `bn` that follows it (moving statistics)
+        as one launch (seg_conv2d_fwd_affine / seg_deconv2d_fwd_affine) - the un-normalised
+        activation is never stored.  Returns False, with nothing launched that matters, where
+        the entry does not take the geometry: the caller then runs the unfused pair."""
+        if impl != N.IMPL_UMMA or os.environ.get('SEGB200_FUSE_BN', '1') == '0':
+            return False
+        st = N.stream_ptr()
+        scale, shift = bn.fold(self.cout_pad)
+        if y.shape[3] > self.cout:
+            y = y[..., :self.cout]
+        N.set_tag(self.name)
+        N.note_work(*self.work(x, y, 2))
+        hw = (x.shape[1], x.shape[2]) if self.kind == 'conv' else (y.shape[1], y.shape[2])
+        d = self.desc(hw[0], hw[1], self.epi_flags(False), impl)
+        name = 'seg_conv2d_fwd_affine' if self.kind == 'conv' else 'seg_deconv2d_fwd_affine'
+        try:
+            N.call(name, ctypes.byref(d), N.vref(x), N.ptr(self.w.shadow()),
+                   N.ptr(self.b.value()), N.ptr(scale), N.ptr(shift), N.vref(y), st)
+        except N.SegError as e:
+            if e.status != N.E_UNSUPPORTED:
+                raise
+            return False
+        return True
 
     # ---- first layer fused with its 2x2 max-pool (seg_conv2d_pool_fwd / _wgrad) ----
     def pool_fusable(self, x, pooled, impl=N.IMPL_UMMA):
@@ -651,6 +680,27 @@ class BatchNorm(object):
             N.call('seg_batchnorm_infer', N.vref(xs), N.ptr(self.moving_mean),
                    N.ptr(self.moving_var), self.eps, N.ptr(self.beta.value()),
                    N.vref(y[..., :self.c]), st)
+
+    def fold(self, c_pad):
+        """(scale, shift) of the moving-statistics normalisation over `c_pad` columns (zero
+        beyond this layer's channels), recomputed on the current stream: the epilogue form
+        ConvLayer.forward_bn_infer hands to the convolution kernels."""
+        buf = getattr(self, '_fold', None)
+        if buf is None or buf.shape[1] != c_pad:
+            buf = self._fold = torch.zeros(2, c_pad, dtype=torch.float32, device=self.scratch.device)
+        N.call('seg_batchnorm_fold', N.ptr(self.moving_mean), N.ptr(self.moving_var), self.eps,
+               N.ptr(self.beta.value()), self.c, c_pad, N.ptr(buf[0]), N.ptr(buf[1]),
+               N.stream_ptr())
+        return buf[0], buf[1]
+
+    def pool_infer(self, x, y, k):
+        """y = batch_norm(maxpool_k(x)) with the moving statistics: bit-identical to pooling
+        the normalised tensor (seg_maxpool_bn_infer), which is then never materialised."""
+        N.set_tag(self.name)
+        N.note_work(0, x.numel() * 2.0 + y.numel() * 2.0)
+        N.call('seg_maxpool_bn_infer', N.vref(x), k, N.ptr(self.moving_mean),
+               N.ptr(self.moving_var), self.eps, N.ptr(self.beta.value()), self.c, N.vref(y),
+               N.stream_ptr())
 
     def backward(self, dy, x, dx, relu_mask=True):
         """dx = BN-grad(dy) masked by the ReluGrad of the layer that produced x;

@@ -234,17 +234,39 @@ class _DeconvExec(ExecBase):
             assert not self.head_fused, 'inference executor: batch statistics not available'
             L['conv1_0'].forward(A['x'], A['conv1_0'], impl=impl); bn('bn1', 'conv1_0')
             E.maxpool_fwd(A['bn1'], A['pool1'], self.amax['pool1'], 2, 2)
-        L['conv2_0'].forward(A['pool1'], A['conv2_0'], impl=impl); bn('bn2', 'conv2_0')
-        E.maxpool_fwd(A['bn2'], A['pool2'], self.amax['pool2'], 3, 3)
-        L['conv3_0'].forward(A['pool2'], A['conv3_0'], impl=impl); bn('bn3', 'conv3_0')
-        E.maxpool_fwd(A['bn3'], A['pool3'], self.amax['pool3'], 3, 3)
-        L['conv4_0'].forward(A['pool3'], A['conv4_0'], impl=impl); bn('bn4', 'conv4_0')
+        # Inference executors never read the un-normalised activations again, so the moving-
+        # statistics batch-norms ride along with a neighbour (SEGB200_FUSE_BN=0: unfused):
+        # in front of a pool they are applied to the pooled tensor (bit-identical, see
+        # seg_maxpool_bn_infer), elsewhere they are the producing layer's epilogue.
+        fuse_bn = (not bn_training and not self.training and impl == N.IMPL_UMMA and
+                   os.environ.get('SEGB200_FUSE_BN', '1') != '0')
+
+        def layer_bn(layer, bn_name, src, limpl):
+            """layer -> ReLU -> batch-norm (-> dropout at the model's sites)"""
+            if fuse_bn and L[layer].forward_bn_infer(A[src], A[bn_name], L[bn_name], impl=limpl):
+                if dropout is not None and bn_name in self.SITES:
+                    self._drop(A[bn_name], self.SITES[bn_name])
+                return
+            L[layer].forward(A[src], A[layer], impl=limpl); bn(bn_name, layer)
+
+        def layer_bn_pool(layer, bn_name, src, pool_name, k):
+            """layer -> ReLU -> batch-norm (-> dropout) -> k x k max-pool"""
+            if fuse_bn and not (dropout is not None and bn_name in self.SITES):
+                L[layer].forward(A[src], A[layer], impl=impl)
+                L[bn_name].pool_infer(A[layer], A[pool_name], k)
+                return
+            L[layer].forward(A[src], A[layer], impl=impl); bn(bn_name, layer)
+            E.maxpool_fwd(A[bn_name], A[pool_name], self.amax[pool_name], k, k)
+
+        layer_bn_pool('conv2_0', 'bn2', 'pool1', 'pool2', 3)
+        layer_bn_pool('conv3_0', 'bn3', 'pool2', 'pool3', 3)
+        layer_bn('conv4_0', 'bn4', 'pool3', impl)
         # 5x5 stride-2 transposed convs: four output-parity classes, each a stride-1
         # correlation with a 3x3 / 3x2 / 2x3 / 2x2 sub-kernel on the halo-tile tcgen05 kernel
         dimpl = N.IMPL_SIMT if os.environ.get('SEGB200_DECONV5', 'umma') == 'simt' else impl
-        L['deconv1_0'].forward(A['bn4'], A['deconv1_0'], impl=dimpl); bn('bn5', 'deconv1_0')
-        L['deconv2_0'].forward(A['bn5'], A['deconv2_0'], impl=dimpl); bn('bn6', 'deconv2_0')
-        L['deconv2_1'].forward(A['bn6'], A['deconv2_1'], impl=dimpl); bn('bn7', 'deconv2_1')
+        layer_bn('deconv1_0', 'bn5', 'bn4', dimpl)
+        layer_bn('deconv2_0', 'bn6', 'bn5', dimpl)
+        layer_bn('deconv2_1', 'bn7', 'bn6', dimpl)
         self._tail_done = False
         if (fused_tail and not bn_training and impl == N.IMPL_UMMA and 2 <= m.n_classes <= 4 and
                 A['bn7'].shape[3] == 32 and os.environ.get('SEGB200_FUSED_TAIL', '1') != '0'):

@@ -17,7 +17,10 @@ EPI_BIAS, EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK = 1, 2, 4, 8
 
 
 class SegError(RuntimeError):
-    pass
+    status = 0
+
+
+E_UNSUPPORTED = -6    # SEG_E_UNSUPPORTED: the entry does not take this geometry (nothing ran)
 
 
 class SegView(ctypes.Structure):
@@ -60,10 +63,13 @@ SIGNATURES = {
     'seg_conv2d_pool_wgrad': [_DP, _VP, _VP, _P, _VP, _P, _P, _P],
     'seg_conv2d_bn_pool_infer': [_DP, _VP, _P, _I32, _P, _P, _P, _F, _P, _VP, _P, _P],
     'seg_deconv2d_fwd': [_DP, _VP, _P, _P, _VP, _P],
+    'seg_conv2d_fwd_affine': [_DP, _VP, _P, _P, _P, _P, _VP, _P],
+    'seg_deconv2d_fwd_affine': [_DP, _VP, _P, _P, _P, _P, _VP, _P],
     'seg_deconv2d_dgrad': [_DP, _VP, _P, _VP, _VP, _P],
     'seg_deconv2d_wgrad': [_DP, _VP, _VP, _P, _P],
     'seg_bias_grad': [_VP, _P, _P],
     'seg_maxpool_fwd': [_VP, _I32, _I32, _VP, _P, _P],
+    'seg_maxpool_bn_infer': [_VP, _I32, _P, _P, _F, _P, _I32, _VP, _P],
     'seg_maxpool_bwd': [_VP, _P, _I32, _I32, _VP, _I32, _I32, _VP, _VP, _P],
     'seg_bilinear_upsample_fwd': [_VP, _I32, _VP, _VP, _I32, _P],
     'seg_bilinear_upsample_bwd': [_VP, _I32, _I32, _VP, _VP, _P],
@@ -76,6 +82,7 @@ SIGNATURES = {
     'seg_batchnorm_finalize': [_P, _P, _I64, _I32, _F, _F, _P, _P, _P, _P, _P],
     'seg_batchnorm_apply': [_VP, _P, _P, _P, _VP, _P],
     'seg_batchnorm_infer': [_VP, _P, _P, _F, _P, _VP, _P],
+    'seg_batchnorm_fold': [_P, _P, _F, _P, _I32, _I32, _P, _P, _P],
     'seg_batchnorm_bwd_reduce': [_VP, _VP, _P, _P, _P, _P, _P],
     'seg_batchnorm_bwd_apply': [_VP, _VP, _P, _P, _P, _P, _I64, _I32, _VP, _P],
     'seg_dropout': [_VP, _U64, _U32, _F, _VP, _P],
@@ -169,8 +176,10 @@ def load():
 def check(status, what):
     if status != 0:
         msg = load().seg_last_error_string()
-        raise SegError('%s failed (status %d): %s' % (what, status,
-                                                      msg.decode() if msg else ''))
+        err = SegError('%s failed (status %d): %s' % (what, status,
+                                                     msg.decode() if msg else ''))
+        err.status = status
+        raise err
 
 
 LAUNCHES = 0          # number of kernel-enqueueing C-ABI calls made so far

@@ -351,6 +351,82 @@ def test_deconv_fwd_bwd(cuda, case):
         assert rec['y'] < TOL_BF16 and rec['dx'] < TOL_BF16 and rec['dw'] < TOL_F32 * 5, rec
 
 
+AFFINE_CASES = [
+    # name, kind, N, H, W, Cin, Cout, k, stride
+    ('conv3_valid_32_64', 'conv', 2, 30, 26, 32, 64, 3, 1),
+    ('conv3_valid_128_256', 'conv', 2, 27, 27, 128, 256, 3, 1),
+    ('k5s2_256_64', 'deconv', 2, 13, 9, 256, 64, 5, 2),
+    ('k5s2_32_32', 'deconv', 2, 27, 25, 32, 32, 5, 2),
+    ('k5s2_64_24', 'deconv', 1, 11, 11, 64, 24, 5, 2),
+]
+
+
+@pytest.mark.parametrize('case', AFFINE_CASES, ids=[c[0] for c in AFFINE_CASES])
+def test_conv_deconv_fwd_with_folded_batchnorm(cuda, case):
+    """seg_conv2d_fwd_affine / seg_deconv2d_fwd_affine + seg_batchnorm_fold (layer -> ReLU ->
+    inference batch-norm as one launch, /root/reference/models/deconvolution.py:120-170)
+    against the oracle's conv -> relu -> batch_norm(is_training=False) and against the unfused
+    C-ABI pair.  The fused form normalises the fp32 accumulator (one bf16 rounding instead of
+    two), so it is compared within the bf16 tolerance, not bitwise; padded output channels
+    must stay zero."""
+    name, kind, Nb, H, W, Ci, Co, k, s = case
+    g = _gen(31)
+    x = bfr(torch.rand(Nb, H, W, Ci, generator=g) - 0.3)
+    b = torch.randn(Co, generator=g) * 0.1
+    beta = torch.randn(Co, generator=g) * 0.2
+    mean = torch.rand(Co, generator=g) * 0.3
+    var = torch.rand(Co, generator=g) * 0.5 + 0.02
+    cin_pad, cout_pad = pad16(Ci), pad16(Co)
+    if kind == 'conv':
+        w = bfr(torch.randn(k, k, Ci, Co, generator=g) * 0.1)
+        z = T.conv2d(x, w, b, s, 'VALID')
+        w_d = shadow_conv(w, cin_pad, cout_pad)
+    else:
+        w = bfr(torch.randn(k, k, Co, Ci, generator=g) * 0.1)
+        z = T.conv2d_transpose(x, w, b, s, 'VALID')
+        w_d = shadow_deconv(w, cin_pad, cout_pad)
+    y_ref, _, _ = T.batch_norm(torch.relu(z), beta, mean, var, False)
+    OH, OW = z.shape[1], z.shape[2]
+    x_d, b_d = dev_bf16(x, cin_pad), b.cuda()
+    mean_d, var_d, beta_d = mean.cuda(), var.cuda(), beta.cuda()
+    fold = torch.full((2, cout_pad), float('nan'), dtype=torch.float32, device='cuda')
+    st = N.stream_ptr()
+    N.call('seg_batchnorm_fold', N.ptr(mean_d), N.ptr(var_d), 1e-3, N.ptr(beta_d), Co, cout_pad,
+           N.ptr(fold[0]), N.ptr(fold[1]), st)
+    d = desc(k, s, (0, 0, 0, 0), Ci, Co, cin_pad, cout_pad, N.EPI_BIAS | N.EPI_RELU, N.IMPL_UMMA)
+    y_d = torch.full((Nb, OH, OW, cout_pad), float('nan'), dtype=torch.bfloat16, device='cuda')
+    entry = 'seg_conv2d_fwd_affine' if kind == 'conv' else 'seg_deconv2d_fwd_affine'
+    y_d[..., Co:] = 0
+    N.call(entry, ctypes.byref(d), N.vref(x_d), N.ptr(w_d), N.ptr(b_d), N.ptr(fold[0]),
+           N.ptr(fold[1]), N.vref(y_d[..., :Co]), st)
+    assert 'hconv' in N.load().seg_last_kernel_name().decode()
+    # the unfused pair
+    t_d = torch.zeros(Nb, OH, OW, cout_pad, dtype=torch.bfloat16, device='cuda')
+    u_d = torch.zeros_like(t_d)
+    plain = 'seg_conv2d_fwd' if kind == 'conv' else 'seg_deconv2d_fwd'
+    if kind == 'conv':
+        N.call(plain, ctypes.byref(d), N.vref(x_d), None, N.ptr(w_d), N.ptr(b_d),
+               N.vref(t_d[..., :Co]), st)
+    else:
+        N.call(plain, ctypes.byref(d), N.vref(x_d), N.ptr(w_d), N.ptr(b_d),
+               N.vref(t_d[..., :Co]), st)
+    N.call('seg_batchnorm_infer', N.vref(t_d[..., :Co]), N.ptr(mean_d), N.ptr(var_d), 1e-3,
+           N.ptr(beta_d), N.vref(u_d[..., :Co]), st)
+    sync()
+    f = fold.cpu()
+    sc = torch.rsqrt(var + 1e-3)
+    assert torch.allclose(f[0, :Co], sc, rtol=1e-5) and torch.allclose(f[1, :Co], beta - mean * sc,
+                                                                      rtol=1e-5, atol=1e-6)
+    assert torch.all(f[:, Co:] == 0)
+    got = y_d.float().cpu()
+    rec = {'case': name, 'vs_oracle': rel_l2(got[..., :Co], y_ref),
+           'vs_unfused': rel_l2(got[..., :Co], u_d.float().cpu()[..., :Co]),
+           'unfused_vs_oracle': rel_l2(u_d.float().cpu()[..., :Co], y_ref)}
+    report('conv_affine', rec)
+    assert torch.all(got[..., Co:] == 0)                       # padded channels untouched
+    assert rec['vs_oracle'] < TOL_BF16 and rec['vs_unfused'] < TOL_BF16, rec
+
+
 def test_conv_crop_view_and_slice_output(cuda):
     """Crop views as inputs (tf.image.resize_image_with_crop_or_pad as a TMA base
     offset) and channel-slice outputs."""

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import nets, tf_ops as T
+from segmentation_b200 import native as N
 
 from gpu_util import bfr, rel_l2, report, sync
 from test_gpu_unet import FeedDataSet
@@ -341,6 +342,27 @@ def test_deconv_fused_tail_matches_unfused(cuda):
         del os.environ['SEGB200_FUSED_HEAD1']
     report('deconv_fused_head', {'logits_rel_l2': e_head})
     assert e_head < 1e-2, e_head
+    # ... and the batch-norms folded into their neighbours (bn2 / bn3 applied to the pooled
+    # tensor, bn4..bn7 as the producing layer's epilogue) against separate normalisation passes
+    os.environ['SEGB200_FUSE_BN'] = '0'
+    try:
+        model._exec.clear()
+        n0 = N.LAUNCHES
+        model.infer(x)
+        n_unfused = N.LAUNCHES - n0
+        ex3 = model._get_exec(B, False)
+        e_bn = rel_l2(ex3.logits.cpu(), logits_f)
+        lab_bn = ex3.labelmap.cpu().clone()
+    finally:
+        del os.environ['SEGB200_FUSE_BN']
+    model._exec.clear()
+    n0 = N.LAUNCHES
+    _, lab_f2 = model.infer(x)
+    n_fused = N.LAUNCHES - n0
+    report('deconv_fused_bn', {'logits_rel_l2': e_bn, 'launches': [n_unfused, n_fused],
+                               'label_mismatch': float((lab_bn != torch.as_tensor(np.asarray(lab_f2))).float().mean())})
+    assert e_bn < 1e-2, e_bn
+    assert n_fused < n_unfused                      # two launches fewer (bn2, bn3 passes)
     e = rel_l2(logits_f, logits_u)
     dmax = float((logits_f - logits_u).abs().max())
     margin = (logits_u[..., 0] - logits_u[..., 1]).abs()

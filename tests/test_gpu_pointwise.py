@@ -193,6 +193,41 @@ def test_batchnorm(cuda):
         assert rel_l2(y_d.float().cpu()[..., :C], y_inf) < 4e-3
 
 
+@pytest.mark.parametrize('shape,k,C', [((2, 12, 15, 64), 3, 64), ((1, 254, 254, 64), 3, 64),
+                                       ((3, 10, 8, 32), 2, 32), ((2, 9, 9, 16), 3, 5)])
+def test_maxpool_bn_infer_is_bit_identical_to_bn_then_pool(cuda, shape, k, C):
+    """seg_maxpool_bn_infer (batch-norm applied to the pooled tensor) against the order the
+    model states, seg_batchnorm_infer then seg_maxpool_fwd: the same bits, because the
+    normalisation is increasing and every rounding monotonic
+    (/root/reference/models/deconvolution.py:126-138)."""
+    g = _gen(21)
+    Nb, H, W, Cp = shape
+    x = torch.zeros(shape)
+    x[..., :C] = torch.relu(torch.round(torch.randn(Nb, H, W, C, generator=g) * 4) / 4)
+    store = E.ParamStore(torch.device('cuda'))
+    bn = E.BatchNorm(store, 'bn', C)
+    store.finalize()
+    bn.beta.value().copy_((torch.randn(C, generator=g) * 0.2).cuda())
+    bn.moving_mean.copy_((torch.rand(C, generator=g) * 0.5).cuda())
+    bn.moving_var.copy_((torch.rand(C, generator=g) * 0.5 + 0.01).cuda())
+    x_d = dev_bf16(x)
+    Ho, Wo = H // k, W // k
+    full = torch.zeros(shape, dtype=BF16, device='cuda')
+    bn.forward(x_d, full, training=False)
+    ref = torch.zeros(Nb, Ho, Wo, Cp, dtype=BF16, device='cuda')
+    am = torch.zeros(Nb, Ho, Wo, Cp, dtype=torch.uint8, device='cuda')
+    E.maxpool_fwd(full, ref, am, k, k)
+    got = torch.full((Nb, Ho, Wo, Cp), float('nan'), dtype=BF16, device='cuda')
+    bn.pool_infer(x_d, got, k)
+    sync()
+    assert torch.equal(got.view(torch.int16).cpu(), ref.view(torch.int16).cpu())
+    # and the CPU oracle: pool(bn(x)) in fp32, rounded once
+    y_inf, _, _ = T.batch_norm(x[..., :C], bn.beta.value().cpu(), bn.moving_mean.cpu(),
+                               bn.moving_var.cpu(), False)
+    y_ref = T.max_pool(bfr(y_inf), k, k)
+    assert rel_l2(got.float().cpu()[..., :C], y_ref) < 4e-3
+
+
 def test_adam_matches_tf_formula(cuda):
     g = _gen(10)
     store = E.ParamStore(torch.device('cuda'))

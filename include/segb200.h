@@ -109,6 +109,8 @@ SEG_API const char* seg_last_kernel_name(void);
  *          seg_stage_input, forward and weight gradient; default 1).
  *   key 17: number of SMs the persistent tile kernels size their grids for (default 0 = all).
  *          Data-parallel training sets it to (SM count - all-reduce CTAs): see parallel.py.
+ *   key 18: seg_classmap_tail_infer with the transposed conv on warp-level tensor-core MMAs
+ *          (default 1; 0 = the CUDA-core form, also taken for unaligned class maps).
  * (Keys 8, 10 and 13 of round 1 - cluster/DSMEM weight-gradient reduction, wave-quantised
  * halo tiles, two-CTA multicast halo clusters - were measured slower and are gone.) */
 SEG_API int32_t seg_set_option(int32_t key, int32_t value);

@@ -44,6 +44,7 @@ int fconv_pool_wgrad(const seg_conv_desc& d, const seg_view& x, const seg_view& 
 
 void hconv_set_row_align(int a);
 void pool_set_rows(int on);
+void tail_set_mma(int on);
 void conv_set_deep_b_ring(int on);
 void hconv_set_rowstage(int on);
 void twgrad_set_tred(int on);
@@ -113,6 +114,7 @@ SEG_API int32_t seg_set_option(int32_t key, int32_t value) {
     case 15: twgrad_set_tred(value); return SEG_OK;
     case 16: fconv_enable(value); return SEG_OK;
     case 17: g_sm_limit = value > 0 ? value : 0; return SEG_OK;
+    case 18: tail_set_mma(value); return SEG_OK;
   }
   set_error("seg_set_option: unknown key %d", key);
   return SEG_E_BAD_SHAPE;

@@ -174,6 +174,8 @@ __global__ void maxpool_bwd_cell8_kernel(seg_view dy, seg_view dy2, const uint8_
 // the same dy / argmax / pooled vectors (L1 hits).
 static int g_pool_rows = 1;     // seg_set_option key 11
 void pool_set_rows(int on) { g_pool_rows = on != 0; }
+static int g_tail_mma = 1;      // seg_set_option key 18
+void tail_set_mma(int on) { g_tail_mma = on != 0; }
 
 // per-halfword mask (0xffff / 0): bf16 pair a > b (ordered compare, false on NaN)
 __device__ __forceinline__ uint32_t bf16x2_gt_mask(uint32_t a, uint32_t b) {
@@ -1269,6 +1271,294 @@ __global__ void __launch_bounds__(256) classmap_tail_kernel(const TailArgs A) {
   }
 }
 
+// ---- the same tail with the transposed conv on the tensor cores
+// Source-level profile of the kernel above (profiles/r02_ncu_tail.md): instruction-issue and
+// LSU bound (L1 88 %, DRAM 1.0 TB/s), 63 % of its instructions in phase A - per
+// half-resolution pixel 256 FFMA + 64 broadcast LDS.128 for the 32 -> 4*NC transposed conv -
+// and 32 % in phase B (one output pixel per thread: 9*NC 16-bit LDS, a quarter of the
+// threads idle in the last pass).  Here:
+//   phase A: a thread still interpolates one half-resolution pixel, but leaves its 32 bf16
+//     channels in shared memory (64-byte rows, 16-byte chunks XOR-swizzled so that both the
+//     row-per-thread stores and ldmatrix are conflict-free); each warp then multiplies its own
+//     32 pixels with the [32][4*NC] weight matrix by mma.sync.m16n8k16 (bf16 products are
+//     exact, fp32 accumulation: the same value as the FFMA chain up to summation order), the
+//     weight fragments living in registers for the whole kernel.  tcgen05 is the wrong tool
+//     for a 32 x 8 product per pixel group: its M = 128 tile, TMEM allocation and
+//     commit / tcgen05.ld round trip cost more than the 4 warp-level MMAs they would replace.
+//   phase B: a thread owns the 2 x 2 outputs of one half-resolution pixel: 16 shared loads
+//     feed four 3x3 windows, every store is 8 or 16 bytes wide.
+// Same rounding points and the same 3x3 summation order as the kernel above.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                            uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1,
+                                                  uint32_t a2, uint32_t a3, uint32_t b0,
+                                                  uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) classmap_tail_mma_kernel(const TailArgs A) {
+  constexpr int C = 32;
+  constexpr int NT = (4 * NC + 7) / 8;             // 8-column tiles of the [32][4*NC] product
+  static_assert(kTailH * kTailH == 256, "one thread per haloed half-resolution pixel");
+  __shared__ __align__(16) uint8_t s_v[256 * C * 2];   // interpolated pixels, bf16 [256][32]
+  __shared__ float s_wout[9 * NC * NC];            // [tap][ci][co]
+  __shared__ float s_aff[5 * NC];                  // b_up, bn rstd, bn mean, bn beta, b_out
+  __shared__ __align__(16) bf16 s_t[kTailO * kTailO * NC];   // bn output tile
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 9 * NC * NC; i += 256) {
+    const int co = i % NC, ci = (i / NC) % NC, tap = i / (NC * NC);
+    s_wout[i] = __bfloat162float(A.w_out[((int64_t)tap * A.out_cip + ci) * A.out_cop + co]);
+  }
+  if (tid < NC) {
+    const int c = tid;
+    s_aff[c] = __ldg(A.b_up + c);
+    s_aff[NC + c] = rsqrtf(__ldg(A.bn_var + c) + A.bn_eps);
+    s_aff[2 * NC + c] = __ldg(A.bn_mean + c);
+    s_aff[3 * NC + c] = __ldg(A.bn_beta + c);
+    s_aff[4 * NC + c] = __ldg(A.b_out + c);
+  }
+  // B fragments of the transposed conv: column n = sub * NC + co, rows = input channels
+  uint32_t bw[NT][2][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int nn = nt * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      bw[nt][ks][0] = bw[nt][ks][1] = 0u;
+      if (nn < 4 * NC) {
+        const bf16* wp = A.w_up + ((int64_t)(nn / NC) * A.up_cop + (nn % NC)) * A.up_cip + ks * 16 + 2 * t;
+        bw[nt][ks][0] = __ldg(reinterpret_cast<const unsigned int*>(wp));
+        bw[nt][ks][1] = __ldg(reinterpret_cast<const unsigned int*>(wp + 8));
+      }
+    }
+  }
+  const int tiles_x = (A.rw + kTailT - 1) / kTailT, tiles_y = (A.rh + kTailT - 1) / kTailT;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x - n * tiles_x * tiles_y;
+  const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+  const int ry0 = ty * kTailT - 1, rx0 = tx * kTailT - 1;   // haloed tile origin (half-res)
+  // ---- phase A.1: thread = one half-resolution pixel of the 16 x 16 haloed tile
+  {
+    const int ly_ = tid / kTailH, lx_ = tid % kTailH;
+    const int ry = ry0 + ly_, rx = rx0 + lx_;
+    const bool inside = ry >= 0 && ry < A.rh && rx >= 0 && rx < A.rw;
+    const uint32_t row = smem_u32(s_v) + (uint32_t)tid * (C * 2);
+    const uint32_t swz = (uint32_t)((tid >> 1) & 3);
+    if (inside) {
+      const float sy = (float)A.x.h / (float)A.rh, sx = (float)A.x.w / (float)A.rw;
+      int y0, y1, x0, x1;
+      float fy, fx;
+      legacy_src(ry, sy, A.x.h, y0, y1, fy);
+      legacy_src(rx, sx, A.x.w, x0, x1, fx);
+      const bf16* p00 = view_at(A.x, n, y0, x0);
+      const bf16* p01 = view_at(A.x, n, y0, x1);
+      const bf16* p10 = view_at(A.x, n, y1, x0);
+      const bf16* p11 = view_at(A.x, n, y1, x1);
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p00 + c0);
+        const uint4 b = *reinterpret_cast<const uint4*>(p01 + c0);
+        const uint4 c = *reinterpret_cast<const uint4*>(p10 + c0);
+        const uint4 d = *reinterpret_cast<const uint4*>(p11 + c0);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bq[4] = {b.x, b.y, b.z, b.w};
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float tl = e ? bf16_hi(aw[j]) : bf16_lo(aw[j]);
+            const float tr = e ? bf16_hi(bq[j]) : bf16_lo(bq[j]);
+            const float bl = e ? bf16_hi(cw[j]) : bf16_lo(cw[j]);
+            const float br = e ? bf16_hi(dw[j]) : bf16_lo(dw[j]);
+            const float top = tl + (tr - tl) * fx;
+            const float bot = bl + (br - bl) * fx;
+            r[e] = top + (bot - top) * fy;
+          }
+          o[j] = pack_bf16x2(r[0], r[1]);           // the bf16 the stored resize output holds
+        }
+        sts128(row + ((((uint32_t)c0 >> 3) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts128(row + ((uint32_t)q << 4), make_uint4(0u, 0u, 0u, 0u));
+    }
+  }
+  __syncthreads();     // (also publishes s_aff / s_wout)
+  // ---- phase A.2: each warp multiplies its 32 pixels with the weight matrix
+  {
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    const uint32_t sv = smem_u32(s_v) + (uint32_t)warp * 32 * (C * 2);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int row = mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const int chunk = 2 * ks + (lane >> 4);
+        uint32_t a0, a1, a2, a3;
+        ldmatrix_x4(sv + (uint32_t)row * (C * 2) + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4), a0,
+                    a1, a2, a3);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          mma_bf16_m16n8k16(acc[mt][nt], a0, a1, a2, a3, bw[nt][ks][0], bw[nt][ks][1]);
+      }
+    // bias, ReLU, bf16, batch-norm, bf16 -> the four sub-pixels of each half-resolution pixel
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = warp * 32 + mt * 16 + h * 8 + g;
+        const int ly_ = p / kTailH, lx_ = p % kTailH;
+        const int ry = ry0 + ly_, rx = rx0 + lx_;
+        const bool inside = ry >= 0 && ry < A.rh && rx >= 0 && rx < A.rw;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float r[2];
+          const int nn0 = nt * 8 + 2 * t;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int nn = nn0 + e;
+            const int co = nn % NC;
+            float v = 0.f;
+            if (inside && nn < 4 * NC) {
+              const float z = fmaxf(acc[mt][nt][2 * h + e] + s_aff[co], 0.f);
+              const float dq = __bfloat162float(__float2bfloat16(z));   // stored deconv output
+              v = bn_infer_value(dq, s_aff[2 * NC + co], s_aff[NC + co], s_aff[3 * NC + co]);
+            }
+            r[e] = v;
+          }
+          if (NC == 2) {
+            // columns (2t, 2t+1) = sub-pixel t, classes 0 and 1: one 4-byte store
+            const int oyl = 2 * ly_ + (t >> 1), oxl = 2 * lx_ + (t & 1);
+            *reinterpret_cast<uint32_t*>(s_t + (oyl * kTailO + oxl) * NC) = pack_bf16x2(r[0], r[1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int nn = nn0 + e;
+              if (nn < 4 * NC) {
+                const int sub = nn / NC, co = nn % NC;
+                const int oyl = 2 * ly_ + (sub >> 1), oxl = 2 * lx_ + (sub & 1);
+                s_t[(oyl * kTailO + oxl) * NC + co] = __float2bfloat16(r[e]);
+              }
+            }
+          }
+        }
+      }
+  }
+  __syncthreads();
+  // ---- phase B: thread = the 2 x 2 outputs of one interior half-resolution pixel
+  if (tid < kTailT * kTailT) {
+    const int hy = tid / kTailT, hx = tid - hy * kTailT;
+    const int H = 2 * A.rh, W = 2 * A.rw;
+    const int oy0 = 2 * (ty * kTailT + hy), ox0 = 2 * (tx * kTailT + hx);
+    if (oy0 < H && ox0 < W) {          // H, W, oy0, ox0 even: the block is inside or outside
+      float win[4][4][NC];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bf16* tp = s_t + ((2 * hy + 1 + r) * kTailO + (2 * hx + 1 + q)) * NC;
+          if (NC == 2) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(tp);
+            win[r][q][0] = bf16_lo(u);
+            win[r][q][NC - 1] = bf16_hi(u);
+          } else if (NC == 4) {
+            const uint2 u = *reinterpret_cast<const uint2*>(tp);
+            win[r][q][0] = bf16_lo(u.x);
+            win[r][q][1] = bf16_hi(u.x);
+            win[r][q][NC - 2] = bf16_lo(u.y);
+            win[r][q][NC - 1] = bf16_hi(u.y);
+          } else {
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) win[r][q][ci] = __bfloat162float(tp[ci]);
+          }
+        }
+      // the four 3x3 windows advance together so that every weight is read once; each
+      // output still accumulates in (row, column, ci) order
+      float out[2][2][NC];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+          for (int co = 0; co < NC; ++co) out[dy][dx][co] = s_aff[4 * NC + co];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int ci = 0; ci < NC; ++ci) {
+            float wv[NC];
+#pragma unroll
+            for (int co = 0; co < NC; ++co) wv[co] = s_wout[((r * 3 + q) * NC + ci) * NC + co];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                const float xv = win[dy + r][dx + q][ci];
+#pragma unroll
+                for (int co = 0; co < NC; ++co) out[dy][dx][co] += xv * wv[co];
+              }
+          }
+      float sg[2][2][NC], lab[2][2];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float best = -1.f;
+          int bi = 0;
+#pragma unroll
+          for (int co = 0; co < NC; ++co) {
+            // fp32 sigmoid, saturating to exactly 1.0f for large logits like TF's
+            const float s1 = 1.f / (1.f + expf(-out[dy][dx][co]));
+            sg[dy][dx][co] = s1;
+            if (s1 > best) { best = s1; bi = co; }   // strict >: first index on ties
+          }
+          lab[dy][dx] = (float)bi;
+        }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int64_t m = ((int64_t)n * H + oy0 + dy) * W + ox0;
+        if (NC == 2) {
+          if (A.logits)
+            *reinterpret_cast<float4*>(A.logits + m * 2) =
+                make_float4(out[dy][0][0], out[dy][0][NC - 1], out[dy][1][0], out[dy][1][NC - 1]);
+          *reinterpret_cast<float4*>(A.probs + m * 2) =
+              make_float4(sg[dy][0][0], sg[dy][0][NC - 1], sg[dy][1][0], sg[dy][1][NC - 1]);
+        } else {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+            for (int co = 0; co < NC; ++co) {
+              if (A.logits) A.logits[(m + dx) * NC + co] = out[dy][dx][co];
+              A.probs[(m + dx) * NC + co] = sg[dy][dx][co];
+            }
+        }
+        *reinterpret_cast<float2*>(A.labelmap + m) = make_float2(lab[dy][0], lab[dy][1]);
+      }
+    }
+  }
+}
+
 __global__ void mc_mean_var_kernel(const float* probs, int T, int64_t count, float* mean,
                                    float* var) {
   GRID_STRIDE(i, count) {
@@ -2250,6 +2540,21 @@ SEG_API int32_t seg_classmap_tail_infer(const seg_view* x, int32_t rh, int32_t r
   const int tiles = ((rw + kTailT - 1) / kTailT) * ((rh + kTailT - 1) / kTailT);
   const dim3 grid((unsigned)(tiles * x->n));
   cudaStream_t st = (cudaStream_t)stream;
+  // the 16- and 8-byte stores of the tensor-core form need aligned class maps and 4-byte
+  // aligned weight pairs; anything else takes the CUDA-core form
+  const bool mma_ok = g_tail_mma && (up_cin_pad % 2) == 0 &&
+                      (reinterpret_cast<uintptr_t>(w_up_bf16) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(probs) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(labelmap) & 7) == 0;
+  if (mma_ok) {
+    switch (n_classes) {
+      case 2: SEG_CHECK_CUDA(launch_k(classmap_tail_mma_kernel<2>, grid, dim3(256), (size_t)0, st, A)); break;
+      case 3: SEG_CHECK_CUDA(launch_k(classmap_tail_mma_kernel<3>, grid, dim3(256), (size_t)0, st, A)); break;
+      default: SEG_CHECK_CUDA(launch_k(classmap_tail_mma_kernel<4>, grid, dim3(256), (size_t)0, st, A)); break;
+    }
+    return SEG_OK;
+  }
   switch (n_classes) {
     case 2: SEG_CHECK_CUDA(launch_k(classmap_tail_kernel<2, 32>, grid, dim3(256), (size_t)0, st, A)); break;
     case 3: SEG_CHECK_CUDA(launch_k(classmap_tail_kernel<3, 32>, grid, dim3(256), (size_t)0, st, A)); break;

@@ -167,6 +167,7 @@ def load():
                      ('SEGB200_HCONV_ROWSTAGE', OPT_HALO_ROWSTAGE),
                      ('SEGB200_TWGRAD_TRED', OPT_WGRAD_TENSOR_RED),
                      ('SEGB200_FIRST_LAYER', OPT_FIRST_LAYER),
+                     ('SEGB200_TAIL_MMA', OPT_TAIL_MMA),
                      ('SEGB200_WGRAD_MIN_TILES', OPT_WGRAD_MIN_TILES)):
         if env in os.environ:
             lib.seg_set_option(key, int(os.environ[env]))
@@ -213,6 +214,7 @@ OPT_HALO_ROWSTAGE = 14 # halo kernel: one filter row (3 taps) per streamed weigh
 OPT_WGRAD_TENSOR_RED = 15  # spatial-tile weight gradient: TMA tensor reduce-add epilogue (default on)
 OPT_FIRST_LAYER = 16   # first-layer kernel on the (R,G,B,1) staged input (default on)
 OPT_SM_LIMIT = 17      # SMs the persistent tile kernels size their grids for (0 = all)
+OPT_TAIL_MMA = 18      # class-map tail: transposed conv on warp-level MMAs (default on)
 
 
 def set_option(key, value):

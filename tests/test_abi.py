@@ -93,7 +93,7 @@ def test_option_keys_are_documented_and_accepted_without_gpu(lib):
                 native.OPT_WGRAD_MIN_TILES: 8, native.OPT_POOL_ROWS: 1,
                 native.OPT_DEEP_B_RING: 1, native.OPT_HALO_ROWSTAGE: 1,
                 native.OPT_WGRAD_TENSOR_RED: 1, native.OPT_FIRST_LAYER: 1,
-                native.OPT_SM_LIMIT: 0}
+                native.OPT_SM_LIMIT: 0, native.OPT_TAIL_MMA: 1}
     assert set(defaults) == set(keys.values())
     lib.seg_set_option.restype = ctypes.c_int32
     lib.seg_set_option.argtypes = [ctypes.c_int32, ctypes.c_int32]

@@ -228,6 +228,76 @@ def test_maxpool_bn_infer_is_bit_identical_to_bn_then_pool(cuda, shape, k, C):
     assert rel_l2(got.float().cpu()[..., :C], y_ref) < 4e-3
 
 
+@pytest.mark.parametrize('nc,B,hs,ws,rh,rw', [(2, 2, 13, 17, 30, 41), (3, 1, 9, 9, 14, 14),
+                                              (4, 2, 11, 7, 29, 15), (2, 1, 55, 55, 128, 128)])
+def test_classmap_tail_infer_forms_agree(cuda, nc, B, hs, ws, rh, rw):
+    """seg_classmap_tail_infer (resize -> 2x2/s2 transposed conv -> bn -> 3x3 conv -> sigmoid /
+    argmax, /root/reference/models/deconvolution.py:163-174): the tensor-core form (option 18)
+    against the CUDA-core form and against the five separate C-ABI calls, for 2..4 classes
+    and grids that are not multiples of the 14-pixel tile.  All three round to bf16 at the
+    same points; they differ by the fp32 summation order of the 32-channel products only."""
+    g = _gen(40 + nc)
+    store = E.ParamStore(torch.device('cuda'))
+    gen = np.random.default_rng(3)
+    up = E.ConvLayer(store, 'up', 'deconv', 2, 2, 'VALID', 32, nc, True, gen)
+    bn = E.BatchNorm(store, 'bn', nc)
+    out = E.ConvLayer(store, 'out', 'conv', 3, 1, 'SAME', nc, nc, False, gen)
+    store.finalize()
+    up.init_values(); out.init_values()
+    up.b.value().copy_((torch.randn(nc, generator=g) * 0.1).cuda())
+    out.b.value().copy_((torch.randn(nc, generator=g) * 0.1).cuda())
+    bn.beta.value().copy_((torch.randn(nc, generator=g) * 0.2).cuda())
+    bn.moving_mean.copy_((torch.rand(nc, generator=g) * 0.3).cuda())
+    bn.moving_var.copy_((torch.rand(nc, generator=g) * 0.4 + 0.05).cuda())
+    store.refresh_shadow()
+    x = dev_bf16(torch.relu(torch.randn(B, hs, ws, 32, generator=g)))
+    H, W = 2 * rh, 2 * rw
+
+    def fused(mma):
+        N.load().seg_set_option(N.OPT_TAIL_MMA, mma)
+        try:
+            lg = torch.full((B, H, W, nc), float('nan'), device='cuda')
+            pr = torch.full((B, H, W, nc), float('nan'), device='cuda')
+            lm = torch.full((B, H, W), float('nan'), device='cuda')
+            E.classmap_tail_infer(x, rh, rw, up, bn, out, lg, pr, lm)
+            sync()
+            name = N.load().seg_last_kernel_name().decode()
+        finally:
+            N.load().seg_set_option(N.OPT_TAIL_MMA, 1)
+        return lg.cpu(), pr.cpu(), lm.cpu(), name
+
+    lg1, pr1, lm1, k1 = fused(1)
+    lg0, pr0, lm0, k0 = fused(0)
+    assert 'tail_mma' in k1 and 'tail_mma' not in k0, (k1, k0)
+    # the separate launches
+    cp = E.pad16(nc)
+    rs = torch.zeros(B, rh, rw, 32, dtype=BF16, device='cuda')
+    E.resize_bilinear_fwd(x, rs)
+    dc = torch.zeros(B, H, W, cp, dtype=BF16, device='cuda')
+    up.forward(rs, dc[..., :nc])
+    nb = torch.zeros_like(dc)
+    bn.forward(dc, nb, training=False)
+    lg = torch.zeros(B, H, W, nc, device='cuda')
+    out.forward(nb, lg, out_f32=True)
+    pr = torch.zeros_like(lg)
+    lm = torch.zeros(B, H, W, device='cuda')
+    E.sigmoid_argmax(lg, pr, lm)
+    sync()
+    lg, pr, lm = lg.cpu(), pr.cpu(), lm.cpu()
+    assert torch.isfinite(lg1).all() and torch.isfinite(pr1).all() and torch.isfinite(lm1).all()
+    rec = {'nc': nc, 'mma_vs_cuda_core': rel_l2(lg1, lg0), 'mma_vs_unfused': rel_l2(lg1, lg),
+           'cuda_core_vs_unfused': rel_l2(lg0, lg)}
+    report('classmap_tail', rec)
+    assert rec['mma_vs_cuda_core'] < 2e-3 and rec['mma_vs_unfused'] < 2e-3, rec
+    # labels: identical wherever the top-two margin exceeds the summation noise
+    dmax = float((lg1 - lg).abs().max())
+    top2 = torch.topk(lg, 2, dim=3).values
+    safe = (top2[..., 0] - top2[..., 1]) > 4 * dmax + 1e-6
+    assert torch.equal(lm1[safe], lm[safe]) and torch.equal(lm1[safe], lm0[safe])
+    assert float(safe.float().mean()) > 0.9
+    assert float((pr1 - torch.sigmoid(lg1)).abs().max()) < 1e-6
+
+
 def test_adam_matches_tf_formula(cuda):
     g = _gen(10)
     store = E.ParamStore(torch.device('cuda'))

@@ -308,6 +308,17 @@ SEG_API int32_t seg_dropout_ex(const seg_view* x, uint64_t seed, uint32_t stream
  * dlogits.c (zero filled). */
 SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view* labels,
                                  float* loss_sum, const seg_view* dlogits, void* stream);
+/* FCN-8s training head in ONE launch (models/fcn.py:207-220 upscore x8 -> basemodel.py:59-70
+ * loss -> the gradient of both): loss_sum += sum xent(bilinear_up8(x), labels), dx = the x8
+ * transposed conv's input gradient of (softmax - onehot) / pixels, optionally masked by the
+ * ReluGrad of mask_src; the full-resolution logits / dlogits tensors are not materialised
+ * (logits: nullable dense fp32 [n,8h,8w,c], written when given).  x, dx bf16 [n,h,w,c],
+ * c <= 32; labels uint8 [n,8h,8w,1].  dx (and logits) are bit-identical to
+ * seg_bilinear_upsample_fwd(factor 8, fp32 out) -> seg_softmax_xent_fwd_bwd (bf16 dlogits)
+ * -> seg_bilinear_upsample_bwd; the loss differs by the order of its final sum. */
+SEG_API int32_t seg_upscore8_xent_fwd_bwd(const seg_view* x, const seg_view* labels,
+                                          float* loss_sum, const seg_view* dx,
+                                          const seg_view* mask_src, float* logits, void* stream);
 
 /* Fused classification head for training: a 1x1 convolution to n_classes <= 4 (x bf16
  * [n,h,w,cin], cin 16 or 32; w_bf16 = its [cin_pad][cout_pad] shadow; models/unet.py:166-167)

@@ -1087,6 +1087,161 @@ __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* los
   }
 }
 
+// ------------------------------------ FCN-8s training head in one launch
+// A train step of FCN-8s ends with  logits = bilinear x8 transposed conv (fixed weights) of
+// the fused score map -> softmax cross-entropy -> dlogits -> the transposed conv's input
+// gradient (reference models/fcn.py:207-220, models/basemodel.py:59-70,360).  Unfused that
+// is three launches around two full-resolution class tensors (config 2, 16 x 512^2 x 21:
+// 352 MB fp32 logits written and read, 268 MB bf16 dlogits written and read as 256 scattered
+// 2-byte loads per input pixel and channel: 240 + 154 + 292 us of a 1.79 ms step).  Here a
+// block owns 4 x 4 pixels of the score map: it evaluates logits, softmax and dlogits for the
+// 40 x 40 outputs those pixels reach (the 32 x 32 it owns for the loss plus a 4-pixel ring
+// recomputed by the neighbours' blocks too, x 1.56), keeps the bf16-rounded dlogits in shared
+// memory, and gathers each input pixel's 16 x 16 window from there.  No full-resolution
+// tensor is written (logits only when the caller asks for them), no atomics on dx.
+// Every value is computed by the same expression, in the same order, as in
+// bilinear_up_fwd_kernel, softmax_xent_kernel and bilinear_up_bwd_kernel (taps that fall
+// outside the image enter as exact zeros instead of being skipped): dx is bit-identical,
+// the loss differs by the order of its final sum.
+constexpr int kUxF = 8, kUxK = 2 * kUxF, kUxTI = 4;
+constexpr int kUxR = (kUxTI + 1) * kUxF;             // 40: output region side per block
+constexpr int kUxXT = kUxTI + 2;                     // 6: input tile side incl. the ring
+constexpr int kUxPitch = kUxR * kUxR + 8;            // dlogits plane pitch (pixels): odd * 16 B
+struct UpXentArgs {
+  seg_view x;            // [n, h, w, C] bf16 score map
+  seg_view labels;       // [n, 8h, 8w, 1] uint8
+  seg_view dx;           // [n, h, w, C] bf16
+  seg_view mask;         // nullable: ReLU-grad source for dx
+  float* loss_sum;
+  float* logits;         // nullable fp32 [n, 8h, 8w, C] (dense)
+  float inv_pixels;
+  int C;
+  int tiles_x, tiles_y;
+};
+
+template <int CT>
+__global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) {
+  constexpr int CMAX = CT ? CT : 32;
+  extern __shared__ __align__(16) uint8_t ux_smem[];
+  bf16* s_g = reinterpret_cast<bf16*>(ux_smem);                       // [C][kUxPitch]
+  const int C = CT ? CT : A.C;
+  float* s_w2 = reinterpret_cast<float*>(ux_smem + (size_t)C * kUxPitch * 2);   // [16][16]
+  float* s_x = s_w2 + kUxK * kUxK;                                    // [6*6][C]
+  __shared__ float s_red[8];
+  pdl_trigger();
+  const int tid = threadIdx.x;
+  {
+    const int a = tid >> 4, b = tid & 15;
+    s_w2[tid] = (float)(bil_w(a, kUxK) * bil_w(b, kUxK));
+  }
+  const int n = blockIdx.x / (A.tiles_x * A.tiles_y);
+  const int trem = blockIdx.x - n * A.tiles_x * A.tiles_y;
+  const int i0 = (trem / A.tiles_x) * kUxTI, j0 = (trem % A.tiles_x) * kUxTI;
+  const int H = A.x.h * kUxF, W = A.x.w * kUxF;
+  pdl_wait();
+  for (int idx = tid; idx < kUxXT * kUxXT * C; idx += 256) {
+    const int c = idx % C, pix = idx / C;
+    const int ii = i0 - 1 + pix / kUxXT, jj = j0 - 1 + pix % kUxXT;
+    float v = 0.f;
+    if (ii >= 0 && ii < A.x.h && jj >= 0 && jj < A.x.w) v = __bfloat162float(view_at(A.x, n, ii, jj)[c]);
+    s_x[idx] = v;
+  }
+  __syncthreads();
+  // ---- phase 1: logits -> softmax -> dlogits of the 40 x 40 region
+  float local = 0.f;
+  for (int p = tid; p < kUxR * kUxR; p += 256) {
+    const int py = p / kUxR, px = p - py * kUxR;
+    const int oy = kUxF * i0 - kUxF / 2 + py, ox = kUxF * j0 - kUxF / 2 + px;
+    if (oy < 0 || oy >= H || ox < 0 || ox >= W) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) s_g[c * kUxPitch + p] = __float2bfloat16(0.f);
+      continue;
+    }
+    // taps in the order of bilinear_up_fwd_kernel: (i_hi, j_hi), (i_hi, j_lo), (i_lo, j_hi),
+    // (i_lo, j_lo); filter tap a = ty - i * f with ty = oy + f/2
+    const int a_hi = py % kUxF, b_hi = px % kUxF;
+    const int li = py / kUxF, lj = px / kUxF;                 // tile row / column of i_lo, j_lo
+    const float w_hh = s_w2[a_hi * kUxK + b_hi], w_hl = s_w2[a_hi * kUxK + b_hi + kUxF];
+    const float w_lh = s_w2[(a_hi + kUxF) * kUxK + b_hi], w_ll = s_w2[(a_hi + kUxF) * kUxK + b_hi + kUxF];
+    const float* x_hh = s_x + ((li + 1) * kUxXT + lj + 1) * C;
+    const float* x_hl = s_x + ((li + 1) * kUxXT + lj) * C;
+    const float* x_lh = s_x + (li * kUxXT + lj + 1) * C;
+    const float* x_ll = s_x + (li * kUxXT + lj) * C;
+    float v[CMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      float acc = 0.f;
+      if (c < C) {
+        acc += x_hh[c] * w_hh;
+        acc += x_hl[c] * w_hl;
+        acc += x_lh[c] * w_lh;
+        acc += x_ll[c] * w_ll;
+      }
+      v[c] = c < C ? acc : -INFINITY;
+      mx = fmaxf(mx, v[c]);
+    }
+    const bool owned = py >= kUxF / 2 && py < kUxR - kUxF / 2 && px >= kUxF / 2 && px < kUxR - kUxF / 2;
+    if (owned && A.logits) {
+      float* lp = A.logits + (((int64_t)n * H + oy) * W + ox) * C;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) lp[c] = v[c];
+    }
+    const int lab = reinterpret_cast<const uint8_t*>(A.labels.ptr)[n * A.labels.sn + oy * A.labels.sh +
+                                                                   ox * A.labels.sw];
+    float se = 0.f, picked = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c == lab) picked = v[c];
+      v[c] = c < C ? expf(v[c] - mx) : 0.f;
+      se += v[c];
+    }
+    if (owned) local += mx + logf(se) - (lab < C ? picked : 0.f);
+    const float inv_se = 1.f / se;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C)
+        s_g[c * kUxPitch + p] =
+            __float2bfloat16((v[c] * inv_se - (c == lab ? 1.f : 0.f)) * A.inv_pixels);
+  }
+  local = warp_sum(local);
+  if ((tid & 31) == 0) s_red[tid >> 5] = local;
+  __syncthreads();
+  if (tid < 32) {
+    float t = tid < 8 ? s_red[tid] : 0.f;
+    t = warp_sum(t);
+    if (tid == 0) atomicAdd(A.loss_sum, t);
+  }
+  // ---- phase 2: each (input pixel, channel) gathers its 16 x 16 window, rows then columns
+  for (int it = tid; it < kUxTI * kUxTI * C; it += 256) {
+    const int c = it % C, cell = it / C;
+    const int ci = cell / kUxTI, cj = cell - ci * kUxTI;
+    const int i = i0 + ci, j = j0 + cj;
+    if (i >= A.x.h || j >= A.x.w) continue;
+    const uint32_t base = smem_u32(s_g) + (uint32_t)((c * kUxPitch + (kUxF * ci) * kUxR + kUxF * cj) * 2);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int a = 0; a < kUxK; ++a) {
+      const uint4 g0 = lds128(base + (uint32_t)(a * kUxR * 2));
+      const uint4 g1 = lds128(base + (uint32_t)(a * kUxR * 2 + 16));
+      const float4* wr = reinterpret_cast<const float4*>(s_w2 + a * kUxK);
+      const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+      acc += bf16_lo(g0.x) * w0.x; acc += bf16_hi(g0.x) * w0.y;
+      acc += bf16_lo(g0.y) * w0.z; acc += bf16_hi(g0.y) * w0.w;
+      acc += bf16_lo(g0.z) * w1.x; acc += bf16_hi(g0.z) * w1.y;
+      acc += bf16_lo(g0.w) * w1.z; acc += bf16_hi(g0.w) * w1.w;
+      acc += bf16_lo(g1.x) * w2.x; acc += bf16_hi(g1.x) * w2.y;
+      acc += bf16_lo(g1.y) * w2.z; acc += bf16_hi(g1.y) * w2.w;
+      acc += bf16_lo(g1.z) * w3.x; acc += bf16_hi(g1.z) * w3.y;
+      acc += bf16_lo(g1.w) * w3.z; acc += bf16_hi(g1.w) * w3.w;
+    }
+    if (A.mask.ptr && !(__bfloat162float(view_at(A.mask, n, i, j)[c]) > 0.f)) acc = 0.f;
+    view_at_mut(A.dx, n, i, j)[c] = __float2bfloat16(acc);
+  }
+}
+
 __global__ void sigmoid_argmax_kernel(seg_view logits, float* probs, float* labelmap) {
   const int C = logits.c;
   const int64_t pixels = (int64_t)logits.n * logits.h * logits.w;
@@ -2479,6 +2634,49 @@ SEG_API int32_t seg_softmax_xent_fwd_bwd(const seg_view* logits, const seg_view*
   const int64_t pixels = (int64_t)logits->n * logits->h * logits->w;
   SEG_CHECK_CUDA(launch_k(softmax_xent_kernel, dim3(grid_for(pixels, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *logits, *labels, loss_sum, dlogits ? *dlogits : null_view(), 1.f / (float)pixels));
   SEG_LAUNCH_CHECK();
+  return SEG_OK;
+}
+
+SEG_API int32_t seg_upscore8_xent_fwd_bwd(const seg_view* x, const seg_view* labels,
+                                          float* loss_sum, const seg_view* dx,
+                                          const seg_view* mask_src, float* logits, void* stream) {
+  SEG_REQUIRE(x && labels && loss_sum && dx, SEG_E_BAD_SHAPE, "upscore8_xent: null argument");
+  SEG_REQUIRE(labels->n == x->n && labels->h == x->h * kUxF && labels->w == x->w * kUxF &&
+                  dx->n == x->n && dx->h == x->h && dx->w == x->w && dx->c == x->c &&
+                  (!mask_src || (mask_src->n == x->n && mask_src->h == x->h &&
+                                 mask_src->w == x->w && mask_src->c == x->c)),
+              SEG_E_BAD_SHAPE, "upscore8_xent: labels must be 8x the score map, dx / mask its shape");
+  SEG_REQUIRE(x->c >= 1 && x->c <= 32, SEG_E_UNSUPPORTED, "upscore8_xent: 1..32 classes");
+  UpXentArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = *x; A.labels = *labels; A.dx = *dx;
+  A.mask = mask_src ? *mask_src : null_view();
+  A.loss_sum = loss_sum; A.logits = logits;
+  const int64_t pixels = (int64_t)x->n * x->h * kUxF * x->w * kUxF;
+  A.inv_pixels = 1.f / (float)pixels;
+  A.C = x->c;
+  A.tiles_x = (x->w + kUxTI - 1) / kUxTI; A.tiles_y = (x->h + kUxTI - 1) / kUxTI;
+  const int64_t blocks = (int64_t)x->n * A.tiles_x * A.tiles_y;
+  SEG_REQUIRE(blocks < ((int64_t)1 << 31), SEG_E_UNSUPPORTED, "upscore8_xent: tensor too large");
+  const size_t smem = (size_t)x->c * kUxPitch * 2 + (kUxK * kUxK + kUxXT * kUxXT * x->c) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->c == 21) {
+    static bool attr21 = false;
+    if (!attr21) {
+      SEG_CHECK_CUDA(cudaFuncSetAttribute(upscore8_xent_kernel<21>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr21 = true;
+    }
+    SEG_CHECK_CUDA(launch_k(upscore8_xent_kernel<21>, dim3((unsigned)blocks), dim3(256), smem, st, A));
+  } else {
+    static size_t attr_any = 0;
+    if (smem > attr_any) {
+      SEG_CHECK_CUDA(cudaFuncSetAttribute(upscore8_xent_kernel<0>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_any = smem;
+    }
+    SEG_CHECK_CUDA(launch_k(upscore8_xent_kernel<0>, dim3((unsigned)blocks), dim3(256), smem, st, A));
+  }
   return SEG_OK;
 }
 

@@ -584,6 +584,19 @@ def softmax_xent(logits, labels, loss_sum, dlogits=None):
            N.vref(dlogits), N.stream_ptr())
 
 
+def upscore8_xent(x, labels, loss_sum, dx, mask=None, logits=None):
+    """seg_upscore8_xent_fwd_bwd: FCN-8s training head in one launch - bilinear x8 upscore of
+    the class-score map `x`, softmax cross-entropy against `labels`, and the upscore's input
+    gradient `dx`; neither the full-resolution logits (unless `logits` is given) nor their
+    gradient touch HBM (reference models/fcn.py:207-220, models/basemodel.py:59-70)."""
+    n, h, w, c = x.shape
+    px = n * h * w * 64
+    N.set_tag('upscore_xent')
+    N.note_work(px * c * 16.0, x.numel() * 4.0 + px * 1.0 + (px * c * 4.0 if logits is not None else 0.0))
+    N.call('seg_upscore8_xent_fwd_bwd', N.vref(x), N.vref(labels), N.ptr(loss_sum), N.vref(dx),
+           N.vref(mask), N.ptr(logits), N.stream_ptr())
+
+
 def head1x1_xent(x, layer, labels, logits, loss_sum, dx):
     """Fused training head: 1x1 conv `layer` (<= 4 classes) + softmax x-entropy + the
     layer's weight / bias gradient + the input gradient dx, one pass over x."""

@@ -419,6 +419,11 @@ class ExecBase(object):
         if not self._loss_prezeroed:
             E.fill_zero(self.loss_sum)
 
+    def forward_for_step(self):
+        """The forward pass of a train step (executors whose step has a shorter route to the
+        loss than forward() + loss() override this)."""
+        self.forward()
+
     def loss(self, with_grad):
         self.zero_loss()
         E.softmax_xent(self.logits, self.mask_view(), self.loss_sum,
@@ -431,7 +436,7 @@ class ExecBase(object):
         self._sm_reserved = False
         self._pending = set(range(len(m.opt_groups)))
         try:
-            self.forward()
+            self.forward_for_step()
             self.loss(True)
             self.backward()                       # may call group_ready() as groups complete
             for i in sorted(self._pending, reverse=True):

@@ -14,6 +14,8 @@ is executed as a depthwise separable bilinear kernel fused with the skip add
 Input sizes must be multiples of 32 (then every crop_or_pad in the reference graph
 is the identity, as at the BASELINE configuration).
 """
+import os
+
 import torch
 
 from .. import engine as E
@@ -136,8 +138,17 @@ class _FCNExec(ExecBase):
         """logical n_classes channels of a class-score tensor."""
         return t[..., :self.m.n_classes]
 
-    def forward(self):
+    def forward_for_step(self):
+        # train step: FCN-8s ends with one launch for upscore x8 + loss + their gradient
+        self.forward(fused_loss=os.environ.get('SEGB200_FCN_FUSED_LOSS', '1') != '0')
+
+    def forward(self, fused_loss=False):
+        """`fused_loss` (train steps of FCN-8s): stop at the fused score map; loss() then runs
+        seg_upscore8_xent_fwd_bwd, which also produces the gradient backward() starts from -
+        the full-resolution logits (m.y_hat) are NOT refreshed by such a step."""
         m, L, A, impl, v = self.m, self.m.layers, self.act, self.m.impl, self.v
+        self._fused_loss = bool(fused_loss and self.training and m.fcn_type == '8s' and
+                                m.n_classes <= 32)
         self.pack()
         src = A['x']
         # conv1 + pool1 as one launch (first-layer kernel): conv1's full-resolution
@@ -165,8 +176,16 @@ class _FCNExec(ExecBase):
             L['fcn8s/pool4_score'].forward(A['pool4'], v(A['pool4_score']), impl=impl)
             E.bilinear_upsample_fwd(v(A['conv_fr']), 2, v(A['fuse4']), add=v(A['pool4_score']))
             E.bilinear_upsample_fwd(v(A['fuse4']), 2, v(A['fuse3']), add=v(A['pool3_score']))
-            E.bilinear_upsample_fwd(v(A['fuse3']), 8, self.logits)
+            if not self._fused_loss:
+                E.bilinear_upsample_fwd(v(A['fuse3']), 8, self.logits)
         m.y_hat = self.logits
+
+    def loss(self, with_grad):
+        if not (getattr(self, '_fused_loss', False) and with_grad):
+            return super(_FCNExec, self).loss(with_grad)
+        self.zero_loss()
+        E.upscore8_xent(self.v(self.act['fuse3']), self.mask_view(), self.loss_sum,
+                        self.v(self.g['fuse3']))
 
     def backward(self):
         m, L, A, G, impl, v = self.m, self.m.layers, self.act, self.g, self.m.impl, self.v
@@ -187,7 +206,8 @@ class _FCNExec(ExecBase):
             E.bilinear_upsample_bwd(v(G['fuse4']), 2, v(G['conv_fr']), mask=v(A['conv_fr']))
             bw('fcn16s/pool4_score', A['pool4'], G['pool4_score'], dx=G['pool4_b'])
         else:
-            E.bilinear_upsample_bwd(dl, 8, v(G['fuse3']))
+            if not getattr(self, '_fused_loss', False):
+                E.bilinear_upsample_bwd(dl, 8, v(G['fuse3']))
             E.relu_grad(v(G['fuse3']), v(A['pool3_score']), v(G['pool3_score']))
             E.bilinear_upsample_bwd(v(G['fuse3']), 2, v(G['fuse4']))
             E.relu_grad(v(G['fuse4']), v(A['pool4_score']), v(G['pool4_score']))

@@ -87,6 +87,7 @@ SIGNATURES = {
     'seg_batchnorm_bwd_apply': [_VP, _VP, _P, _P, _P, _P, _I64, _I32, _VP, _P],
     'seg_dropout': [_VP, _U64, _U32, _F, _VP, _P],
     'seg_dropout_ex': [_VP, _U64, _U32, _U32, _P, _U32, _F, _VP, _P],
+    'seg_upscore8_xent_fwd_bwd': [_VP, _VP, _P, _VP, _VP, _P, _P],
     'seg_softmax_xent_fwd_bwd': [_VP, _VP, _P, _VP, _P],
     'seg_sigmoid_argmax': [_VP, _P, _P, _P],
     'seg_mc_mean_var': [_P, _I32, _I64, _P, _P, _P],

@@ -124,6 +124,44 @@ def test_fcn_train_step_runs_and_tracks_oracle_loss(cuda):
     assert model.global_step == 3
 
 
+def test_fcn8s_fused_loss_head_matches_unfused_gradients(cuda):
+    """A train step of FCN-8s takes forward(fused_loss=True): upscore x8 + loss + their gradient
+    in one launch (seg_upscore8_xent_fwd_bwd).  Same loss and the same parameter gradients as
+    forward() + loss() + backward() - the score-map gradient is bit-identical, what follows
+    differs by the order of the weight-gradient reductions only."""
+    os.environ['SEGB200_IMPL'] = 'umma'
+    from segmentation_b200.models.fcn import FCNModel
+    B, S, nk, nc = 2, 128, 16, 21
+    ds = FeedDataSet(B, S, S, n_classes=nc, seed=5)
+    model = FCNModel(dataset=ds, n_classes=nc, input_dims=S, n_kernels=nk, fcn_type='8s',
+                     load_snapshot=False, save_dir=None)
+    p = _nonzero_biases(nets.fcn_params(n_kernels=nk, n_classes=nc, fcn_type='8s', seed=2))
+    model.load_weights({k: v.numpy() for k, v in p.items()})
+    x, y = ds.next_batch()
+    ex = _run_fwd_bwd(model, B, torch.from_numpy(x), torch.from_numpy(y))
+    loss_u = float(ex.loss_sum.item())
+    g_fuse3 = ex.g['fuse3'].clone()
+    grads_u = model.store.grad.clone()
+    model.store.grad.zero_()
+    n0 = N.LAUNCHES
+    ex.forward(fused_loss=True)
+    assert ex._fused_loss
+    ex.loss(True)
+    ex.backward()
+    sync()
+    n_fused = N.LAUNCHES - n0
+    loss_f = float(ex.loss_sum.item())
+    assert torch.equal(ex.g['fuse3'].view(torch.int16), g_fuse3.view(torch.int16))
+    assert abs(loss_f - loss_u) <= 1e-5 * abs(loss_u)
+    e = rel_l2(model.store.grad.cpu(), grads_u.cpu())
+    report('fcn8s_fused_loss', {'grad_rel_l2': e, 'loss': [loss_u, loss_f], 'launches': n_fused})
+    assert e < 1e-4, e
+    # and a whole train step takes that route
+    model.store.grad.zero_()
+    model.train_step((x, y))
+    assert model._last_train_exec._fused_loss
+
+
 def _deconv_model(bayesian, mode='TRAINING', B=2, S=256, nk=16):
     os.environ['SEGB200_IMPL'] = 'umma'
     from segmentation_b200.models.deconvolution import DeconvModel

@@ -298,6 +298,58 @@ def test_classmap_tail_infer_forms_agree(cuda, nc, B, hs, ws, rh, rw):
     assert float((pr1 - torch.sigmoid(lg1)).abs().max()) < 1e-6
 
 
+@pytest.mark.parametrize('B,h,w,C,masked', [(2, 8, 8, 21, False), (1, 7, 10, 21, True),
+                                            (2, 5, 3, 2, False), (1, 16, 12, 32, True)])
+def test_upscore8_xent_is_bit_identical_to_the_three_launches(cuda, B, h, w, C, masked):
+    """seg_upscore8_xent_fwd_bwd (FCN-8s training head, /root/reference/models/fcn.py:207-220 +
+    models/basemodel.py:59-70) against seg_bilinear_upsample_fwd -> seg_softmax_xent_fwd_bwd ->
+    seg_bilinear_upsample_bwd: the same bits for the score-map gradient and the logits, the
+    loss to the order of its final sum; grids that are not multiples of the 4-pixel block;
+    and against the CPU oracle."""
+    g = _gen(60 + C)
+    cp = E.pad16(C)
+    x = bfr(torch.randn(B, h, w, C, generator=g) * 2)
+    lab = torch.randint(0, C, (B, 8 * h, 8 * w, 1), generator=g).to(torch.uint8)
+    x_d = dev_bf16(x, cp)
+    xv = x_d[..., :C]
+    lab_d = lab.cuda()
+    mask_d = dev_bf16(torch.randn(B, h, w, C, generator=g), cp)[..., :C] if masked else None
+    H, W = 8 * h, 8 * w
+    # unfused
+    lg = torch.zeros(B, H, W, C, device='cuda')
+    E.bilinear_upsample_fwd(xv, 8, lg)
+    dl = torch.zeros(B, H, W, cp, dtype=BF16, device='cuda')
+    ls = torch.zeros(1, device='cuda')
+    E.softmax_xent(lg, lab_d, ls, dl)
+    dx = torch.zeros(B, h, w, cp, dtype=BF16, device='cuda')
+    E.bilinear_upsample_bwd(dl[..., :C], 8, dx[..., :C], mask=mask_d)
+    # fused
+    lg2 = torch.full((B, H, W, C), float('nan'), device='cuda')
+    ls2 = torch.zeros(1, device='cuda')
+    dx2 = torch.zeros(B, h, w, cp, dtype=BF16, device='cuda')
+    E.upscore8_xent(xv, lab_d, ls2, dx2[..., :C], mask=mask_d, logits=lg2)
+    # and without the logits output
+    ls3 = torch.zeros(1, device='cuda')
+    dx3 = torch.zeros(B, h, w, cp, dtype=BF16, device='cuda')
+    E.upscore8_xent(xv, lab_d, ls3, dx3[..., :C], mask=mask_d)
+    sync()
+    assert torch.equal(lg2.cpu(), lg.cpu())
+    assert torch.equal(dx2.view(torch.int16).cpu(), dx.view(torch.int16).cpu())
+    assert torch.equal(dx3.view(torch.int16).cpu(), dx.view(torch.int16).cpu())
+    assert float(dx.float().abs().max()) > 0
+    assert abs(float(ls2) - float(ls)) <= 1e-5 * abs(float(ls)) + 1e-6
+    assert abs(float(ls3) - float(ls)) <= 1e-5 * abs(float(ls)) + 1e-6
+    # oracle: loss and gradient of the x8 bilinear transposed conv + mean softmax x-entropy
+    xr = x.clone().requires_grad_(True)
+    loss_ref = T.softmax_xent_mean(T.bilinear_upsample(xr, 8), lab)
+    (dx_ref,) = torch.autograd.grad(loss_ref, xr)
+    if masked:
+        dx_ref = dx_ref * (mask_d.float().cpu() > 0).float()
+    assert abs(float(ls2) / (B * H * W) - float(loss_ref)) < 1e-4
+    # the stored dlogits are bf16 (as in the unfused path): relative error ~2^-9 / sqrt(256)
+    assert rel_l2(dx2.float().cpu()[..., :C], dx_ref) < 4e-3
+
+
 def test_adam_matches_tf_formula(cuda):
     g = _gen(10)
     store = E.ParamStore(torch.device('cuda'))

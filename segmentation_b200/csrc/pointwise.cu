@@ -1106,7 +1106,10 @@ __global__ void softmax_xent_kernel(seg_view logits, seg_view labels, float* los
 constexpr int kUxF = 8, kUxK = 2 * kUxF, kUxTI = 4;
 constexpr int kUxR = (kUxTI + 1) * kUxF;             // 40: output region side per block
 constexpr int kUxXT = kUxTI + 2;                     // 6: input tile side incl. the ring
-constexpr int kUxPitch = kUxR * kUxR + 8;            // dlogits plane pitch (pixels): odd * 16 B
+// dlogits in shared memory: one plane per channel PAIR, a 32-bit word (bf16 c, bf16 c+1) per
+// region pixel; plane pitch an odd multiple of 16 bytes, so the 16-byte window loads of lanes
+// that differ in the pair hit different banks
+constexpr int kUxPitch = kUxR * kUxR + 4;            // words per plane: 1604 * 4 B = 401 * 16 B
 struct UpXentArgs {
   seg_view x;            // [n, h, w, C] bf16 score map
   seg_view labels;       // [n, 8h, 8w, 1] uint8
@@ -1118,15 +1121,23 @@ struct UpXentArgs {
   int C;
   int tiles_x, tiles_y;
 };
+static inline int ux_xpitch(int c) { return (c + 3) & ~3; }   // floats per input-tile pixel
+static inline size_t ux_smem_bytes(int c) {
+  return (size_t)((c + 1) / 2) * kUxPitch * 4 +
+         (kUxK * kUxK + kUxXT * kUxXT * ux_xpitch(c)) * sizeof(float);
+}
 
 template <int CT>
 __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) {
   constexpr int CMAX = CT ? CT : 32;
+  constexpr int C4MAX = (CMAX + 3) / 4;
   extern __shared__ __align__(16) uint8_t ux_smem[];
-  bf16* s_g = reinterpret_cast<bf16*>(ux_smem);                       // [C][kUxPitch]
   const int C = CT ? CT : A.C;
-  float* s_w2 = reinterpret_cast<float*>(ux_smem + (size_t)C * kUxPitch * 2);   // [16][16]
-  float* s_x = s_w2 + kUxK * kUxK;                                    // [6*6][C]
+  const int XP = (C + 3) & ~3;                                        // s_x pixel pitch (floats)
+  const int NP = (C + 1) >> 1;                                        // channel pairs
+  uint32_t* s_g = reinterpret_cast<uint32_t*>(ux_smem);               // [NP][kUxPitch]
+  float* s_w2 = reinterpret_cast<float*>(ux_smem + (size_t)NP * kUxPitch * 4);   // [16][16]
+  float* s_x = s_w2 + kUxK * kUxK;                                    // [6*6][XP]
   __shared__ float s_red[8];
   pdl_trigger();
   const int tid = threadIdx.x;
@@ -1139,11 +1150,12 @@ __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) 
   const int i0 = (trem / A.tiles_x) * kUxTI, j0 = (trem % A.tiles_x) * kUxTI;
   const int H = A.x.h * kUxF, W = A.x.w * kUxF;
   pdl_wait();
-  for (int idx = tid; idx < kUxXT * kUxXT * C; idx += 256) {
-    const int c = idx % C, pix = idx / C;
+  for (int idx = tid; idx < kUxXT * kUxXT * XP; idx += 256) {
+    const int c = idx % XP, pix = idx / XP;
     const int ii = i0 - 1 + pix / kUxXT, jj = j0 - 1 + pix % kUxXT;
     float v = 0.f;
-    if (ii >= 0 && ii < A.x.h && jj >= 0 && jj < A.x.w) v = __bfloat162float(view_at(A.x, n, ii, jj)[c]);
+    if (c < C && ii >= 0 && ii < A.x.h && jj >= 0 && jj < A.x.w)
+      v = __bfloat162float(view_at(A.x, n, ii, jj)[c]);
     s_x[idx] = v;
   }
   __syncthreads();
@@ -1153,9 +1165,7 @@ __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) 
     const int py = p / kUxR, px = p - py * kUxR;
     const int oy = kUxF * i0 - kUxF / 2 + py, ox = kUxF * j0 - kUxF / 2 + px;
     if (oy < 0 || oy >= H || ox < 0 || ox >= W) {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) s_g[c * kUxPitch + p] = __float2bfloat16(0.f);
+      for (int q = 0; q < NP; ++q) s_g[q * kUxPitch + p] = 0u;
       continue;
     }
     // taps in the order of bilinear_up_fwd_kernel: (i_hi, j_hi), (i_hi, j_lo), (i_lo, j_hi),
@@ -1164,23 +1174,36 @@ __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) 
     const int li = py / kUxF, lj = px / kUxF;                 // tile row / column of i_lo, j_lo
     const float w_hh = s_w2[a_hi * kUxK + b_hi], w_hl = s_w2[a_hi * kUxK + b_hi + kUxF];
     const float w_lh = s_w2[(a_hi + kUxF) * kUxK + b_hi], w_ll = s_w2[(a_hi + kUxF) * kUxK + b_hi + kUxF];
-    const float* x_hh = s_x + ((li + 1) * kUxXT + lj + 1) * C;
-    const float* x_hl = s_x + ((li + 1) * kUxXT + lj) * C;
-    const float* x_lh = s_x + (li * kUxXT + lj + 1) * C;
-    const float* x_ll = s_x + (li * kUxXT + lj) * C;
-    float v[CMAX];
+    const float* x_hh = s_x + ((li + 1) * kUxXT + lj + 1) * XP;
+    const float* x_hl = s_x + ((li + 1) * kUxXT + lj) * XP;
+    const float* x_lh = s_x + (li * kUxXT + lj + 1) * XP;
+    const float* x_ll = s_x + (li * kUxXT + lj) * XP;
+    float v[C4MAX * 4];
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      float acc = 0.f;
-      if (c < C) {
-        acc += x_hh[c] * w_hh;
-        acc += x_hl[c] * w_hl;
-        acc += x_lh[c] * w_lh;
-        acc += x_ll[c] * w_ll;
+    for (int c4 = 0; c4 < C4MAX; ++c4) {
+      if (4 * c4 < C) {
+        const float4 hh = reinterpret_cast<const float4*>(x_hh)[c4];
+        const float4 hl = reinterpret_cast<const float4*>(x_hl)[c4];
+        const float4 lh = reinterpret_cast<const float4*>(x_lh)[c4];
+        const float4 ll = reinterpret_cast<const float4*>(x_ll)[c4];
+        const float xa[4] = {hh.x, hh.y, hh.z, hh.w}, xb[4] = {hl.x, hl.y, hl.z, hl.w};
+        const float xc[4] = {lh.x, lh.y, lh.z, lh.w}, xd[4] = {ll.x, ll.y, ll.z, ll.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float acc = 0.f;
+          acc += xa[e] * w_hh;
+          acc += xb[e] * w_hl;
+          acc += xc[e] * w_lh;
+          acc += xd[e] * w_ll;
+          const int c = 4 * c4 + e;
+          v[c] = c < C ? acc : -INFINITY;
+          mx = fmaxf(mx, v[c]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[4 * c4 + e] = -INFINITY;
       }
-      v[c] = c < C ? acc : -INFINITY;
-      mx = fmaxf(mx, v[c]);
     }
     const bool owned = py >= kUxF / 2 && py < kUxR - kUxF / 2 && px >= kUxF / 2 && px < kUxR - kUxF / 2;
     if (owned && A.logits) {
@@ -1191,20 +1214,38 @@ __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) 
     }
     const int lab = reinterpret_cast<const uint8_t*>(A.labels.ptr)[n * A.labels.sn + oy * A.labels.sh +
                                                                    ox * A.labels.sw];
-    float se = 0.f, picked = 0.f;
+    // the label's logit, re-evaluated from the tile (same expression, same bits) instead of a
+    // 21-way register select
+    float picked = 0.f;
+    if (lab < C) {
+      float acc = 0.f;
+      acc += x_hh[lab] * w_hh;
+      acc += x_hl[lab] * w_hl;
+      acc += x_lh[lab] * w_lh;
+      acc += x_ll[lab] * w_ll;
+      picked = acc;
+    }
+    float se = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-      if (c == lab) picked = v[c];
       v[c] = c < C ? expf(v[c] - mx) : 0.f;
       se += v[c];
     }
-    if (owned) local += mx + logf(se) - (lab < C ? picked : 0.f);
+    if (owned) local += mx + logf(se) - picked;
     const float inv_se = 1.f / se;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C)
-        s_g[c * kUxPitch + p] =
-            __float2bfloat16((v[c] * inv_se - (c == lab ? 1.f : 0.f)) * A.inv_pixels);
+    for (int q = 0; q < (CMAX + 1) / 2; ++q) {
+      if (q < NP) {
+        const float g0 = (v[2 * q] * inv_se - 0.f) * A.inv_pixels;
+        const float g1 = 2 * q + 1 < C ? (v[2 * q + 1 < CMAX ? 2 * q + 1 : 0] * inv_se - 0.f) * A.inv_pixels : 0.f;
+        s_g[q * kUxPitch + p] = pack_bf16x2(g0, g1);
+      }
+    }
+    if (lab < C) {
+      const float e_lab = expf(picked - mx);
+      reinterpret_cast<bf16*>(s_g)[((lab >> 1) * kUxPitch + p) * 2 + (lab & 1)] =
+          __float2bfloat16((e_lab * inv_se - 1.f) * A.inv_pixels);
+    }
   }
   local = warp_sum(local);
   if ((tid & 31) == 0) s_red[tid >> 5] = local;
@@ -1214,31 +1255,37 @@ __global__ void __launch_bounds__(256) upscore8_xent_kernel(const UpXentArgs A) 
     t = warp_sum(t);
     if (tid == 0) atomicAdd(A.loss_sum, t);
   }
-  // ---- phase 2: each (input pixel, channel) gathers its 16 x 16 window, rows then columns
-  for (int it = tid; it < kUxTI * kUxTI * C; it += 256) {
-    const int c = it % C, cell = it / C;
+  // ---- phase 2: each (input pixel, channel pair) gathers its 16 x 16 window, rows then
+  // columns, one accumulator per channel (the summation order of bilinear_up_bwd_kernel)
+  for (int it = tid; it < kUxTI * kUxTI * NP; it += 256) {
+    const int q = it % NP, cell = it / NP;
     const int ci = cell / kUxTI, cj = cell - ci * kUxTI;
     const int i = i0 + ci, j = j0 + cj;
     if (i >= A.x.h || j >= A.x.w) continue;
-    const uint32_t base = smem_u32(s_g) + (uint32_t)((c * kUxPitch + (kUxF * ci) * kUxR + kUxF * cj) * 2);
-    float acc = 0.f;
-#pragma unroll 4
+    const uint32_t base = smem_u32(s_g) + (uint32_t)((q * kUxPitch + (kUxF * ci) * kUxR + kUxF * cj) * 4);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
     for (int a = 0; a < kUxK; ++a) {
-      const uint4 g0 = lds128(base + (uint32_t)(a * kUxR * 2));
-      const uint4 g1 = lds128(base + (uint32_t)(a * kUxR * 2 + 16));
       const float4* wr = reinterpret_cast<const float4*>(s_w2 + a * kUxK);
-      const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-      acc += bf16_lo(g0.x) * w0.x; acc += bf16_hi(g0.x) * w0.y;
-      acc += bf16_lo(g0.y) * w0.z; acc += bf16_hi(g0.y) * w0.w;
-      acc += bf16_lo(g0.z) * w1.x; acc += bf16_hi(g0.z) * w1.y;
-      acc += bf16_lo(g0.w) * w1.z; acc += bf16_hi(g0.w) * w1.w;
-      acc += bf16_lo(g1.x) * w2.x; acc += bf16_hi(g1.x) * w2.y;
-      acc += bf16_lo(g1.y) * w2.z; acc += bf16_hi(g1.y) * w2.w;
-      acc += bf16_lo(g1.z) * w3.x; acc += bf16_hi(g1.z) * w3.y;
-      acc += bf16_lo(g1.w) * w3.z; acc += bf16_hi(g1.w) * w3.w;
+#pragma unroll
+      for (int b4 = 0; b4 < 4; ++b4) {
+        const uint4 g = lds128(base + (uint32_t)((a * kUxR + 4 * b4) * 4));
+        const float4 w = wr[b4];
+        acc0 += bf16_lo(g.x) * w.x; acc1 += bf16_hi(g.x) * w.x;
+        acc0 += bf16_lo(g.y) * w.y; acc1 += bf16_hi(g.y) * w.y;
+        acc0 += bf16_lo(g.z) * w.z; acc1 += bf16_hi(g.z) * w.z;
+        acc0 += bf16_lo(g.w) * w.w; acc1 += bf16_hi(g.w) * w.w;
+      }
     }
-    if (A.mask.ptr && !(__bfloat162float(view_at(A.mask, n, i, j)[c]) > 0.f)) acc = 0.f;
-    view_at_mut(A.dx, n, i, j)[c] = __float2bfloat16(acc);
+    const int c0 = 2 * q;
+    if (A.mask.ptr) {
+      const bf16* mp = view_at(A.mask, n, i, j);
+      if (!(__bfloat162float(mp[c0]) > 0.f)) acc0 = 0.f;
+      if (c0 + 1 < C && !(__bfloat162float(mp[c0 + 1]) > 0.f)) acc1 = 0.f;
+    }
+    bf16* dp = view_at_mut(A.dx, n, i, j);
+    dp[c0] = __float2bfloat16(acc0);
+    if (c0 + 1 < C) dp[c0 + 1] = __float2bfloat16(acc1);
   }
 }
 
@@ -2658,7 +2705,7 @@ SEG_API int32_t seg_upscore8_xent_fwd_bwd(const seg_view* x, const seg_view* lab
   A.tiles_x = (x->w + kUxTI - 1) / kUxTI; A.tiles_y = (x->h + kUxTI - 1) / kUxTI;
   const int64_t blocks = (int64_t)x->n * A.tiles_x * A.tiles_y;
   SEG_REQUIRE(blocks < ((int64_t)1 << 31), SEG_E_UNSUPPORTED, "upscore8_xent: tensor too large");
-  const size_t smem = (size_t)x->c * kUxPitch * 2 + (kUxK * kUxK + kUxXT * kUxXT * x->c) * sizeof(float);
+  const size_t smem = ux_smem_bytes(x->c);
   cudaStream_t st = (cudaStream_t)stream;
   if (x->c == 21) {
     static bool attr21 = false;

@@ -237,6 +237,11 @@ SEG_API int32_t seg_maxpool_bwd_y(const seg_view* dy, const uint8_t* argmax, int
 SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
                          int32_t k, int32_t s, const seg_view* mask_src, const seg_view* dx,
                          void* stream);
+/* ... and given the forward pool output: the ReLU mask comes from pooled_y, the pool input
+ * (mask_src) is not read. */
+SEG_API int32_t seg_maxpool_bwd2_y(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                                   int32_t k, int32_t s, const seg_view* mask_src,
+                                   const seg_view* pooled_y, const seg_view* dx, void* stream);
 /* ReluGrad as a copy: dz = (y > 0) ? dy : 0 (dy, y, dz same geometry). */
 SEG_API int32_t seg_relu_grad(const seg_view* dy, const seg_view* y, const seg_view* dz, void* stream);
 

@@ -2449,24 +2449,30 @@ SEG_API int32_t seg_maxpool_bwd_y(const seg_view* dy, const uint8_t* argmax, int
   return maxpool_bwd_impl(dy, argmax, k, s, add, add_y0, add_x0, mask_src, pooled_y, dx, stream);
 }
 
-SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
-                         int32_t k, int32_t s, const seg_view* mask_src, const seg_view* dx,
-                         void* stream) {
+static int maxpool_bwd2_impl(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                             int32_t k, int32_t s, const seg_view* mask_src,
+                             const seg_view* pooled, const seg_view* dx, void* stream) {
   SEG_REQUIRE(dy && dy2 && argmax && dx, SEG_E_BAD_SHAPE, "maxpool_bwd2: null argument");
   SEG_REQUIRE(k == s, SEG_E_UNSUPPORTED, "maxpool_bwd2: only non-overlapping windows (k == s)");
   cudaStream_t st = (cudaStream_t)stream;
   const seg_view mk = mask_src ? *mask_src : null_view();
   const bool v8 = vec8_ok(*dx) && vec8_ok(*dy) && vec8_ok(*dy2) &&
                   (reinterpret_cast<uintptr_t>(argmax) % 8) == 0 && (!mask_src || vec8_ok(mk));
+  // the pool output as the ReLU mask of the routed gradient (x at the argmax IS the pooled
+  // value): the pool input is then not read at all
+  const bool use_y = v8 && pooled && pooled->ptr && mask_src && vec8_ok(*pooled) &&
+                     pooled->h == dy->h && pooled->w == dy->w && pooled->c == dy->c &&
+                     pooled->n == dy->n;
+  const seg_view py = use_y ? *pooled : null_view();
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (v8 ? dx->c / 8 : dx->c);
   if (v8)
   {
     cudaError_t e = cudaSuccess;
-    if (launch_pool_bwd_rows(*dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx, st, &e)) {
+    if (launch_pool_bwd_rows(*dy, *dy2, argmax, k, null_view(), 0, 0, mk, py, *dx, st, &e)) {
       SEG_CHECK_CUDA(e);
     } else {
       const int64_t cells = (int64_t)dx->n * ((dx->h + k - 1) / k) * ((dx->w + k - 1) / k) * (dx->c / 8);
-      SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, null_view(), *dx));
+      SEG_CHECK_CUDA(launch_k(maxpool_bwd_cell8_kernel, dim3(grid_for(cells, 256)), dim3(256), (size_t)(0), st, *dy, *dy2, argmax, k, null_view(), 0, 0, mk, py, *dx));
     }
   }
   else
@@ -2474,6 +2480,18 @@ SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const 
                                                                null_view(), 0, 0, mk, *dx);
   SEG_LAUNCH_CHECK();
   return SEG_OK;
+}
+
+SEG_API int32_t seg_maxpool_bwd2(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                         int32_t k, int32_t s, const seg_view* mask_src, const seg_view* dx,
+                         void* stream) {
+  return maxpool_bwd2_impl(dy, dy2, argmax, k, s, mask_src, nullptr, dx, stream);
+}
+
+SEG_API int32_t seg_maxpool_bwd2_y(const seg_view* dy, const seg_view* dy2, const uint8_t* argmax,
+                                   int32_t k, int32_t s, const seg_view* mask_src,
+                                   const seg_view* pooled_y, const seg_view* dx, void* stream) {
+  return maxpool_bwd2_impl(dy, dy2, argmax, k, s, mask_src, pooled_y, dx, stream);
 }
 
 SEG_API int32_t seg_relu_grad(const seg_view* dy, const seg_view* y, const seg_view* dz, void* stream) {

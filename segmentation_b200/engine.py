@@ -627,9 +627,18 @@ def bilinear_upsample_bwd(dy, factor, dx, mask=None):
            factor, N.vref(mask), N.vref(dx), N.stream_ptr())
 
 
-def maxpool_bwd2(dy, dy2, argmax, dx, k=2, s=2, mask=None):
-    N.call('seg_maxpool_bwd2', N.vref(dy), N.vref(dy2), N.ptr(argmax), k, s, N.vref(mask),
-           N.vref(dx), N.stream_ptr())
+def maxpool_bwd2(dy, dy2, argmax, dx, k=2, s=2, mask=None, pooled=None):
+    """`pooled`: the forward pool output; the ReLU mask is then taken from it and the pool
+    input `mask` is not read."""
+    N.note_work(0, dy.numel() * 4.0 + argmax.numel() + dx.numel() * 2.0 +
+                (pooled.numel() * 2.0 if pooled is not None else
+                 (mask.numel() * 2.0 if mask is not None else 0.0)))
+    if pooled is not None:
+        N.call('seg_maxpool_bwd2_y', N.vref(dy), N.vref(dy2), N.ptr(argmax), k, s, N.vref(mask),
+               N.vref(pooled), N.vref(dx), N.stream_ptr())
+    else:
+        N.call('seg_maxpool_bwd2', N.vref(dy), N.vref(dy2), N.ptr(argmax), k, s, N.vref(mask),
+               N.vref(dx), N.stream_ptr())
 
 
 def relu_grad(dy, y, dz):

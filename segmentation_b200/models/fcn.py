@@ -227,7 +227,8 @@ class _FCNExec(ExecBase):
                 self.layer_done(conv)
                 continue
             if second is not None:
-                E.maxpool_bwd2(G[pool], second, self.amax[pool], G[conv], mask=A[conv])
+                E.maxpool_bwd2(G[pool], second, self.amax[pool], G[conv], mask=A[conv],
+                               pooled=A[pool])
             else:
                 E.maxpool_bwd(G[pool], self.amax[pool], G[conv], mask=A[conv], pooled=A[pool])
             if i > 1:

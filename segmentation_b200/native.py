@@ -75,6 +75,7 @@ SIGNATURES = {
     'seg_bilinear_upsample_bwd': [_VP, _I32, _I32, _VP, _VP, _P],
     'seg_maxpool_bwd_y': [_VP, _P, _I32, _I32, _VP, _I32, _I32, _VP, _VP, _VP, _P],
     'seg_maxpool_bwd2': [_VP, _VP, _P, _I32, _I32, _VP, _VP, _P],
+    'seg_maxpool_bwd2_y': [_VP, _VP, _P, _I32, _I32, _VP, _VP, _VP, _P],
     'seg_relu_grad': [_VP, _VP, _VP, _P],
     'seg_resize_bilinear_fwd': [_VP, _VP, _P],
     'seg_resize_bilinear_bwd': [_VP, _VP, _P],

@@ -69,6 +69,35 @@ def test_maxpool_fwd_bwd_bit_exact(cuda, shape, k):
     assert torch.equal(dx_d.float().cpu(), ref2)
 
 
+@pytest.mark.parametrize('shape,k', [((2, 8, 12, 32), 2), ((1, 64, 64, 256), 2), ((2, 9, 9, 16), 3)])
+def test_maxpool_bwd_two_consumers(cuda, shape, k):
+    """seg_maxpool_bwd2 / seg_maxpool_bwd2_y: the pooled tensor feeds two layers (FCN pool3 /
+    pool4, /root/reference/models/fcn.py:192-195), dx = ReluGrad(MaxPoolGrad(dy + dy2)).  With
+    the forward pool output as the mask source the pool input is not read; same bits."""
+    g = _gen(9)
+    x = torch.relu(torch.round(bfr(torch.randn(shape, generator=g)) * 2) / 2)
+    y_ref, slot_ref = T.max_pool_with_argmax(x, k, k)
+    Nb, H, W, C = shape
+    Ho, Wo = y_ref.shape[1], y_ref.shape[2]
+    x_d = dev_bf16(x)
+    y_d = torch.zeros(Nb, Ho, Wo, C, dtype=BF16, device='cuda')
+    am = torch.zeros(Nb, Ho, Wo, C, dtype=torch.uint8, device='cuda')
+    E.maxpool_fwd(x_d, y_d, am, k, k)
+    dy = bfr(torch.randn(y_ref.shape, generator=g))
+    dy2 = bfr(torch.randn(y_ref.shape, generator=g))
+    xr = x.clone().requires_grad_(True)
+    (dx_ref,) = torch.autograd.grad(T.max_pool(xr, k, k), xr, dy + dy2)
+    ref = bfr(dx_ref * (x > 0).float())
+    a = torch.full(shape, float('nan'), dtype=BF16, device='cuda')
+    b = torch.full(shape, float('nan'), dtype=BF16, device='cuda')
+    E.maxpool_bwd2(dev_bf16(dy), dev_bf16(dy2), am, a, k, k, mask=x_d)
+    E.maxpool_bwd2(dev_bf16(dy), dev_bf16(dy2), am, b, k, k, mask=x_d, pooled=y_d)
+    sync()
+    # rows / columns beyond the last full window receive no gradient
+    assert torch.equal(a.float().cpu(), ref)
+    assert torch.equal(b.view(torch.int16).cpu(), a.view(torch.int16).cpu())
+
+
 def test_softmax_xent_and_head(cuda):
     g = _gen(2)
     for C, cpad in ((2, 16), (21, 32), (5, 16)):

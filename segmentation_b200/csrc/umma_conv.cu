@@ -839,20 +839,13 @@ static int launch_tconv(const TconvJob& J, cudaStream_t st) {
   const int chunks = (J.a1.c + c2) / KC;
   TconvPlan L;
   memset(&L, 0, sizeof(L));
-  // prefer a resident B; shrink BN (more N-slices re-reading A) before giving that up only
-  // when the slice count stays small, else stream B through a ring
+  // The widest N-slice the layer allows, even when its weights then stream through a ring
+  // instead of staying resident: a 128 x 128 x 16 MMA runs at the tensor pipe's rate, two
+  // 128 x 64 x 16 ones take 1.5x as long (operand-read bound), and halving BN also re-reads
+  // the activation tile once more.  Measured against "shrink BN until the weights are
+  // resident" (round 1's rule): U-Net step 0.944 -> 0.937 ms, FCN-8s config 2 1.270 ->
+  // 1.196 ms (its 128- and 256-channel layers), profiles/r02_experiments.md #26.
   bool ok = tconv_plan(J, KC, BN, MT, chunks, &L);
-  if (ok && !L.resident) {
-    TconvPlan L2;
-    memset(&L2, 0, sizeof(L2));
-    for (int bn = BN / 2; bn >= 32; bn >>= 1) {
-      if (J.N_total / bn > 4) break;
-      if (tconv_plan(J, KC, bn, MT, chunks, &L2) && L2.resident) { L = L2; BN = bn; break; }
-      if (MT == 2 && tconv_plan(J, KC, bn, 1, chunks, &L2) && L2.resident) {
-        L = L2; BN = bn; MT = 1; break;
-      }
-    }
-  }
   while (!ok) {
     if (MT == 2) MT = 1;
     else if (BN > 32) BN >>= 1;

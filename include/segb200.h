@@ -91,7 +91,7 @@ SEG_API const char* seg_last_kernel_name(void);
  *   key 1: halo-tile tcgen05 conv kernel where it applies (default 1; 0 forces TMA-im2col).
  *   key 2: smem row alignment of the halo kernel's row staging in pixels (0 = natural).
  *   key 3: spatial-tile tcgen05 conv kernel for 3x3 stride-1 fwd / dgrad (default 1).
- *   key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles (default 70).
+ *   key 4: minimum useful-pixel percentage of its 16 x 8/16 tiles (default 65).
  *   key 5 / key 6: the same two switches for the spatial-tile weight-gradient kernel
  *          (defaults 1 and 40).
  *   key 7: programmatic dependent launch of the hot-path kernels (default 1); every such

@@ -88,7 +88,7 @@ def test_option_keys_are_documented_and_accepted_without_gpu(lib):
     for name, key in keys.items():
         assert key in doc, (name, key)
     defaults = {native.OPT_HALO_CONV: 1, native.OPT_HALO_ROW_ALIGN: 0, native.OPT_TILE_CONV: 1,
-                native.OPT_TILE_CONV_MIN_EFF: 70, native.OPT_TILE_WGRAD: 1,
+                native.OPT_TILE_CONV_MIN_EFF: 65, native.OPT_TILE_WGRAD: 1,
                 native.OPT_TILE_WGRAD_MIN_EFF: 40, native.OPT_PDL: 1,
                 native.OPT_WGRAD_MIN_TILES: 8, native.OPT_POOL_ROWS: 1,
                 native.OPT_DEEP_B_RING: 1, native.OPT_HALO_ROWSTAGE: 1,

@@ -48,7 +48,7 @@ def main():
                 g.integers(0, 2, (B, S, S, 1)).astype(np.uint8)) for _ in range(steps)]
 
     def build(ds):
-        return UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=nk, learning_rate=1e-3,
+        return UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=nk, learning_rate=1e-4,
                          load_snapshot=False, save_dir=None, seed=0)
 
     # ---- single-GPU reference at the full batch: one fwd+bwd (gradients), then `steps` steps

@@ -16,8 +16,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _model(ds, S):
+    # lr 1e-4 (the reference default): two runs of the same steps differ by the order of the
+    # fp32 gradient reductions only (<= 1e-8 on the parameters after three steps).  At 1e-3 the
+    # freshly initialised net is chaotic - 1.7 k parameters differing by 3e-7 after step 1
+    # become 2.4 M after step 2, serial or multi-stream alike (tools/diverge_check.py) - and
+    # comparing two runs tests nothing.
     os.environ['SEGB200_IMPL'] = 'umma'
-    return UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=32, learning_rate=1e-3,
+    return UNetModel(dataset=ds, n_classes=2, input_dims=S, n_kernels=32, learning_rate=1e-4,
                      load_snapshot=False, save_dir=None, seed=0)
 
 

@@ -47,7 +47,15 @@ struct TconvParams {
 constexpr int kTconvMaxSA = 8;
 constexpr int kTconvMaxSB = 40;
 constexpr int kTconvTH = 16;
-constexpr int kTconvThreads = 320;        // producer, MMA issuer, 8 epilogue warps
+// Epilogue warps per TMEM lane quadrant.  The drain of one 32-column chunk (TMEM load, bias by
+// shuffle, ReLU / mask, bf16, staging box, TMA store) is ~450 dependent instructions: one warp
+// issues it at ~0.2 IPC (ncu: 41 % of its samples in fixed-latency waits, 12 % instruction
+// fetch), so with two warps per scheduler the drain of a tile took ~1780 cycles per chunk and
+// was LONGER than the tile's MMAs for every layer with <= 64 input channels (FCN conv2: tensor
+// pipe active 27 % of the kernel, the issuer spinning on tempty).  Four warps per quadrant
+// (16 epilogue warps, 4 per scheduler) interleave four such chains.
+constexpr int kTconvEW = 4;
+constexpr int kTconvThreads = 64 + 128 * kTconvEW;   // producer, MMA issuer, 4 * kTconvEW epilogue warps
 
 template <int KC, int BN, bool B_MN, int MT>
 __global__ void __launch_bounds__(kTconvThreads, 1)
@@ -85,7 +93,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint64_t* tfull = b_empty + kTconvMaxSB;
   uint64_t* tempty = tfull + 2;
   uint64_t* mask_bar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 4 * kTconvEW);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,10 +108,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD0);
     tma_prefetch_desc(&tmD1);
-    for (int i = 0; i < 8; ++i) mbar_init(&mask_bar[i], 1);
+    for (int i = 0; i < 4 * kTconvEW; ++i) mbar_init(&mask_bar[i], 1);
     for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < P.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MT * (BN / 32) >= 2 ? 8 : 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * (MT * (BN / 32) < kTconvEW ? MT * (BN / 32) : kTconvEW)); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -267,12 +275,12 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     // cycles behind its commit) is never waited for, and the TMEM load of the warp's next
     // chunk is in flight while the current one is processed.
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    const int half = (warp - 2) >> 2;                // which warp of the quadrant's pair
+    const int sub = (warp - 2) >> 2;                 // which warp of the quadrant's group
     constexpr int NCH = BN / 32;                     // 32-column chunks per column block
     constexpr int NLD = MT * NCH;                    // chunks (TMEM loads) per tile
     constexpr int kBoxBytes = 32 * 32 * 2;           // [4 rows][8 cols][32 ch] bf16
-    constexpr int kMyMax = (NLD + 1) / 2;            // chunks per warp per tile
-    if (half < NLD) {
+    constexpr int kMyMax = (NLD + kTconvEW - 1) / kTconvEW;   // chunks per warp per tile
+    if (sub < NLD) {
       uint8_t* stg = smem + P.off_stage + (warp - 2) * (P.nstg * kBoxBytes);
       const uint32_t msk_u32 = smem_u32(smem + P.off_mask + (warp - 2) * (kMyMax * kBoxBytes));
       // swizzled (64-byte rows) offset of this lane's pixel, 16-byte chunk q: ^ ((lane>>1)&3)
@@ -299,15 +307,17 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         if (has_mask && lane == 0) {
           int cnt = 0;
 #pragma unroll
-          for (int i = 0; i < NLD; ++i)
-            if ((i & 1) == half) ++cnt;
+          for (int k = 0; k < kMyMax; ++k)
+            if (sub + k * kTconvEW < NLD) ++cnt;
           mbar_expect_tx(&mask_bar[warp - 2], cnt * kBoxBytes);
 #pragma unroll
-          for (int i = 0; i < NLD; ++i)
-            if ((i & 1) == half)
+          for (int k = 0; k < kMyMax; ++k) {
+            const int i = sub + k * kTconvEW;
+            if (i < NLD)
               tma_load_4d(tmM, &mask_bar[warp - 2], smem + P.off_mask +
-                              ((warp - 2) * kMyMax + (i >> 1)) * kBoxBytes,
+                              ((warp - 2) * kMyMax + k) * kBoxBytes,
                           nl0 + 32 * (i % NCH), x0 + 8 * (i / NCH), yw, img);
+          }
         }
         // bias of this tile's columns: lane l holds column 32*c + l of chunk c
         float bl[NCH];
@@ -317,15 +327,15 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         tc_fence_after();
         prof_mark(eprof, 2, ti, 1);
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols;
-        uint32_t rr[2][32];
-        tmem_ld_32x32(tbase + (half / NCH) * BN + (half % NCH) * 32, rr[0]);
+        uint32_t rr[kMyMax > 1 ? 2 : 1][32];
+        tmem_ld_32x32(tbase + (sub / NCH) * BN + (sub % NCH) * 32, rr[0]);
         if (has_mask) {
           mbar_wait(&mask_bar[warp - 2], mphase);
           mphase ^= 1u;
         }
 #pragma unroll
-        for (int i0 = 0; i0 < NLD; i0 += 2) {
-          const int i = i0 + half;                   // this warp's chunk (runtime: half)
+        for (int k = 0; k < kMyMax; ++k) {
+          const int i = sub + k * kTconvEW;          // this warp's chunk (runtime: sub)
           if (i < NLD) {
             const int mb = i / NCH, c = i % NCH;
             // rotate to the next staging box; the store that last read it was committed
@@ -334,19 +344,21 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             if (lane == 0) {
               if (P.nstg >= 4) bulk_wait_group_read<3>();
               else if (P.nstg == 3) bulk_wait_group_read<2>();
-              else bulk_wait_group_read<1>();
+              else if (P.nstg == 2) bulk_wait_group_read<1>();
+              else bulk_wait_group_read<0>();
             }
             __syncwarp();
             tmem_ld_wait();
-            if (i + 2 < NLD)
-              tmem_ld_32x32(tbase + ((i + 2) / NCH) * BN + ((i + 2) % NCH) * 32, rr[((i0 >> 1) + 1) & 1]);
-            const uint32_t* r = rr[(i0 >> 1) & 1];
+            if (k + 1 < kMyMax && i + kTconvEW < NLD)
+              tmem_ld_32x32(tbase + ((i + kTconvEW) / NCH) * BN + ((i + kTconvEW) % NCH) * 32,
+                            rr[(k + 1) & (kMyMax > 1 ? 1 : 0)]);
+            const uint32_t* r = rr[k & (kMyMax > 1 ? 1 : 0)];
             float bias_l = bl[0];
 #pragma unroll
             for (int cc = 1; cc < NCH; ++cc)
               if (cc == c) bias_l = bl[cc];
             const uint32_t sb32 = smem_u32(sbp) + row_off;
-            const uint32_t mk32 = msk_u32 + (i >> 1) * kBoxBytes + row_off;
+            const uint32_t mk32 = msk_u32 + k * kBoxBytes + row_off;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float v[8];
@@ -372,7 +384,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               o.w = pack_bf16x2(v[6], v[7]);
               sts128(sb32 + off, o);
             }
-            if (i + 2 >= NLD) {                      // this warp's share of the stage is read
+            if (i + kTconvEW >= NLD) {               // this warp's share of the stage is read
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[as]);

@@ -776,12 +776,16 @@ static bool tconv_plan(const TconvJob& J, int KC, int BN, int MT, int chunks, Tc
   const int bbytes = BN * KC * 2;
   const int box = 32 * 32 * 2;                          // one [4][8][32] staging / mask box
   const int nld = MT * (BN / 32);
-  const int msk = (J.flags & SEG_EPI_RELU_MASK) ? 8 * ((nld + 1) / 2) * box : 0;
-  // staging boxes per epilogue warp: 4 if that still leaves room for a resident B and 3 A
-  // stages, else fewer
-  int nstg = 4;
-  while (nstg > 2 && 9 * chunks * bbytes + 3 * a_stage + 8 * nstg * box + msk + 3072 > budget) --nstg;
-  const int stg = 8 * nstg * box;
+  const int ew = 4 * kTconvEW;                          // epilogue warps
+  const int my_max = (nld + kTconvEW - 1) / kTconvEW;   // chunks per warp per tile
+  const int msk = (J.flags & SEG_EPI_RELU_MASK) ? ew * my_max * box : 0;
+  // staging boxes per epilogue warp: a box is reused only after the TMA store that read it
+  // has left shared memory (~1000 cycles behind its commit): at least one per chunk the
+  // warp drains per tile, two if that still leaves room for a resident B next to 3 A stages
+  int nstg = my_max > 2 ? my_max : 2;
+  const int nstg_min = my_max > 1 ? my_max : 1;
+  while (nstg > nstg_min && 9 * chunks * bbytes + 3 * a_stage + ew * nstg * box + msk + 3072 > budget) --nstg;
+  const int stg = ew * nstg * box;
   const int fixed = stg + msk + 2048 /*bias*/ + 1024 /*barriers*/;
   int SB, resident;
   if (9 * chunks <= kTconvMaxSB && 9 * chunks * bbytes + 2 * a_stage + fixed <= budget) {

@@ -48,12 +48,12 @@ constexpr int kTconvMaxSA = 8;
 constexpr int kTconvMaxSB = 40;
 constexpr int kTconvTH = 16;
 // Epilogue warps per TMEM lane quadrant.  The drain of one 32-column chunk (TMEM load, bias by
-// shuffle, ReLU / mask, bf16, staging box, TMA store) is ~450 dependent instructions: one warp
-// issues it at ~0.2 IPC (ncu: 41 % of its samples in fixed-latency waits, 12 % instruction
-// fetch), so with two warps per scheduler the drain of a tile took ~1780 cycles per chunk and
-// was LONGER than the tile's MMAs for every layer with <= 64 input channels (FCN conv2: tensor
-// pipe active 27 % of the kernel, the issuer spinning on tempty).  Four warps per quadrant
-// (16 epilogue warps, 4 per scheduler) interleave four such chains.
+// shuffle, ReLU / mask, bf16, staging box, TMA store) is ~450 dependent instructions that one
+// warp issues at ~0.2 IPC (ncu: 41 % of its samples in fixed-latency waits, 12 % instruction
+// fetch).  In steady state it hides behind the next tile's MMAs (in-kernel timeline,
+// profiles/r02_ncu_tconv.md), but it is exposed after a CTA's last tile and before the next
+// kernel can start: four warps per quadrant (16 epilogue warps, 4 per scheduler) instead of
+// two interleave the chains and shorten that tail - U-Net step 0.934 -> 0.926 ms.
 constexpr int kTconvEW = 4;
 constexpr int kTconvThreads = 64 + 128 * kTconvEW;   // producer, MMA issuer, 4 * kTconvEW epilogue warps
 

@@ -234,3 +234,65 @@ def test_bf16_emulation_close_to_fp32_and_train_step_decreases_loss():
     losses = [nets.train_step(lambda q, xx: nets.unet_forward(q, xx), p, st, x, y, lr=1e-2)
               for _ in range(4)]
     assert losses[-1] < losses[0] and st.step == 4
+
+
+def test_inference_batchnorm_commutes_with_maxpool_bitwise():
+    """The identity seg_maxpool_bn_infer relies on: slim.batch_norm with moving
+    statistics is an increasing map (slope rsqrt(var + eps) > 0) and every rounding on the way
+    (fp32 arithmetic, bf16 storage) is monotonic, so bn(pool(x)) == pool(bn(x)) bit for bit —
+    the order the reference states is conv -> bn -> pool (models/deconvolution.py:126-138)."""
+    g = torch.Generator().manual_seed(3)
+    for k in (2, 3):
+        C = 16
+        x = T.bf16_round(torch.relu(torch.randn(2, 12, 18, C, generator=g)))
+        beta = torch.randn(C, generator=g) * 0.2
+        mean = torch.rand(C, generator=g) * 0.5
+        var = torch.rand(C, generator=g) * 0.5 + 0.01
+
+        def bn(t):
+            y, _, _ = T.batch_norm(t, beta, mean, var, False)
+            return T.bf16_round(y)
+
+        a = T.max_pool(bn(x), k, k)
+        b = bn(T.max_pool(x, k, k))
+        assert torch.equal(a, b)
+
+
+def test_fcn_upscore_gradient_is_a_16x16_window_gather():
+    """The formulation seg_upscore8_xent_fwd_bwd uses for the input gradient of the x8 bilinear
+    transposed conv (models/fcn.py:207-220): dx[i, j, c] = sum over the 16 x 16 output window
+    starting at (8i - 4, 8j - 4) of dy * filt, taps outside the image contributing nothing —
+    checked against autograd through the oracle's dense conv2d_transpose."""
+    g = torch.Generator().manual_seed(5)
+    B, h, w, C, f = 1, 5, 4, 3, 8
+    k = T.get_kernel_size(f)
+    x = torch.randn(B, h, w, C, generator=g, requires_grad=True)
+    y = T.bilinear_upsample(x, f)
+    assert tuple(y.shape) == (B, f * h, f * w, C)
+    dy = torch.randn(y.shape, generator=g)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    filt = torch.from_numpy(np.asarray(T.upsample_filt(k), dtype=np.float32))
+    dx = torch.zeros_like(dx_ref)
+    before = (k - f) // 2
+    for i in range(h):
+        for j in range(w):
+            for a in range(k):
+                oy = i * f + a - before
+                if not 0 <= oy < f * h:
+                    continue
+                for b in range(k):
+                    ox = j * f + b - before
+                    if 0 <= ox < f * w:
+                        dx[0, i, j] += dy[0, oy, ox] * filt[a, b]
+    assert torch.allclose(dx, dx_ref, rtol=1e-5, atol=1e-6)
+    # and the forward: every output pixel reads exactly two input rows and two input columns
+    yy = torch.zeros_like(y)
+    xd = x.detach()
+    for oy in range(f * h):
+        for ox in range(f * w):
+            ty, tx = oy + before, ox + before
+            for i in (ty // f, ty // f - 1):
+                for j in (tx // f, tx // f - 1):
+                    if 0 <= i < h and 0 <= j < w:
+                        yy[0, oy, ox] += xd[0, i, j] * filt[ty - i * f, tx - j * f]
+    assert torch.allclose(yy, y.detach(), rtol=1e-5, atol=1e-6)

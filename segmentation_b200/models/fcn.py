@@ -57,6 +57,12 @@ class FCNModel(BaseModel):
         self.fcn_type = fcn_type
         if self.input_dims[0] % 32 or self.input_dims[1] % 32:
             raise Exception('FCNModel: input_dims must be multiples of 32')
+        # optimizer groups in variable order: conv1-3 | conv4-5 | conv6, conv7, conv_fr, score
+        # convs (58 % of the parameters).  The backward pass completes them back to front, so
+        # the (all-reduce +) Adam of the 1x1 head runs beside the encoder's backward and only
+        # the small conv1-3 update is exposed at the end of the step.
+        self.opt_splits = tuple(s for s in os.environ.get('SEGB200_FCN_OPT_SPLITS',
+                                                          'conv4,conv6').split(',') if s)
         self._finish_init(seed)
         self.y_hat = self.y_hat_sig = self.output = None
         self.inference_ops = ['y_hat_sig', 'output']
